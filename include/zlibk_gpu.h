@@ -1,0 +1,159 @@
+/*
+ * zlibk_gpu.h -- C ABI of the B200 (sm_100a) DEFLATE engine that drops in behind
+ * ZLib.kotlin's compression hot path.
+ *
+ * Every entry point is extern "C", takes plain pointers and 64-bit sizes, returns a
+ * zlib code (common/Constants.kt:98-106), never throws and keeps no global state
+ * beyond the per-thread default context.  One zk_ctx per host thread ("not
+ * thread-safe, one ZStream per thread", docs/API.md:725); contexts are independent.
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns
+ * ZK_ERRNO / a null context.
+ *
+ * Citations are into /root/reference/src/commonMain/kotlin/ai/solace/zlib/ unless a
+ * path is given.  The Kotlin/Native cinterop binding a maintainer would add is in
+ * INTEGRATION.md (zlib.kotlin_b200/kotlin/zlibk.def + ZlibkGpu.kt).
+ */
+#ifndef ZLIBK_GPU_H
+#define ZLIBK_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- codes and constants (common/Constants.kt) ----------------------------- */
+#define ZK_OK 0             /* K:98  */
+#define ZK_STREAM_END 1     /* K:99  */
+#define ZK_NEED_DICT 2      /* K:100 */
+#define ZK_ERRNO (-1)       /* K:101: CUDA runtime failure, no device */
+#define ZK_STREAM_ERROR (-2)/* K:102: bad parameter / bad handle state */
+#define ZK_DATA_ERROR (-3)  /* K:103 */
+#define ZK_MEM_ERROR (-4)   /* K:104: device or pinned allocation failed */
+#define ZK_BUF_ERROR (-5)   /* K:105: output too small / input truncated */
+#define ZK_VERSION_ERROR (-6)
+
+#define ZK_NO_COMPRESSION 0        /* K:54 */
+#define ZK_BEST_SPEED 1            /* K:55 */
+#define ZK_BEST_COMPRESSION 9      /* K:56 */
+#define ZK_DEFAULT_COMPRESSION (-1)/* K:57 -- the reference maps every level <= 0 to stored (DS:307-311) */
+
+#define ZK_DEFAULT_STRATEGY 0 /* K:66 */
+#define ZK_FILTERED 1         /* K:67 */
+#define ZK_HUFFMAN_ONLY 2     /* K:68 */
+
+#define ZK_NO_FLUSH 0      /* K:79 */
+#define ZK_PARTIAL_FLUSH 1 /* K:80 */
+#define ZK_SYNC_FLUSH 2    /* K:81 */
+#define ZK_FULL_FLUSH 3    /* K:82 */
+#define ZK_FINISH 4        /* K:83 */
+
+typedef struct zk_ctx zk_ctx;       /* device, stream, scratch arena */
+typedef struct zk_stream zk_stream; /* streaming deflate / inflate state */
+
+/* ---- library ---------------------------------------------------------------- */
+/* replaces version(): String, common/Constants.kt:44 ("1.0.2"), suffixed with the engine tag */
+const char *zk_version(void);
+/* number of CUDA devices visible (0 = none: the engine is unusable) */
+int zk_device_count(void);
+/* text of the last CUDA error seen by this thread ("" if none) */
+const char *zk_last_error(void);
+
+/* ---- contexts ----------------------------------------------------------------- */
+/* Create a context bound to CUDA device `device` with its own stream.  Returns NULL
+ * (and sets zk_last_error) when the device cannot be used. */
+zk_ctx *zk_ctx_create(int device);
+void zk_ctx_destroy(zk_ctx *ctx);
+/* Run the context's kernels on a caller-owned cudaStream_t (e.g. torch's current
+ * stream) instead of its own; pass NULL to restore the private stream. */
+int zk_ctx_set_stream(zk_ctx *ctx, void *cuda_stream);
+int zk_ctx_synchronize(zk_ctx *ctx);
+/* Tunables: "chunk_bytes" (LZ unit, default auto), "block_bytes" (deflate block span,
+ * default 32768), "inflate_index" (emit/consume the side index, default 1). */
+int zk_ctx_set_option(zk_ctx *ctx, const char *name, int64_t value);
+/* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes"}. */
+int64_t zk_ctx_get_counter(zk_ctx *ctx, const char *name);
+
+/* ---- Adler-32 ------------------------------------------------------------------ */
+/* replaces Adler32Utils.adler32(adler, buf, index, len), bitwise/checksum/Adler32Utils.kt:31-57
+ * (and the wrapper deflate/Adler32.kt:35).  buf is HOST memory; buf == NULL -> 1 (AU:37). */
+uint32_t zk_adler32(zk_ctx *ctx, uint32_t adler, const uint8_t *buf, uint64_t len);
+/* same on a DEVICE buffer, asynchronous result written to *d_out (device uint32_t[1]) */
+int zk_adler32_device(zk_ctx *ctx, uint32_t adler, const uint8_t *d_buf, uint64_t len, uint32_t *d_out);
+/* zlib's adler32_combine: checksum of A||B from adler(A), adler(B), len(B).  Pure integer
+ * arithmetic on three scalars, used to fold per-shard checksums. */
+uint32_t zk_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
+
+/* ---- one-shot zlib deflate / inflate, HOST buffers ------------------------------ */
+/* upper bound of the compressed size for n input bytes at any level */
+uint64_t zk_compress_bound(uint64_t n);
+
+/* replaces DeflateStream.compressZlibResult(source, sink, level), deflate/DeflateStream.kt:302-328.
+ *   level > 9            -> ZK_STREAM_ERROR, *out_len = 0, nothing written (DS:323-325)
+ *   level <= 0           -> stored blocks (DS:307-308)
+ *   level 1 / 2..9       -> fastest / dynamic-Huffman blocks; FLEVEL per DS:27-33
+ *   strategy             -> zlib.h semantics (the reference defines the constants only, K:66-68)
+ * Returns ZK_OK, ZK_BUF_ERROR if cap < needed (nothing usable in out), or an error code.
+ * *adler (optional) receives the Adler-32 of the input. */
+int zk_deflate_zlib(zk_ctx *ctx, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out,
+                    uint64_t cap, uint64_t *out_len, uint32_t *adler);
+
+/* replaces InflateStream.inflateZlib(source, sink), inflate/InflateStream.kt:376-438.
+ * Returns ZK_STREAM_END on success (IS:424 -- not ZK_OK), ZK_NEED_DICT for FDICT streams
+ * (IS:36-43, *consumed = 6), ZK_DATA_ERROR, ZK_BUF_ERROR (truncated input, IS:425-428, or
+ * cap too small).  *out_len = bytes written, *consumed = input bytes used (trailing bytes
+ * of a second member are left unread, as in the reference).  The two exceptions the
+ * reference lets escape (IS:243 -> CH:127,133) are reported as ZK_DATA_ERROR. */
+int zk_inflate_zlib(zk_ctx *ctx, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                    uint64_t *consumed);
+
+/* ---- one-shot, DEVICE buffers (no host copies; asynchronous on the context stream) -- */
+/* d_out must hold zk_compress_bound(n) bytes.  d_result (device uint64_t[4]) receives
+ * {out_len, adler32, status, 0}.  Call zk_ctx_synchronize before reading it. */
+int zk_deflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t n, int level, int strategy, uint8_t *d_out,
+                           uint64_t cap, uint64_t *d_result);
+/* d_result (device uint64_t[4]) receives {out_len, consumed, status, adler32}. */
+int zk_inflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t m, uint8_t *d_out, uint64_t cap,
+                           uint64_t *d_result);
+
+/* ---- sharded deflate across GPUs ------------------------------------
+ * Each rank compresses a contiguous range of the input as a headerless, byte-aligned body
+ * (every block ends with a sync marker).  Ranks exchange {body_len, adler, raw_len} with
+ * ONE allgather (NCCL, done by the caller), then every rank knows its global offset and
+ * the folded checksum.  Rank 0 prepends the 2-byte header, the last rank appends the final
+ * empty block and the trailer. */
+/* d_hist: the 32 KiB of input that precede this shard (device), hist_len in [0, 32768].
+ * d_meta (device uint64_t[4]) receives {body_len, adler32(shard), n, status}. */
+int zk_deflate_shard_device(zk_ctx *ctx, const uint8_t *d_hist, uint32_t hist_len, const uint8_t *d_in, uint64_t n,
+                            int level, int strategy, uint8_t *d_body, uint64_t cap, uint64_t *d_meta);
+/* zlib header for `level` (2 bytes, DS:35-50) and stream tail (final empty block + big-endian
+ * Adler-32, 6 bytes) as host helpers for the rank that owns them. */
+void zk_zlib_header(int level, uint8_t out2[2]);
+void zk_zlib_tail(uint32_t adler, uint8_t out6[6]);
+
+/* ---- streaming (the documented ZStream surface, docs/API.md:205-281) ---------------- */
+/* deflateInit(level, method=8, windowBits=15, memLevel, strategy) */
+zk_stream *zk_deflate_init(zk_ctx *ctx, int level, int strategy);
+/* deflate(flush): consumes *in_len bytes from `in`, writes at most *out_len bytes to `out`;
+ * both are updated to the amounts used.  zlib.h flush semantics. */
+int zk_deflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush);
+int zk_deflate_reset(zk_stream *s);
+int zk_deflate_params(zk_stream *s, int level, int strategy);
+int zk_deflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len);
+/* inflateInit(windowBits=15) */
+zk_stream *zk_inflate_init(zk_ctx *ctx);
+int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush);
+int zk_inflate_reset(zk_stream *s);
+int zk_inflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len);
+/* totals and running checksum (ZStream.total_in / total_out / adler, docs/API.md:217-234) */
+uint64_t zk_stream_total_in(const zk_stream *s);
+uint64_t zk_stream_total_out(const zk_stream *s);
+uint32_t zk_stream_adler(const zk_stream *s);
+/* deflateEnd / inflateEnd / free */
+void zk_stream_end(zk_stream *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,678 @@
+// zk_api.cu -- the C ABI of include/zlibk_gpu.h: contexts, orchestration of K1..K5, host-buffer wrappers
+// and the streaming handles.  Host code only; every kernel lives in its own translation unit.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "zk_common.cuh"
+
+namespace zk {
+
+// launchers defined next to their kernels
+int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_hist, uint32_t hist_len,
+                uint32_t unit_bytes, uint32_t block_bytes, const LevelParams &lp, uint32_t *tokens,
+                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist);
+int launch_huffman(zk_ctx *c, const uint32_t *block_hist, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
+                   int force_type, BlockPlan *plans);
+int launch_plan_offsets(zk_ctx *c, const BlockPlan *plans, uint32_t num_blocks, uint64_t *offsets, uint64_t *cursor,
+                        uint64_t cap);
+int launch_pack(zk_ctx *c, const uint8_t *d_in, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
+                const uint32_t *tokens, const uint32_t *block_tok_begin, const uint32_t *block_tok_count,
+                const BlockPlan *plans, const uint64_t *offsets, const uint64_t *cursor, uint8_t *out);
+int launch_stored(zk_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *out, uint32_t num_blocks, int final_flag);
+int launch_frame(zk_ctx *c, uint8_t *out, uint64_t cap, int level, int write_header, int write_final_block,
+                 const uint64_t *cursor, int64_t body_override, const uint32_t *adler, uint64_t n, uint64_t *result);
+
+static thread_local char g_last_error[256] = "";
+
+void set_last_error(const char *what, cudaError_t e) {
+    snprintf(g_last_error, sizeof g_last_error, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// ---- arena ---------------------------------------------------------------------------------------------
+int Arena::reserve(size_t bytes) {
+    if (bytes <= cap) return ZK_OK;
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    const size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&base, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&base, bytes);
+        if (e != cudaSuccess) {
+            set_last_error("cudaMalloc(arena)", e);
+            base = nullptr;
+            return ZK_MEM_ERROR;
+        }
+        cap = bytes;
+        return ZK_OK;
+    }
+    cap = want;
+    return ZK_OK;
+}
+void *Arena::take(size_t bytes, size_t align) {
+    size_t at = (used + align - 1) / align * align;
+    if (at + bytes > cap) return nullptr;
+    used = at + bytes;
+    return base + at;
+}
+void Arena::release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = used = 0;
+}
+
+// ---- deflate orchestration ---------------------------------------------------------------------------------
+static uint32_t pick_unit_bytes(const zk_ctx *c, uint64_t n, uint32_t block_bytes) {
+    if (c->opt_chunk_bytes > 0) {
+        uint64_t u = (uint64_t)c->opt_chunk_bytes / block_bytes * block_bytes;
+        return (uint32_t)tmax<uint64_t>(u, block_bytes);
+    }
+    // at least ~4 units per SM so the tail wave is short; history re-priming costs 32 KiB per unit
+    uint64_t u = 1u << 20;
+    while (u > block_bytes && n / u < (uint64_t)c->sm_count * 4) u >>= 1;
+    return (uint32_t)tmax<uint64_t>(u, block_bytes);
+}
+
+constexpr uint64_t kSlabBytes = 256ull << 20;  // tokens for one slab: 4 B per input byte
+
+int run_deflate(zk_ctx *c, const DeflateJob &job) {
+    const uint64_t n = job.n;
+    const int level = job.level;
+    const uint32_t block_bytes = (uint32_t)c->opt_block_bytes;
+    uint8_t *body = job.d_out + (job.framed ? 2 : 0);
+    const uint64_t frame_bytes = job.framed ? 2 + 2 + 4 : 0;
+    const uint64_t body_cap = job.cap > frame_bytes ? job.cap - frame_bytes : 0;
+
+    c->arena.reset();
+    const bool stored_only = level <= 0;
+    const uint64_t slab = tmin<uint64_t>(n, kSlabBytes);
+    const uint32_t slab_blocks = (uint32_t)((slab + block_bytes - 1) / block_bytes) + 1;
+    size_t need = 8192 + adler_partials_bytes(n);
+    if (!stored_only)
+        need += (size_t)slab * 4 + (size_t)slab_blocks * (8 + kHistStride * 4 + sizeof(BlockPlan) + 8) + 4096;
+    if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
+    uint64_t *d_cursor = static_cast<uint64_t *>(c->arena.take(256));
+    uint32_t *d_adler = static_cast<uint32_t *>(c->arena.take(256));
+    void *d_partials = c->arena.take(adler_partials_bytes(n));
+    ZK_CUDA(cudaMemsetAsync(d_cursor, 0, 16, c->stream));
+
+    int rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
+    if (rc != ZK_OK) return rc;
+
+    if (stored_only) {
+        // DS:331-373: 65535-byte stored blocks; an input that is a multiple of 65535 (0 included) ends with an
+        // empty final block, exactly as the reference's loop does.
+        const uint32_t nb = (uint32_t)(n / 65535u) + 1;
+        const uint64_t body_len = n + 5ull * nb;
+        if (body_len > body_cap) {
+            ZK_CUDA(cudaMemsetAsync(d_cursor + 1, 1, 1, c->stream));
+        } else {
+            rc = launch_stored(c, job.d_in, n, body, nb, job.framed ? 1 : 0);
+            if (rc != ZK_OK) return rc;
+        }
+        return launch_frame(c, job.d_out, job.cap, level, job.framed, 0, d_cursor, (int64_t)body_len, d_adler, n,
+                            job.d_result);
+    }
+
+    const LevelParams lp = level_params(level, job.strategy);
+    uint32_t *d_tokens = static_cast<uint32_t *>(c->arena.take((size_t)slab * 4));
+    uint32_t *d_tok_begin = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
+    uint32_t *d_tok_count = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
+    uint32_t *d_hist = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * kHistStride * 4));
+    BlockPlan *d_plans = static_cast<BlockPlan *>(c->arena.take((size_t)slab_blocks * sizeof(BlockPlan)));
+    uint64_t *d_offsets = static_cast<uint64_t *>(c->arena.take((size_t)slab_blocks * 8));
+    if (!d_offsets) return ZK_MEM_ERROR;
+
+    for (uint64_t s0 = 0; s0 < n; s0 += kSlabBytes) {
+        const uint64_t sn = tmin<uint64_t>(kSlabBytes, n - s0);
+        const uint32_t nb = (uint32_t)((sn + block_bytes - 1) / block_bytes);
+        const uint32_t unit = pick_unit_bytes(c, sn, block_bytes);
+        const uint8_t *hist = s0 ? job.d_in + s0 - kWindow : job.d_hist;
+        const uint32_t hist_len = s0 ? (uint32_t)kWindow : (job.d_hist ? job.hist_len : 0);
+        rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, d_tokens, d_tok_begin, d_tok_count,
+                         d_hist);
+        if (rc != ZK_OK) return rc;
+        rc = launch_huffman(c, d_hist, sn, block_bytes, nb, -1, d_plans);
+        if (rc != ZK_OK) return rc;
+        // offsets continue from the previous slab: the cursor lives on the device, no host round trip
+        rc = launch_plan_offsets(c, d_plans, nb, d_offsets, d_cursor, body_cap);
+        if (rc != ZK_OK) return rc;
+        rc = launch_pack(c, job.d_in + s0, sn, block_bytes, nb, d_tokens, d_tok_begin, d_tok_count, d_plans, d_offsets,
+                         d_cursor, body);
+        if (rc != ZK_OK) return rc;
+    }
+    return launch_frame(c, job.d_out, job.cap, level, job.framed, job.framed, d_cursor, -1, d_adler, n, job.d_result);
+}
+
+}  // namespace zk
+
+// ========================================================================================================
+// C ABI
+// ========================================================================================================
+using namespace zk;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *zk_version(void) { return "1.0.2+b200"; }
+
+int zk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *zk_last_error(void) { return g_last_error; }
+
+zk_ctx *zk_ctx_create(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        set_last_error("zk_ctx_create: no such CUDA device", e == cudaSuccess ? cudaErrorInvalidDevice : e);
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    zk_ctx *c = new (std::nothrow) zk_ctx();
+    if (!c) return nullptr;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return nullptr;
+    }
+    c->stream = c->own_stream;
+    c->pinned_cap = 4096;
+    if (cudaHostAlloc(&c->pinned, c->pinned_cap, cudaHostAllocDefault) != cudaSuccess) c->pinned = nullptr;
+    return c;
+}
+
+void zk_ctx_destroy(zk_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->arena.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int zk_ctx_set_stream(zk_ctx *c, void *cuda_stream) {
+    if (!c) return ZK_STREAM_ERROR;
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return ZK_OK;
+}
+
+int zk_ctx_synchronize(zk_ctx *c) {
+    if (!c) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
+    return ZK_OK;
+}
+
+int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
+    if (!c || !name) return ZK_STREAM_ERROR;
+    if (!strcmp(name, "chunk_bytes")) {
+        if (value < 0) return ZK_STREAM_ERROR;
+        c->opt_chunk_bytes = value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "block_bytes")) {
+        // power of two, a multiple of the LZ group, at most one stored block (<= 65535 bytes)
+        if (value < kGroup || value > 32768 || (value & (value - 1))) return ZK_STREAM_ERROR;
+        c->opt_block_bytes = value;
+        return ZK_OK;
+    }
+    return ZK_STREAM_ERROR;
+}
+
+int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
+    if (!c || !name) return -1;
+    if (!strcmp(name, "kernel_launches")) return c->launches;
+    if (!strcmp(name, "h2d_bytes")) return c->h2d_bytes;
+    if (!strcmp(name, "d2h_bytes")) return c->d2h_bytes;
+    return -1;
+}
+
+uint32_t zk_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
+
+uint64_t zk_compress_bound(uint64_t n) { return n + (n >> 12) + (n >> 14) + 64; }
+
+void zk_zlib_header(int level, uint8_t out2[2]) {
+    const int flevel = level >= 9 ? 3 : level >= 6 ? 2 : level >= 2 ? 1 : 0;  // DS:27-33
+    const int cmf = 0x78, flg = flevel << 6;
+    out2[0] = (uint8_t)cmf;
+    out2[1] = (uint8_t)(flg | ((31 - (((cmf << 8) | flg) % 31)) % 31));
+}
+
+void zk_zlib_tail(uint32_t adler, uint8_t out6[6]) {
+    out6[0] = 0x03;
+    out6[1] = 0x00;
+    out6[2] = (uint8_t)(adler >> 24);
+    out6[3] = (uint8_t)(adler >> 16);
+    out6[4] = (uint8_t)(adler >> 8);
+    out6[5] = (uint8_t)adler;
+}
+
+// ---- device-buffer entry points ------------------------------------------------------------------------------
+int zk_adler32_device(zk_ctx *c, uint32_t adler, const uint8_t *d_buf, uint64_t len, uint32_t *d_out) {
+    if (!c || !d_out || (!d_buf && len)) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    c->arena.reset();
+    if (c->arena.reserve(adler_partials_bytes(len) + 1024) != ZK_OK) return ZK_MEM_ERROR;
+    void *partials = c->arena.take(adler_partials_bytes(len));
+    return launch_adler32(c, adler, d_buf, len, partials, d_out);
+}
+
+int zk_deflate_zlib_device(zk_ctx *c, const uint8_t *d_in, uint64_t n, int level, int strategy, uint8_t *d_out,
+                           uint64_t cap, uint64_t *d_result) {
+    if (!c || !d_out || !d_result || (!d_in && n)) return ZK_STREAM_ERROR;
+    if (level > 9) return ZK_STREAM_ERROR;  // DS:323-325
+    if (strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    DeflateJob job{d_in, n, nullptr, 0, level, strategy, d_out, cap, true, d_result};
+    return run_deflate(c, job);
+}
+
+int zk_deflate_shard_device(zk_ctx *c, const uint8_t *d_hist, uint32_t hist_len, const uint8_t *d_in, uint64_t n,
+                            int level, int strategy, uint8_t *d_body, uint64_t cap, uint64_t *d_meta) {
+    if (!c || !d_body || !d_meta || (!d_in && n) || hist_len > (uint32_t)kWindow) return ZK_STREAM_ERROR;
+    if (level > 9) return ZK_STREAM_ERROR;
+    if (strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    DeflateJob job{d_in, n, hist_len ? d_hist : nullptr, hist_len, level, strategy, d_body, cap, false, d_meta};
+    return run_deflate(c, job);
+}
+
+int zk_inflate_zlib_device(zk_ctx *c, const uint8_t *d_in, uint64_t m, uint8_t *d_out, uint64_t cap,
+                           uint64_t *d_result) {
+    if (!c || !d_result || (!d_in && m) || (!d_out && cap)) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    InflateJob job{d_in, m, d_out, cap, d_result};
+    return run_inflate(c, job);
+}
+
+// ---- host-buffer entry points ----------------------------------------------------------------------------------
+// Device staging for host calls: one grow-only buffer per context, separate from the kernel arena.
+struct Staging {
+    uint8_t *base = nullptr;
+    size_t cap = 0;
+};
+static thread_local std::vector<std::pair<zk_ctx *, Staging>> g_staging;
+
+static Staging *staging_for(zk_ctx *c, size_t bytes) {
+    Staging *s = nullptr;
+    for (auto &p : g_staging)
+        if (p.first == c) s = &p.second;
+    if (!s) {
+        g_staging.push_back({c, Staging()});
+        s = &g_staging.back().second;
+    }
+    if (s->cap < bytes) {
+        if (s->base) cudaFree(s->base);
+        s->base = nullptr;
+        s->cap = 0;
+        if (cudaMalloc(&s->base, bytes + (bytes >> 4) + 4096) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&s->base, bytes) != cudaSuccess) {
+                set_last_error("cudaMalloc(staging)", cudaErrorMemoryAllocation);
+                return nullptr;
+            }
+            s->cap = bytes;
+        } else {
+            s->cap = bytes + (bytes >> 4) + 4096;
+        }
+    }
+    return s;
+}
+
+uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len) {
+    if (buf == nullptr) return 1u;  // AU:37
+    if (!c || len == 0) return len == 0 ? adler : 0u;
+    if (cudaSetDevice(c->device) != cudaSuccess) return 0u;
+    Staging *s = staging_for(c, (size_t)len + 256);
+    if (!s) return 0u;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(s->base);
+    uint8_t *d_buf = s->base + 256;
+    if (cudaMemcpyAsync(d_buf, buf, len, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return 0u;
+    c->h2d_bytes += (int64_t)len;
+    if (zk_adler32_device(c, adler, d_buf, len, d_out) != ZK_OK) return 0u;
+    uint32_t out = 0;
+    if (cudaMemcpyAsync(&out, d_out, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return 0u;
+    cudaStreamSynchronize(c->stream);
+    c->d2h_bytes += 4;
+    return out;
+}
+
+int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
+                    uint64_t *out_len, uint32_t *adler) {
+    if (out_len) *out_len = 0;
+    if (!c || !out_len || (!in && n) || (!out && cap)) return ZK_STREAM_ERROR;
+    if (level > 9) return ZK_STREAM_ERROR;  // DS:323-325: nothing written
+    if (strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    const uint64_t bound = zk_compress_bound(n);
+    const uint64_t dcap = cap < bound ? cap : bound;
+    const size_t in_room = ((size_t)n + 255) / 256 * 256;
+    Staging *s = staging_for(c, 256 + in_room + (size_t)dcap + 256);
+    if (!s) return ZK_MEM_ERROR;
+    uint64_t *d_result = reinterpret_cast<uint64_t *>(s->base);
+    uint8_t *d_in = s->base + 256;
+    uint8_t *d_out = d_in + in_room;
+    if (n) ZK_CUDA(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (int64_t)n;
+    int rc = zk_deflate_zlib_device(c, d_in, n, level, strategy, d_out, dcap, d_result);
+    if (rc != ZK_OK) return rc;
+    uint64_t res[4];
+    ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += 32;
+    const int status = (int)(int64_t)res[2];
+    if (adler) *adler = (uint32_t)res[1];
+    if (status != ZK_OK) return status;
+    ZK_CUDA(cudaMemcpyAsync(out, d_out, res[0], cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (int64_t)res[0];
+    *out_len = res[0];
+    return ZK_OK;
+}
+
+int zk_inflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                    uint64_t *consumed) {
+    if (out_len) *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (!c || !out_len || (!in && m) || (!out && cap)) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    const size_t in_room = ((size_t)m + 255) / 256 * 256;
+    Staging *s = staging_for(c, 256 + in_room + (size_t)cap + 256);
+    if (!s) return ZK_MEM_ERROR;
+    uint64_t *d_result = reinterpret_cast<uint64_t *>(s->base);
+    uint8_t *d_in = s->base + 256;
+    uint8_t *d_out = d_in + in_room;
+    if (m) ZK_CUDA(cudaMemcpyAsync(d_in, in, m, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (int64_t)m;
+    int rc = zk_inflate_zlib_device(c, d_in, m, d_out, cap, d_result);
+    if (rc != ZK_OK) return rc;
+    uint64_t res[4];
+    ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += 32;
+    const int status = (int)(int64_t)res[2];
+    if (res[0] && res[0] <= cap) {
+        ZK_CUDA(cudaMemcpyAsync(out, d_out, res[0], cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += (int64_t)res[0];
+    }
+    *out_len = res[0] <= cap ? res[0] : 0;
+    if (consumed) *consumed = res[1];
+    return status;
+}
+
+// ---- streaming handles (docs/API.md:205-281) ------------------------------------------------------------------
+// deflate: input is gathered into slabs; a slab is compressed as a headerless body primed with the previous
+// 32 KiB (the same mechanism as a shard), so output produced for different slabs concatenates byte-wise.
+// inflate: the compressed input is gathered until the stream can be decoded as a whole.
+struct zk_stream {
+    zk_ctx *ctx;
+    int mode;  // 0 deflate, 1 inflate
+    int level, strategy;
+    bool header_done, finished;
+    uint64_t total_in, total_out;
+    uint32_t adler;
+    std::vector<uint8_t> pending_in;   // input not yet compressed / decoded
+    std::vector<uint8_t> history;      // last 32 KiB of compressed-so-far input (deflate) / dictionary
+    std::vector<uint8_t> pending_out;  // produced, not yet handed to the caller
+    size_t out_pos;
+};
+
+static const size_t kStreamSlab = 8u << 20;
+
+zk_stream *zk_deflate_init(zk_ctx *ctx, int level, int strategy) {
+    if (!ctx || level > 9 || strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return nullptr;
+    zk_stream *s = new (std::nothrow) zk_stream();
+    if (!s) return nullptr;
+    s->ctx = ctx;
+    s->mode = 0;
+    s->level = level;
+    s->strategy = strategy;
+    s->header_done = s->finished = false;
+    s->total_in = s->total_out = 0;
+    s->adler = 1;
+    s->out_pos = 0;
+    return s;
+}
+
+// compress pending_in as one headerless body and append it to pending_out
+static int stream_flush_slab(zk_stream *s) {
+    zk_ctx *c = s->ctx;
+    const size_t n = s->pending_in.size();
+    if (n == 0) return ZK_OK;
+    ZK_CUDA(cudaSetDevice(c->device));
+    const uint64_t bound = zk_compress_bound(n);
+    const size_t in_room = (n + 255) / 256 * 256;
+    Staging *st = staging_for(c, 256 + 32768 + in_room + (size_t)bound + 256);
+    if (!st) return ZK_MEM_ERROR;
+    uint64_t *d_meta = reinterpret_cast<uint64_t *>(st->base);
+    uint8_t *d_hist = st->base + 256;
+    uint8_t *d_in = d_hist + 32768;
+    uint8_t *d_out = d_in + in_room;
+    const uint32_t hl = (uint32_t)s->history.size();
+    if (hl) ZK_CUDA(cudaMemcpyAsync(d_hist, s->history.data(), hl, cudaMemcpyHostToDevice, c->stream));
+    ZK_CUDA(cudaMemcpyAsync(d_in, s->pending_in.data(), n, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (int64_t)(n + hl);
+    int rc = zk_deflate_shard_device(c, d_hist, hl, d_in, n, s->level, s->strategy, d_out, bound, d_meta);
+    if (rc != ZK_OK) return rc;
+    uint64_t meta[4];
+    ZK_CUDA(cudaMemcpyAsync(meta, d_meta, sizeof meta, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
+    if ((int)(int64_t)meta[2] != ZK_OK) return (int)(int64_t)meta[2];
+    const size_t at = s->pending_out.size();
+    s->pending_out.resize(at + meta[0]);
+    ZK_CUDA(cudaMemcpyAsync(s->pending_out.data() + at, d_out, meta[0], cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (int64_t)meta[0] + 32;
+    s->adler = adler32_combine(s->adler, (uint32_t)meta[1], n);
+    // keep the last 32 KiB as the next slab's dictionary
+    std::vector<uint8_t> h;
+    if (n >= 32768) h.assign(s->pending_in.end() - 32768, s->pending_in.end());
+    else {
+        const size_t keep = s->history.size() + n > 32768 ? 32768 - n : s->history.size();
+        h.assign(s->history.end() - keep, s->history.end());
+        h.insert(h.end(), s->pending_in.begin(), s->pending_in.end());
+    }
+    s->history.swap(h);
+    s->pending_in.clear();
+    return ZK_OK;
+}
+
+int zk_deflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush) {
+    if (!s || s->mode != 0 || !in_len || !out_len || flush < 0 || flush > ZK_FINISH) return ZK_STREAM_ERROR;
+    const uint64_t avail_in = *in_len, avail_out = *out_len;
+    *in_len = 0;
+    *out_len = 0;
+    if (s->finished && avail_in) return ZK_STREAM_ERROR;
+    if (!s->header_done) {
+        uint8_t h[2];
+        zk_zlib_header(s->level, h);
+        s->pending_out.insert(s->pending_out.end(), h, h + 2);
+        s->header_done = true;
+    }
+    if (avail_in) {
+        if (!in) return ZK_STREAM_ERROR;
+        s->pending_in.insert(s->pending_in.end(), in, in + avail_in);
+        s->total_in += avail_in;
+        *in_len = avail_in;
+    }
+    if (!s->finished && (s->pending_in.size() >= kStreamSlab || (flush != ZK_NO_FLUSH && !s->pending_in.empty()))) {
+        int rc = stream_flush_slab(s);
+        if (rc != ZK_OK) return rc;
+        if (flush == ZK_FULL_FLUSH) s->history.clear();  // later data may not refer to earlier data
+    }
+    if (flush == ZK_FINISH && !s->finished) {
+        uint8_t t[6];
+        zk_zlib_tail(s->adler, t);
+        s->pending_out.insert(s->pending_out.end(), t, t + 6);
+        s->finished = true;
+    }
+    const size_t have = s->pending_out.size() - s->out_pos;
+    const size_t give = have < avail_out ? have : (size_t)avail_out;
+    if (give) {
+        if (!out) return ZK_STREAM_ERROR;
+        memcpy(out, s->pending_out.data() + s->out_pos, give);
+        s->out_pos += give;
+        s->total_out += give;
+        *out_len = give;
+    }
+    if (s->out_pos == s->pending_out.size()) {
+        s->pending_out.clear();
+        s->out_pos = 0;
+        if (s->finished) return ZK_STREAM_END;
+    }
+    if (!*in_len && !give) return ZK_BUF_ERROR;  // zlib.h: no progress possible
+    return ZK_OK;
+}
+
+int zk_deflate_reset(zk_stream *s) {
+    if (!s || s->mode != 0) return ZK_STREAM_ERROR;
+    s->header_done = s->finished = false;
+    s->total_in = s->total_out = 0;
+    s->adler = 1;
+    s->pending_in.clear();
+    s->history.clear();
+    s->pending_out.clear();
+    s->out_pos = 0;
+    return ZK_OK;
+}
+
+int zk_deflate_params(zk_stream *s, int level, int strategy) {
+    if (!s || s->mode != 0 || level > 9 || strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    if (!s->pending_in.empty()) {  // zlib.h: data so far is compressed with the old parameters
+        int rc = stream_flush_slab(s);
+        if (rc != ZK_OK) return rc;
+    }
+    s->level = level;
+    s->strategy = strategy;
+    return ZK_OK;
+}
+
+int zk_deflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len) {
+    // Raw priming only: the zlib wrapper's FDICT/DICTID is not emitted (the reference refuses FDICT streams,
+    // IS:36-43), so this is accepted before any input and only affects match finding.
+    if (!s || s->mode != 0 || !dict || s->total_in) return ZK_STREAM_ERROR;
+    const uint32_t keep = len > 32768 ? 32768 : len;
+    s->history.assign(dict + (len - keep), dict + len);
+    return ZK_OK;
+}
+
+zk_stream *zk_inflate_init(zk_ctx *ctx) {
+    if (!ctx) return nullptr;
+    zk_stream *s = new (std::nothrow) zk_stream();
+    if (!s) return nullptr;
+    s->ctx = ctx;
+    s->mode = 1;
+    s->level = s->strategy = 0;
+    s->header_done = s->finished = false;
+    s->total_in = s->total_out = 0;
+    s->adler = 1;
+    s->out_pos = 0;
+    return s;
+}
+
+int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush) {
+    if (!s || s->mode != 1 || !in_len || !out_len) return ZK_STREAM_ERROR;
+    const uint64_t avail_in = *in_len, avail_out = *out_len;
+    *in_len = 0;
+    *out_len = 0;
+    if (!s->finished && avail_in) {
+        if (!in) return ZK_STREAM_ERROR;
+        s->pending_in.insert(s->pending_in.end(), in, in + avail_in);
+        *in_len = avail_in;
+        s->total_in += avail_in;
+    }
+    if (!s->finished && !s->pending_in.empty()) {
+        // try to decode what has arrived; a truncated stream reports ZK_BUF_ERROR and we wait for more
+        uint64_t cap = (uint64_t)s->pending_in.size() * 4 + 65536;
+        for (;;) {
+            std::vector<uint8_t> buf(cap);
+            uint64_t got = 0, used = 0;
+            int rc = zk_inflate_zlib(s->ctx, s->pending_in.data(), s->pending_in.size(), buf.data(), cap, &got, &used);
+            if (rc == ZK_STREAM_END) {
+                buf.resize(got);
+                s->pending_out.swap(buf);
+                s->out_pos = 0;
+                s->finished = true;
+                s->adler = 0;
+                // Adler-32 of the output is the stream's trailer
+                if (used >= 4) {
+                    const uint8_t *t = s->pending_in.data() + used - 4;
+                    s->adler = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+                }
+                s->total_in -= s->pending_in.size() - used;  // trailing bytes are not consumed
+                *in_len -= tmin<uint64_t>(*in_len, s->pending_in.size() - used);
+                s->pending_in.clear();
+                break;
+            }
+            if (rc == ZK_BUF_ERROR && got == 0 && cap < (1ull << 36)) {
+                // either the output did not fit or the input is still incomplete: grow once, then decide
+                if (cap >= (uint64_t)s->pending_in.size() * 1100 + 65536) {
+                    if (flush == ZK_FINISH) return ZK_BUF_ERROR;
+                    break;  // need more input
+                }
+                cap *= 16;
+                continue;
+            }
+            if (rc == ZK_BUF_ERROR) {
+                if (flush == ZK_FINISH) return ZK_BUF_ERROR;
+                break;  // need more input
+            }
+            return rc;  // ZK_NEED_DICT, ZK_DATA_ERROR, ...
+        }
+    }
+    const size_t have = s->pending_out.size() - s->out_pos;
+    const size_t give = have < avail_out ? have : (size_t)avail_out;
+    if (give) {
+        if (!out) return ZK_STREAM_ERROR;
+        memcpy(out, s->pending_out.data() + s->out_pos, give);
+        s->out_pos += give;
+        s->total_out += give;
+        *out_len = give;
+    }
+    if (s->finished && s->out_pos == s->pending_out.size()) return ZK_STREAM_END;
+    if (!*in_len && !give) return ZK_BUF_ERROR;
+    return ZK_OK;
+}
+
+int zk_inflate_reset(zk_stream *s) {
+    if (!s || s->mode != 1) return ZK_STREAM_ERROR;
+    s->header_done = s->finished = false;
+    s->total_in = s->total_out = 0;
+    s->adler = 1;
+    s->pending_in.clear();
+    s->pending_out.clear();
+    s->out_pos = 0;
+    return ZK_OK;
+}
+
+int zk_inflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len) {
+    // The reference has no dictionary API and answers FDICT streams with Z_NEED_DICT (IS:36-43); preset
+    // dictionaries are a SURVEY.md 8(f) "next" row.
+    (void)dict;
+    (void)len;
+    if (!s || s->mode != 1) return ZK_STREAM_ERROR;
+    return ZK_STREAM_ERROR;
+}
+
+uint64_t zk_stream_total_in(const zk_stream *s) { return s ? s->total_in : 0; }
+uint64_t zk_stream_total_out(const zk_stream *s) { return s ? s->total_out : 0; }
+uint32_t zk_stream_adler(const zk_stream *s) { return s ? s->adler : 0; }
+
+void zk_stream_end(zk_stream *s) { delete s; }
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,122 @@
+// zk_common.cuh -- shared declarations of the sm_100a DEFLATE engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/zlibk_gpu.h"
+
+namespace zk {
+
+// ---- geometry -------------------------------------------------------------------------
+constexpr int kWindow = 32768;     // DEFLATE window (DeflateStream.kt:573-574, InflateStream.kt:26)
+constexpr int kMinMatch = 3;       // common/Constants.kt MIN_MATCH
+constexpr int kMaxMatch = 258;     // common/Constants.kt MAX_MATCH
+constexpr int kNumLitLen = 286;    // literal/length alphabet
+constexpr int kNumDist = 30;       // distance alphabet
+constexpr int kHistStride = 320;   // u32 counters per block: [0,286) lit/len, [288,318) dist
+constexpr int kDistHistBase = 288;
+constexpr int kGroup = 4096;       // LZ pipeline group (positions per pipeline step)
+constexpr int kBlockBytesDefault = 32768;  // input span of one deflate block
+constexpr int kMaxHeaderBytes = 320;       // dynamic block header: <= 17 + 57 + 316*(7+7) bits
+
+// token / per-position match word: len << 16 | (dist - 1); len == 0 -> literal (low 8 bits = byte)
+constexpr uint32_t kTokStart = 0x80000000u;   // parser mark: a token starts here
+constexpr uint32_t kTokLiteral = 0x40000000u; // parser mark: emit the byte although a match exists
+
+struct LevelParams {
+    int chain;     // hash-chain steps per search
+    int nice;      // stop searching once a match this long is found
+    int good;      // quarter the chain when the inherited match is at least this long
+    int lazy;      // one-step lazy evaluation
+    int skip_deep; // 1: from the 3rd inherited position on, do not search
+    int far3;      // a length-3 match farther than this is dropped
+    int min_len;   // 3, or 259 for Z_HUFFMAN_ONLY (no matches)
+    int filtered;  // Z_FILTERED: matches of length <= 5 become literals
+};
+
+// Per-block record written by the Huffman kernel and consumed by the packer.
+struct BlockPlan {
+    uint32_t type;        // 0 stored, 1 fixed, 2 dynamic
+    uint32_t header_bits; // bits of `header` (block header incl. BFINAL/BTYPE and code tables)
+    uint32_t body_bits;   // token bits incl. end-of-block
+    uint32_t out_bytes;   // bytes this block occupies in the stream (incl. the sync marker)
+    uint32_t litlen_code[kNumLitLen]; // code | len << 16  (code already bit-reversed)
+    uint32_t dist_code[kNumDist];
+    uint8_t header[kMaxHeaderBytes];
+};
+
+template <typename T>
+__host__ __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
+template <typename T>
+__host__ __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_last_error(const char *what, cudaError_t e);
+#define ZK_CUDA(expr)                                      \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) {                           \
+            ::zk::set_last_error(#expr, _e);               \
+            return _e == cudaErrorMemoryAllocation ? ZK_MEM_ERROR : ZK_ERRNO; \
+        }                                                  \
+    } while (0)
+
+// ---- device scratch arena ------------------------------------------------------------------
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes); // grow-only; invalidates earlier pointers (call before take)
+    void reset() { used = 0; }
+    void *take(size_t bytes, size_t align = 256);
+    void release();
+};
+
+}  // namespace zk
+
+struct zk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    zk::Arena arena;       // device scratch (tokens, histograms, plans, staging)
+    uint8_t *pinned = nullptr; // pinned host staging for small results
+    size_t pinned_cap = 0;
+    int64_t opt_chunk_bytes = 0; // 0 = auto
+    int64_t opt_block_bytes = zk::kBlockBytesDefault;
+    int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+namespace zk {
+
+// ---- kernels' host launchers (each returns a ZK_* code) ------------------------------------
+// K4: Adler-32 of d_buf[0,n) seeded with `seed`; result to d_out[0].  d_partials needs
+// adler_partials_bytes(n) bytes of scratch.
+size_t adler_partials_bytes(uint64_t n);
+int launch_adler32(zk_ctx *c, uint32_t seed, const uint8_t *d_buf, uint64_t n, void *d_partials, uint32_t *d_out);
+
+struct DeflateJob {
+    const uint8_t *d_in;   // shard input (device)
+    uint64_t n;
+    const uint8_t *d_hist; // up to 32 KiB preceding the shard (device) or nullptr
+    uint32_t hist_len;
+    int level, strategy;
+    uint8_t *d_out;        // body destination (device)
+    uint64_t cap;
+    bool framed;           // true: emit zlib header + final block + trailer around the body
+    uint64_t *d_result;    // {out_len, adler, status, n}
+};
+int run_deflate(zk_ctx *c, const DeflateJob &job);
+
+struct InflateJob {
+    const uint8_t *d_in;
+    uint64_t m;
+    uint8_t *d_out;
+    uint64_t cap;
+    uint64_t *d_result; // {out_len, consumed, status, adler}
+};
+int run_inflate(zk_ctx *c, const InflateJob &job);
+
+LevelParams level_params(int level, int strategy);
+uint32_t adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);
+
+}  // namespace zk

@@ -1,0 +1,413 @@
+// zk_huffman.cu -- K2: per-block code construction and block planning, one warp per deflate block.
+//
+// Replaces HuffmanBuilder.buildLengths (deflate/HuffmanBuilder.kt:10-83), CanonicalHuffman.buildEncoder
+// (inflate/CanonicalHuffman.kt:85-120), the code-length RLE + header of DeflateStream.kt:818-900 and the
+// stored / fixed / dynamic cost choice of DeflateStream.kt:902-955.
+//
+// Differences from the reference that matter for parity (SURVEY.md section 7 "hard parts"):
+//   - lengths come from a real Huffman tree, limited to 15 / 7 bits by moving leaves down on the length
+//     counts; the code is always COMPLETE (the reference's Shannon-Fano split can over-subscribe, HB:58-62,
+//     and its own inflate rejects incomplete multi-symbol trees, InflateStream.kt:151);
+//   - at least two symbols get a code in every tree, so lit[256] > 0 and the distance tree is never empty
+//     (InflateStream.kt:102-119);
+//   - the literal/length and distance length sequences are run-length coded SEPARATELY, because the
+//     reference inflate reads them as two sequences (InflateStream.kt:316-317);
+//   - length 258 is symbol 285 (the reference writes 284 + 31, DS:193-203 -- both are valid DEFLATE).
+//
+// Input:  block_hist[b][320]  (lit/len counts at [0,286), distance counts at [288,318))
+// Output: BlockPlan[b]: block type, header bit string, code tables, exact size in bytes.
+#include "zk_common.cuh"
+
+namespace zk {
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kMaxSyms = 288;
+
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct WarpScratch {
+    uint32_t freq[kMaxSyms];      // working copy of the counts (>= 1 for coded symbols)
+    uint16_t order[kMaxSyms];     // symbols sorted by ascending (freq, symbol)
+    uint32_t weight[2 * kMaxSyms];
+    uint16_t parent[2 * kMaxSyms];
+    uint8_t depth[2 * kMaxSyms];
+    uint8_t lit_len[kMaxSyms];
+    uint8_t dist_len[32];
+    uint8_t cl_len[20];
+    uint8_t cl_sym[320];          // run-length coded code lengths: symbol
+    uint8_t cl_extra[320];        //                              : extra-bit value
+    uint32_t cl_freq[20];
+    uint32_t cl_code[20];
+    int used;
+};
+
+__device__ __forceinline__ uint32_t bit_reverse(uint32_t code, int len) { return __brev(code) >> (32 - len); }
+
+// Length-limited Huffman code lengths for freq[0,n).  Warp-cooperative where it is cheap (sort by rank),
+// lane 0 for the sequential tree walk.  Every lane returns after the lengths are in `out`.
+__device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, int maxbits, uint8_t *out, int lane) {
+    // 1. working counts; make sure at least two symbols are coded
+    int used = 0;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t f = freq_in[i];
+        w.freq[i] = f;
+        out[i] = 0;
+        used += f != 0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) used += __shfl_xor_sync(0xFFFFFFFFu, used, off);
+    __syncwarp();
+    if (lane == 0 && used < 2) {
+        for (int i = 0; i < n && used < 2; ++i)
+            if (w.freq[i] == 0) {
+                w.freq[i] = 1;
+                ++used;
+            }
+    }
+    used = __shfl_sync(0xFFFFFFFFu, used, 0);
+    __syncwarp();
+    // 2. rank sort of the coded symbols by (freq, symbol)
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t f = w.freq[i];
+        if (f == 0) continue;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t g = w.freq[j];
+            rank += (g != 0) && (g < f || (g == f && j < i));
+        }
+        w.order[rank] = (uint16_t)i;
+    }
+    __syncwarp();
+    // 3. tree with two queues (leaves in sorted order, internal nodes in creation order)
+    for (int i = lane; i < used; i += 32) w.weight[i] = w.freq[w.order[i]];
+    __syncwarp();
+    if (lane == 0) {
+        int leaf = 0, inner = used, next = used;
+        while (next < 2 * used - 1) {
+            int pick[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (leaf < used && (inner >= next || w.weight[leaf] <= w.weight[inner])) pick[k] = leaf++;
+                else pick[k] = inner++;
+            }
+            w.weight[next] = w.weight[pick[0]] + w.weight[pick[1]];
+            w.parent[pick[0]] = (uint16_t)next;
+            w.parent[pick[1]] = (uint16_t)next;
+            ++next;
+        }
+        // 4. depths from the root down, counts per length with the overflow folded to maxbits
+        const int root = 2 * used - 2;
+        w.depth[root] = 0;
+        int count[40];
+        for (int b = 0; b < 40; ++b) count[b] = 0;
+        int overflow = 0;
+        for (int i = root - 1; i >= 0; --i) {
+            int d = w.depth[w.parent[i]] + 1;
+            if (d > 39) d = 39;  // counts beyond maxbits are folded below; keep the byte from wrapping
+            w.depth[i] = (uint8_t)d;
+            if (i < used) {
+                if (d > maxbits) {
+                    d = maxbits;
+                    ++overflow;
+                }
+                count[d]++;
+            }
+        }
+        // 5. repair: move one leaf down from the deepest non-full level per two overflowing leaves
+        while (overflow > 0) {
+            int bits = maxbits - 1;
+            while (count[bits] == 0) --bits;
+            count[bits]--;
+            count[bits + 1] += 2;
+            count[maxbits]--;
+            overflow -= 2;
+        }
+        // 6. longest codes to the rarest symbols (order[] is ascending by weight)
+        int idx = 0;
+        for (int bits = maxbits; bits >= 1; --bits)
+            for (int k = count[bits]; k > 0; --k) out[w.order[idx++]] = (uint8_t)bits;
+    }
+    __syncwarp();
+}
+
+// Canonical codes for `len`, bit-reversed for LSB-first emission; packed as code | len << 16.
+__device__ void assign_codes(const uint8_t *len, int n, int maxbits, uint32_t *packed, int lane) {
+    // every lane computes the tiny per-length table; symbols are then handled in parallel with a rank
+    int count[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) count[b] = 0;
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    count[0] = 0;
+    int next[16];
+    int code = 0;
+    next[0] = 0;
+    for (int b = 1; b <= maxbits; ++b) {
+        code = (code + count[b - 1]) << 1;
+        next[b] = code;
+    }
+    for (int i = lane; i < n; i += 32) {
+        const int l = len[i];
+        uint32_t v = 0;
+        if (l) {
+            int rank = 0;
+            for (int j = 0; j < i; ++j) rank += len[j] == l;
+            v = bit_reverse((uint32_t)(next[l] + rank), l) | ((uint32_t)l << 16);
+        }
+        packed[i] = v;
+    }
+    __syncwarp();
+}
+
+struct BitSink {
+    uint8_t *dst;
+    uint32_t nbits;
+    uint64_t acc;
+    int fill;
+    __device__ void put(uint32_t value, int count) {
+        acc |= (uint64_t)value << fill;
+        fill += count;
+        nbits += count;
+        while (fill >= 8) {
+            *dst++ = (uint8_t)acc;
+            acc >>= 8;
+            fill -= 8;
+        }
+    }
+    __device__ void flush() {
+        if (fill > 0) *dst++ = (uint8_t)acc;
+        fill = 0;
+        acc = 0;
+    }
+};
+
+// Run-length code `len[0,n)` into (symbol, extra) pairs appended at w.cl_sym[at..]; returns the new count.
+__device__ int rle_lengths(WarpScratch &w, const uint8_t *len, int n, int at) {
+    int i = 0;
+    while (i < n) {
+        const int v = len[i];
+        int j = i + 1;
+        while (j < n && len[j] == v) ++j;
+        int run = j - i;
+        i = j;
+        if (v == 0) {
+            while (run >= 11) {
+                const int r = run < 138 ? run : 138;
+                w.cl_sym[at] = 18;
+                w.cl_extra[at++] = (uint8_t)(r - 11);
+                run -= r;
+            }
+            if (run >= 3) {
+                w.cl_sym[at] = 17;
+                w.cl_extra[at++] = (uint8_t)(run - 3);
+                run = 0;
+            }
+            while (run-- > 0) {
+                w.cl_sym[at] = 0;
+                w.cl_extra[at++] = 0;
+            }
+        } else {
+            w.cl_sym[at] = (uint8_t)v;
+            w.cl_extra[at++] = 0;
+            --run;
+            while (run >= 3) {
+                const int r = run < 6 ? run : 6;
+                w.cl_sym[at] = 16;
+                w.cl_extra[at++] = (uint8_t)(r - 3);
+                run -= r;
+            }
+            while (run-- > 0) {
+                w.cl_sym[at] = (uint8_t)v;
+                w.cl_extra[at++] = 0;
+            }
+        }
+    }
+    return at;
+}
+
+__device__ __forceinline__ int fixed_litlen_bits(int sym) { return sym < 144 ? 8 : sym < 256 ? 9 : sym < 280 ? 7 : 8; }
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32_t *__restrict__ block_hist,
+                                                                    uint64_t n, uint32_t block_bytes,
+                                                                    uint32_t num_blocks, int force_type,
+                                                                    BlockPlan *__restrict__ plans) {
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t blk = blockIdx.x * kWarpsPerCta + wid;
+    if (blk >= num_blocks) return;
+    WarpScratch &w = scratch[wid];
+    const uint32_t *hist = block_hist + (uint64_t)blk * kHistStride;
+    BlockPlan &plan = plans[blk];
+
+    build_lengths(w, hist, kNumLitLen, 15, w.lit_len, lane);
+    build_lengths(w, hist + kDistHistBase, kNumDist, 15, w.dist_len, lane);
+
+    // header: run-length code the two length sequences separately, then code the RLE alphabet
+    int hlit = kNumLitLen, hdist = kNumDist, ncl = 0;
+    if (lane == 0) {
+        while (hlit > 257 && w.lit_len[hlit - 1] == 0) --hlit;
+        while (hdist > 1 && w.dist_len[hdist - 1] == 0) --hdist;
+        ncl = rle_lengths(w, w.lit_len, hlit, 0);
+        ncl = rle_lengths(w, w.dist_len, hdist, ncl);
+        for (int i = 0; i < 19; ++i) w.cl_freq[i] = 0;
+        for (int i = 0; i < ncl; ++i) w.cl_freq[w.cl_sym[i]]++;
+    }
+    hlit = __shfl_sync(0xFFFFFFFFu, hlit, 0);
+    hdist = __shfl_sync(0xFFFFFFFFu, hdist, 0);
+    ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
+    __syncwarp();
+    build_lengths(w, w.cl_freq, 19, 7, w.cl_len, lane);
+    assign_codes(w.cl_len, 19, 7, w.cl_code, lane);
+
+    // exact sizes of the three encodings
+    uint64_t dyn_bits = 0, fix_bits = 0;
+    for (int i = lane; i < kNumLitLen; i += 32) {
+        const uint64_t f = hist[i];
+        const int extra = i >= 257 ? c_len_extra[i - 257] : 0;
+        dyn_bits += f * (uint64_t)(w.lit_len[i] + extra);
+        fix_bits += f * (uint64_t)(fixed_litlen_bits(i) + extra);
+    }
+    if (lane < kNumDist) {
+        const uint64_t f = hist[kDistHistBase + lane];
+        dyn_bits += f * (uint64_t)(w.dist_len[lane] + c_dist_extra[lane]);
+        fix_bits += f * (uint64_t)(5 + c_dist_extra[lane]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        dyn_bits += __shfl_xor_sync(0xFFFFFFFFu, dyn_bits, off);
+        fix_bits += __shfl_xor_sync(0xFFFFFFFFu, fix_bits, off);
+    }
+    int hclen = 19;
+    uint32_t head_bits = 0;
+    if (lane == 0) {
+        while (hclen > 4 && w.cl_len[c_cl_order[hclen - 1]] == 0) --hclen;
+        head_bits = 3 + 5 + 5 + 4 + 3 * hclen;
+        for (int i = 0; i < ncl; ++i) {
+            const int s = w.cl_sym[i];
+            head_bits += w.cl_len[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
+        }
+    }
+    hclen = __shfl_sync(0xFFFFFFFFu, hclen, 0);
+    head_bits = __shfl_sync(0xFFFFFFFFu, head_bits, 0);
+
+    const uint32_t raw = (uint32_t)tmin<uint64_t>(block_bytes, n - (uint64_t)blk * block_bytes);
+    const uint64_t dyn_total = head_bits + dyn_bits, fix_total = 3 + fix_bits;
+    // a Huffman block is followed by an empty stored block (3 bits, pad, 00 00 FF FF) so that the next
+    // block starts on a byte; a stored block already ends on one
+    const uint64_t dyn_bytes = ((dyn_total + 3 + 7) >> 3) + 4, fix_bytes = ((fix_total + 3 + 7) >> 3) + 4;
+    const uint64_t sto_bytes = 5ull + raw;
+    int type;
+    if (force_type >= 0) type = force_type;
+    else if (sto_bytes <= dyn_bytes && sto_bytes <= fix_bytes) type = 0;  // tie order of DS:950-955
+    else if (dyn_bytes <= fix_bytes) type = 2;
+    else type = 1;
+    // a forced encoding must still fit the packer's shared image (block span + header slack)
+    if (type != 0 && (type == 2 ? dyn_bytes : fix_bytes) > sto_bytes + 256) type = 0;
+
+    if (type == 2) {
+        assign_codes(w.lit_len, kNumLitLen, 15, plan.litlen_code, lane);
+        assign_codes(w.dist_len, kNumDist, 15, plan.dist_code, lane);
+    } else {
+        // fixed codes (RFC 1951 3.2.6); also filled for stored blocks so the plan is always defined
+        for (int i = lane; i < kNumLitLen; i += 32) w.lit_len[i] = (uint8_t)fixed_litlen_bits(i);
+        if (lane < kNumDist) w.dist_len[lane] = 5;
+        __syncwarp();
+        for (int i = lane; i < kNumLitLen; i += 32) {
+            const int l = w.lit_len[i];
+            uint32_t code;
+            if (i < 144) code = 0x30 + i;
+            else if (i < 256) code = 0x190 + (i - 144);
+            else if (i < 280) code = i - 256;
+            else code = 0xC0 + (i - 280);
+            plan.litlen_code[i] = bit_reverse(code, l) | ((uint32_t)l << 16);
+        }
+        if (lane < kNumDist) plan.dist_code[lane] = bit_reverse((uint32_t)lane, 5) | (5u << 16);
+    }
+    __syncwarp();
+
+    if (lane == 0) {
+        BitSink sink{plan.header, 0, 0, 0};
+        if (type == 2) {
+            sink.put(0, 1);  // BFINAL = 0: the stream is closed by a separate final block
+            sink.put(2, 2);
+            sink.put((uint32_t)(hlit - 257), 5);
+            sink.put((uint32_t)(hdist - 1), 5);
+            sink.put((uint32_t)(hclen - 4), 4);
+            for (int i = 0; i < hclen; ++i) sink.put(w.cl_len[c_cl_order[i]], 3);
+            for (int i = 0; i < ncl; ++i) {
+                const int s = w.cl_sym[i];
+                sink.put(w.cl_code[s] & 0xFFFFu, (int)(w.cl_code[s] >> 16));
+                if (s == 16) sink.put(w.cl_extra[i], 2);
+                else if (s == 17) sink.put(w.cl_extra[i], 3);
+                else if (s == 18) sink.put(w.cl_extra[i], 7);
+            }
+        } else if (type == 1) {
+            sink.put(0, 1);
+            sink.put(1, 2);
+        }
+        const uint32_t hb = sink.nbits;
+        sink.flush();
+        plan.type = (uint32_t)type;
+        plan.header_bits = hb;
+        plan.body_bits = (uint32_t)(type == 2 ? dyn_bits : type == 1 ? fix_bits : 0);
+        plan.out_bytes = (uint32_t)(type == 2 ? dyn_bytes : type == 1 ? fix_bytes : sto_bytes);
+    }
+}
+
+// Exclusive scan of the block sizes -> byte offsets (relative to the body start) and the running total.
+// cursor[0] = bytes of body emitted so far (carried across slabs), cursor[1] = error flag.
+__global__ void __launch_bounds__(1024) plan_offsets_kernel(const BlockPlan *__restrict__ plans, uint32_t num_blocks,
+                                                            uint64_t *__restrict__ offsets, uint64_t *cursor,
+                                                            uint64_t cap) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = cursor[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < num_blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < num_blocks ? plans[i].out_bytes : 0;
+        uint64_t incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if ((threadIdx.x & 31) >= off) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint64_t before = 0;
+        for (int wdx = 0; wdx < (int)(threadIdx.x >> 5); ++wdx) before += warp_sum[wdx];
+        const uint64_t start = carry + before + incl - v;
+        if (i < num_blocks) offsets[i] = start;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = start + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cursor[0] = carry;
+        if (carry > cap) cursor[1] = 1;  // output does not fit: the packer will not write
+    }
+}
+
+}  // namespace
+
+int launch_huffman(zk_ctx *c, const uint32_t *block_hist, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
+                   int force_type, BlockPlan *plans) {
+    const uint32_t grid = (num_blocks + kWarpsPerCta - 1) / kWarpsPerCta;
+    huffman_kernel<<<grid, kWarpsPerCta * 32, 0, c->stream>>>(block_hist, n, block_bytes, num_blocks, force_type, plans);
+    c->launches += 1;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+int launch_plan_offsets(zk_ctx *c, const BlockPlan *plans, uint32_t num_blocks, uint64_t *offsets, uint64_t *cursor,
+                        uint64_t cap) {
+    plan_offsets_kernel<<<1, 1024, 0, c->stream>>>(plans, num_blocks, offsets, cursor, cap);
+    c->launches += 1;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+}  // namespace zk

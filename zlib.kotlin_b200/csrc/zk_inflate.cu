@@ -1,0 +1,826 @@
+// zk_inflate.cu -- K5: zlib inflate, parallel across chunks, one warp per chunk.
+//
+// Replaces InflateStream.inflateZlib (inflate/InflateStream.kt:376-438) with its block decoders
+// (copyStored IS:47-74, decodeFixed IS:265-297, decodeDynamic IS:299-371, readCodeLengths IS:235-263,
+// validation IS:102-152), CanonicalHuffman.buildFull/decodeOne (inflate/CanonicalHuffman.kt:54-82,123-138)
+// and StreamingBitReader (inflate/StreamingBitReader.kt:9-58).
+//
+// A DEFLATE stream has no entry points, but streams made by this engine (and by pigz) end every chunk with
+// an empty stored block: the bytes 00 00 FF FF, after which a block starts on a byte boundary.  The engine
+//   1. scans the stream for that pattern and keeps at most one candidate start per span of input,
+//   2. decodes every candidate chunk with one warp, first only to SIZE it (it must end exactly on the next
+//      candidate), then -- once a prefix sum has given every chunk its output offset -- to WRITE it as 16-bit
+//      symbols: a byte, or 0x8000 | i for "byte i of the 32 KiB that precede this chunk" (the chunk's
+//      dictionary is not known yet, so references into it are carried symbolically, copies included),
+//   3. resolves the last 32 KiB of every chunk in stream order (a short dependent chain),
+//   4. turns all symbols into bytes in parallel and checks the Adler-32 trailer.
+// A candidate that is not a real block start fails step 2 and is merged into its predecessor; a stream
+// with no candidates (reference or libz output) is one chunk decoded by one warp -- "replicas only".
+//
+// Error behaviour follows the reference: Z_STREAM_END on success (IS:424), Z_NEED_DICT for FDICT (IS:36-43),
+// Z_DATA_ERROR for bad headers / block type 3 / LEN-NLEN / invalid codes / distance too far back
+// (IS:287-291) / trailer mismatch, Z_BUF_ERROR for truncated input (IS:425-428: a symbol needs maxLen bits
+// available, BR:48-57).  The code-length-code table is built exactly like buildFull, without validation
+// (IS:315), so even over-subscribed tables made by the reference's own compressor decode as the reference
+// decodes them; the two exceptions that escape inflateZlib (IS:243 -> CH:127,133) become Z_DATA_ERROR.
+#include "zk_common.cuh"
+
+namespace zk {
+
+namespace {
+
+constexpr int kInfWarps = 4;
+constexpr int kLitLutBits = 10;
+constexpr int kDistLutBits = 8;
+constexpr uint32_t kNoCand = 0xFFFFFFFFu;
+
+__constant__ uint16_t i_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t i_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t i_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t i_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t i_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// Canonical decoder: a direct table for short codes, first-code arithmetic for the long ones.
+struct Decoder {
+    uint16_t lut[1 << kLitLutBits];  // sym | len << 12 (len 0 = not a short code)
+    uint16_t sorted[288];            // symbols in canonical order
+    uint16_t first_code[16];         // first canonical code of each length (MSB-first numbering)
+    uint16_t first_index[16];        // index into sorted[] of the first symbol of each length
+    uint16_t count[16];
+    int max_len;
+    int lut_bits;
+};
+
+struct WarpState {
+    Decoder lit, dist;
+    uint8_t lengths[320];   // code lengths being read (lit then dist)
+    uint8_t cl_bits[128];   // code-length-code full table, built like CanonicalHuffman.buildFull
+    uint8_t cl_vals[128];
+    int cl_max;
+};
+
+struct ChunkInfo {
+    uint64_t in_begin;   // byte offset of the chunk's first block
+    uint64_t in_end;     // byte offset where it must end (next chunk's start), or stream length for the last
+    uint64_t out_len;    // decoded size
+    uint64_t out_begin;  // prefix sum of out_len
+    uint64_t end_byte;   // byte offset after the chunk's last block (byte-aligned position)
+    int32_t status;      // ZK_OK, or the error the reference would report
+    int32_t final_seen;  // the chunk ended with a BFINAL block
+    int32_t retries;     // times this chunk has absorbed a successor after failing
+    int32_t pad;
+};
+
+struct BitReader {
+    const uint8_t *base;
+    uint64_t len;    // stream length in bytes
+    uint64_t next;   // next byte to load
+    uint64_t hold;
+    int held;
+    __device__ __forceinline__ void refill() {
+        while (held <= 56 && next < len) {
+            hold |= (uint64_t)__ldg(base + next) << held;
+            ++next;
+            held += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(hold & ((1ull << n) - 1ull)); }
+    __device__ __forceinline__ void drop(int n) {
+        hold >>= n;
+        held -= n;
+    }
+    // position of the next unread bit
+    __device__ __forceinline__ uint64_t bit_pos() const { return next * 8 - (uint64_t)held; }
+};
+
+__device__ __forceinline__ uint32_t rev_bits(uint32_t v, int len) { return __brev(v) >> (32 - len); }
+
+// Build a canonical decoder from code lengths (already validated: complete or single-code).
+__device__ void build_decoder(Decoder &d, const uint8_t *lens, int n, int lut_bits, int lane) {
+    if (lane < 16) d.count[lane] = 0;
+    for (int i = lane; i < (1 << lut_bits); i += 32) d.lut[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        int maxl = 0;
+        for (int i = 0; i < n; ++i) {
+            const int l = lens[i];
+            if (l) {
+                d.count[l]++;
+                if (l > maxl) maxl = l;
+            }
+        }
+        int code = 0, idx = 0;
+        d.first_code[0] = 0;
+        d.first_index[0] = 0;
+        for (int b = 1; b < 16; ++b) {
+            code = (code + (b > 1 ? d.count[b - 1] : 0)) << 1;
+            d.first_code[b] = (uint16_t)code;
+            d.first_index[b] = (uint16_t)idx;
+            idx += d.count[b];
+        }
+        d.max_len = maxl;
+        d.lut_bits = lut_bits;
+        // canonical order = by length, then by symbol
+        int fill[16];
+        for (int b = 0; b < 16; ++b) fill[b] = d.first_index[b];
+        for (int i = 0; i < n; ++i) {
+            const int l = lens[i];
+            if (l) d.sorted[fill[l]++] = (uint16_t)i;
+        }
+    }
+    __syncwarp();
+    // direct table: every symbol with a short code fills its stride
+    const int total = d.first_index[15] + d.count[15];
+    for (int k = lane; k < total; k += 32) {
+        const int sym = d.sorted[k];
+        const int l = lens[sym];
+        if (l > lut_bits) continue;
+        const uint32_t code = d.first_code[l] + (uint32_t)(k - d.first_index[l]);
+        const uint16_t entry = (uint16_t)(sym | (l << 12));
+        for (uint32_t idx = rev_bits(code, l); idx < (1u << lut_bits); idx += 1u << l) d.lut[idx] = entry;
+    }
+    __syncwarp();
+}
+
+// Decode one symbol; returns -1 for an invalid prefix.  `br` holds at least max_len bits or the end of
+// the stream has been reached (missing bits read as zero; the caller checks availability first).
+__device__ __forceinline__ int decode_sym(const Decoder &d, BitReader &br) {
+    const uint32_t e = d.lut[br.peek(d.lut_bits)];
+    if (e) {
+        br.drop((int)(e >> 12));
+        return (int)(e & 0x0FFFu);
+    }
+    // long code: walk the lengths above the table width
+    uint32_t code = rev_bits(br.peek(d.lut_bits), d.lut_bits);
+    for (int l = d.lut_bits + 1; l <= d.max_len; ++l) {
+        code = (code << 1) | ((uint32_t)(br.hold >> (l - 1)) & 1u);
+        const uint32_t rel = code - d.first_code[l];
+        if (code >= d.first_code[l] && rel < d.count[l]) {
+            br.drop(l);
+            return d.sorted[d.first_index[l] + rel];
+        }
+    }
+    return -1;
+}
+
+struct ChunkResult {
+    uint64_t out_len;
+    uint64_t end_byte;
+    int status;
+    int final_seen;
+};
+
+// Decode the blocks of one chunk.  kWrite = false: size only.  kWrite = true: 16-bit symbols to
+// sym[out_begin ...]; references that reach before the chunk become 0x8000 | window index.
+template <bool kWrite>
+__device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m, uint64_t in_begin, uint64_t in_end,
+                                    bool first_chunk, uint16_t *sym, uint64_t out_begin, uint64_t out_cap, int lane) {
+    BitReader br{in, m, in_begin, 0, 0};
+    uint64_t produced = 0;
+    ChunkResult res{0, 0, ZK_OK, 0};
+    // every lane runs the same decode; only the copies are split across lanes
+    for (;;) {
+        br.refill();
+        if (br.held < 3) {
+            res.status = ZK_BUF_ERROR;
+            break;
+        }
+        const int last = (int)br.peek(1);
+        br.drop(1);
+        const int type = (int)br.peek(2);
+        br.drop(2);
+        if (type == 3) {  // IS:406
+            res.status = ZK_DATA_ERROR;
+            break;
+        }
+        if (type == 0) {  // IS:47-74
+            br.drop(br.held & 7);
+            br.refill();
+            if (br.held < 32) {
+                res.status = ZK_BUF_ERROR;
+                break;
+            }
+            const uint32_t len = br.peek(16);
+            br.drop(16);
+            const uint32_t nlen = br.peek(16);
+            br.drop(16);
+            if (((~len) & 0xFFFFu) != nlen) {
+                res.status = ZK_DATA_ERROR;
+                break;
+            }
+            // the payload is byte-aligned: step the reader back to a byte position and copy
+            const uint64_t src0 = br.next - (uint64_t)(br.held >> 3);
+            const uint64_t avail = m - src0;
+            const uint32_t take = (uint32_t)tmin<uint64_t>(len, avail);
+            if (kWrite) {
+                if (produced + take > out_cap) {
+                    res.status = ZK_BUF_ERROR;
+                    break;
+                }
+                for (uint32_t i = lane; i < take; i += 32) sym[out_begin + produced + i] = in[src0 + i];
+                __syncwarp();
+            }
+            produced += take;
+            br.next = src0 + take;
+            br.hold = 0;
+            br.held = 0;
+            if (take < len) {  // IS:62-70 runs out of source mid-copy
+                res.status = ZK_BUF_ERROR;
+                break;
+            }
+        } else {
+            if (type == 1) {  // IS:154-173
+                for (int i = lane; i < 288; i += 32) ws.lengths[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+                __syncwarp();
+                build_decoder(ws.lit, ws.lengths, 288, kLitLutBits, lane);
+                if (lane < 32) ws.lengths[lane] = 5;
+                __syncwarp();
+                build_decoder(ws.dist, ws.lengths, 32, kDistLutBits, lane);
+            } else {  // IS:299-348
+                br.refill();
+                if (br.held < 14) {
+                    res.status = ZK_BUF_ERROR;
+                    break;
+                }
+                const int hlit = (int)br.peek(5) + 257;
+                br.drop(5);
+                const int hdist = (int)br.peek(5) + 1;
+                br.drop(5);
+                const int hclen = (int)br.peek(4) + 4;
+                br.drop(4);
+                int clen[19];
+#pragma unroll
+                for (int i = 0; i < 19; ++i) clen[i] = 0;
+                int bad = 0;
+                for (int i = 0; i < hclen; ++i) {
+                    br.refill();
+                    if (br.held < 3) {
+                        bad = ZK_BUF_ERROR;
+                        break;
+                    }
+                    clen[i_cl_order[i]] = (int)br.peek(3);
+                    br.drop(3);
+                }
+                if (bad) {
+                    res.status = bad;
+                    break;
+                }
+                // code-length-code table exactly as CanonicalHuffman.buildFull makes it (CH:54-82): later
+                // symbols overwrite earlier ones when the lengths over-subscribe the code space
+                int cl_max = 0;
+                for (int i = 0; i < 19; ++i) cl_max = max(cl_max, clen[i]);
+                if (lane == 0) {
+                    ws.cl_max = cl_max;
+                    for (int i = 0; i < 128; ++i) ws.cl_bits[i] = 0;
+                    int per[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nextc[8];
+                    for (int i = 0; i < 19; ++i)
+                        if (clen[i]) per[clen[i]]++;
+                    int code = 0;
+                    nextc[0] = 0;
+                    for (int b = 1; b <= 7; ++b) {
+                        code = (code + per[b - 1]) << 1;
+                        nextc[b] = code;
+                    }
+                    for (int s = 0; s < 19; ++s) {
+                        const int l = clen[s];
+                        if (!l) continue;
+                        const uint32_t assigned = (uint32_t)nextc[l]++;
+                        for (uint32_t idx = rev_bits(assigned & ((1u << l) - 1u), l); idx < (1u << cl_max); idx += 1u << l) {
+                            ws.cl_bits[idx] = (uint8_t)l;
+                            ws.cl_vals[idx] = (uint8_t)s;
+                        }
+                    }
+                }
+                __syncwarp();
+                // IS:235-263, twice: literal/length lengths, then distance lengths, never merged
+                int fail = 0;
+                for (int pass = 0; pass < 2 && !fail; ++pass) {
+                    const int count = pass == 0 ? hlit : hdist;
+                    const int base = pass == 0 ? 0 : 288;
+                    int i = 0;
+                    while (i < count) {
+                        br.refill();
+                        if (cl_max == 0) {  // "Empty Huffman table": escapes in the reference (CH:127)
+                            fail = ZK_DATA_ERROR;
+                            break;
+                        }
+                        if (br.held < cl_max) {
+                            fail = ZK_BUF_ERROR;
+                            break;
+                        }
+                        const uint32_t look = br.peek(cl_max);
+                        const int l = ws.cl_bits[look];
+                        if (l == 0) {  // invalid prefix: escapes in the reference (CH:133)
+                            fail = ZK_DATA_ERROR;
+                            break;
+                        }
+                        const int s = ws.cl_vals[look];
+                        br.drop(l);
+                        if (s <= 15) {
+                            if (lane == 0) ws.lengths[base + i] = (uint8_t)s;
+                            ++i;
+                            continue;
+                        }
+                        if (s == 16 && i == 0) {  // IS:246: checked before the repeat count is read
+                            fail = ZK_DATA_ERROR;
+                            break;
+                        }
+                        const int nb = s == 16 ? 2 : s == 17 ? 3 : 7;
+                        br.refill();
+                        if (br.held < nb) {
+                            fail = ZK_BUF_ERROR;
+                            break;
+                        }
+                        const int rep = (s == 16 ? 3 : s == 17 ? 3 : 11) + (int)br.peek(nb);
+                        br.drop(nb);
+                        if (i + rep > count) {
+                            fail = ZK_DATA_ERROR;
+                            break;
+                        }
+                        __syncwarp();
+                        const uint8_t v = s == 16 ? ws.lengths[base + i - 1] : (uint8_t)0;
+                        __syncwarp();
+                        if (lane < rep) ws.lengths[base + i + lane] = v;
+                        if (lane + 32 < rep) ws.lengths[base + i + lane + 32] = v;
+                        if (lane + 64 < rep) ws.lengths[base + i + lane + 64] = v;
+                        if (lane + 96 < rep) ws.lengths[base + i + lane + 96] = v;
+                        if (lane + 128 < rep) ws.lengths[base + i + lane + 128] = v;
+                        i += rep;
+                    }
+                    __syncwarp();
+                }
+                if (fail) {
+                    res.status = fail;
+                    break;
+                }
+                // IS:102-152: EOB present, a distance code present, neither tree over-subscribed nor
+                // incomplete (a single code may be incomplete)
+                int ok = 1;
+                {
+                    int any = 0, used = 0, left = 1, maxl = 0;
+                    int per[16];
+                    for (int b = 0; b < 16; ++b) per[b] = 0;
+                    for (int i = 0; i < hlit; ++i) {
+                        const int l = ws.lengths[i];
+                        if (l) {
+                            any = 1;
+                            ++used;
+                            per[l]++;
+                            maxl = max(maxl, l);
+                        }
+                    }
+                    if (!any || ws.lengths[256] == 0) ok = 0;
+                    for (int b = 1; b <= maxl && ok; ++b) {
+                        left = (left << 1) - per[b];
+                        if (left < 0) ok = 0;
+                    }
+                    if (ok && left != 0 && used > 1) ok = 0;
+                    int dany = 0, dused = 0, dmax = 0;
+                    for (int b = 0; b < 16; ++b) per[b] = 0;
+                    for (int i = 0; i < hdist; ++i) {
+                        const int l = ws.lengths[288 + i];
+                        if (l) {
+                            dany = 1;
+                            ++dused;
+                            per[l]++;
+                            dmax = max(dmax, l);
+                        }
+                    }
+                    if (!dany) ok = 0;
+                    left = 1;
+                    for (int b = 1; b <= dmax && ok; ++b) {
+                        left = (left << 1) - per[b];
+                        if (left < 0) ok = 0;
+                    }
+                    if (ok && left != 0 && dused > 1) ok = 0;
+                }
+                if (!ok) {
+                    res.status = ZK_DATA_ERROR;
+                    break;
+                }
+                build_decoder(ws.lit, ws.lengths, hlit, kLitLutBits, lane);
+                build_decoder(ws.dist, ws.lengths + 288, hdist, kDistLutBits, lane);
+            }
+            // symbol loop, IS:276-295 / IS:350-369
+            int err = 0;
+            const int lit_need = ws.lit.max_len, dist_need = ws.dist.max_len;
+            for (;;) {
+                br.refill();
+                if (br.held < lit_need) {  // BR:48-57: peek(maxLen) needs that many bits
+                    err = ZK_BUF_ERROR;
+                    break;
+                }
+                const int s = decode_sym(ws.lit, br);
+                if (s < 0) {
+                    err = ZK_DATA_ERROR;
+                    break;
+                }
+                if (s < 256) {
+                    if (kWrite) {
+                        if (produced >= out_cap) {
+                            err = ZK_BUF_ERROR;
+                            break;
+                        }
+                        if (lane == 0) sym[out_begin + produced] = (uint16_t)s;
+                    }
+                    ++produced;
+                    continue;
+                }
+                if (s == 256) break;
+                const int lc = s - 257;
+                if (lc > 28) {  // IS:195
+                    err = ZK_DATA_ERROR;
+                    break;
+                }
+                br.refill();
+                const int le = i_len_extra[lc];
+                if (br.held < le) {
+                    err = ZK_BUF_ERROR;
+                    break;
+                }
+                const int length = i_len_base[lc] + (int)br.peek(le);
+                br.drop(le);
+                br.refill();
+                if (br.held < dist_need) {
+                    err = ZK_BUF_ERROR;
+                    break;
+                }
+                const int dsym = decode_sym(ws.dist, br);
+                if (dsym < 0 || dsym > 29) {  // IS:207
+                    err = ZK_DATA_ERROR;
+                    break;
+                }
+                br.refill();
+                const int de = i_dist_extra[dsym];
+                if (br.held < de) {
+                    err = ZK_BUF_ERROR;
+                    break;
+                }
+                const int dist = i_dist_base[dsym] + (int)br.peek(de);
+                br.drop(de);
+                // IS:287-291 / 361-365: distance bounded by min(bytes out, 32768).  For a later chunk the
+                // bytes before it exist (the predecessor decoded them); the bound is checked when the
+                // symbol is resolved.
+                if (dist > kWindow || (first_chunk && (uint64_t)dist > produced)) {
+                    err = ZK_DATA_ERROR;
+                    break;
+                }
+                if (kWrite) {
+                    if (produced + (uint64_t)length > out_cap) {
+                        err = ZK_BUF_ERROR;
+                        break;
+                    }
+                    __syncwarp();
+                    uint16_t *dst = sym + out_begin + produced;
+                    for (int i = lane; i < length; i += 32) {
+                        const int k = dist >= length ? i : i % dist;
+                        const int64_t rel = (int64_t)produced - dist + k;  // position inside this chunk
+                        uint16_t v;
+                        if (rel >= 0) v = sym[out_begin + (uint64_t)rel];
+                        else v = (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
+                        dst[i] = v;
+                    }
+                    __syncwarp();
+                }
+                produced += (uint64_t)length;
+            }
+            if (err) {
+                res.status = err;
+                break;
+            }
+        }
+        // block boundary
+        const uint64_t bits = br.bit_pos();
+        if (last) {
+            res.final_seen = 1;
+            res.end_byte = (bits + 7) >> 3;
+            break;
+        }
+        if ((bits & 7) == 0) {
+            const uint64_t at = bits >> 3;
+            if (at == in_end) {
+                res.end_byte = at;
+                break;
+            }
+            if (at > in_end) {  // ran past a candidate that was not a real block start
+                res.status = ZK_DATA_ERROR;
+                break;
+            }
+        } else if ((bits >> 3) >= in_end) {
+            res.status = ZK_DATA_ERROR;
+            break;
+        }
+    }
+    res.out_len = produced;
+    return res;
+}
+
+// ---- kernels --------------------------------------------------------------------------------------------
+
+// zlib header (IS:28-45) -> header[0] = status (ZK_OK / ZK_DATA_ERROR / ZK_NEED_DICT / ZK_BUF_ERROR)
+__global__ void header_kernel(const uint8_t *in, uint64_t m, int32_t *header) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int st = ZK_OK;
+    if (m < 2) st = ZK_BUF_ERROR;
+    else {
+        const int cmf = in[0], flg = in[1];
+        if ((cmf & 0x0F) != 8 || ((cmf >> 4) & 0x0F) > 7 || (((cmf << 8) | flg) % 31) != 0) st = ZK_DATA_ERROR;
+        else if (flg & 0x20) st = m >= 6 ? ZK_NEED_DICT : ZK_BUF_ERROR;
+    }
+    header[0] = st;
+}
+
+// one candidate chunk start per span: the first byte offset p in the span with in[p-4..p) == 00 00 FF FF
+__global__ void __launch_bounds__(256) marker_kernel(const uint8_t *__restrict__ in, uint64_t m, uint32_t span_shift,
+                                                     uint32_t *__restrict__ cand) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 6; p < m; p += stride) {
+        if (in[p - 1] == 0xFF && in[p - 2] == 0xFF && in[p - 3] == 0 && in[p - 4] == 0) {
+            // a block must be able to start at p: BTYPE != 3
+            if (((in[p] >> 1) & 3) != 3) atomicMin(&cand[p >> span_shift], (uint32_t)p);
+        }
+    }
+}
+
+// candidates -> chunk list (keeps every `every`-th span's candidate); single thread, a few thousand spans
+__global__ void chunk_list_kernel(const uint32_t *cand, uint32_t num_spans, uint32_t every, uint64_t m,
+                                  ChunkInfo *chunks, uint32_t *num_chunks, uint32_t max_chunks) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t n = 0;
+    chunks[0].in_begin = 2;
+    n = 1;
+    uint32_t since = 0;
+    for (uint32_t s = 0; s < num_spans && n < max_chunks; ++s) {
+        const uint32_t c = cand[s];
+        if (c == kNoCand) continue;
+        if (++since < every) continue;
+        if ((uint64_t)c <= chunks[n - 1].in_begin) continue;
+        chunks[n].in_begin = c;
+        ++n;
+        since = 0;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        chunks[i].in_end = i + 1 < n ? chunks[i + 1].in_begin : m;
+        chunks[i].status = ZK_OK;
+        chunks[i].final_seen = 0;
+        chunks[i].out_len = ~0ull;  // not sized yet
+        chunks[i].out_begin = 0;
+        chunks[i].end_byte = 0;
+        chunks[i].retries = 0;
+    }
+    num_chunks[0] = n;
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(kInfWarps * 32) decode_kernel(const uint8_t *__restrict__ in, uint64_t m,
+                                                                ChunkInfo *chunks, const uint32_t *num_chunks,
+                                                                uint16_t *sym, uint64_t out_cap) {
+    __shared__ WarpState state[kInfWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t c = blockIdx.x * kInfWarps + wid;
+    if (c >= num_chunks[0]) return;
+    ChunkInfo &ci = chunks[c];
+    if (!kWrite && ci.out_len != ~0ull) return;  // sized in an earlier round
+    const uint64_t room = kWrite ? (ci.out_begin <= out_cap ? out_cap - ci.out_begin : 0) : ~0ull;
+    const ChunkResult r = decode_chunk<kWrite>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0, sym, ci.out_begin, room, lane);
+    if (lane == 0) {
+        ci.status = r.status;
+        if (!kWrite) {
+            ci.out_len = r.out_len;
+            ci.end_byte = r.end_byte;
+            ci.final_seen = r.final_seen;
+        }
+    }
+}
+
+// After the size pass: merge chunks whose predecessor did not end on them, prefix-sum the sizes.
+// verdict[0] = number of chunks after merging, verdict[1] = 1 if anything was merged (size pass must be
+// repeated for the merged chunks), verdict[2] = status of the stream so far, verdict[3..4] = total output.
+__global__ void plan_chunks_kernel(ChunkInfo *chunks, uint32_t *num_chunks, uint64_t *verdict) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t n = num_chunks[0];
+    uint32_t w = 0;
+    bool merged = false, fold_rest = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        // chunk i is trusted only if the chunk before it ended exactly on its first byte
+        if (w > 0 && (fold_rest || chunks[w - 1].status != ZK_OK || chunks[w - 1].final_seen)) {
+            if (!fold_rest && chunks[w - 1].final_seen && chunks[w - 1].status == ZK_OK) break;  // stream ended
+            // predecessor failed: fold this chunk into it and have it sized again.  A first failure is taken
+            // for a false candidate (absorb one successor); a second one for real damage (absorb the rest, so
+            // that one warp reports what the reference would report).
+            if (!fold_rest && chunks[w - 1].retries >= 1) fold_rest = true;
+            chunks[w - 1].in_end = chunks[i].in_end;
+            if (!fold_rest) chunks[w - 1].retries += 1;
+            chunks[w - 1].status = fold_rest ? ZK_DATA_ERROR : ZK_OK;
+            chunks[w - 1].final_seen = 0;
+            chunks[w - 1].out_len = ~0ull;  // marks "needs sizing"
+            merged = true;
+            continue;
+        }
+        if (w != i) chunks[w] = chunks[i];
+        ++w;
+    }
+    if (fold_rest) chunks[w - 1].status = ZK_OK;
+    num_chunks[0] = w;
+    uint64_t total = 0;
+    int status = ZK_OK;
+    for (uint32_t i = 0; i < w; ++i) {
+        chunks[i].out_begin = total;
+        if (chunks[i].out_len != ~0ull) total += chunks[i].out_len;
+        if (chunks[i].status != ZK_OK && i + 1 == w) status = chunks[i].status;
+    }
+    verdict[0] = w;
+    verdict[1] = merged ? 1 : 0;
+    verdict[2] = (uint64_t)(int64_t)status;
+    verdict[3] = total;
+    verdict[4] = w ? chunks[w - 1].end_byte : 0;
+    verdict[5] = w ? (uint64_t)chunks[w - 1].final_seen : 0;
+}
+
+// Resolve the last 32 KiB of every chunk in order.  windows[c][i] = byte at (chunk c's end - 32768 + i).
+__global__ void __launch_bounds__(1024) window_chain_kernel(const ChunkInfo *chunks, const uint32_t *num_chunks,
+                                                            const uint16_t *__restrict__ sym, uint8_t *windows,
+                                                            uint32_t *error_flag) {
+    const uint32_t n = num_chunks[0];
+    for (uint32_t c = 0; c < n; ++c) {
+        const uint64_t begin = chunks[c].out_begin, len = chunks[c].out_len;
+        const uint8_t *prev = c ? windows + (uint64_t)(c - 1) * kWindow : nullptr;
+        uint8_t *cur = windows + (uint64_t)c * kWindow;
+        for (int i = threadIdx.x; i < kWindow; i += 1024) {
+            // absolute output position of window slot i
+            const int64_t pos = (int64_t)(begin + len) - kWindow + i;
+            uint8_t v = 0;
+            if (pos >= (int64_t)begin) {
+                const uint16_t s = sym[pos];
+                if (s & 0x8000u) {
+                    const uint32_t idx = s & 0x7FFFu;
+                    // slot idx of the previous window must lie inside the stream
+                    if (!prev || (int64_t)begin - kWindow + (int64_t)idx < 0) atomicExch(error_flag, 1u);
+                    else v = prev[idx];
+                } else {
+                    v = (uint8_t)s;
+                }
+            } else if (prev && pos >= 0) {
+                v = prev[(int64_t)kWindow - ((int64_t)begin - pos)];
+            }
+            cur[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// Symbols -> bytes.  One CTA per 16 KiB of output; the chunk of a position is found by binary search.
+__global__ void __launch_bounds__(256) materialize_kernel(const ChunkInfo *__restrict__ chunks,
+                                                          const uint32_t *__restrict__ num_chunks,
+                                                          const uint16_t *__restrict__ sym,
+                                                          const uint8_t *__restrict__ windows, uint8_t *__restrict__ out,
+                                                          uint64_t total, uint32_t *error_flag) {
+    const uint32_t n = num_chunks[0];
+    const uint64_t tile0 = (uint64_t)blockIdx.x * 16384;
+    for (uint64_t p = tile0 + threadIdx.x; p < tile0 + 16384 && p < total; p += 256) {
+        const uint16_t s = sym[p];
+        uint8_t v;
+        if (s & 0x8000u) {
+            uint32_t lo = 0, hi = n;  // last chunk with out_begin <= p
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (chunks[mid].out_begin <= p) lo = mid;
+                else hi = mid;
+            }
+            const uint32_t idx = s & 0x7FFFu;
+            if (lo == 0 || (int64_t)chunks[lo].out_begin - kWindow + (int64_t)idx < 0) {
+                atomicExch(error_flag, 1u);
+                v = 0;
+            } else {
+                v = windows[(uint64_t)(lo - 1) * kWindow + idx];
+            }
+        } else {
+            v = (uint8_t)s;
+        }
+        out[p] = v;
+    }
+}
+
+// Trailer check and result record.  result = {out_len, consumed, status, adler}
+__global__ void finish_inflate_kernel(const uint8_t *in, uint64_t m, const uint64_t *verdict, const uint32_t *adler,
+                                      const uint32_t *error_flag, uint64_t *result) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int status = (int)(int64_t)verdict[2];
+    const uint64_t total = verdict[3], end_byte = verdict[4];
+    uint64_t consumed = end_byte;
+    if (status == ZK_OK && error_flag[0]) status = ZK_DATA_ERROR;  // distance too far back (IS:287-291)
+    if (status == ZK_OK) {
+        if (!verdict[5]) status = ZK_BUF_ERROR;  // ran out of input before a final block
+        else if (end_byte + 4 > m) status = ZK_BUF_ERROR;  // IS:414-418 trailer bytes missing
+        else {
+            const uint32_t t = ((uint32_t)in[end_byte] << 24) | ((uint32_t)in[end_byte + 1] << 16) |
+                               ((uint32_t)in[end_byte + 2] << 8) | (uint32_t)in[end_byte + 3];
+            consumed = end_byte + 4;
+            status = t == adler[0] ? ZK_STREAM_END : ZK_DATA_ERROR;  // IS:419-424
+        }
+    }
+    result[0] = total;
+    result[1] = consumed;
+    result[2] = (uint64_t)(int64_t)status;
+    result[3] = adler[0];
+}
+
+__global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void set_result_kernel(uint64_t *result, uint64_t a, uint64_t b, int64_t status, uint64_t d) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        result[0] = a;
+        result[1] = b;
+        result[2] = (uint64_t)status;
+        result[3] = d;
+    }
+}
+
+}  // namespace
+
+int run_inflate(zk_ctx *c, const InflateJob &job) {
+    cudaStream_t st = c->stream;
+    const uint64_t m = job.m;
+    // ---- scratch ------------------------------------------------------------------------------------
+    uint32_t span_shift = 9;  // >= 512-byte spans, at most ~4096 spans
+    while ((m >> span_shift) > 4096) ++span_shift;
+    const uint32_t num_spans = (uint32_t)(m >> span_shift) + 1;
+    const uint32_t max_chunks = num_spans + 1;
+    c->arena.reset();
+    const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
+                        (size_t)max_chunks * kWindow + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192;
+    if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
+    int32_t *d_header = static_cast<int32_t *>(c->arena.take(256));
+    uint32_t *d_cand = static_cast<uint32_t *>(c->arena.take((size_t)num_spans * 4));
+    ChunkInfo *d_chunks = static_cast<ChunkInfo *>(c->arena.take((size_t)max_chunks * sizeof(ChunkInfo)));
+    uint32_t *d_num = static_cast<uint32_t *>(c->arena.take(256));
+    uint64_t *d_verdict = static_cast<uint64_t *>(c->arena.take(256));
+    uint32_t *d_flag = static_cast<uint32_t *>(c->arena.take(256));
+    uint32_t *d_adler = static_cast<uint32_t *>(c->arena.take(256));
+    void *d_partials = c->arena.take(adler_partials_bytes(job.cap));
+    uint8_t *d_windows = static_cast<uint8_t *>(c->arena.take((size_t)max_chunks * kWindow));
+    uint16_t *d_sym = static_cast<uint16_t *>(c->arena.take((job.cap + 64) * 2));
+
+    // ---- header -------------------------------------------------------------------------------------
+    header_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_header);
+    c->launches++;
+    int32_t hst = 0;
+    ZK_CUDA(cudaMemcpyAsync(&hst, d_header, 4, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    if (hst != ZK_OK) {
+        // (hdr, 0): nothing decoded; FDICT consumes the 4 DICTID bytes (IS:41)
+        set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, hst == ZK_NEED_DICT ? 6 : (m < 2 ? m : 2), hst, 1);
+        c->launches++;
+        ZK_CUDA(cudaGetLastError());
+        return ZK_OK;
+    }
+    // ---- candidates -> chunks -------------------------------------------------------------------------
+    fill_u32_kernel<<<32, 256, 0, st>>>(d_cand, num_spans, kNoCand);
+    ZK_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+    {
+        const uint32_t grid = (uint32_t)tmin<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
+        marker_kernel<<<grid ? grid : 1, 256, 0, st>>>(job.d_in, m, span_shift, d_cand);
+    }
+    chunk_list_kernel<<<1, 32, 0, st>>>(d_cand, num_spans, 1, m, d_chunks, d_num, max_chunks);
+    c->launches += 3;
+    // ---- size pass, repeated while candidates turn out to be false ----------------------------------------
+    uint64_t verdict[6] = {0, 0, 0, 0, 0, 0};
+    for (int round = 0; round < 64; ++round) {
+        const uint32_t grid = (max_chunks + kInfWarps - 1) / kInfWarps;
+        decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0);
+        plan_chunks_kernel<<<1, 32, 0, st>>>(d_chunks, d_num, d_verdict);
+        c->launches += 2;
+        ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+        if (!verdict[1]) break;
+    }
+    const uint64_t total = verdict[3];
+    int status = (int)(int64_t)verdict[2];
+    if (total > job.cap) {
+        set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, 0, ZK_BUF_ERROR, 1);
+        c->launches++;
+        ZK_CUDA(cudaGetLastError());
+        return ZK_OK;
+    }
+    // ---- write pass, window chain, bytes ------------------------------------------------------------------
+    {
+        const uint32_t nchunks = (uint32_t)verdict[0];
+        const uint32_t grid = (nchunks + kInfWarps - 1) / kInfWarps;
+        decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap);
+        window_chain_kernel<<<1, 1024, 0, st>>>(d_chunks, d_num, d_sym, d_windows, d_flag);
+        const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
+        if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag);
+        c->launches += 3;
+    }
+    (void)status;
+    int rc = launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
+    if (rc != ZK_OK) return rc;
+    finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result);
+    c->launches++;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+}  // namespace zk

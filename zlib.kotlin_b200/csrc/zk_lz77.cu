@@ -1,0 +1,527 @@
+// zk_lz77.cu -- K1: LZ77 match finding + lazy parse, one CTA per LZ unit.
+//
+// Replaces the tokeniser of DeflateStream.compressZlibDynamic (deflate/DeflateStream.kt:573-790:
+// hash3 DS:588-595, insertTripletAt DS:127-144, chain walk DS:668-692, advanceMatch DS:165-184)
+// with a design that maps to an SM instead of a scalar loop.  It is not a port: the reference's
+// look-ahead/window arrays, its pre-seeded chains and its stale-window compare do not exist here.
+//
+// Layout in shared memory (one CTA per SM, ~198 KB):
+//   ring  u8 [65536]   input bytes at (q & 0xFFFF); q = unit-relative position, history first
+//   prev  u16[32768]   hash-chain links at (q & 32767): previous position with the same 3-byte hash
+//   head  u16[16384]   most recent position per hash
+//   match u32[2][4096] per-position best match of the group in flight / the group being parsed
+//   hist  u32[320]     literal/length + distance counts of the deflate block being parsed
+//
+// Software pipeline over groups of 4096 positions, one __syncthreads per step.  In step i
+//   - one elected thread stages group i+3 into the ring with a TMA bulk copy (mbarrier-tracked),
+//   - warp 0 inserts group i+1 into the hash chains, 32 positions per instruction sequence
+//     (match.any resolves duplicates inside the batch, so chains are exact and deterministic),
+//   - warp 1 parses group i-1: a speculative pass finds every lane-segment's exit, a warp scan
+//     stitches them, a second pass marks the tokens, a third emits them densely + histograms,
+//   - every warp (0 and 1 join when done) steals 128-position strips of group i and searches
+//     the chains; a lane walks 4 consecutive positions and inherits (len-1, dist) from the last.
+// A search only follows links of candidates within 32768 - 2*4096 bytes, which the builder (one
+// group ahead) can not have overwritten: results do not depend on warp timing.
+//
+// HBM traffic per input byte: 1 B read (+ 32 KiB halo per unit) and 4 B x tokens/byte written.
+#include "zk_common.cuh"
+
+namespace zk {
+
+namespace {
+
+constexpr int kThreadsLz = 1024;
+constexpr int kWarpsLz = kThreadsLz / 32;
+constexpr int kHashBits = 14;
+constexpr int kRun = 4;                      // consecutive positions per lane
+constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
+constexpr int kStripsPerGroup = kGroup / kStrip;
+constexpr int kSeg = kGroup / 32;            // parser: positions per lane segment
+constexpr int kHistGroups = kWindow / kGroup;
+constexpr int kMaxDist = kWindow - 2 * kGroup;
+constexpr int kStages = 4;                   // ring staging barriers
+
+struct LzSmem {
+    uint32_t ring[65536 / 4];
+    uint16_t prev[32768];
+    uint16_t head[1 << kHashBits];
+    uint32_t match[2][kGroup];
+    uint32_t hist[kHistStride];
+    unsigned long long bar[kStages];
+    int work[2];
+    int trunc_pos[32];
+    uint32_t trunc_tok[32];
+};
+
+struct LzArgs {
+    const uint8_t *in;      // shard input
+    uint64_t n;             // shard length
+    const uint8_t *hist;    // bytes preceding the shard (hist_len of them), or nullptr
+    uint32_t hist_len;
+    uint32_t unit_bytes;    // multiple of block_bytes
+    uint32_t block_bytes;   // power of two, multiple of kGroup
+    uint32_t block_shift;   // log2(block_bytes)
+    uint32_t num_units;
+    LevelParams lp;
+    uint32_t *tokens;       // [n] dense per unit, unit u starts at u * unit_bytes
+    uint32_t *block_tok_begin;  // [num_blocks] index into tokens
+    uint32_t *block_tok_count;  // [num_blocks]
+    uint32_t *block_hist;       // [num_blocks][kHistStride]
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 4 bytes at byte offset q of the ring (any alignment, wraps at 64 KiB)
+__device__ __forceinline__ uint32_t ring_load32(const uint32_t *ring, uint32_t q) {
+    const uint32_t w = (q >> 2) & 0x3FFFu;
+    const uint32_t lo = ring[w], hi = ring[(w + 1) & 0x3FFFu];
+    return __funnelshift_r(lo, hi, (q & 3u) << 3);
+}
+__device__ __forceinline__ uint32_t ring_load8(const uint32_t *ring, uint32_t q) {
+    return (ring[(q >> 2) & 0x3FFFu] >> ((q & 3u) << 3)) & 0xFFu;
+}
+__device__ __forceinline__ uint32_t hash3(uint32_t four_bytes) {
+    return ((four_bytes & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - kHashBits);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+struct UnitGeom {
+    uint64_t unit_start;  // shard offset of the unit's first byte
+    uint32_t ulen;        // bytes in the unit
+    int32_t h0q;          // first valid q (history start)
+    int32_t data_end_q;   // kWindow + ulen
+    int first_group;      // group holding h0q
+    int last_group;       // last data group
+};
+
+// Stage group t of the unit into the ring.  Source bytes may come from the shard itself or, for the
+// history of unit 0, from the separate history buffer.  Returns true when the TMA path was used.
+__device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, bool issue) {
+    const int32_t q0 = t * kGroup;
+    // valid source range of this group in q coordinates
+    int32_t lo = max(q0, g.h0q);
+    // bytes past the unit end are only ever hashed, never matched: stage what the input still has
+    const int64_t avail_q = (int64_t)kWindow + (int64_t)tmin<uint64_t>(a.n - g.unit_start, (uint64_t)g.ulen + kGroup);
+    int32_t hi = (int32_t)tmin<int64_t>((int64_t)q0 + kGroup, avail_q);
+    if (hi <= lo) return false;
+    const uint8_t *src;
+    if (g.unit_start == 0 && q0 < kWindow) {
+        src = a.hist + (int64_t)a.hist_len - kWindow;  // q = 0 maps to hist_len - 32768 (may be "before" hist)
+    } else {
+        src = a.in + g.unit_start - kWindow;
+    }
+    uint8_t *ring8 = reinterpret_cast<uint8_t *>(s.ring);
+    const bool tma = lo == q0 && ((hi - lo) & 15) == 0 && ((reinterpret_cast<uintptr_t>(src + lo)) & 15) == 0;
+    if (tma) {
+        if (issue && threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s.bar[t & (kStages - 1)], (uint32_t)(hi - lo));
+            tma_load(ring8 + (q0 & 0xFFFF), src + lo, (uint32_t)(hi - lo), &s.bar[t & (kStages - 1)]);
+        }
+    } else if (issue) {
+        for (int32_t q = lo + (int32_t)threadIdx.x; q < hi; q += kThreadsLz) ring8[q & 0xFFFF] = src[q];
+    }
+    return tma;
+}
+
+// ---- builder: warp 0 inserts group t into the hash chains ------------------------------------
+__device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
+    const uint32_t q0 = (uint32_t)t * kGroup + lane;
+#pragma unroll 1
+    for (int b = 0; b < kGroup / 32; b += 4) {
+        uint32_t h[4], m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            h[u] = hash3(ring_load32(s.ring, q0 + (b + u) * 32));
+            m[u] = __match_any_sync(0xFFFFFFFFu, h[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t q = q0 + (b + u) * 32;
+            const uint32_t below = m[u] & ((1u << lane) - 1u);
+            uint16_t link;
+            if (below) link = (uint16_t)(q - (uint32_t)(lane - (31 - __clz(below))));
+            else link = s.head[h[u]];
+            s.prev[q & 32767u] = link;
+            if (((m[u] >> lane) >> 1) == 0u) s.head[h[u]] = (uint16_t)q;  // last of its hash in the batch
+            __syncwarp();
+        }
+    }
+}
+
+// ---- searcher: best match of 4 consecutive positions ------------------------------------------
+__device__ __forceinline__ uint32_t match_length(const uint32_t *ring, uint32_t p, uint32_t c, int maxlen) {
+    int len = 0;
+    while (len < maxlen) {
+        const uint32_t x = ring_load32(ring, p + len) ^ ring_load32(ring, c + len);
+        if (x) {
+            len += (__ffs(x) - 1) >> 3;
+            break;
+        }
+        len += 4;
+    }
+    return (uint32_t)min(len, maxlen);
+}
+
+__device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, const UnitGeom &g, int t, int strip,
+                                             int lane, uint32_t block_shift) {
+    uint32_t *mv = s.match[t & 1];
+    const int32_t base = t * kGroup + strip * kStrip + lane * kRun;
+    int inh_len = 0, inh_dist = 0, inh_run = 0;
+#pragma unroll 1
+    for (int r = 0; r < kRun; ++r) {
+        const int32_t p = base + r;
+        int best = 0, bestd = 0;
+        if (p < g.data_end_q) {
+            // matches never cross the end of their deflate block
+            const int32_t off = p - kWindow;
+            const int32_t blk_end = min((int32_t)g.ulen, ((off >> block_shift) + 1) << block_shift);
+            const int maxlen = min(kMaxMatch, blk_end - off);
+            if (r > 0 && inh_len - 1 >= lp.min_len) {
+                best = min(inh_len - 1, maxlen);
+                bestd = inh_dist;
+                ++inh_run;
+            } else {
+                inh_run = 0;
+            }
+            int budget = lp.chain;
+            if (best >= lp.good) budget >>= 2;
+            if (lp.skip_deep && inh_run >= 2) budget = 0;
+            if (best < lp.nice && best < maxlen && maxlen >= lp.min_len && budget > 0) {
+                const uint32_t cur = ring_load32(s.ring, (uint32_t)p);
+                uint32_t tail = best >= 3 ? ring_load32(s.ring, (uint32_t)(p + best - 3)) : 0u;
+                uint32_t c16 = s.prev[p & 32767];
+                uint32_t lastd = 0;
+                const uint32_t reach = (uint32_t)min(kMaxDist, p - g.h0q);
+                for (int step = 0; step < budget; ++step) {
+                    const uint32_t d = ((uint32_t)p - c16) & 0xFFFFu;
+                    if (d == 0u || d > reach || d <= lastd) break;
+                    lastd = d;
+                    const uint32_t c = (uint32_t)p - d;
+                    bool worth;
+                    if (best >= 3) worth = ring_load32(s.ring, c + best - 3) == tail;
+                    else worth = ((ring_load32(s.ring, c) ^ cur) & 0xFFFFFFu) == 0u;
+                    if (worth) {
+                        const int len = (int)match_length(s.ring, (uint32_t)p, c, maxlen);
+                        if (len > best && len >= lp.min_len) {
+                            best = len;
+                            bestd = (int)d;
+                            if (len >= lp.nice) break;
+                            tail = ring_load32(s.ring, (uint32_t)(p + best - 3));
+                        }
+                    }
+                    c16 = s.prev[c & 32767u];
+                }
+            }
+            if (best == 3 && bestd > lp.far3) best = 0;
+        }
+        inh_len = best;
+        inh_dist = bestd;
+        uint32_t word = 0;
+        if (best >= lp.min_len && !(lp.filtered && best <= 5)) word = ((uint32_t)best << 16) | (uint32_t)(bestd - 1);
+        mv[p - t * kGroup] = word;
+    }
+}
+
+// ---- parser: warp 1 turns the per-position matches of group t into tokens ------------------------
+__device__ __forceinline__ int tok_len(uint32_t w) { return (int)((w >> 16) & 0x1FFu); }
+
+__device__ __forceinline__ int length_symbol(int len) {  // 257..285
+    const int y = len - 3;
+    if (y < 8) return 257 + y;
+    if (len == 258) return 285;
+    const int b = 31 - __clz(y);
+    return 257 + 4 * (b - 1) + ((y >> (b - 2)) & 3);
+}
+__device__ __forceinline__ int dist_symbol(int dist_minus1) {  // 0..29
+    if (dist_minus1 < 4) return dist_minus1;
+    const int b = 31 - __clz(dist_minus1);
+    return 2 * b + ((dist_minus1 >> (b - 1)) & 1);
+}
+
+// Decide the token at p: returns the step (1 for a literal, len for a match).
+__device__ __forceinline__ int decide(const uint32_t *mv, int32_t g0, int32_t gend, int32_t p, int lazy) {
+    const int len = tok_len(mv[p - g0]);
+    if (len == 0) return 1;
+    if (lazy && p + 1 < gend && tok_len(mv[p + 1 - g0]) > len) return 1;
+    return len;
+}
+
+struct ParseCarry {
+    int32_t entry;        // first unparsed q (>= start of the next group)
+    uint32_t tok_off;     // tokens emitted so far in this unit
+    uint32_t blk_begin;   // tok_off at the start of the current block
+};
+
+__device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, int lane,
+                                            ParseCarry &carry, uint32_t unit_index) {
+    uint32_t *mv = s.match[t & 1];
+    const int32_t g0 = t * kGroup;
+    const int32_t gend = min(g0 + kGroup, g.data_end_q);
+    const int lazy = a.lp.lazy;
+    const int32_t seg0 = min(g0 + lane * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
+
+    // pass A: speculative parse of this lane's segment, only the exit matters
+    int32_t exit_q = seg0;
+    {
+        int32_t p = seg0;
+        while (p < seg1) p += decide(mv, g0, gend, p, lazy);
+        exit_q = p;
+    }
+    // stitch: lane l really starts where the parse left lane l-1 (or earlier lanes, for long matches)
+    int32_t x = carry.entry, my_start = 0, my_stop = 0;
+#pragma unroll 1
+    for (int l = 0; l < 32; ++l) {
+        const int32_t e = __shfl_sync(0xFFFFFFFFu, exit_q, l);
+        const int32_t send = __shfl_sync(0xFFFFFFFFu, seg1, l);
+        const int32_t nx = (x < send) ? e : x;
+        if (lane == l) {
+            my_start = x;
+            my_stop = (x < send) ? nx : x;  // empty range when the segment is already covered
+        }
+        x = nx;
+    }
+    // pass B: mark the tokens of [my_start, my_stop); a match that would overshoot is cut (rare: only
+    // when the speculative parse had not yet converged with the real one at the segment end)
+    int cnt = 0;
+    s.trunc_pos[lane] = -1;
+    {
+        int32_t p = my_start;
+        while (p < my_stop) {
+            uint32_t w = mv[p - g0];
+            int step = decide(mv, g0, gend, p, lazy);
+            uint32_t mark = kTokStart;
+            if (step == 1 && tok_len(w) != 0) mark |= kTokLiteral;
+            if (p + step > my_stop) {
+                step = my_stop - p;
+                if (step < 3) {
+                    step = 1;
+                    mark |= kTokLiteral;
+                } else {
+                    s.trunc_pos[lane] = p;
+                    s.trunc_tok[lane] = ((uint32_t)step << 16) | (w & 0xFFFFu);
+                }
+            }
+            mv[p - g0] = w | mark;
+            p += step;
+            ++cnt;
+        }
+    }
+    __syncwarp();
+    // dense offsets
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    // pass C: emit + histogram
+    {
+        uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + carry.tok_off + (uint32_t)(incl - cnt);
+        const int tp = s.trunc_pos[lane];
+        int32_t p = my_start;
+        while (p < my_stop) {
+            uint32_t w = mv[p - g0];
+            if (p == tp) w = s.trunc_tok[lane];
+            const int len = tok_len(w);
+            if (len == 0 || (w & kTokLiteral)) {
+                const uint32_t byte = ring_load8(s.ring, (uint32_t)p);
+                *dst++ = byte;
+                atomicAdd(&s.hist[byte], 1u);
+                p += 1;
+            } else {
+                *dst++ = w & 0x01FFFFFFu;
+                atomicAdd(&s.hist[length_symbol(len)], 1u);
+                atomicAdd(&s.hist[kDistHistBase + dist_symbol((int)(w & 0xFFFFu))], 1u);
+                p += len;
+            }
+        }
+    }
+    __syncwarp();
+    carry.entry = x;
+    carry.tok_off += (uint32_t)total;
+
+    // close the deflate block when this group ends it
+    const int32_t off_end = gend - kWindow;
+    if (off_end == (int32_t)g.ulen || (off_end & (int32_t)(a.block_bytes - 1)) == 0) {
+        const uint32_t blk = (uint32_t)((g.unit_start + (uint64_t)(off_end - 1)) >> a.block_shift);
+        uint32_t *out = a.block_hist + (uint64_t)blk * kHistStride;
+        for (int i = lane; i < kHistStride; i += 32) {
+            uint32_t v = s.hist[i];
+            if (i == 256) v += 1;  // end-of-block
+            out[i] = v;
+            s.hist[i] = 0;
+        }
+        if (lane == 0) {
+            a.block_tok_begin[blk] = (uint32_t)((uint64_t)unit_index * a.unit_bytes) + carry.blk_begin;
+            a.block_tok_count[blk] = carry.tok_off - carry.blk_begin;
+        }
+        carry.blk_begin = carry.tok_off;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    LzSmem &s = *reinterpret_cast<LzSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (uint32_t unit = blockIdx.x; unit < a.num_units; unit += gridDim.x) {
+        UnitGeom g;
+        g.unit_start = (uint64_t)unit * a.unit_bytes;
+        g.ulen = (uint32_t)tmin<uint64_t>(a.unit_bytes, a.n - g.unit_start);
+        g.h0q = unit == 0 ? (int32_t)(kWindow - a.hist_len) : 0;
+        g.data_end_q = kWindow + (int32_t)g.ulen;
+        g.first_group = g.h0q / kGroup;
+        g.last_group = (g.data_end_q - 1) / kGroup;
+
+        // reset tables (deterministic start) and barriers
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(s.prev);
+            const int nvec = (int)((sizeof(s.prev) + sizeof(s.head)) / 16);
+            for (int i = threadIdx.x; i < nvec; i += kThreadsLz) z[i] = make_uint4(0, 0, 0, 0);
+            for (int i = threadIdx.x; i < kHistStride; i += kThreadsLz) s.hist[i] = 0;
+            if (threadIdx.x == 0) {
+                for (int b = 0; b < kStages; ++b) mbar_init(&s.bar[b], 1);
+                s.work[0] = s.work[1] = 0;
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+        }
+        __syncthreads();
+        // stage uses per barrier slot, to derive the parity of the next wait
+        uint32_t stage_uses[kStages] = {0, 0, 0, 0};
+        // prologue: groups first_group, first_group+1 (the loop stages i+3 = first_group+2 onwards)
+        bool staged_tma[2];
+        for (int k = 0; k < 2; ++k) staged_tma[k] = stage_group(s, a, g, g.first_group + k, true);
+        for (int k = 0; k < 2; ++k) {
+            if (staged_tma[k]) {
+                const int slot = (g.first_group + k) & (kStages - 1);
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&s.bar[slot], stage_uses[slot] & 1u)) {
+                    if (++spins > (1u << 26)) break;  // never hang the device on a lost transaction
+                }
+                stage_uses[slot]++;
+            }
+        }
+        __syncthreads();
+
+        ParseCarry carry;
+        carry.entry = kWindow;
+        carry.tok_off = 0;
+        carry.blk_begin = 0;
+
+        // step i: stage(i+3) | build(i+1) | search(i) | parse(i-1)
+        for (int i = g.first_group - 1; i <= g.last_group + 1; ++i) {
+            const bool tma_next = (i + 3 <= g.last_group + 1) ? stage_group(s, a, g, i + 3, true) : false;
+            if (threadIdx.x == 0) s.work[(i + 1) & 1] = 0;
+
+            if (warp == 0 && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
+            if (warp == 1 && i - 1 >= kHistGroups && i - 1 <= g.last_group) parse_group(s, a, g, i - 1, lane, carry, unit);
+            if (i >= kHistGroups && i <= g.last_group) {
+                for (;;) {
+                    int strip = 0;
+                    if (lane == 0) strip = atomicAdd(&s.work[i & 1], 1);
+                    strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
+                    if (strip >= kStripsPerGroup) break;
+                    search_strip(s, a.lp, g, i, strip, lane, a.block_shift);
+                }
+            }
+            if (tma_next) {
+                const int slot = (i + 3) & (kStages - 1);
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&s.bar[slot], stage_uses[slot] & 1u)) {
+                    if (++spins > (1u << 26)) break;
+                }
+                stage_uses[slot]++;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+LevelParams level_params(int level, int strategy) {
+    // chain / nice / good / lazy / skip_deep per level.  The reference only varies the chain length
+    // (8/16/32/64 for level <=2/<=4/<=6/else, DS:603-609) and never parses lazily (DS:610); these are
+    // tuned with tools/lzmodel.cpp so that level 6 lands on libz level-6 sizes.
+    LevelParams p;
+    p.far3 = 256;
+    p.min_len = 3;
+    p.filtered = strategy == ZK_FILTERED;
+    p.skip_deep = 1;
+    if (level <= 1) {
+        p.chain = 2; p.nice = 32; p.good = 4; p.lazy = 0;
+    } else if (level <= 3) {
+        p.chain = 4; p.nice = 32; p.good = 4; p.lazy = level == 3;
+    } else if (level <= 5) {
+        p.chain = 8; p.nice = 64; p.good = 8; p.lazy = 1;
+    } else if (level <= 7) {
+        p.chain = level == 6 ? 16 : 32; p.nice = 128; p.good = 8; p.lazy = 1;
+    } else {
+        p.chain = level == 8 ? 64 : 128; p.nice = 258; p.good = 32; p.lazy = 1; p.skip_deep = 0;
+    }
+    if (strategy == ZK_HUFFMAN_ONLY) {
+        p.chain = 0;
+        p.min_len = kMaxMatch + 1;
+    }
+    return p;
+}
+
+size_t lz77_smem_bytes() { return sizeof(LzSmem); }
+
+int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_hist, uint32_t hist_len,
+                uint32_t unit_bytes, uint32_t block_bytes, const LevelParams &lp, uint32_t *tokens,
+                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist) {
+    LzArgs a;
+    a.in = d_in;
+    a.n = n;
+    a.hist = d_hist;
+    a.hist_len = d_hist ? hist_len : 0;
+    a.unit_bytes = unit_bytes;
+    a.block_bytes = block_bytes;
+    a.block_shift = 0;
+    while ((1u << a.block_shift) < block_bytes) ++a.block_shift;
+    a.num_units = (uint32_t)((n + unit_bytes - 1) / unit_bytes);
+    a.lp = lp;
+    a.tokens = tokens;
+    a.block_tok_begin = block_tok_begin;
+    a.block_tok_count = block_tok_count;
+    a.block_hist = block_hist;
+    // per-device attribute: set on every launch (cheap) so multi-device processes stay correct
+    ZK_CUDA(cudaFuncSetAttribute(lz77_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzSmem)));
+    const uint32_t grid = a.num_units;
+    lz77_kernel<<<grid, kThreadsLz, sizeof(LzSmem), c->stream>>>(a);
+    c->launches += 1;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+}  // namespace zk
