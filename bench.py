@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- deflate / inflate throughput of the B200 engine on BASELINE.json's workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size-mib M] [--level L]
+
+One "step" = one level-6 zlib deflate of the whole synthetic buffer (the hot path), device-resident:
+the input is already in HBM when the timed region starts and the stream stays in HBM.  N = 1 uses
+BASELINE.json configs[1] (1 GiB mixed-entropy, level 6); N > 1 shards chunk ranges across ranks
+(weak scaling: 1 GiB per rank), with one all_gather of {body_len, adler, raw_len} per step.
+Prints ONE JSON line on rank 0.  `value` = uncompressed GB/s of deflate (10^9 B/s, whole job);
+`inflate` carries the same measurement for the inflate of the produced stream; `e2e` is deflate
+through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "deflate uncompressed GB/s at level 6 (zlib-wrapped, chunked)"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size-mib", type=int, default=1024, help="uncompressed MiB per GPU")
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--workload", default="mixed", choices=["mixed", "text"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-mib", type=int, default=32)
+    return ap.parse_args()
+
+
+def make_corpus(kind, nbytes, rank=0):
+    from zlibk_b200 import corpus
+
+    seed_shift = 0x10000 * rank
+    if kind == "text":
+        return corpus.text_like(nbytes, corpus.SEED_TEXT + seed_shift)
+    return corpus.mixed_entropy(nbytes, corpus.SEED_MIXED + seed_shift)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()  # the exact process we started
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(kind, level, sample_mib, cores_note=""):
+    """The oracle (C restatement of the reference algorithm, kind "port") timed on one host core over a
+    bounded sample of the same workload.  The reference is single-threaded; it could not be built here."""
+    from tests.oracle_binding import Oracle
+
+    so = os.path.join(ROOT, "oracle", "libzk_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    oracle = Oracle(so)
+    data = make_corpus(kind, sample_mib << 20).tobytes()
+    t0 = time.perf_counter()
+    rc, stream, used = oracle.deflate(data, level)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    oracle.inflate(stream, cap=len(data) + 64)
+    dti = time.perf_counter() - t1
+    return {
+        "value": len(data) / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": "first %d MiB of the %s corpus, level %d, one pass" % (sample_mib, kind, level),
+        "compressed_ratio": len(stream) / len(data), "inflate_gbs_of_its_own_stream": len(data) / dti / 1e9,
+        "note": "C restatement of the reference algorithm (single thread, -O2): an upper bound on the Kotlin/Native binary, "
+                "which could not be built in this image" + cores_note,
+    }
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Kotlin reference can
+    not be compiled here), one host thread -- the reference is single-threaded -- on a bounded sample per step."""
+    if rank != 0:
+        return
+    from tests.oracle_binding import Oracle
+
+    so = os.path.join(ROOT, "oracle", "libzk_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    oracle = Oracle(so)
+    sample_mib = min(args.cpu_sample_mib, 16)
+    data = make_corpus(args.workload, sample_mib << 20).tobytes()
+    for _ in range(min(args.warmup, 1)):
+        oracle.deflate(data[: 1 << 20], args.level)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        oracle.deflate(data, args.level)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    value = len(data) / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%d GiB-class %s corpus, level %d (bounded sample: first %d MiB per step)" % (
+            max(1, args.size_mib >> 10), args.workload, args.level, sample_mib)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "first %d MiB of the %s corpus per step" % (sample_mib, args.workload)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import zlibk_b200
+    from zlibk_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.size_mib << 20
+    host = make_corpus(args.workload, n, rank)
+    h_in = torch.from_numpy(host).pin_memory()
+    d_in = h_in.to(dev, non_blocking=True)
+    eng = zlibk_b200.Engine(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_option("timing", 1)
+    cap = eng.compress_bound(n)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    d_back = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_res2 = torch.zeros(4, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize(dev)
+
+    shard = None
+    if world > 1:
+        # the 32 KiB halo comes from the source (here: the previous rank's generator), not from a collective
+        hist = None
+        if rank > 0:
+            from zlibk_b200 import corpus
+            hist = torch.from_numpy(corpus.tail(args.workload, n, rank - 1, 32768)).to(dev)
+        shard = sharding.ShardedDeflate(eng, rank, world, dev, hist)
+
+    def deflate_step():
+        if shard is None:
+            rc = eng.deflate_device(d_in.data_ptr(), n, args.level, 0, d_out.data_ptr(), cap, d_res.data_ptr())
+        else:
+            rc = shard.step(d_in, n, args.level, d_out, cap)
+        if rc != 0:
+            raise SystemExit("deflate failed rc=%d %s" % (rc, eng.last_error()))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        deflate_step()
+    barrier()
+    eng.counter("reset_timing")
+    launches0 = eng.counter("kernel_launches")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        deflate_step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = eng.counter("kernel_launches") - launches0
+    lz_us, lz_spans = eng.counter("lz77_us"), eng.counter("lz77_spans")
+    huff_us, pack_us, adler_us = eng.counter("huffman_us"), eng.counter("pack_us"), eng.counter("adler_us")
+    if shard is None:
+        res = d_res.cpu().tolist()
+        out_len, status = res[0], res[2]
+    else:
+        offsets, stream_len, folded = shard.finish()
+        out_len, status = shard.last_body_len, shard.last_status
+    if status != 0:
+        raise SystemExit("deflate status %d" % status)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([float(out_len)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_out = float(tot.item())
+    else:
+        total_out = float(out_len)
+    ms_per_step = ms / args.steps
+    value = (n * world) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- inflate of the produced stream (rank-local stream, device-resident) -------------------------------
+    inflate = None
+    if shard is None:
+        m = int(out_len)
+        for _ in range(min(args.warmup, 2)):
+            eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
+        torch.cuda.synchronize(dev)
+        eng.counter("reset_timing")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        isteps = max(1, min(args.steps, 3))
+        e0.record(stream)
+        for _ in range(isteps):
+            eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ims = e0.elapsed_time(e1) / isteps
+        r2 = d_res2.cpu().tolist()
+        ok = r2[2] == 1 and r2[0] == n and bool(torch.equal(d_back, d_in))
+        inflate = {"value": n / (ims * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ims, "status": r2[2], "bit_exact": ok,
+                   "decode_kernel_ms": eng.counter("inflate_decode_us") / 1e3 / isteps,
+                   "other_kernels_ms": eng.counter("inflate_other_us") / 1e3 / isteps}
+
+    # ---- e2e through the host-buffer C-ABI call (pinned memory; H2D + D2H inside) ----------------------------
+    e2e = None
+    if shard is None:
+        h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        e_steps = max(1, min(args.steps, 3))
+        eng.deflate(h_in, args.level, out=h_out)  # warm-up: staging allocation
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            rc, s, _ = eng.deflate(h_in, args.level, out=h_out)
+        dt = (time.perf_counter() - t0) / e_steps
+        e2e = {"value": n / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(len(s)) + 32,
+               "ms_per_step": dt * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # dominant kernel: lz77_kernel.  Algorithmic bytes of the launches timed = uncompressed + compressed bytes of
+    # this rank's steps; duration = CUDA-event time around those launches on their stream.
+    alg_bytes = (n + total_out / world) * args.steps
+    lz_s = lz_us * 1e-6
+    achieved = alg_bytes / lz_s / 1e9 if lz_s > 0 else None
+    roofline = {"bound": "hbm", "kernel": "lz77_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "peak_source": peak_kind, "traffic": None,
+                "launches_timed": lz_spans, "avg_launch_ms": lz_us / 1e3 / max(1, lz_spans),
+                "share_of_step": {"lz77": lz_us / 1e3 / args.steps / ms_per_step, "huffman+offsets": huff_us / 1e3 / args.steps / ms_per_step,
+                                  "pack": pack_us / 1e3 / args.steps / ms_per_step, "adler": adler_us / 1e3 / args.steps / ms_per_step}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": "%d MiB %s corpus per GPU (seed 0x5EED000%d), level %d, zlib stream, 32 KiB blocks; input larger than L2 (no flush needed)" % (
+            args.size_mib, "mixed-entropy" if args.workload == "mixed" else "text-like", 2 if args.workload == "mixed" else 1, args.level),
+            "parallelism": "chunk ranges per GPU x%d" % world},
+        "compressed_ratio": total_out / (n * world),
+        "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+        "inflate": inflate, "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, args.level, args.cpu_sample_mib)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,3 +24,29 @@ def oracle():
     from tests.oracle_binding import Oracle
 
     return Oracle(so)
+
+
+def _have_gpu():
+    try:
+        import zlibk_b200
+
+        return zlibk_b200.library().zk_device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """The CUDA engine through the C ABI.  GPU tests fail loudly (not skip) when the library is missing."""
+    import zlibk_b200
+
+    return zlibk_b200.Engine(0)
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (GPU tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -1,0 +1,357 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the oracle.
+
+Gates (BASELINE.json north_star):
+  1. the reference's inflate (oracle restatement) of the GPU stream reproduces the input bit-exactly;
+  2. GPU inflate of the reference's deflate output equals the reference inflate's result -- bytes AND
+     return code, including the streams the reference itself gets wrong;
+  3. Adler-32 bit-exact;
+  4. compressed size <= 1.02 x the reference's at the same level (in fact far below).
+libz 1.3 is the independent cross-check both ways (it is the code pigz links).
+"""
+import io
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.bitio import BitWriter, fixed_litlen_lengths, zlib_header
+from tests.oracle_binding import Z_BUF_ERROR, Z_DATA_ERROR, Z_NEED_DICT, Z_OK, Z_STREAM_END, Z_STREAM_ERROR
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = [0, 1, 2, 6, 9]
+
+
+def _edge_cases():
+    from zlibk_b200 import corpus
+
+    return corpus.edge_cases(chunk=1 << 20)
+
+
+# ---- Adler-32 -------------------------------------------------------------------------------------------
+def test_adler_known_answers(engine, oracle):
+    from tests.test_oracle_adler import KATS
+
+    for data, want in KATS:
+        assert engine.adler32(data) == want == oracle.adler32(data)
+    assert engine.adler32(None, adler=0) == 1  # null buffer (Adler32Test.kt:20-21)
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 31, 33, 255, 5551, 5552, 5553, 11104, 11000, 65535, 65536, 65537,
+                               (1 << 20) - 1, (1 << 20) + 1, 3 * 5552 * 7 + 5, 9_000_001])
+def test_adler_sizes_and_alignments(engine, oracle, n):
+    data = random.Random(n).randbytes(n + 3)
+    for off in (0, 1, 3):  # unaligned starts exercise the scalar head / tail
+        piece = data[off:off + n]
+        assert engine.adler32(piece) == oracle.adler32(piece) == zlib.adler32(piece)
+    assert engine.adler32(bytes([0xFF]) * n) == zlib.adler32(bytes([0xFF]) * n)
+
+
+def test_adler_incremental_equals_one_shot(engine, oracle):
+    data = random.Random(3).randbytes(700_000)
+    whole = engine.adler32(data)
+    for cut in (1, 5552, 65521, 333_333):
+        assert engine.adler32(data[cut:], adler=engine.adler32(data[:cut])) == whole
+    assert whole == oracle.adler32(data)
+
+
+# ---- deflate: reference inflate must reproduce the input ---------------------------------------------------
+@pytest.mark.parametrize("level", LEVELS)
+def test_edge_cases_round_trip_through_reference_inflate(engine, oracle, level):
+    for name, data in _edge_cases():
+        rc, stream, adler = engine.deflate(data, level)
+        assert rc == Z_OK, (name, rc, engine.last_error())
+        stream = bytes(stream)
+        orc, out, second, used = oracle.inflate(stream, cap=len(data) + 64)
+        assert (orc, second, used) == (Z_STREAM_END, len(data), len(stream)), (name, level, orc)
+        assert out == data, (name, level)
+        assert zlib.decompress(stream) == data, (name, level)
+        assert adler == oracle.adler32(data), (name, level)
+        assert len(stream) <= engine.compress_bound(len(data))
+
+
+@pytest.mark.parametrize("level,flg", [(0, 0x01), (1, 0x01), (2, 0x5E), (5, 0x5E), (6, 0x9C), (8, 0x9C), (9, 0xDA)])
+def test_header_and_empty_stream(engine, oracle, level, flg):
+    rc, stream, _ = engine.deflate(b"", level)
+    stream = bytes(stream)
+    assert rc == Z_OK and stream[:2] == bytes([0x78, flg]) and len(stream) >= 6
+    if level >= 1:
+        assert stream == oracle.deflate(b"", level)[1]  # 78 xx 03 00 00 00 00 01, byte for byte
+    assert oracle.inflate(stream)[:2] == (Z_STREAM_END, b"")
+
+
+def test_level_above_nine_is_stream_error(engine):
+    rc, stream, _ = engine.deflate(b"abc", 10)
+    assert rc == Z_STREAM_ERROR and len(stream) == 0
+
+
+def test_negative_level_is_stored(engine, oracle):
+    data = b"stored please " * 100
+    rc, stream, _ = engine.deflate(data, -1)
+    stream = bytes(stream)
+    assert rc == Z_OK and stream[:2] == bytes([0x78, 0x01]) and (stream[2] & 6) == 0
+    assert len(stream) == len(data) + 5 + 6
+    assert oracle.inflate(stream)[:2] == (Z_STREAM_END, data)
+
+
+def test_stored_level_matches_reference_layout(engine, oracle):
+    # for inputs of at most one Okio segment the reference's stored path is sound: same bytes expected
+    for n in (0, 1, 100, 8192):
+        data = random.Random(n).randbytes(n)
+        assert bytes(engine.deflate(data, 0)[1]) == oracle.deflate(data, 0)[1]
+    data = random.Random(1).randbytes(200_000)  # longer: the reference corrupts, the engine must not
+    stream = bytes(engine.deflate(data, 0)[1])
+    assert len(stream) == len(oracle.deflate(data, 0)[1])
+    assert zlib.decompress(stream) == data
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+@pytest.mark.parametrize("kind", ["text", "mixed"])
+def test_ratio_against_reference_and_libz(engine, oracle, level, kind):
+    from zlibk_b200 import corpus
+
+    data = (corpus.text_like(6 << 20) if kind == "text" else corpus.mixed_entropy(6 << 20)).tobytes()
+    rc, stream, _ = engine.deflate(data, level)
+    assert rc == Z_OK
+    assert zlib.decompress(bytes(stream)) == data
+    ref_size = len(oracle.deflate(data, level)[1])
+    assert len(stream) <= 1.02 * ref_size, (len(stream), ref_size)  # north_star tolerance
+    if level >= 6:  # and close to libz at the same level
+        assert len(stream) <= 1.03 * len(zlib.compress(data, level))
+
+
+def test_strategies(engine, oracle):
+    from zlibk_b200 import Z_FILTERED, Z_HUFFMAN_ONLY, corpus
+
+    data = corpus.text_like(1 << 20).tobytes()
+    sizes = {}
+    for strat in (0, Z_FILTERED, Z_HUFFMAN_ONLY):
+        rc, stream, _ = engine.deflate(data, 6, strategy=strat)
+        assert rc == Z_OK and oracle.inflate(bytes(stream), cap=len(data) + 8)[:2] == (Z_STREAM_END, data)
+        sizes[strat] = len(stream)
+    assert sizes[0] < sizes[Z_FILTERED] < sizes[Z_HUFFMAN_ONLY] < len(data)
+    assert engine.deflate(data, 6, strategy=7)[0] == Z_STREAM_ERROR
+
+
+def test_output_too_small_is_buf_error(engine):
+    data = random.Random(8).randbytes(100_000)
+    out = np.empty(50_000, dtype=np.uint8)
+    rc, stream, _ = engine.deflate(data, 6, out=out)
+    assert rc == Z_BUF_ERROR and len(stream) == 0
+
+
+def test_deterministic_output(engine):
+    from zlibk_b200 import corpus
+
+    data = corpus.mixed_entropy(5 << 20).tobytes()
+    a = bytes(engine.deflate(data, 6)[1])
+    for _ in range(3):
+        assert bytes(engine.deflate(data, 6)[1]) == a
+
+
+def test_unaligned_input_pointer(engine, oracle):
+    from zlibk_b200 import corpus
+
+    base = corpus.text_like((1 << 20) + 64)
+    for off in (1, 7, 16, 33):
+        view = base[off:off + (1 << 20) - 5]
+        rc, stream, _ = engine.deflate(view, 6)
+        assert rc == Z_OK and zlib.decompress(bytes(stream)) == view.tobytes()
+
+
+# ---- inflate: same bytes and return code as the reference inflate ----------------------------------------------
+def _same_as_reference(engine, oracle, stream, cap):
+    want_rc, want_out, _, want_used = oracle.inflate(stream, cap=cap)
+    rc, out, used = engine.inflate(stream, cap)
+    assert rc == want_rc, (rc, want_rc)
+    assert bytes(out) == want_out
+    if want_rc == Z_STREAM_END:
+        assert used == want_used
+    return rc
+
+
+def test_reference_error_vectors(engine, oracle):
+    lit_codes, lit_bits = oracle.build_encoder(fixed_litlen_lengths())
+    dist_codes, dist_bits = oracle.build_encoder([5] * 32)
+    far = BitWriter().raw(zlib_header()).bits(1, 1).bits(1, 2).bits(lit_codes[257], lit_bits[257]).bits(dist_codes[0], dist_bits[0]).done()
+    assert _same_as_reference(engine, oracle, far, 1024) == Z_DATA_ERROR  # InflateErrorCasesTest.kt:17-60
+    bad_type = BitWriter().raw(zlib_header()).bits(1, 1).bits(3, 2).done()
+    assert _same_as_reference(engine, oracle, bad_type, 1024) == Z_DATA_ERROR  # InvalidBlockTypeTest.kt:11-29
+    fdict = zlib_header(2, 1) + bytes([0x12, 0x34, 0x56, 0x78])
+    rc, out, used = engine.inflate(fdict, 1024)
+    assert (rc, len(out), used) == (Z_NEED_DICT, 0, 6)  # InflateFdictTest.kt:11-38
+    empty = oracle.deflate(b"")[1]
+    assert _same_as_reference(engine, oracle, empty[:2], 1024) == Z_BUF_ERROR  # InflateBasicTests.kt:31-48
+    assert _same_as_reference(engine, oracle, bytes([0x78, 0x9D, 3, 0, 0, 0, 0, 1]), 64) == Z_DATA_ERROR
+    nlen = BitWriter().raw(zlib_header()).bits(1, 1).bits(0, 2).align().raw(bytes([5, 0, 0xFF, 0xFF])).raw(b"hello").done()
+    assert _same_as_reference(engine, oracle, nlen, 64) == Z_DATA_ERROR
+    z = bytearray(zlib.compress(b"some text some text some text", 6))
+    z[-1] ^= 1
+    assert _same_as_reference(engine, oracle, bytes(z), 64) == Z_DATA_ERROR  # trailer mismatch, bytes still out
+
+
+def test_truncations_report_like_the_reference(engine, oracle):
+    data = b"truncate me " * 3000
+    full = zlib.compress(data, 6)
+    for cut in (3, 10, len(full) // 2, len(full) - 5, len(full) - 1):
+        piece = full[:cut]
+        want_rc, want_out, _, _ = oracle.inflate(piece, cap=len(data) + 8)
+        rc, out, _ = engine.inflate(piece, len(data) + 8)
+        assert rc == want_rc == Z_BUF_ERROR
+        # the reference needs maxLen bits before each symbol; both stop within a few symbols of each other
+        assert abs(len(out) - len(want_out)) <= 258 * 2
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_libz_streams(engine, oracle, level):
+    from zlibk_b200 import corpus
+
+    for data in (corpus.text_like(2 << 20).tobytes(), corpus.mixed_entropy(7 << 20).tobytes(), b"hello world", bytes(100_000)):
+        stream = zlib.compress(data, level)
+        assert _same_as_reference(engine, oracle, stream, len(data) + 16) == Z_STREAM_END
+
+
+def test_reference_deflate_streams_valid_and_invalid(engine, oracle):
+    """Streams made by the reference's own compressor: GPU inflate must do exactly what the reference inflate
+    does with them, including the ones the reference corrupts (stale window, over-subscribed code-length code)."""
+    from zlibk_b200 import corpus
+
+    text = corpus.text_like(400_000).tobytes()
+    lines = b"".join(b"2024-01-01 12:00:%02d INFO request id=%06d status=200 OK\n" % (i % 60, i) for i in range(4000))
+    mixed = corpus.mixed_entropy(300_000).tobytes() + bytes(5000) + text[:50_000]
+    seen = set()
+    for name, data in (("hello", b"hello world"), ("stale", b"abcabc\0\0\0"), ("a1000", b"a" * 1000), ("text", text),
+                       ("lines", lines), ("random", random.Random(5).randbytes(150_000)), ("mixed", mixed)):
+        for level in (0, 1, 2, 6, 9):
+            _, stream, _ = oracle.deflate(data, level)
+            seen.add(_same_as_reference(engine, oracle, stream, 2 * len(data) + 1024))
+    assert Z_STREAM_END in seen and Z_DATA_ERROR in seen  # both kinds were exercised
+
+
+def test_pigz_style_streams_decode_in_parallel(engine, oracle):
+    """pigz -z framing rebuilt with libz (the pigz binary is not in the image): 128 KiB chunks primed with the
+    previous 32 KiB, each ended by a sync flush -- the layout docs/CLI_PIGZ_TESTING.md exercises."""
+    from zlibk_b200 import corpus
+
+    data = corpus.text_like(5 << 20).tobytes()
+    chunk = 128 * 1024
+    body = bytearray()
+    for off in range(0, len(data), chunk):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15, zdict=data[max(0, off - 32768):off]) if off else zlib.compressobj(6, zlib.DEFLATED, -15)
+        body += c.compress(data[off:off + chunk])
+        body += c.flush(zlib.Z_FINISH if off + chunk >= len(data) else zlib.Z_SYNC_FLUSH)
+    stream = zlib_header() + bytes(body) + zlib.adler32(data).to_bytes(4, "big")
+    rc, out, used = engine.inflate(stream, len(data))
+    assert rc == Z_STREAM_END and bytes(out) == data and used == len(stream)
+
+
+def test_false_sync_markers_in_payload(engine, oracle):
+    # stored data full of 00 00 FF FF: every candidate but the real ones must be rejected and merged
+    payload = (bytes([0, 0, 0xFF, 0xFF]) * 40_000) + random.Random(4).randbytes(100_000) + bytes([0, 0, 0xFF, 0xFF, 0x05]) * 9000
+    for level in (0, 6):
+        stream = zlib.compress(payload, level)
+        assert _same_as_reference(engine, oracle, stream, len(payload) + 8) == Z_STREAM_END
+    rc, own, _ = engine.deflate(payload, 6)
+    assert _same_as_reference(engine, oracle, bytes(own), len(payload) + 8) == Z_STREAM_END
+
+
+def test_trailing_member_is_left_unread(engine, oracle):
+    first = zlib.compress(b"first member " * 50)
+    stream = first + zlib.compress(b"second")
+    rc, out, used = engine.inflate(stream, 4096)
+    assert rc == Z_STREAM_END and bytes(out) == b"first member " * 50 and used == len(first)
+
+
+def test_output_capacity_too_small(engine):
+    stream = zlib.compress(bytes(100_000), 6)
+    rc, out, _ = engine.inflate(stream, 1000)
+    assert rc == Z_BUF_ERROR
+
+
+# ---- full-size properties (BASELINE.json configs) -----------------------------------------------------------------
+def test_config2_1gib_mixed_level6_device_round_trip(engine, oracle):
+    """configs[1]: 1 GiB mixed-entropy, level 6 deflate + inflate on one B200.  Bit-exact round trip on the
+    device, Adler-32 equal to a checksum of checksums (zlib combine over 64 MiB pieces computed by libz), and a
+    sampled prefix verified by the reference inflate."""
+    import torch
+
+    from zlibk_b200 import corpus
+
+    n = 1 << 30
+    host = corpus.mixed_entropy(n)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(host).to(dev)
+    cap = engine.compress_bound(n)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    assert engine.deflate_device(d_in.data_ptr(), n, 6, 0, d_out.data_ptr(), cap, d_res.data_ptr()) == 0
+    engine.synchronize()
+    out_len, adler, status, _ = d_res.cpu().tolist()
+    assert status == 0 and 0 < out_len < n
+    want = 1
+    for off in range(0, n, 64 << 20):
+        piece = host[off:off + (64 << 20)]
+        want = engine.adler32_combine(want, zlib.adler32(piece), piece.size)
+    assert adler == want
+    d_back = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_res2 = torch.zeros(4, dtype=torch.int64, device=dev)
+    assert engine.inflate_device(d_out.data_ptr(), out_len, d_back.data_ptr(), n, d_res2.data_ptr()) == 0
+    engine.synchronize()
+    r = d_res2.cpu().tolist()
+    assert r[2] == Z_STREAM_END and r[0] == n and r[1] == out_len
+    assert torch.equal(d_back, d_in)
+    # the reference inflate on a prefix of the stream: it must decode the first 48 MiB bit-exactly and then run
+    # out of input (Z_BUF_ERROR), since the prefix is cut mid-stream
+    prefix = d_out[: min(out_len, 24 << 20)].cpu().numpy().tobytes()
+    rc, out, _, _ = oracle.inflate(prefix, cap=n)
+    assert rc in (Z_BUF_ERROR, Z_STREAM_END) and len(out) > (16 << 20)
+    assert out == host[: len(out)].tobytes()
+
+
+def test_api_mirror_reads_like_the_reference_tests(engine):
+    """InflateBasicTests.kt:13-29 and DeflateParameterValidationTest.kt, through the reference-shaped API."""
+    import zlibk_b200 as zk
+
+    src, sink = io.BytesIO(b"hello world"), io.BytesIO()
+    assert zk.DeflateStream.compressZlib(src, sink) == 11
+    out = io.BytesIO()
+    assert zk.InflateStream.inflateZlib(io.BytesIO(sink.getvalue()), out) == (zk.Z_STREAM_END, 11)
+    assert out.getvalue() == b"hello world"
+    snk = io.BytesIO()
+    assert zk.DeflateStream.compressZlibResult(io.BytesIO(b""), snk, level=9) == (zk.Z_OK, 0) and len(snk.getvalue()) >= 6
+    snk = io.BytesIO()
+    assert zk.DeflateStream.compressZlibResult(io.BytesIO(b""), snk, level=-1) == (zk.Z_OK, 0) and len(snk.getvalue()) >= 6
+    assert zk.Adler32Utils.adler32(1, b"xxWikipediaxx", 2, 9) == 0x11E60398
+    assert zk.Adler32().adler32(1, None, 0, 0) == 1
+    assert zk.ZLib.decompress(zk.ZLib.compress(b"abc" * 1000)) == b"abc" * 1000
+    with pytest.raises(zk.ZStreamException):
+        zk.ZLib.decompress(b"\x78\x9c\x07")
+
+
+def test_zstream_streaming_surface(engine):
+    """docs/API.md:205-281: deflate in pieces with flushes, inflate in pieces; zlib.h semantics."""
+    import zlibk_b200 as zk
+    from zlibk_b200 import corpus
+
+    data = corpus.text_like(3 << 20).tobytes()
+    z = zk.ZStream()
+    assert z.deflateInit(6) == zk.Z_OK
+    produced = bytearray()
+    pieces = [data[:100_000], data[100_000:1_500_000], data[1_500_000:]]
+    for i, piece in enumerate(pieces):
+        z.next_in, z.next_in_index, z.avail_in = piece, 0, len(piece)
+        flush = zk.Z_FINISH if i == len(pieces) - 1 else (zk.Z_SYNC_FLUSH if i == 0 else zk.Z_NO_FLUSH)
+        while True:
+            z.next_out, z.next_out_index, z.avail_out = bytearray(1 << 18), 0, 1 << 18
+            rc = z.deflate(flush)
+            produced += z.next_out[:z.next_out_index]
+            assert rc in (zk.Z_OK, zk.Z_STREAM_END, zk.Z_BUF_ERROR)
+            if rc == zk.Z_STREAM_END or (flush != zk.Z_FINISH and z.avail_in == 0 and z.next_out_index < (1 << 18)):
+                break
+    assert z.total_in == len(data) and z.total_out == len(produced) and z.adler == zlib.adler32(data)
+    assert z.deflateEnd() == zk.Z_OK
+    assert zlib.decompress(bytes(produced)) == data
+    zi = zk.ZInputStream(io.BytesIO(bytes(produced)))
+    assert zi.read() == data
+    zi.close()

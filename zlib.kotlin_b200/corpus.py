@@ -166,3 +166,28 @@ def edge_cases(chunk=None):
         big = text_like(chunk + 1).tobytes()
         cases += [("chunk_minus1", big[: chunk - 1]), ("chunk", big[:chunk]), ("chunk_plus1", big)]
     return cases
+
+
+def tail(kind, n, rank, nbytes):
+    """Last `nbytes` of the corpus a rank with index `rank` generates for size n (bench.py's per-rank seeds),
+    without generating the rest: only the final pieces / segments are built."""
+    shift = 0x10000 * rank
+    parts, have = [], 0
+    if kind == "text":
+        piece = 16 << 20
+        i = (n - 1) // piece
+        while have < nbytes and i >= 0:
+            p = _text_piece(min(piece, n - i * piece), SEED_TEXT + shift + 0x1000 * i)
+            parts.insert(0, p)
+            have += p.size
+            i -= 1
+    else:
+        seg = 1 << 20
+        i = (n - 1) // seg
+        while have < nbytes and i >= 0:
+            p = _segment(i % 6, min(seg, n - i * seg), SEED_MIXED + shift + 0x100 * i)
+            parts.insert(0, p)
+            have += p.size
+            i -= 1
+    last = np.concatenate(parts)
+    return last[-nbytes:].copy()

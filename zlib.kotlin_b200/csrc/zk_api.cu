@@ -31,6 +31,39 @@ void set_last_error(const char *what, cudaError_t e) {
     snprintf(g_last_error, sizeof g_last_error, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// ---- optional device timing per kernel class -------------------------------------------------------------
+ScopedTimer::ScopedTimer(zk_ctx *ctx, int cls) : c(ctx), idx(-1) {
+    if (!c->opt_timing) return;
+    if (c->span_count == c->span_cap) {
+        const int ncap = c->span_cap ? c->span_cap * 2 : 64;
+        zk_ctx::TimedSpan *n = static_cast<zk_ctx::TimedSpan *>(realloc(c->spans, sizeof(zk_ctx::TimedSpan) * ncap));
+        if (!n) return;
+        for (int i = c->span_cap; i < ncap; ++i) {
+            cudaEventCreate(&n[i].a);
+            cudaEventCreate(&n[i].b);
+        }
+        c->spans = n;
+        c->span_cap = ncap;
+    }
+    idx = c->span_count++;
+    c->spans[idx].cls = cls;
+    cudaEventRecord(c->spans[idx].a, c->stream);
+}
+ScopedTimer::~ScopedTimer() {
+    if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream);
+}
+void collect_timers(zk_ctx *c) {
+    for (int i = 0; i < c->span_count; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->spans[i].a, c->spans[i].b) == cudaSuccess) {
+            c->class_ms[c->spans[i].cls] += ms;
+            c->class_launches[c->spans[i].cls] += 1;
+        }
+    }
+    c->span_count = 0;
+    cudaGetLastError();
+}
+
 // ---- arena ---------------------------------------------------------------------------------------------
 int Arena::reserve(size_t bytes) {
     if (bytes <= cap) return ZK_OK;
@@ -99,7 +132,11 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     void *d_partials = c->arena.take(adler_partials_bytes(n));
     ZK_CUDA(cudaMemsetAsync(d_cursor, 0, 16, c->stream));
 
-    int rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
+    int rc;
+    {
+        ScopedTimer t(c, 3);
+        rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
+    }
     if (rc != ZK_OK) return rc;
 
     if (stored_only) {
@@ -132,16 +169,24 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
         const uint32_t unit = pick_unit_bytes(c, sn, block_bytes);
         const uint8_t *hist = s0 ? job.d_in + s0 - kWindow : job.d_hist;
         const uint32_t hist_len = s0 ? (uint32_t)kWindow : (job.d_hist ? job.hist_len : 0);
-        rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, d_tokens, d_tok_begin, d_tok_count,
-                         d_hist);
+        {
+            ScopedTimer t(c, 0);
+            rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, d_tokens, d_tok_begin,
+                             d_tok_count, d_hist);
+        }
         if (rc != ZK_OK) return rc;
-        rc = launch_huffman(c, d_hist, sn, block_bytes, nb, -1, d_plans);
+        {
+            ScopedTimer t(c, 1);
+            rc = launch_huffman(c, d_hist, sn, block_bytes, nb, -1, d_plans);
+            // offsets continue from the previous slab: the cursor lives on the device, no host round trip
+            if (rc == ZK_OK) rc = launch_plan_offsets(c, d_plans, nb, d_offsets, d_cursor, body_cap);
+        }
         if (rc != ZK_OK) return rc;
-        // offsets continue from the previous slab: the cursor lives on the device, no host round trip
-        rc = launch_plan_offsets(c, d_plans, nb, d_offsets, d_cursor, body_cap);
-        if (rc != ZK_OK) return rc;
-        rc = launch_pack(c, job.d_in + s0, sn, block_bytes, nb, d_tokens, d_tok_begin, d_tok_count, d_plans, d_offsets,
-                         d_cursor, body);
+        {
+            ScopedTimer t(c, 2);
+            rc = launch_pack(c, job.d_in + s0, sn, block_bytes, nb, d_tokens, d_tok_begin, d_tok_count, d_plans,
+                             d_offsets, d_cursor, body);
+        }
         if (rc != ZK_OK) return rc;
     }
     return launch_frame(c, job.d_out, job.cap, level, job.framed, job.framed, d_cursor, -1, d_adler, n, job.d_result);
@@ -200,6 +245,11 @@ void zk_ctx_destroy(zk_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->arena.release();
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < c->span_cap; ++i) {
+        cudaEventDestroy(c->spans[i].a);
+        cudaEventDestroy(c->spans[i].b);
+    }
+    free(c->spans);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -223,6 +273,10 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         c->opt_chunk_bytes = value;
         return ZK_OK;
     }
+    if (!strcmp(name, "timing")) {
+        c->opt_timing = value != 0;
+        return ZK_OK;
+    }
     if (!strcmp(name, "block_bytes")) {
         // power of two, a multiple of the LZ group, at most one stored block (<= 65535 bytes)
         if (value < kGroup || value > 32768 || (value & (value - 1))) return ZK_STREAM_ERROR;
@@ -237,6 +291,29 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
     if (!strcmp(name, "kernel_launches")) return c->launches;
     if (!strcmp(name, "h2d_bytes")) return c->h2d_bytes;
     if (!strcmp(name, "d2h_bytes")) return c->d2h_bytes;
+    // device time per kernel class in microseconds / launches timed; call after zk_ctx_synchronize
+    static const char *cls[] = {"lz77", "huffman", "pack", "adler", "inflate_decode", "inflate_other"};
+    for (int i = 0; i < zk_ctx::kTimedClasses; ++i) {
+        char key[48];
+        snprintf(key, sizeof key, "%s_us", cls[i]);
+        if (!strcmp(name, key)) {
+            collect_timers(c);
+            return (int64_t)(c->class_ms[i] * 1000.0);
+        }
+        snprintf(key, sizeof key, "%s_spans", cls[i]);
+        if (!strcmp(name, key)) {
+            collect_timers(c);
+            return c->class_launches[i];
+        }
+    }
+    if (!strcmp(name, "reset_timing")) {
+        collect_timers(c);
+        for (int i = 0; i < zk_ctx::kTimedClasses; ++i) {
+            c->class_ms[i] = 0;
+            c->class_launches[i] = 0;
+        }
+        return 0;
+    }
     return -1;
 }
 

@@ -84,7 +84,29 @@ struct zk_ctx {
     int64_t opt_chunk_bytes = 0; // 0 = auto
     int64_t opt_block_bytes = zk::kBlockBytesDefault;
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    // optional per-kernel-class device timing (option "timing"): event pairs recorded around launches
+    int64_t opt_timing = 0;
+    static constexpr int kTimedClasses = 6;  // 0 lz77, 1 huffman, 2 pack, 3 adler, 4 inflate-decode, 5 inflate-other
+    struct TimedSpan {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    TimedSpan *spans = nullptr;
+    int span_count = 0, span_cap = 0;
+    double class_ms[kTimedClasses] = {0, 0, 0, 0, 0, 0};
+    int64_t class_launches[kTimedClasses] = {0, 0, 0, 0, 0, 0};
 };
+
+namespace zk {
+// RAII event pair around one launch (no-op unless timing is on)
+struct ScopedTimer {
+    zk_ctx *c;
+    int idx;
+    ScopedTimer(zk_ctx *ctx, int cls);
+    ~ScopedTimer();
+};
+void collect_timers(zk_ctx *c);  // after a stream sync: fold finished spans into class_ms
+}  // namespace zk
 
 namespace zk {
 

@@ -789,7 +789,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     uint64_t verdict[6] = {0, 0, 0, 0, 0, 0};
     for (int round = 0; round < 64; ++round) {
         const uint32_t grid = (max_chunks + kInfWarps - 1) / kInfWarps;
-        decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0);
+        {
+            ScopedTimer t(c, 4);
+            decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0);
+        }
         plan_chunks_kernel<<<1, 32, 0, st>>>(d_chunks, d_num, d_verdict);
         c->launches += 2;
         ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
@@ -808,7 +811,11 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     {
         const uint32_t nchunks = (uint32_t)verdict[0];
         const uint32_t grid = (nchunks + kInfWarps - 1) / kInfWarps;
-        decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap);
+        {
+            ScopedTimer t(c, 4);
+            decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap);
+        }
+        ScopedTimer t(c, 5);
         window_chain_kernel<<<1, 1024, 0, st>>>(d_chunks, d_num, d_sym, d_windows, d_flag);
         const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
         if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag);

@@ -1,0 +1,83 @@
+"""Chunk-range sharding of one zlib stream across GPUs.
+
+Every rank deflates a contiguous range of the input as a headerless, byte-aligned body primed with the
+32 KiB that precede it (zk_deflate_shard_device).  The ONLY exchange is one all_gather of
+{body_len, adler32(shard), raw_len} per rank; every rank then computes the same exclusive scan (its
+body's offset in the stream) and folds the checksums with zlib's combine identity.  Rank 0 owns the
+2-byte header, the last rank the final empty block + Adler-32 trailer.  No other collective is used.
+"""
+BASE = 65521
+
+
+def adler32_combine(adler1, adler2, len2):
+    """zlib's adler32_combine on three integers (same arithmetic as zk_adler32_combine)."""
+    rem = len2 % BASE
+    s1, s2 = adler1 & 0xFFFF, (adler1 >> 16) & 0xFFFF
+    t1 = (adler2 & 0xFFFF) + BASE - 1
+    t2 = ((adler2 >> 16) & 0xFFFF) + BASE - rem
+    s2 = (s2 + rem * s1 + t2) % BASE
+    s1 = (s1 + t1) % BASE
+    return (s2 << 16) | s1
+
+
+def plan_shards(n, world, align=32768):
+    """Contiguous [begin, end) per rank, boundaries aligned to the deflate block span."""
+    per = (n + world - 1) // world
+    per = (per + align - 1) // align * align
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def assemble(metas):
+    """metas: per rank (body_len, adler, raw_len) in rank order ->
+    (offsets of each body in the stream, total stream length, adler of the whole input)."""
+    offsets, at, adler = [], 2, 1
+    for body_len, a, raw_len in metas:
+        offsets.append(at)
+        at += int(body_len)
+        adler = adler32_combine(adler, int(a) & 0xFFFFFFFF, int(raw_len))
+    return offsets, at + 6, adler
+
+
+def exchange(meta_tensor, world):
+    """The one collective: all_gather of the 3-word meta record.  meta_tensor: int64[3] on the rank's device
+    (NCCL) or host (gloo).  Returns int64[world, 3]."""
+    import torch
+    import torch.distributed as dist
+
+    out = torch.empty(world * 3, dtype=torch.int64, device=meta_tensor.device)
+    dist.all_gather_into_tensor(out, meta_tensor.contiguous())
+    return out.view(world, 3)
+
+
+class ShardedDeflate:
+    """Per-rank driver used by bench.py and the multi-GPU tests."""
+
+    def __init__(self, engine, rank, world, device, hist=None):
+        import torch
+
+        self.eng, self.rank, self.world, self.dev = engine, rank, world, device
+        self.d_meta = torch.zeros(4, dtype=torch.int64, device=device)
+        self.d_hist = hist  # uint8 tensor with the 32 KiB before this shard, or None for rank 0
+        self.gathered = None
+        self.last_body_len = 0
+        self.last_status = 0
+
+    def step(self, d_in, n, level, d_body, cap):
+        hist_ptr = self.d_hist.data_ptr() if self.d_hist is not None else None
+        hist_len = int(self.d_hist.numel()) if self.d_hist is not None else 0
+        rc = self.eng.deflate_shard_device(hist_ptr, hist_len, d_in.data_ptr(), n, level, 0, d_body.data_ptr(), cap, self.d_meta.data_ptr())
+        if rc != 0:
+            return rc
+        self.gathered = exchange(self.d_meta[:3], self.world)  # the only collective
+        return 0
+
+    def finish(self):
+        """Host view after the timed region: offsets, total length, folded Adler-32."""
+        g = self.gathered.cpu().tolist()
+        meta = self.d_meta.cpu().tolist()
+        self.last_body_len, self.last_status = meta[0], meta[3]
+        return assemble([tuple(row) for row in g])
+
+    @property
+    def ready(self):
+        return self.gathered is not None
