@@ -193,7 +193,9 @@ def main():
     h_in = torch.from_numpy(host).pin_memory()
     d_in = h_in.to(dev, non_blocking=True)
     eng = zlibk_b200.Engine(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated stream: torch's default stream has handle 0, which the C ABI reads as "use the private stream"
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.set_option("timing", 1)
     cap = eng.compress_bound(n)

