@@ -13,7 +13,11 @@ kinds = {"text": lambda n: corpus.text_like(n), "random": lambda n: corpus._rand
          "mixed": lambda n: corpus.mixed_entropy(n)}
 n = 148 << 20
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+strategy = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
 for name, gen in kinds.items():
+    if only and name not in only:
+        continue
     host = gen(n)
     d_in = torch.from_numpy(host).to(dev)
     cap = eng.compress_bound(n)
@@ -26,7 +30,7 @@ for name, gen in kinds.items():
     eng.set_option("timing", 1)
     for it in range(2):
         eng.counter("reset_timing")
-        eng.deflate_device(d_in.data_ptr(), n, level, 0, d_out.data_ptr(), cap, d_res.data_ptr())
+        eng.deflate_device(d_in.data_ptr(), n, level, strategy, d_out.data_ptr(), cap, d_res.data_ptr())
         eng.synchronize()
     p = prof.cpu().numpy().reshape(units, 16)[: n >> 20].astype(np.float64)
     tot = p[:, 0].mean()
@@ -35,5 +39,6 @@ for name, gen in kinds.items():
         name, level, lz_ms, n / lz_ms / 1e6, eng.counter("huffman_us") / 1e3, eng.counter("pack_us") / 1e3, d_res.cpu().tolist()[0] / n, tot / (1 << 20),
         100 * p[:, 1].mean() / tot, 100 * p[:, 2].mean() / tot, 100 * p[:, 3].mean() / tot,
         100 * p[:, 4].mean() / tot, 100 * p[:, 5].mean() / tot, 100 * p[:, 6].mean() / tot,
-        100 * p[:, 8].mean() / tot, 100 * p[:, 9].mean() / tot, 100 * p[:, 11].mean() / tot, 100 * p[:, 12].mean() / tot))
+        100 * p[:, 8].mean() / tot, 100 * p[:, 9].mean() / tot, 100 * p[:, 11].mean() / tot, 100 * p[:, 12].mean() / tot),
+        "| builder slow passes %.0f of 8448 (%.0f%% of unit cycles)" % (p[:, 14].mean(), 100 * p[:, 13].mean() / tot))
 eng.set_option("lz_profile_buffer", 0)

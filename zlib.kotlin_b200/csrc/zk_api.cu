@@ -13,8 +13,9 @@ namespace zk {
 // launchers defined next to their kernels
 int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_hist, uint32_t hist_len,
                 uint32_t unit_bytes, uint32_t block_bytes, const LevelParams &lp, uint32_t *tokens,
-                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist,
-                unsigned long long *prof);
+                uint32_t *block_tok_begin, uint32_t *block_tok_count, unsigned long long *prof);
+int launch_hist(zk_ctx *c, const uint32_t *tokens, const uint32_t *block_tok_begin, const uint32_t *block_tok_count,
+                uint32_t num_blocks, uint32_t *block_hist);
 int launch_huffman(zk_ctx *c, const uint32_t *block_hist, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
                    int force_type, BlockPlan *plans);
 int launch_plan_offsets(zk_ctx *c, const BlockPlan *plans, uint32_t num_blocks, uint64_t *offsets, uint64_t *cursor,
@@ -173,12 +174,13 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
         {
             ScopedTimer t(c, 0);
             rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, d_tokens, d_tok_begin,
-                             d_tok_count, d_hist, c->lz_prof);
+                             d_tok_count, c->lz_prof);
         }
         if (rc != ZK_OK) return rc;
         {
             ScopedTimer t(c, 1);
-            rc = launch_huffman(c, d_hist, sn, block_bytes, nb, -1, d_plans);
+            rc = launch_hist(c, d_tokens, d_tok_begin, d_tok_count, nb, d_hist);
+            if (rc == ZK_OK) rc = launch_huffman(c, d_hist, sn, block_bytes, nb, -1, d_plans);
             // offsets continue from the previous slab: the cursor lives on the device, no host round trip
             if (rc == ZK_OK) rc = launch_plan_offsets(c, d_plans, nb, d_offsets, d_cursor, body_cap);
         }

@@ -228,6 +228,56 @@ __device__ int rle_lengths(WarpScratch &w, const uint8_t *len, int n, int at) {
     return at;
 }
 
+// ---- per-block symbol histograms from the token stream ------------------------------------------------------
+// Replaces the frequency counting of DeflateStream.kt:626-627,726,740-744,755.  One CTA per deflate block; every
+// warp counts into its own shared-memory copy (no contention between warps, the hardware aggregates equal addresses
+// inside a warp), the copies are summed into block_hist[b][320] with end-of-block added.
+constexpr int kHistThreads = 256;
+__device__ __forceinline__ int hist_length_symbol(int len) {  // 257..285
+    const int y = len - 3;
+    if (y < 8) return 257 + y;
+    if (len == 258) return 285;
+    const int b = 31 - __clz(y);
+    return 257 + 4 * (b - 1) + ((y >> (b - 2)) & 3);
+}
+__device__ __forceinline__ int hist_dist_symbol(int dist_minus1) {  // 0..29
+    if (dist_minus1 < 4) return dist_minus1;
+    const int b = 31 - __clz(dist_minus1);
+    return 2 * b + ((dist_minus1 >> (b - 1)) & 1);
+}
+__global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint32_t *__restrict__ tokens,
+                                                            const uint32_t *__restrict__ block_tok_begin,
+                                                            const uint32_t *__restrict__ block_tok_count,
+                                                            uint32_t *__restrict__ block_hist) {
+    __shared__ uint32_t copy[kHistThreads / 32][kHistStride];
+    const int wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (kHistThreads / 32) * kHistStride; i += kHistThreads) (&copy[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t blk = blockIdx.x;
+    const uint32_t *tok = tokens + block_tok_begin[blk];
+    const uint32_t n = block_tok_count[blk];
+    uint32_t *mine = copy[wid];
+    for (uint32_t i = threadIdx.x; i < n; i += kHistThreads) {
+        const uint32_t t = tok[i];
+        const int len = (int)(t >> 16);
+        if (len == 0) {
+            atomicAdd(&mine[t & 0xFFu], 1u);
+        } else {
+            atomicAdd(&mine[hist_length_symbol(len)], 1u);
+            atomicAdd(&mine[kDistHistBase + hist_dist_symbol((int)(t & 0xFFFFu))], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t *out = block_hist + (uint64_t)blk * kHistStride;
+    for (int i = threadIdx.x; i < kHistStride; i += kHistThreads) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int w = 0; w < kHistThreads / 32; ++w) v += copy[w][i];
+        if (i == 256) v += 1;  // end-of-block
+        out[i] = v;
+    }
+}
+
 __device__ __forceinline__ int fixed_litlen_bits(int sym) { return sym < 144 ? 8 : sym < 256 ? 9 : sym < 280 ? 7 : 8; }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32_t *__restrict__ block_hist,
@@ -392,6 +442,14 @@ __global__ void __launch_bounds__(1024) plan_offsets_kernel(const BlockPlan *__r
 }
 
 }  // namespace
+
+int launch_hist(zk_ctx *c, const uint32_t *tokens, const uint32_t *block_tok_begin, const uint32_t *block_tok_count,
+                uint32_t num_blocks, uint32_t *block_hist) {
+    hist_kernel<<<num_blocks, kHistThreads, 0, c->stream>>>(tokens, block_tok_begin, block_tok_count, block_hist);
+    c->launches += 1;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
 
 int launch_huffman(zk_ctx *c, const uint32_t *block_hist, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
                    int force_type, BlockPlan *plans) {

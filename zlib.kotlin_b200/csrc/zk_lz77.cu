@@ -10,7 +10,7 @@
 //   prev  u16[32768]   hash-chain links at (q & 32767): previous position with the same 4-byte hash
 //   head  u16[16384]   most recent position per hash
 //   match u32[2][4096] per-position best match of the group in flight / the group being parsed
-//   hist  u32[320]     literal/length + distance counts of the deflate block being parsed
+//   stage u32[34][128] tokens of the group being parsed, one column per parser lane
 //
 // Software pipeline over groups of 4096 positions, one __syncthreads per step.  In step i
 //   - one elected thread stages group i+3 into the ring with a TMA bulk copy (mbarrier-tracked),
@@ -26,6 +26,7 @@
 // group ahead) can not have overwritten: results do not depend on warp timing.
 //
 // HBM traffic per input byte: 1 B read (+ 32 KiB halo per unit) and 4 B x tokens/byte written.
+// The symbol histograms are built from the token stream by hist_kernel (zk_huffman.cu).
 #include "zk_common.cuh"
 
 namespace zk {
@@ -56,8 +57,8 @@ struct LzSmem {
     uint32_t ring[65536 / 4 + 8];  // + 32 mirrored bytes so a 20-byte read never wraps
     uint16_t prev[32768];
     uint32_t head[1 << kHashBits];  // most recent position (q) per hash, 0 = none
-    uint32_t match[2][kGroup];
-    uint32_t hist[kHistStride];
+    uint32_t match[2][kGroup + 4];  // + slack: the parser reads one word past the group
+    uint32_t stage[(kSeg + 2) * kParserWarps * 32];  // tokens of the group being parsed: [k][parser lane]
     unsigned long long bar[kStages];
     int work[2];
     int roles_done[2];  // role warps that have finished their part of the step (parity = step)
@@ -65,6 +66,7 @@ struct LzSmem {
     int32_t pstart[kParserWarps * 32];
     int32_t pstop[kParserWarps * 32];
     int32_t pfinal;
+    int32_t plast[kParserWarps * 32];  // distance-1 of the speculative parse's last match (closes a gap)
     int pcount[kParserWarps];
     int32_t carry_entry;       // first unparsed q
     uint32_t carry_tok_off;    // tokens emitted so far in this unit
@@ -84,7 +86,6 @@ struct LzArgs {
     uint32_t *tokens;       // [n] dense per unit, unit u starts at u * unit_bytes
     uint32_t *block_tok_begin;  // [num_blocks] index into tokens
     uint32_t *block_tok_count;  // [num_blocks]
-    uint32_t *block_hist;       // [num_blocks][kHistStride]
     unsigned long long *prof;   // optional [num_units][8] cycle counters (nullptr = off)
 };
 
@@ -167,39 +168,96 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
 }
 
 // ---- builder: one warp inserts group t into the hash chains ----------------------------------
-// Exact chains without a serial dependency: head[h] takes the batch's highest position per hash with a shared
-// atomicMax, so the next batch can be issued before this one's links are stored.  A lane whose position did not
-// win has a duplicate hash inside the batch; only then (rare, or cheap when the duplicates are a byte run) is
-// match.any used to find the nearest lower lane with the same hash.  MATCH.ANY costs time per DISTINCT value, which
-// is why it is kept off the common path.
-__device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
+// Exact, deterministic chains at LSU issue rate.  Per batch of 32 positions: read head[h] (the link), store the
+// position, read head[h] back.  The three accesses of a batch follow each other in program order and the LSU keeps
+// that order, so four batches are issued back to back and the loaded values are consumed afterwards.  A lane that
+// does not read its own position back shares its hash with another lane of the batch (the store picked one of
+// them): those hashes are resolved with one ballot round each -- every lane of the hash links to the nearest lower
+// lane with it and the highest one stays in head[].  (MATCH.ANY would do this in one instruction but was measured at
+// ~500 cycles per call on B200.)  Links of later batches that were read while head[] held an arbitrary duplicate
+// are corrected from the group masks, so the result never depends on which lane the hardware let win.
+// Resolve the repeated hashes of one batch (rare path, kept out of line and compact: a lone warp runs serial code at
+// ~10 cycles per instruction, so its size is its cost).  Returns this lane's link; grp = lanes sharing its hash.
+__device__ __noinline__ uint32_t resolve_batch(volatile uint32_t *vhead, uint32_t h, uint32_t old, uint32_t won,
+                                               uint32_t q, int lane, uint32_t *grp_out) {
+    uint32_t link = old, grp = 0;
+    uint32_t unresolved = __ballot_sync(0xFFFFFFFFu, won != q);
+    while (unresolved) {
+        const int leader = __ffs(unresolved) - 1;
+        const uint32_t hl = __shfl_sync(0xFFFFFFFFu, h, leader);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, h == hl);
+        if (h == hl) {
+            grp = m;
+            const uint32_t below = m & ((1u << lane) - 1u);
+            if (below) link = q - (uint32_t)(lane - (31 - __clz(below)));
+            // the highest lane of the hash restores head[] unless a later batch already moved it on
+            if (((m >> lane) >> 1) == 0u) {
+                const uint32_t cur = vhead[h];
+                if (cur - (q - lane) < 32u) vhead[h] = q;
+            }
+        }
+        unresolved &= ~m;
+    }
+    *grp_out = grp;
+    return link;
+}
+
+__device__ __forceinline__ void build_group(LzSmem &s, int t, int lane, long long &slow_cycles, int &slow_passes) {
     const uint32_t q0 = (uint32_t)t * kGroup + lane;
+    volatile uint32_t *vhead = s.head;
 #pragma unroll 1
     for (int b = 0; b < kGroup / 32; b += 4) {
         uint32_t h[4], old[4], won[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) h[u] = hash4(ring_load32(s.ring, q0 + (b + u) * 32));
+        // No __syncwarp between the accesses: it would wait for each one to complete (three loaded round trips per
+        // batch).  The warp is converged here and the LSU handles one warp's shared accesses in issue order, so the
+        // read-back sees this batch's store and the next batch's read sees it too; `volatile` pins the order.
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint32_t q = q0 + (b + u) * 32;
-            old[u] = s.head[h[u]];
-            __syncwarp();
-            atomicMax(&s.head[h[u]], q);
-            __syncwarp();
-            won[u] = s.head[h[u]];
+            old[u] = vhead[h[u]];
+            vhead[h[u]] = q;
+            won[u] = vhead[h[u]];
         }
+        const uint32_t qb = q0 + b * 32;
+        // which batches of the pass have a repeated hash (bit u)
+        uint32_t bad = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t q = q0 + (b + u) * 32;
-            uint32_t link = old[u];
-            if (__any_sync(0xFFFFFFFFu, won[u] != q)) {
-                // some hash occurs twice in this batch: every lane links to the nearest lower lane with its hash
-                const uint32_t m = __match_any_sync(0xFFFFFFFFu, h[u]);
-                const uint32_t below = m & ((1u << lane) - 1u);
-                if (below) link = q - (uint32_t)(lane - (31 - __clz(below)));
+        for (int u = 0; u < 4; ++u) bad |= (won[u] != qb + u * 32u) ? (1u << u) : 0u;
+        bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+        if (bad == 0u) {
+            // common case: 128 distinct hashes -- every link is the value head[] held before the position
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s.prev[(qb + u * 32u) & 32767u] = (uint16_t)old[u];
+        } else {
+            const long long ts = clock64();
+            ++slow_passes;
+            uint32_t grp[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t q = qb + u * 32u;
+                uint32_t link = old[u];
+                bool in_batch = false;
+                if (bad & (1u << u)) {
+                    link = resolve_batch(vhead, h[u], old[u], won[u], q, lane, &grp[u]);
+                    in_batch = link != old[u];
+                }
+                // a link read from head[] while an earlier batch of this pass held an arbitrary duplicate
+#pragma unroll
+                for (int v = 0; v < u; ++v) {
+                    if (bad & (1u << v)) {
+                        const uint32_t vstart = (q - lane) - (uint32_t)(u - v) * 32u;
+                        const uint32_t j = old[u] - vstart;
+                        const uint32_t mm = __shfl_sync(0xFFFFFFFFu, grp[v], (int)(j & 31u));
+                        if (j < 32u && mm != 0u && !in_batch) link = vstart + (uint32_t)(31 - __clz(mm));
+                    }
+                }
+                s.prev[q & 32767u] = (uint16_t)link;
             }
-            s.prev[q & 32767u] = (uint16_t)link;
+            slow_cycles += clock64() - ts;
         }
+        __syncwarp();
     }
 }
 
@@ -358,10 +416,12 @@ __device__ __forceinline__ int dist_symbol(int dist_minus1) {  // 0..29
 
 // Decide the token at p: returns the step (1 for a literal, len for a match).
 __device__ __forceinline__ int decide(const uint32_t *mv, int32_t g0, int32_t gend, int32_t p, int lazy) {
+    // both words are loaded unconditionally (one slot of slack behind the group keeps p + 1 in bounds): no
+    // dependent second load, no branch
     const int len = tok_len(mv[p - g0]);
-    if (len == 0) return 1;
-    if (lazy && p + 1 < gend && tok_len(mv[p + 1 - g0]) > len) return 1;
-    return len;
+    const int next = tok_len(mv[p + 1 - g0]);
+    const bool defer = lazy && p + 1 < gend && next > len;
+    return (len == 0 || defer) ? 1 : len;
 }
 
 __device__ __forceinline__ void parser_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kParserWarps * 32) : "memory"); }
@@ -377,11 +437,17 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     const int lazy = a.lp.lazy;
     const int32_t seg0 = min(g0 + L * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
 
-    // pass A: speculative parse of this lane's segment, only the exit matters
+    // pass A: speculative parse of this lane's segment; only the exit (and the distance of the match that makes
+    // it) matter
     {
-        int32_t p = seg0;
-        while (p < seg1) p += decide(mv, g0, gend, p, lazy);
+        int32_t p = seg0, lastd = -1;
+        while (p < seg1) {
+            const int step = decide(mv, g0, gend, p, lazy);
+            lastd = step > 1 ? (int32_t)(mv[p - g0] & 0xFFFFu) : -1;
+            p += step;
+        }
         s.pexit[L] = p;
+        s.plast[L] = lastd;
     }
     parser_barrier();
     // stitch (first parser warp): segment l really starts where the parse left the segments before it
@@ -402,29 +468,38 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     }
     parser_barrier();
     const int32_t my_start = s.pstart[L], my_stop = s.pstop[L];
-    // pass B: mark the tokens of [my_start, my_stop); a match that would overshoot is cut (rare: only when the
-    // speculative parse had not converged with the real one by the end of the segment)
+    // pass B: the tokens of [my_start, my_stop) go to this lane's column of the staging area.  When the real parse
+    // leaves the segment before my_stop (it had not converged with the speculative one), the rest is the tail of the
+    // speculative parse's last match: one match at that distance, or up to two literals, closes the gap.
     int cnt = 0;
-    int32_t tp = -1;
-    uint32_t ttok = 0;
     {
+        uint32_t *col = s.stage + L;
         int32_t p = my_start;
         while (p < my_stop) {
-            const uint32_t w = mv[p - g0];
-            int step = decide(mv, g0, gend, p, lazy);
-            uint32_t mark = kTokStart;
-            if (step == 1 && tok_len(w) != 0) mark |= kTokLiteral;
-            if (p + step > my_stop) {
-                step = my_stop - p;
-                if (step < 3) {
-                    step = 1;
-                    mark |= kTokLiteral;
+            uint32_t tok;
+            int step;
+            if (p >= seg1) {
+                const int gap = my_stop - p;
+                const int32_t d1 = s.plast[L];
+                if (gap >= 3 && d1 >= 0) {
+                    tok = ((uint32_t)gap << 16) | (uint32_t)d1;
+                    step = gap;
                 } else {
-                    tp = p;
-                    ttok = ((uint32_t)step << 16) | (w & 0xFFFFu);
+                    tok = ring_load8(s.ring, (uint32_t)p);
+                    step = 1;
+                }
+            } else {
+                const uint32_t w = mv[p - g0];
+                step = decide(mv, g0, gend, p, lazy);
+                if (p + step > my_stop) step = my_stop - p;  // overshoot: cut (a match of < 3 becomes literals)
+                if (step >= 3) {
+                    tok = ((uint32_t)step << 16) | (w & 0xFFFFu);
+                } else {
+                    tok = ring_load8(s.ring, (uint32_t)p);
+                    step = 1;
                 }
             }
-            mv[p - g0] = w | mark;
+            col[cnt * (kParserWarps * 32)] = tok;
             p += step;
             ++cnt;
         }
@@ -446,52 +521,27 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         total += c;
     }
     const uint32_t tok_off = s.carry_tok_off;
-    // pass C: emit + histogram
+    // copy-out: independent loads from the staging column, dense stores (adjacent lanes write adjacent runs)
     {
         uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + tok_off + (uint32_t)(before + incl - cnt);
-        int32_t p = my_start;
-        while (p < my_stop) {
-            uint32_t w = mv[p - g0];
-            if (p == tp) w = ttok;
-            const int len = tok_len(w);
-            if (len == 0 || (w & kTokLiteral)) {
-                const uint32_t byte = ring_load8(s.ring, (uint32_t)p);
-                *dst++ = byte;
-                atomicAdd(&s.hist[byte], 1u);
-                p += 1;
-            } else {
-                *dst++ = w & 0x01FFFFFFu;
-                atomicAdd(&s.hist[length_symbol(len)], 1u);
-                atomicAdd(&s.hist[kDistHistBase + dist_symbol((int)(w & 0xFFFFu))], 1u);
-                p += len;
-            }
-        }
+        const uint32_t *col = s.stage + L;
+        for (int k = 0; k < cnt; ++k) dst[k] = col[k * (kParserWarps * 32)];
     }
-    parser_barrier();
-    // close the deflate block when this group ends it (parser warp 0), then advance the carry
+    // close the deflate block when this group ends it, then advance the carry (one lane; the next group's parse
+    // starts after the CTA-wide barrier of the step)
     const int32_t off_end = gend - kWindow;
     const bool closes = off_end == (int32_t)g.ulen || (off_end & (int32_t)(a.block_bytes - 1)) == 0;
-    if (pw == 0) {
+    parser_barrier();  // every parser lane has read the carry
+    if (L == 0) {
         const uint32_t new_off = tok_off + (uint32_t)total;
         if (closes) {
             const uint32_t blk = (uint32_t)((g.unit_start + (uint64_t)(off_end - 1)) >> a.block_shift);
-            uint32_t *out = a.block_hist + (uint64_t)blk * kHistStride;
-            for (int i = lane; i < kHistStride; i += 32) {
-                uint32_t v = s.hist[i];
-                if (i == 256) v += 1;  // end-of-block
-                out[i] = v;
-                s.hist[i] = 0;
-            }
-            if (lane == 0) {
-                a.block_tok_begin[blk] = (uint32_t)((uint64_t)unit_index * a.unit_bytes) + s.carry_blk_begin;
-                a.block_tok_count[blk] = new_off - s.carry_blk_begin;
-                s.carry_blk_begin = new_off;
-            }
+            a.block_tok_begin[blk] = (uint32_t)((uint64_t)unit_index * a.unit_bytes) + s.carry_blk_begin;
+            a.block_tok_count[blk] = new_off - s.carry_blk_begin;
+            s.carry_blk_begin = new_off;
         }
-        if (lane == 0) {
-            s.carry_entry = s.pfinal;
-            s.carry_tok_off = new_off;
-        }
+        s.carry_entry = s.pfinal;
+        s.carry_tok_off = new_off;
     }
 }
 
@@ -519,7 +569,6 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             uint4 *z = reinterpret_cast<uint4 *>(s.prev);
             const int nvec = (int)((sizeof(s.prev) + sizeof(s.head)) / 16);
             for (int i = threadIdx.x; i < nvec; i += kThreadsLz) z[i] = make_uint4(0, 0, 0, 0);
-            for (int i = threadIdx.x; i < kHistStride; i += kThreadsLz) s.hist[i] = 0;
             if (threadIdx.x == 0) {
                 for (int b = 0; b < kStages; ++b) mbar_init(&s.bar[b], 1);
                 s.work[0] = s.work[1] = 0;
@@ -551,7 +600,8 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         __syncthreads();
 
         // step i: stage(i+3) | build(i+1) | search(i) | parse(i-1)
-        long long t_role = 0, t_search = 0;
+        long long t_role = 0, t_search = 0, t_slow = 0;
+        int n_slow = 0;
         const long long t_unit0 = clock64();
         for (int i = g.first_group - 1; i <= g.last_group + 1; ++i) {
             const bool tma_next = (i + 3 <= g.last_group + 1) ? stage_group(s, a, g, i + 3, true) : false;
@@ -561,7 +611,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             }
 
             const long long t0 = clock64();
-            if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
+            if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane, t_slow, n_slow);
             if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
                 parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit);
             if ((is_builder || is_parser) && lane == 0) atomicAdd(&s.roles_done[i & 1], 1);
@@ -604,7 +654,11 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             // per unit: [0] total, then {role, search} of the builder, the first parser warp, a searcher and a guest
             unsigned long long *o = a.prof + (size_t)unit * 16;
             const int k = warp == builder_warp ? 0 : warp == parser_warp ? 1 : warp == 2 ? 2 : 3;
-            if (warp == builder_warp) o[0] = (unsigned long long)(clock64() - t_unit0);
+            if (warp == builder_warp) {
+                o[0] = (unsigned long long)(clock64() - t_unit0);
+                o[13] = (unsigned long long)t_slow;
+                o[14] = (unsigned long long)n_slow;
+            }
             o[1 + 3 * k] = (unsigned long long)t_role;
             o[2 + 3 * k] = (unsigned long long)t_search;
             o[3 + 3 * k] = 0;
@@ -650,8 +704,7 @@ size_t lz77_smem_bytes() { return sizeof(LzSmem); }
 
 int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_hist, uint32_t hist_len,
                 uint32_t unit_bytes, uint32_t block_bytes, const LevelParams &lp, uint32_t *tokens,
-                uint32_t *block_tok_begin, uint32_t *block_tok_count, uint32_t *block_hist,
-                unsigned long long *prof) {
+                uint32_t *block_tok_begin, uint32_t *block_tok_count, unsigned long long *prof) {
     LzArgs a;
     a.prof = prof;
     a.in = d_in;
@@ -667,7 +720,6 @@ int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_his
     a.tokens = tokens;
     a.block_tok_begin = block_tok_begin;
     a.block_tok_count = block_tok_count;
-    a.block_hist = block_hist;
     // per-device attribute: set on every launch (cheap) so multi-device processes stay correct
     ZK_CUDA(cudaFuncSetAttribute(lz77_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzSmem)));
     const uint32_t grid = a.num_units;
