@@ -110,7 +110,7 @@ int zk_inflate_zlib(zk_ctx *ctx, const uint8_t *in, uint64_t m, uint8_t *out, ui
 
 /* ---- one-shot, DEVICE buffers (no host copies; asynchronous on the context stream) -- */
 /* d_out must hold zk_compress_bound(n) bytes.  d_result (device uint64_t[4]) receives
- * {out_len, adler32, status, 0}.  Call zk_ctx_synchronize before reading it. */
+ * {out_len, adler32, status, n}.  Call zk_ctx_synchronize before reading it. */
 int zk_deflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t n, int level, int strategy, uint8_t *d_out,
                            uint64_t cap, uint64_t *d_result);
 /* d_result (device uint64_t[4]) receives {out_len, consumed, status, adler32}. */
@@ -124,7 +124,8 @@ int zk_inflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t m, uint8_t
  * the folded checksum.  Rank 0 prepends the 2-byte header, the last rank appends the final
  * empty block and the trailer. */
 /* d_hist: the 32 KiB of input that precede this shard (device), hist_len in [0, 32768].
- * d_meta (device uint64_t[4]) receives {body_len, adler32(shard), n, status}. */
+ * d_meta (device uint64_t[4]) receives {body_len, adler32(shard), status, n} -- the same record layout as
+ * zk_deflate_zlib_device's d_result. */
 int zk_deflate_shard_device(zk_ctx *ctx, const uint8_t *d_hist, uint32_t hist_len, const uint8_t *d_in, uint64_t n,
                             int level, int strategy, uint8_t *d_body, uint64_t cap, uint64_t *d_meta);
 /* zlib header for `level` (2 bytes, DS:35-50) and stream tail (final empty block + big-endian

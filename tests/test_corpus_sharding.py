@@ -37,7 +37,7 @@ def test_plan_and_assemble():
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     assert all(s[0] % 32768 == 0 for s in spans)
     data = np.random.default_rng(1).integers(0, 256, 10_000_000, dtype=np.uint8).tobytes()
-    metas = [(1000 + r, zlib.adler32(data[a:b]), b - a) for r, (a, b) in enumerate(spans)]
+    metas = [(1000 + r, zlib.adler32(data[a:b]), 0, b - a) for r, (a, b) in enumerate(spans)]
     offsets, total, adler = sharding.assemble(metas)
     assert offsets == [2, 1002, 2003, 3005] and total == 2 + sum(m[0] for m in metas) + 6
     assert adler == zlib.adler32(data)
@@ -57,7 +57,7 @@ def _worker(rank, world, port, q):
     a, b = sharding.plan_shards(n, world)[rank]
     shard = data[a:b]
     # stand-in for the per-rank GPU call: any body length, the true checksum of the shard
-    meta = torch.tensor([len(zlib.compress(shard, 1)), zlib.adler32(shard), len(shard)], dtype=torch.int64)
+    meta = torch.tensor([len(zlib.compress(shard, 1)), zlib.adler32(shard), 0, len(shard)], dtype=torch.int64)
     g = sharding.exchange(meta, world)  # the one collective
     offsets, total, adler = sharding.assemble([tuple(r) for r in g.tolist()])
     q.put((rank, offsets, total, adler, zlib.adler32(data)))

@@ -105,8 +105,9 @@ static uint32_t pick_unit_bytes(const zk_ctx *c, uint64_t n, uint32_t block_byte
         uint64_t u = (uint64_t)c->opt_chunk_bytes / block_bytes * block_bytes;
         return (uint32_t)tmax<uint64_t>(u, block_bytes);
     }
-    // at least ~4 units per SM so the tail wave is short; history re-priming costs 32 KiB per unit
-    uint64_t u = 1u << 20;
+    // at least ~4 units per SM so the tail wave is short (units differ a lot in cost: a unit of long repeats takes
+    // twice as long as a unit of text); history re-priming costs 32 KiB per unit
+    uint64_t u = 512u << 10;
     while (u > block_bytes && n / u < (uint64_t)c->sm_count * 4) u >>= 1;
     return (uint32_t)tmax<uint64_t>(u, block_bytes);
 }

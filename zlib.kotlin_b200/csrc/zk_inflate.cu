@@ -78,10 +78,20 @@ struct BitReader {
     uint64_t hold;
     int held;
     __device__ __forceinline__ void refill() {
-        while (held <= 56 && next < len) {
-            hold |= (uint64_t)__ldg(base + next) << held;
-            ++next;
-            held += 8;
+        // one aligned 32-bit load per refill once `next` is 4-byte aligned; bytes only at the edges
+        if (held <= 32) {
+            if ((((uintptr_t)(base + next)) & 3u) == 0 && next + 4 <= len) {
+                hold |= (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(base + next)) << held;
+                next += 4;
+                held += 32;
+            } else {
+                while (held <= 56 && next < len) {
+                    hold |= (uint64_t)__ldg(base + next) << held;
+                    ++next;
+                    held += 8;
+                    if ((((uintptr_t)(base + next)) & 3u) == 0 && held > 24) break;
+                }
+            }
         }
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(hold & ((1ull << n) - 1ull)); }
@@ -638,32 +648,45 @@ __global__ void plan_chunks_kernel(ChunkInfo *chunks, uint32_t *num_chunks, uint
 }
 
 // Resolve the last 32 KiB of every chunk in order.  windows[c][i] = byte at (chunk c's end - 32768 + i).
+// One CTA walks the chunks; the previous window lives in shared memory (ping-pong), so the dependent lookup of a
+// symbolic reference is a shared load, and the tail symbols of a chunk are fetched with independent loads.
 __global__ void __launch_bounds__(1024) window_chain_kernel(const ChunkInfo *chunks, const uint32_t *num_chunks,
                                                             const uint16_t *__restrict__ sym, uint8_t *windows,
                                                             uint32_t *error_flag) {
+    extern __shared__ __align__(16) uint8_t wsm[];  // two windows of 32 KiB
     const uint32_t n = num_chunks[0];
+    constexpr int kPer = kWindow / 1024;  // window slots per thread, interleaved: thread t owns t, t+1024, ...
     for (uint32_t c = 0; c < n; ++c) {
         const uint64_t begin = chunks[c].out_begin, len = chunks[c].out_len;
-        const uint8_t *prev = c ? windows + (uint64_t)(c - 1) * kWindow : nullptr;
-        uint8_t *cur = windows + (uint64_t)c * kWindow;
-        for (int i = threadIdx.x; i < kWindow; i += 1024) {
-            // absolute output position of window slot i
-            const int64_t pos = (int64_t)(begin + len) - kWindow + i;
+        const uint8_t *prev = wsm + ((c + 1) & 1) * kWindow;
+        uint8_t *cur = wsm + (c & 1) * kWindow;
+        const int64_t pos0 = (int64_t)(begin + len) - kWindow + threadIdx.x;
+        uint16_t sy[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int64_t pos = pos0 + k * 1024;
+            sy[k] = pos >= (int64_t)begin ? sym[pos] : (uint16_t)0xFFFFu;  // 0xFFFF: not in this chunk
+        }
+        uint8_t *glob = windows + (uint64_t)c * kWindow;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = threadIdx.x + k * 1024;
+            const int64_t pos = pos0 + k * 1024;
             uint8_t v = 0;
+            const uint16_t s16 = sy[k];
             if (pos >= (int64_t)begin) {
-                const uint16_t s = sym[pos];
-                if (s & 0x8000u) {
-                    const uint32_t idx = s & 0x7FFFu;
-                    // slot idx of the previous window must lie inside the stream
-                    if (!prev || (int64_t)begin - kWindow + (int64_t)idx < 0) atomicExch(error_flag, 1u);
+                if (s16 & 0x8000u) {
+                    const uint32_t idx = s16 & 0x7FFFu;
+                    if (c == 0 || (int64_t)begin - kWindow + (int64_t)idx < 0) atomicExch(error_flag, 1u);
                     else v = prev[idx];
                 } else {
-                    v = (uint8_t)s;
+                    v = (uint8_t)s16;
                 }
-            } else if (prev && pos >= 0) {
+            } else if (c > 0 && pos >= 0) {
                 v = prev[(int64_t)kWindow - ((int64_t)begin - pos)];
             }
             cur[i] = v;
+            glob[i] = v;
         }
         __syncthreads();
     }
@@ -816,7 +839,8 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap);
         }
         ScopedTimer t(c, 5);
-        window_chain_kernel<<<1, 1024, 0, st>>>(d_chunks, d_num, d_sym, d_windows, d_flag);
+        ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
+        window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(d_chunks, d_num, d_sym, d_windows, d_flag);
         const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
         if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag);
         c->launches += 3;

@@ -1,0 +1,208 @@
+// ZlibkGpu.kt -- Kotlin/Native host side of the B200 DEFLATE engine.
+//
+// UNBUILT in this repository's image (no Kotlin/Native toolchain).  It is the thin pass-through a maintainer
+// adds to ZLib.kotlin's nativeMain source set: same signatures as the reference's entry points
+// (deflate/DeflateStream.kt:302-328, inflate/InflateStream.kt:376-438, bitwise/checksum/Adler32Utils.kt:31-57),
+// every byte of work done behind the C ABI of include/zlibk_gpu.h.  No JNI-style fallback, no CPU path: if the
+// library or a device is missing, construction fails.
+@file:OptIn(kotlinx.cinterop.ExperimentalForeignApi::class)
+
+package ai.solace.zlib.gpu
+
+import ai.solace.zlib.gpu.cinterop.*
+import kotlinx.cinterop.*
+import okio.Buffer
+import okio.BufferedSink
+import okio.BufferedSource
+
+class ZStreamException(message: String) : Exception(message)
+
+/** One engine per thread ("not thread-safe, one ZStream per thread", docs/API.md:725). */
+class GpuEngine(device: Int = 0) {
+    internal val ctx: CPointer<zk_ctx> =
+        zk_ctx_create(device) ?: throw ZStreamException("no B200 engine: ${zk_last_error()?.toKString()}")
+
+    fun close() = zk_ctx_destroy(ctx)
+}
+
+private val engine by lazy { GpuEngine(0) }
+
+/** Drains an Okio source into one ByteArray slab (the ABI is 64-bit; a ByteArray caps a slab at 2 GiB - 1). */
+private fun BufferedSource.drain(): ByteArray = Buffer().also { it.writeAll(this) }.readByteArray()
+
+object DeflateStream {
+    /** DeflateStream.compressZlib (DS:302-311): returns the bytes consumed. */
+    fun compressZlib(source: BufferedSource, sink: BufferedSink, level: Int = 6): Long {
+        val (rc, n) = compressZlibResult(source, sink, level)
+        if (rc != ZK_OK) throw ZStreamException("compressZlib failed: $rc")
+        return n
+    }
+
+    /** DeflateStream.compressZlibResult (DS:318-328): (Z_STREAM_ERROR, 0) and an untouched sink for level > 9. */
+    fun compressZlibResult(source: BufferedSource, sink: BufferedSink, level: Int = 6): Pair<Int, Long> {
+        if (level > 9) return ZK_STREAM_ERROR to 0L
+        val input = source.drain()
+        val bound = zk_compress_bound(input.size.toULong()).toInt()
+        val out = ByteArray(bound)
+        memScoped {
+            val outLen = alloc<ULongVar>()
+            val rc = input.usePinned { inp ->
+                out.usePinned { o ->
+                    zk_deflate_zlib(
+                        engine.ctx,
+                        if (input.isEmpty()) null else inp.addressOf(0).reinterpret(), input.size.toULong(),
+                        level, ZK_DEFAULT_STRATEGY,
+                        o.addressOf(0).reinterpret(), bound.toULong(), outLen.ptr, null,
+                    )
+                }
+            }
+            if (rc != ZK_OK) return rc to 0L
+            sink.write(out, 0, outLen.value.toInt())
+            sink.flush()
+        }
+        return ZK_OK to input.size.toLong()
+    }
+}
+
+object InflateStream {
+    /** InflateStream.inflateZlib (IS:376-438): (Z_STREAM_END, bytesOut) on success. */
+    fun inflateZlib(source: BufferedSource, sink: BufferedSink): Pair<Int, Long> {
+        val input = source.drain()
+        var cap = maxOf(65536L, input.size.toLong() * 8)
+        memScoped {
+            val outLen = alloc<ULongVar>()
+            val used = alloc<ULongVar>()
+            while (true) {
+                val out = ByteArray(cap.toInt())
+                val rc = input.usePinned { inp ->
+                    out.usePinned { o ->
+                        zk_inflate_zlib(
+                            engine.ctx,
+                            if (input.isEmpty()) null else inp.addressOf(0).reinterpret(), input.size.toULong(),
+                            o.addressOf(0).reinterpret(), cap.toULong(), outLen.ptr, used.ptr,
+                        )
+                    }
+                }
+                // ZK_BUF_ERROR with nothing written: the output did not fit (or the input is truncated); DEFLATE
+                // expands at most 1032:1
+                if (rc == ZK_BUF_ERROR && outLen.value == 0uL && cap < input.size.toLong() * 1100 + 65536) {
+                    cap *= 8
+                    continue
+                }
+                if (outLen.value > 0uL) sink.write(out, 0, outLen.value.toInt())
+                return rc to outLen.value.toLong()
+            }
+        }
+        @Suppress("UNREACHABLE_CODE")
+        return ZK_STREAM_ERROR to 0L
+    }
+}
+
+object Adler32Utils {
+    /** Adler32Utils.adler32 (AU:31-57): a null buffer resets to 1. */
+    fun adler32(adler: Long, buf: ByteArray?, index: Int, len: Int): Long {
+        if (buf == null) return 1L
+        if (len == 0) return adler and 0xFFFFFFFFL
+        return buf.usePinned { p ->
+            zk_adler32(engine.ctx, adler.toUInt(), p.addressOf(index).reinterpret(), len.toULong()).toLong()
+        }
+    }
+}
+
+/** ZLib.compress / ZLib.decompress (README.md:84-92). */
+object ZLib {
+    fun compress(data: ByteArray, level: Int = 6): ByteArray {
+        val sink = Buffer()
+        val (rc, _) = DeflateStream.compressZlibResult(Buffer().write(data), sink, level)
+        if (rc != ZK_OK) throw ZStreamException("compress failed: $rc")
+        return sink.readByteArray()
+    }
+
+    fun decompress(data: ByteArray): ByteArray {
+        val sink = Buffer()
+        val (rc, _) = InflateStream.inflateZlib(Buffer().write(data), sink)
+        if (rc != ZK_STREAM_END) throw ZStreamException("decompress failed: $rc")
+        return sink.readByteArray()
+    }
+}
+
+/** The documented ZStream (docs/API.md:205-281) over the streaming handles of the C ABI. */
+class ZStream {
+    var next_in: ByteArray = ByteArray(0)
+    var next_in_index = 0
+    var avail_in = 0
+    var total_in = 0L
+    var next_out: ByteArray = ByteArray(0)
+    var next_out_index = 0
+    var avail_out = 0
+    var total_out = 0L
+    var msg: String? = null
+    var adler = 1L
+    var data_type = 2 // Z_UNKNOWN
+
+    private var handle: CPointer<zk_stream>? = null
+    private var deflating = false
+
+    fun deflateInit(level: Int = 6, method: Int = 8, windowBits: Int = 15, memLevel: Int = 8, strategy: Int = 0): Int {
+        if (method != 8 || windowBits !in 8..15 || level > 9) return ZK_STREAM_ERROR
+        end()
+        handle = zk_deflate_init(engine.ctx, level, strategy)
+        deflating = true
+        return if (handle != null) ZK_OK else ZK_STREAM_ERROR
+    }
+
+    fun inflateInit(windowBits: Int = 15): Int {
+        if (windowBits !in 8..15) return ZK_STREAM_ERROR
+        end()
+        handle = zk_inflate_init(engine.ctx)
+        deflating = false
+        return if (handle != null) ZK_OK else ZK_STREAM_ERROR
+    }
+
+    fun deflate(flush: Int = ZK_NO_FLUSH): Int = run(flush, true)
+    fun inflate(flush: Int = ZK_NO_FLUSH): Int = run(flush, false)
+    fun deflateParams(level: Int, strategy: Int): Int = handle?.let { zk_deflate_params(it, level, strategy) } ?: ZK_STREAM_ERROR
+    fun deflateSetDictionary(dictionary: ByteArray, dictLength: Int = dictionary.size): Int =
+        handle?.let { h -> dictionary.usePinned { zk_deflate_set_dictionary(h, it.addressOf(0).reinterpret(), dictLength.toUInt()) } }
+            ?: ZK_STREAM_ERROR
+    fun inflateSetDictionary(dictionary: ByteArray, dictLength: Int = dictionary.size): Int =
+        handle?.let { h -> dictionary.usePinned { zk_inflate_set_dictionary(h, it.addressOf(0).reinterpret(), dictLength.toUInt()) } }
+            ?: ZK_STREAM_ERROR
+    fun deflateReset(): Int = handle?.let { zk_deflate_reset(it) } ?: ZK_STREAM_ERROR
+    fun inflateReset(): Int = handle?.let { zk_inflate_reset(it) } ?: ZK_STREAM_ERROR
+    fun inflateSync(): Int = ZK_DATA_ERROR
+    fun deflateEnd(): Int = end()
+    fun inflateEnd(): Int = end()
+    fun free() { end(); next_in = ByteArray(0); next_out = ByteArray(0) }
+
+    private fun run(flush: Int, wantDeflate: Boolean): Int {
+        val h = handle ?: return ZK_STREAM_ERROR
+        if (wantDeflate != deflating) return ZK_STREAM_ERROR
+        memScoped {
+            val inLen = alloc<ULongVar>().apply { value = avail_in.toULong() }
+            val outLen = alloc<ULongVar>().apply { value = avail_out.toULong() }
+            val rc = next_in.usePinned { i ->
+                next_out.usePinned { o ->
+                    val ip = if (avail_in > 0) i.addressOf(next_in_index).reinterpret<UByteVar>() else null
+                    val op = if (avail_out > 0) o.addressOf(next_out_index).reinterpret<UByteVar>() else null
+                    if (wantDeflate) zk_deflate(h, ip, inLen.ptr, op, outLen.ptr, flush)
+                    else zk_inflate(h, ip, inLen.ptr, op, outLen.ptr, flush)
+                }
+            }
+            next_in_index += inLen.value.toInt(); avail_in -= inLen.value.toInt()
+            next_out_index += outLen.value.toInt(); avail_out -= outLen.value.toInt()
+            total_in = zk_stream_total_in(h).toLong()
+            total_out = zk_stream_total_out(h).toLong()
+            adler = zk_stream_adler(h).toLong()
+            if (rc < 0) msg = "zlibk error $rc"
+            return rc
+        }
+    }
+
+    private fun end(): Int {
+        val h = handle ?: return ZK_STREAM_ERROR
+        zk_stream_end(h)
+        handle = null
+        return ZK_OK
+    }
+}

@@ -2,7 +2,7 @@
 
 Every rank deflates a contiguous range of the input as a headerless, byte-aligned body primed with the
 32 KiB that precede it (zk_deflate_shard_device).  The ONLY exchange is one all_gather of
-{body_len, adler32(shard), raw_len} per rank; every rank then computes the same exclusive scan (its
+{body_len, adler32(shard), status, raw_len} per rank; every rank then computes the same exclusive scan (its
 body's offset in the stream) and folds the checksums with zlib's combine identity.  Rank 0 owns the
 2-byte header, the last rank the final empty block + Adler-32 trailer.  No other collective is used.
 """
@@ -28,10 +28,12 @@ def plan_shards(n, world, align=32768):
 
 
 def assemble(metas):
-    """metas: per rank (body_len, adler, raw_len) in rank order ->
-    (offsets of each body in the stream, total stream length, adler of the whole input)."""
+    """metas: per rank (body_len, adler, status, raw_len) -- the record zk_deflate_shard_device writes -- in rank
+    order -> (offsets of each body in the stream, total stream length, adler of the whole input)."""
     offsets, at, adler = [], 2, 1
-    for body_len, a, raw_len in metas:
+    for body_len, a, status, raw_len in metas:
+        if status != 0:
+            raise RuntimeError("a shard failed with zlib code %d" % status)
         offsets.append(at)
         at += int(body_len)
         adler = adler32_combine(adler, int(a) & 0xFFFFFFFF, int(raw_len))
@@ -39,14 +41,14 @@ def assemble(metas):
 
 
 def exchange(meta_tensor, world):
-    """The one collective: all_gather of the 3-word meta record.  meta_tensor: int64[3] on the rank's device
-    (NCCL) or host (gloo).  Returns int64[world, 3]."""
+    """The one collective: all_gather of the 4-word meta record {body_len, adler, status, raw_len}.  meta_tensor:
+    int64[4] on the rank's device (NCCL) or host (gloo).  Returns int64[world, 4]."""
     import torch
     import torch.distributed as dist
 
-    out = torch.empty(world * 3, dtype=torch.int64, device=meta_tensor.device)
+    out = torch.empty(world * 4, dtype=torch.int64, device=meta_tensor.device)
     dist.all_gather_into_tensor(out, meta_tensor.contiguous())
-    return out.view(world, 3)
+    return out.view(world, 4)
 
 
 class ShardedDeflate:
@@ -68,14 +70,14 @@ class ShardedDeflate:
         rc = self.eng.deflate_shard_device(hist_ptr, hist_len, d_in.data_ptr(), n, level, 0, d_body.data_ptr(), cap, self.d_meta.data_ptr())
         if rc != 0:
             return rc
-        self.gathered = exchange(self.d_meta[:3], self.world)  # the only collective
+        self.gathered = exchange(self.d_meta, self.world)  # the only collective
         return 0
 
     def finish(self):
         """Host view after the timed region: offsets, total length, folded Adler-32."""
         g = self.gathered.cpu().tolist()
         meta = self.d_meta.cpu().tolist()
-        self.last_body_len, self.last_status = meta[0], meta[3]
+        self.last_body_len, self.last_status = meta[0], meta[2]
         return assemble([tuple(row) for row in g])
 
     @property
