@@ -39,6 +39,5 @@ for name, gen in kinds.items():
         name, level, lz_ms, n / lz_ms / 1e6, eng.counter("huffman_us") / 1e3, eng.counter("pack_us") / 1e3, d_res.cpu().tolist()[0] / n, tot / (1 << 20),
         100 * p[:, 1].mean() / tot, 100 * p[:, 2].mean() / tot, 100 * p[:, 3].mean() / tot,
         100 * p[:, 4].mean() / tot, 100 * p[:, 5].mean() / tot, 100 * p[:, 6].mean() / tot,
-        100 * p[:, 8].mean() / tot, 100 * p[:, 9].mean() / tot, 100 * p[:, 11].mean() / tot, 100 * p[:, 12].mean() / tot),
-        "| builder slow passes %.0f of 8448 (%.0f%% of unit cycles)" % (p[:, 14].mean(), 100 * p[:, 13].mean() / tot))
+        100 * p[:, 8].mean() / tot, 100 * p[:, 9].mean() / tot, 100 * p[:, 11].mean() / tot, 100 * p[:, 12].mean() / tot))
 eng.set_option("lz_profile_buffer", 0)

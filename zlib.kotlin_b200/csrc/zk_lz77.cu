@@ -13,7 +13,7 @@
 //   stage u32[34][128] tokens of the group being parsed, one column per parser lane
 //
 // Software pipeline over groups of 4096 positions, one __syncthreads per step.  In step i
-//   - one elected thread stages group i+3 into the ring with a TMA bulk copy (mbarrier-tracked),
+//   - one elected thread stages group i+4 into the ring with a TMA bulk copy (mbarrier-tracked),
 //   - warp 31 inserts group i+1 into the 4-byte hash chains, 32 positions per instruction sequence
 //     (a shared atomicMax per hash; match.any only resolves duplicates inside a batch: exact, deterministic),
 //   - warps 15/19/23/27 parse group i-1: a speculative pass finds the exit of every 32-byte lane segment,
@@ -36,7 +36,7 @@ namespace {
 constexpr int kThreadsLz = 1024;
 constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 13;  // 8192 buckets of 32-bit positions (atomicMax needs 32 bits)
-constexpr int kRun = 4;                      // consecutive positions per lane
+constexpr int kRun = 2;                      // consecutive positions per lane (strip = 64 positions)
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
 constexpr int kStripsPerGroup = kGroup / kStrip;
 constexpr int kParserWarps = 4;
@@ -58,6 +58,8 @@ struct LzSmem {
     uint16_t prev[32768];
     uint32_t head[1 << kHashBits];  // most recent position (q) per hash, 0 = none
     uint32_t match[2][kGroup + 4];  // + slack: the parser reads one word past the group
+    uint8_t prep[2][kGroup];  // per position of a group to be built: 0x80 last of its hash in its batch, 0x40 | lane of
+                              // the nearest lower lane with the same hash
     uint32_t stage[(kSeg + 2) * kParserWarps * 32];  // tokens of the group being parsed: [k][parser lane]
     unsigned long long bar[kStages];
     int work[2];
@@ -176,89 +178,61 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
 // lane with it and the highest one stays in head[].  (MATCH.ANY would do this in one instruction but was measured at
 // ~500 cycles per call on B200.)  Links of later batches that were read while head[] held an arbitrary duplicate
 // are corrected from the group masks, so the result never depends on which lane the hardware let win.
-// Resolve the repeated hashes of one batch (rare path, kept out of line and compact: a lone warp runs serial code at
-// ~10 cycles per instruction, so its size is its cost).  Returns this lane's link; grp = lanes sharing its hash.
-__device__ __noinline__ uint32_t resolve_batch(volatile uint32_t *vhead, uint32_t h, uint32_t old, uint32_t won,
-                                               uint32_t q, int lane, uint32_t *grp_out) {
-    uint32_t link = old, grp = 0;
-    uint32_t unresolved = __ballot_sync(0xFFFFFFFFu, won != q);
-    while (unresolved) {
-        const int leader = __ffs(unresolved) - 1;
-        const uint32_t hl = __shfl_sync(0xFFFFFFFFu, h, leader);
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, h == hl);
-        if (h == hl) {
-            grp = m;
-            const uint32_t below = m & ((1u << lane) - 1u);
-            if (below) link = q - (uint32_t)(lane - (31 - __clz(below)));
-            // the highest lane of the hash restores head[] unless a later batch already moved it on
-            if (((m >> lane) >> 1) == 0u) {
-                const uint32_t cur = vhead[h];
-                if (cur - (q - lane) < 32u) vhead[h] = q;
-            }
+// Preparation of four batches (one strip) of group t, done by whichever warp searches the matching strip: for every
+// position, which lower lane of its 32-position batch has the same hash, and whether it is the last of its hash in
+// the batch.  The lane groups are an exact match.any, emulated with one ballot per hash bit (MATCH.ANY itself was
+// measured at several hundred cycles per call on B200); it is a pure function of the batch, so it runs in parallel
+// on the searcher warps and the serial builder is left with table updates only.
+__device__ __forceinline__ void prep_strip(LzSmem &s, int t, int strip, int lane) {
+    uint8_t *pp = s.prep[t & 1] + strip * kStrip;
+    const uint32_t q0 = (uint32_t)t * kGroup + strip * kStrip + lane;
+#pragma unroll
+    for (int u = 0; u < kStrip / 32; ++u) {
+        const uint32_t hv = hash4(ring_load32(s.ring, q0 + u * 32));
+        uint32_t eq = 0xFFFFFFFFu;
+#pragma unroll
+        for (int bit = 0; bit < kHashBits; ++bit) {
+            const bool one = (hv >> bit) & 1u;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, one);
+            eq &= one ? bal : ~bal;
         }
-        unresolved &= ~m;
+        const uint32_t below = eq & ((1u << lane) - 1u);
+        uint32_t info = below ? (0x40u | (uint32_t)(31 - __clz(below))) : 0u;
+        if (((eq >> lane) >> 1) == 0u) info |= 0x80u;
+        pp[u * 32 + lane] = (uint8_t)info;
     }
-    *grp_out = grp;
-    return link;
 }
 
-__device__ __forceinline__ void build_group(LzSmem &s, int t, int lane, long long &slow_cycles, int &slow_passes) {
+// ---- builder: one warp inserts group t into the hash chains ----------------------------------
+// Exact, deterministic chains at LSU issue rate: per batch of 32 positions read head[h] (the link for lanes that have
+// no lower lane with their hash in the batch), then the last lane of every hash stores its position.  The shared
+// accesses of one warp are handled in issue order, so the next batch's read sees this batch's store; the loaded links
+// are consumed only after eight batches have been issued.  No votes, no branches, no read-backs.
+__device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
     const uint32_t q0 = (uint32_t)t * kGroup + lane;
     volatile uint32_t *vhead = s.head;
+    const uint8_t *pp = s.prep[t & 1] + lane;
 #pragma unroll 1
-    for (int b = 0; b < kGroup / 32; b += 4) {
-        uint32_t h[4], old[4], won[4];
+    for (int b = 0; b < kGroup / 32; b += 8) {
+        uint32_t h[8], old[8], info[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = hash4(ring_load32(s.ring, q0 + (b + u) * 32));
-        // No __syncwarp between the accesses: it would wait for each one to complete (three loaded round trips per
-        // batch).  The warp is converged here and the LSU handles one warp's shared accesses in issue order, so the
-        // read-back sees this batch's store and the next batch's read sees it too; `volatile` pins the order.
+        for (int u = 0; u < 8; ++u) {
+            h[u] = hash4(ring_load32(s.ring, q0 + (b + u) * 32));
+            info[u] = pp[(b + u) * 32];
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t q = q0 + (b + u) * 32;
+        for (int u = 0; u < 8; ++u) {
             old[u] = vhead[h[u]];
-            vhead[h[u]] = q;
-            won[u] = vhead[h[u]];
+            if (info[u] & 0x80u) vhead[h[u]] = q0 + (b + u) * 32;
         }
-        const uint32_t qb = q0 + b * 32;
-        // which batches of the pass have a repeated hash (bit u)
-        uint32_t bad = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bad |= (won[u] != qb + u * 32u) ? (1u << u) : 0u;
-        bad = __reduce_or_sync(0xFFFFFFFFu, bad);
-        if (bad == 0u) {
-            // common case: 128 distinct hashes -- every link is the value head[] held before the position
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s.prev[(qb + u * 32u) & 32767u] = (uint16_t)old[u];
-        } else {
-            const long long ts = clock64();
-            ++slow_passes;
-            uint32_t grp[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t q = qb + u * 32u;
-                uint32_t link = old[u];
-                bool in_batch = false;
-                if (bad & (1u << u)) {
-                    link = resolve_batch(vhead, h[u], old[u], won[u], q, lane, &grp[u]);
-                    in_batch = link != old[u];
-                }
-                // a link read from head[] while an earlier batch of this pass held an arbitrary duplicate
-#pragma unroll
-                for (int v = 0; v < u; ++v) {
-                    if (bad & (1u << v)) {
-                        const uint32_t vstart = (q - lane) - (uint32_t)(u - v) * 32u;
-                        const uint32_t j = old[u] - vstart;
-                        const uint32_t mm = __shfl_sync(0xFFFFFFFFu, grp[v], (int)(j & 31u));
-                        if (j < 32u && mm != 0u && !in_batch) link = vstart + (uint32_t)(31 - __clz(mm));
-                    }
-                }
-                s.prev[q & 32767u] = (uint16_t)link;
-            }
-            slow_cycles += clock64() - ts;
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t q = q0 + (b + u) * 32;
+            const uint32_t link = (info[u] & 0x40u) ? (q - lane) + (info[u] & 31u) : old[u];
+            s.prev[q & 32767u] = (uint16_t)link;
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // ---- searcher: best match of kRun consecutive positions per lane ----------------------------------
@@ -279,12 +253,14 @@ __device__ __forceinline__ Bytes16 ring_load128(const uint32_t *ring, uint32_t q
 }
 // number of equal leading bytes of two 16-byte strings (0..16)
 __device__ __forceinline__ int common_prefix16(const Bytes16 &a, const Bytes16 &b) {
-    // branch-free: first differing byte of each 8-byte half (8 = none), then combine
-    const unsigned long long lo = ((unsigned long long)(a.w[1] ^ b.w[1]) << 32) | (a.w[0] ^ b.w[0]);
-    const unsigned long long hi = ((unsigned long long)(a.w[3] ^ b.w[3]) << 32) | (a.w[2] ^ b.w[2]);
-    const int n0 = ((__ffsll((long long)lo) - 1) & 127) >> 3;  // 0..7, or 15 when lo == 0
-    const int n1 = ((__ffsll((long long)hi) - 1) & 127) >> 3;
-    return lo ? n0 : 8 + min(n1, 8);
+    // branch-free: pick the first differing word with selects, then one 32-bit find-first-set
+    const uint32_t x0 = a.w[0] ^ b.w[0], x1 = a.w[1] ^ b.w[1], x2 = a.w[2] ^ b.w[2], x3 = a.w[3] ^ b.w[3];
+    const uint32_t w01 = x0 ? x0 : x1, w23 = x2 ? x2 : x3;
+    const int b01 = x0 ? 0 : 4, b23 = x2 ? 8 : 12;
+    const bool lowhalf = (x0 | x1) != 0u;
+    const uint32_t w = lowhalf ? w01 : w23;
+    const int base = lowhalf ? b01 : b23;
+    return w ? base + ((__ffs((int)w) - 1) >> 3) : 16;
 }
 
 constexpr int kCap = 16;  // candidates are compared over 16 bytes; the nearest one that reaches 16 is extended
@@ -313,7 +289,8 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
         int budget = lp.chain;
         if (best >= lp.good) budget >>= 2;
         if (lp.skip_deep && inh_run >= 2) budget = 0;
-        if (best >= lp.nice || best >= maxlen || maxlen < lp.min_len) budget = 0;
+        // an inherited match that already fills the 16-byte compare cannot be beaten by it
+        if (best >= lp.nice || best >= kCap || best >= maxlen || maxlen < lp.min_len) budget = 0;
         const uint32_t reach = (uint32_t)min(kMaxDist, max(p - g.h0q, 0));
         const Bytes16 cur = ring_load128(s.ring, (uint32_t)p);
         // ---- hash-chain candidates: the loop is uniform across the warp, lanes drop out by predicate --------
@@ -330,7 +307,11 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
                     lastd = d;
                     const uint32_t c = (uint32_t)p - d;
                     c16 = s.prev[c & 32767u];
-                    const int len = min(common_prefix16(cur, ring_load128(s.ring, c)), maxlen);
+                    // only a candidate that also matches the byte at index `best` can be longer than the best so far
+                    int len = 0;
+                    const uint32_t cw = best < 8 ? (best < 4 ? cur.w[0] : cur.w[1]) : (best < 12 ? cur.w[2] : cur.w[3]);
+                    const bool may_win = ring_load8(s.ring, c + (uint32_t)best) == ((cw >> ((best & 3) << 3)) & 0xFFu);
+                    if (may_win) len = min(common_prefix16(cur, ring_load128(s.ring, c)), maxlen);
                     if (len > best && len >= 4) {
                         best = len;
                         bestd = (int)d;
@@ -367,26 +348,66 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
                 }
             }
         }
-        // ---- extension of a match that filled the 16-byte compare ----------------------------------------------
+        // ---- extension of matches that filled the 16-byte compare: cooperative, one round per distinct distance -----
+        // For a distance d the end of every match of the strip is the first x with byte[x] != byte[x-d]; the lanes of
+        // the warp compare 3 x 32 words (384 bytes from the strip's first position + 16) and ballot the mismatching
+        // words, then each lane with that distance finds the first mismatch at or after its own position + 16.
         {
             bool ext = capped && best < maxlen;
-            int len = best;
-            while (__any_sync(0xFFFFFFFFu, ext)) {
-                if (ext) {
-                    const uint32_t x = ring_load32(s.ring, (uint32_t)(p + len)) ^ ring_load32(s.ring, (uint32_t)(p - bestd + len));
-                    if (x) {
-                        len += (__ffs(x) - 1) >> 3;
-                        ext = false;
-                    } else {
-                        len += 4;
-                    }
-                    if (len >= maxlen) {
-                        len = maxlen;
-                        ext = false;
-                    }
+            uint32_t pending = __ballot_sync(0xFFFFFFFFu, ext);
+            const uint32_t scan0 = ((uint32_t)(t * kGroup + strip * kStrip + r) + kCap) & ~3u;  // word aligned
+            while (pending) {
+                const int leader = __ffs(pending) - 1;
+                const uint32_t d = (uint32_t)__shfl_sync(0xFFFFFFFFu, bestd, leader);
+                const bool mine = ext && (uint32_t)bestd == d;
+                uint32_t diff[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t x = scan0 + (uint32_t)(k * 32 + lane) * 4u;
+                    diff[k] = __ballot_sync(0xFFFFFFFFu, ring_load32(s.ring, x) != ring_load32(s.ring, x - d));
                 }
+                if (mine) {
+                    // first mismatching word at or after my position + 16
+                    const uint32_t from = (uint32_t)p + kCap;            // first byte not yet compared
+                    const uint32_t w0 = (from - scan0) >> 2;             // its word index in the bitmap (0..~20)
+                    int len = maxlen;
+                    uint32_t wfound = 96;
+#pragma unroll
+                    for (int k = 2; k >= 0; --k) {
+                        uint32_t bits = diff[k];
+                        const int lo = (int)w0 - k * 32;
+                        if (lo > 0) bits = lo >= 32 ? 0u : bits & ~((1u << lo) - 1u);
+                        if (bits) wfound = (uint32_t)(k * 32 + __ffs(bits) - 1);
+                    }
+                    if (wfound < 96) {
+                        // the exact byte: compare from max(from, word start)
+                        const uint32_t wx = scan0 + wfound * 4u;
+                        const uint32_t start = wx > from ? wx : from;
+                        const uint32_t xr = ring_load32(s.ring, start) ^ ring_load32(s.ring, start - d);
+                        // bytes [start, start+4): the first differing one (there is one inside the word; if `from`
+                        // cut the word and the difference lies before it, the next word decides -- handled by the
+                        // conservative fallback below)
+                        if (xr) len = (int)(start - (uint32_t)p) + ((__ffs((int)xr) - 1) >> 3);
+                        else len = (int)(start - (uint32_t)p) + 4;
+                        if (!xr) {
+                            // rare: the mismatch of that word was before `from`; continue byte-exact with a short loop
+                            int l2 = len;
+                            while (l2 < maxlen) {
+                                const uint32_t y = ring_load32(s.ring, (uint32_t)p + l2) ^ ring_load32(s.ring, (uint32_t)p + l2 - d);
+                                if (y) {
+                                    l2 += (__ffs((int)y) - 1) >> 3;
+                                    break;
+                                }
+                                l2 += 4;
+                            }
+                            len = l2;
+                        }
+                    }
+                    best = min(len, maxlen);
+                    ext = false;
+                }
+                pending &= ~__ballot_sync(0xFFFFFFFFu, mine);
             }
-            best = len;
         }
         if (best == 3 && bestd > lp.far3) best = 0;
         if (best == 4 && bestd > lp.far4) best = 0;
@@ -582,7 +603,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         __syncthreads();
         // stage uses per barrier slot, to derive the parity of the next wait
         uint32_t stage_uses[kStages] = {0, 0, 0, 0};
-        // prologue: groups first_group, first_group+1 (the loop stages i+3 = first_group+2 onwards)
+        // prologue: groups first_group, first_group+1 (the loop stages i+4 = first_group+2 onwards)
         bool staged_tma[2];
         for (int k = 0; k < 2; ++k) staged_tma[k] = stage_group(s, a, g, g.first_group + k, true);
         for (int k = 0; k < 2; ++k) {
@@ -599,19 +620,18 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         if (threadIdx.x < 8) s.ring[65536 / 4 + threadIdx.x] = s.ring[threadIdx.x];
         __syncthreads();
 
-        // step i: stage(i+3) | build(i+1) | search(i) | parse(i-1)
-        long long t_role = 0, t_search = 0, t_slow = 0;
-        int n_slow = 0;
+        // step i: stage(i+4) | prepare(i+2) | build(i+1) | search(i) | parse(i-1)
+        long long t_role = 0, t_search = 0;
         const long long t_unit0 = clock64();
-        for (int i = g.first_group - 1; i <= g.last_group + 1; ++i) {
-            const bool tma_next = (i + 3 <= g.last_group + 1) ? stage_group(s, a, g, i + 3, true) : false;
+        for (int i = g.first_group - 2; i <= g.last_group + 1; ++i) {
+            const bool tma_next = (i + 4 <= g.last_group + 1) ? stage_group(s, a, g, i + 4, true) : false;
             if (threadIdx.x == 0) {
                 s.work[(i + 1) & 1] = 0;
                 s.roles_done[(i + 1) & 1] = 0;
             }
 
             const long long t0 = clock64();
-            if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane, t_slow, n_slow);
+            if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
             if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
                 parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit);
             if ((is_builder || is_parser) && lane == 0) atomicAdd(&s.roles_done[i & 1], 1);
@@ -619,30 +639,33 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                 // keep the role sub-partition quiet until the builder and the parsers have finished this step
                 volatile int *done = &s.roles_done[i & 1];
                 uint32_t spins = 0;
-                while (*done < kRoleWarps && ++spins < (1u << 20)) __nanosleep(200);
+                while (*done < kRoleWarps && ++spins < (1u << 18)) __nanosleep(1500);
             }
             const long long t1 = clock64();
-            if (i >= kHistGroups && i <= g.last_group) {
+            const bool searching = i >= kHistGroups && i <= g.last_group;
+            const bool preparing = i + 2 >= g.first_group && i + 2 <= g.last_group;
+            if (searching || preparing) {
                 for (;;) {
                     int strip = 0;
                     if (lane == 0) strip = atomicAdd(&s.work[i & 1], 1);
                     strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
                     if (strip >= kStripsPerGroup) break;
-                    search_strip(s, a.lp, g, i, strip, lane, a.block_shift);
+                    if (preparing) prep_strip(s, i + 2, strip, lane);
+                    if (searching) search_strip(s, a.lp, g, i, strip, lane, a.block_shift);
                 }
             }
             const long long t2 = clock64();
             t_role += t1 - t0;
             t_search += t2 - t1;
             if (tma_next) {
-                const int slot = (i + 3) & (kStages - 1);
+                const int slot = (i + 4) & (kStages - 1);
                 uint32_t spins = 0;
                 while (!mbar_try_wait(&s.bar[slot], stage_uses[slot] & 1u)) {
                     if (++spins > (1u << 26)) break;
                 }
                 stage_uses[slot]++;
             }
-            if ((((i + 3) * kGroup) & 0xFFFF) == 0) {  // the group staged in this step sits at ring offset 0
+            if ((((i + 4) * kGroup) & 0xFFFF) == 0) {  // the group staged in this step sits at ring offset 0
                 __syncthreads();
                 if (threadIdx.x < 8) s.ring[65536 / 4 + threadIdx.x] = s.ring[threadIdx.x];
             }
@@ -654,11 +677,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             // per unit: [0] total, then {role, search} of the builder, the first parser warp, a searcher and a guest
             unsigned long long *o = a.prof + (size_t)unit * 16;
             const int k = warp == builder_warp ? 0 : warp == parser_warp ? 1 : warp == 2 ? 2 : 3;
-            if (warp == builder_warp) {
-                o[0] = (unsigned long long)(clock64() - t_unit0);
-                o[13] = (unsigned long long)t_slow;
-                o[14] = (unsigned long long)n_slow;
-            }
+            if (warp == builder_warp) o[0] = (unsigned long long)(clock64() - t_unit0);
             o[1 + 3 * k] = (unsigned long long)t_role;
             o[2 + 3 * k] = (unsigned long long)t_search;
             o[3 + 3 * k] = 0;
