@@ -327,7 +327,7 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
 
 uint32_t zk_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
 
-uint64_t zk_compress_bound(uint64_t n) { return n + (n >> 12) + (n >> 14) + 64; }
+uint64_t zk_compress_bound(uint64_t n) { return n + (n >> 11) + 64; }  // 10 bytes per stored 32 KiB block + framing
 
 void zk_zlib_header(int level, uint8_t out2[2]) {
     const int flevel = level >= 9 ? 3 : level >= 6 ? 2 : level >= 2 ? 1 : 0;  // DS:27-33

@@ -345,10 +345,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
 
     const uint32_t raw = (uint32_t)tmin<uint64_t>(block_bytes, n - (uint64_t)blk * block_bytes);
     const uint64_t dyn_total = head_bits + dyn_bits, fix_total = 3 + fix_bits;
-    // a Huffman block is followed by an empty stored block (3 bits, pad, 00 00 FF FF) so that the next
-    // block starts on a byte; a stored block already ends on one
+    // every block is followed by an empty stored block (3 bits, pad, 00 00 FF FF): the next block starts on a byte
+    // and inflate finds one entry point per block (a stored block ends on a byte already; it gets the marker too so
+    // that a run of stored blocks is not one long chunk)
     const uint64_t dyn_bytes = ((dyn_total + 3 + 7) >> 3) + 4, fix_bytes = ((fix_total + 3 + 7) >> 3) + 4;
-    const uint64_t sto_bytes = 5ull + raw;
+    const uint64_t sto_bytes = 5ull + raw + 5ull;
     int type;
     if (force_type >= 0) type = force_type;
     else if (sto_bytes <= dyn_bytes && sto_bytes <= fix_bytes) type = 0;  // tie order of DS:950-955

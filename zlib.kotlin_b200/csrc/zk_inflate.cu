@@ -106,10 +106,18 @@ struct BitReader {
 __device__ __forceinline__ uint32_t rev_bits(uint32_t v, int len) { return __brev(v) >> (32 - len); }
 
 // Build a canonical decoder from code lengths (already validated: complete or single-code).
+// kCoop = true: the 32 lanes of a warp work on ONE decoder (lane = lane id).  kCoop = false: the calling thread
+// owns the decoder alone (pass lane = 0) -- used when every lane of a warp decodes its own block.
+template <bool kCoop>
+__device__ __forceinline__ void coop_sync() {
+    if (kCoop) __syncwarp();
+}
+template <bool kCoop>
 __device__ void build_decoder(Decoder &d, const uint8_t *lens, int n, int lut_bits, int lane) {
-    if (lane < 16) d.count[lane] = 0;
-    for (int i = lane; i < (1 << lut_bits); i += 32) d.lut[i] = 0;
-    __syncwarp();
+    constexpr int kStep = kCoop ? 32 : 1;
+    for (int i = lane; i < 16; i += kStep) d.count[i] = 0;
+    for (int i = lane; i < (1 << lut_bits); i += kStep) d.lut[i] = 0;
+    coop_sync<kCoop>();
     if (lane == 0) {
         int maxl = 0;
         for (int i = 0; i < n; ++i) {
@@ -138,10 +146,10 @@ __device__ void build_decoder(Decoder &d, const uint8_t *lens, int n, int lut_bi
             if (l) d.sorted[fill[l]++] = (uint16_t)i;
         }
     }
-    __syncwarp();
+    coop_sync<kCoop>();
     // direct table: every symbol with a short code fills its stride
     const int total = d.first_index[15] + d.count[15];
-    for (int k = lane; k < total; k += 32) {
+    for (int k = lane; k < total; k += kStep) {
         const int sym = d.sorted[k];
         const int l = lens[sym];
         if (l > lut_bits) continue;
@@ -149,7 +157,7 @@ __device__ void build_decoder(Decoder &d, const uint8_t *lens, int n, int lut_bi
         const uint16_t entry = (uint16_t)(sym | (l << 12));
         for (uint32_t idx = rev_bits(code, l); idx < (1u << lut_bits); idx += 1u << l) d.lut[idx] = entry;
     }
-    __syncwarp();
+    coop_sync<kCoop>();
 }
 
 // Decode one symbol; returns -1 for an invalid prefix.  `br` holds at least max_len bits or the end of
@@ -173,6 +181,178 @@ __device__ __forceinline__ int decode_sym(const Decoder &d, BitReader &br) {
     return -1;
 }
 
+// Read the header of a fixed (type 1) or dynamic (type 2) block and build both decoders.  Returns ZK_OK or the
+// code the reference reports (IS:299-348).
+template <bool kCoop>
+__device__ int parse_huffman_header(WarpState &ws, BitReader &br, int type, int lane) {
+    constexpr int kStep = kCoop ? 32 : 1;
+    if (type == 1) {  // IS:154-173
+        for (int i = lane; i < 288; i += kStep) ws.lengths[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+        coop_sync<kCoop>();
+        build_decoder<kCoop>(ws.lit, ws.lengths, 288, kLitLutBits, lane);
+        for (int i = lane; i < 32; i += kStep) ws.lengths[i] = 5;
+        coop_sync<kCoop>();
+        build_decoder<kCoop>(ws.dist, ws.lengths, 32, kDistLutBits, lane);
+    } else {  // IS:299-348
+        br.refill();
+        if (br.held < 14) {
+            return ZK_BUF_ERROR;
+        }
+        const int hlit = (int)br.peek(5) + 257;
+        br.drop(5);
+        const int hdist = (int)br.peek(5) + 1;
+        br.drop(5);
+        const int hclen = (int)br.peek(4) + 4;
+        br.drop(4);
+        int clen[19];
+#pragma unroll
+        for (int i = 0; i < 19; ++i) clen[i] = 0;
+        int bad = 0;
+        for (int i = 0; i < hclen; ++i) {
+            br.refill();
+            if (br.held < 3) {
+                bad = ZK_BUF_ERROR;
+                break;
+            }
+            clen[i_cl_order[i]] = (int)br.peek(3);
+            br.drop(3);
+        }
+        if (bad) {
+            return bad;
+        }
+        // code-length-code table exactly as CanonicalHuffman.buildFull makes it (CH:54-82): later
+        // symbols overwrite earlier ones when the lengths over-subscribe the code space
+        int cl_max = 0;
+        for (int i = 0; i < 19; ++i) cl_max = max(cl_max, clen[i]);
+        if (lane == 0) {
+            ws.cl_max = cl_max;
+            for (int i = 0; i < 128; ++i) ws.cl_bits[i] = 0;
+            int per[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nextc[8];
+            for (int i = 0; i < 19; ++i)
+                if (clen[i]) per[clen[i]]++;
+            int code = 0;
+            nextc[0] = 0;
+            for (int b = 1; b <= 7; ++b) {
+                code = (code + per[b - 1]) << 1;
+                nextc[b] = code;
+            }
+            for (int s = 0; s < 19; ++s) {
+                const int l = clen[s];
+                if (!l) continue;
+                const uint32_t assigned = (uint32_t)nextc[l]++;
+                for (uint32_t idx = rev_bits(assigned & ((1u << l) - 1u), l); idx < (1u << cl_max); idx += 1u << l) {
+                    ws.cl_bits[idx] = (uint8_t)l;
+                    ws.cl_vals[idx] = (uint8_t)s;
+                }
+            }
+        }
+        coop_sync<kCoop>();
+        // IS:235-263, twice: literal/length lengths, then distance lengths, never merged
+        int fail = 0;
+        for (int pass = 0; pass < 2 && !fail; ++pass) {
+            const int count = pass == 0 ? hlit : hdist;
+            const int base = pass == 0 ? 0 : 288;
+            int i = 0;
+            while (i < count) {
+                br.refill();
+                if (cl_max == 0) {  // "Empty Huffman table": escapes in the reference (CH:127)
+                    fail = ZK_DATA_ERROR;
+                    break;
+                }
+                if (br.held < cl_max) {
+                    fail = ZK_BUF_ERROR;
+                    break;
+                }
+                const uint32_t look = br.peek(cl_max);
+                const int l = ws.cl_bits[look];
+                if (l == 0) {  // invalid prefix: escapes in the reference (CH:133)
+                    fail = ZK_DATA_ERROR;
+                    break;
+                }
+                const int s = ws.cl_vals[look];
+                br.drop(l);
+                if (s <= 15) {
+                    if (lane == 0) ws.lengths[base + i] = (uint8_t)s;
+                    ++i;
+                    continue;
+                }
+                if (s == 16 && i == 0) {  // IS:246: checked before the repeat count is read
+                    fail = ZK_DATA_ERROR;
+                    break;
+                }
+                const int nb = s == 16 ? 2 : s == 17 ? 3 : 7;
+                br.refill();
+                if (br.held < nb) {
+                    fail = ZK_BUF_ERROR;
+                    break;
+                }
+                const int rep = (s == 16 ? 3 : s == 17 ? 3 : 11) + (int)br.peek(nb);
+                br.drop(nb);
+                if (i + rep > count) {
+                    fail = ZK_DATA_ERROR;
+                    break;
+                }
+                coop_sync<kCoop>();
+                const uint8_t v = s == 16 ? ws.lengths[base + i - 1] : (uint8_t)0;
+                coop_sync<kCoop>();
+                for (int r = lane; r < rep; r += kStep) ws.lengths[base + i + r] = v;
+                i += rep;
+            }
+            coop_sync<kCoop>();
+        }
+        if (fail) {
+            return fail;
+        }
+        // IS:102-152: EOB present, a distance code present, neither tree over-subscribed nor
+        // incomplete (a single code may be incomplete)
+        int ok = 1;
+        {
+            int any = 0, used = 0, left = 1, maxl = 0;
+            int per[16];
+            for (int b = 0; b < 16; ++b) per[b] = 0;
+            for (int i = 0; i < hlit; ++i) {
+                const int l = ws.lengths[i];
+                if (l) {
+                    any = 1;
+                    ++used;
+                    per[l]++;
+                    maxl = max(maxl, l);
+                }
+            }
+            if (!any || ws.lengths[256] == 0) ok = 0;
+            for (int b = 1; b <= maxl && ok; ++b) {
+                left = (left << 1) - per[b];
+                if (left < 0) ok = 0;
+            }
+            if (ok && left != 0 && used > 1) ok = 0;
+            int dany = 0, dused = 0, dmax = 0;
+            for (int b = 0; b < 16; ++b) per[b] = 0;
+            for (int i = 0; i < hdist; ++i) {
+                const int l = ws.lengths[288 + i];
+                if (l) {
+                    dany = 1;
+                    ++dused;
+                    per[l]++;
+                    dmax = max(dmax, l);
+                }
+            }
+            if (!dany) ok = 0;
+            left = 1;
+            for (int b = 1; b <= dmax && ok; ++b) {
+                left = (left << 1) - per[b];
+                if (left < 0) ok = 0;
+            }
+            if (ok && left != 0 && dused > 1) ok = 0;
+        }
+        if (!ok) {
+            return ZK_DATA_ERROR;
+        }
+        build_decoder<kCoop>(ws.lit, ws.lengths, hlit, kLitLutBits, lane);
+        build_decoder<kCoop>(ws.dist, ws.lengths + 288, hdist, kDistLutBits, lane);
+    }
+    return ZK_OK;
+}
+
 struct ChunkResult {
     uint64_t out_len;
     uint64_t end_byte;
@@ -182,9 +362,14 @@ struct ChunkResult {
 
 // Decode the blocks of one chunk.  kWrite = false: size only.  kWrite = true: 16-bit symbols to
 // sym[out_begin ...]; references that reach before the chunk become 0x8000 | window index.
-template <bool kWrite>
+// kTokens = true (single-lane mode only): instead of decoded symbols the output is the block's token stream in 16-bit
+// units -- a literal is one unit (its byte), a match two (0x8000 | length, distance - 1); `units` counts them.
+template <bool kWrite, bool kCoop, bool kTokens = false>
 __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m, uint64_t in_begin, uint64_t in_end,
-                                    bool first_chunk, uint16_t *sym, uint64_t out_begin, uint64_t out_cap, int lane) {
+                                    bool first_chunk, uint16_t *sym, uint64_t out_begin, uint64_t out_cap, int lane,
+                                    uint32_t *units_out = nullptr) {
+    constexpr int kStep = kCoop ? 32 : 1;
+    uint32_t units = 0;
     BitReader br{in, m, in_begin, 0, 0};
     uint64_t produced = 0;
     ChunkResult res{0, 0, ZK_OK, 0};
@@ -227,8 +412,13 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
                     res.status = ZK_BUF_ERROR;
                     break;
                 }
-                for (uint32_t i = lane; i < take; i += 32) sym[out_begin + produced + i] = in[src0 + i];
-                __syncwarp();
+                if (kTokens) {
+                    for (uint32_t i = 0; i < take; ++i) sym[out_begin + units + i] = in[src0 + i];
+                    units += take;
+                } else {
+                    for (uint32_t i = lane; i < take; i += kStep) sym[out_begin + produced + i] = in[src0 + i];
+                }
+                coop_sync<kCoop>();
             }
             produced += take;
             br.next = src0 + take;
@@ -239,177 +429,12 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
                 break;
             }
         } else {
-            if (type == 1) {  // IS:154-173
-                for (int i = lane; i < 288; i += 32) ws.lengths[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
-                __syncwarp();
-                build_decoder(ws.lit, ws.lengths, 288, kLitLutBits, lane);
-                if (lane < 32) ws.lengths[lane] = 5;
-                __syncwarp();
-                build_decoder(ws.dist, ws.lengths, 32, kDistLutBits, lane);
-            } else {  // IS:299-348
-                br.refill();
-                if (br.held < 14) {
-                    res.status = ZK_BUF_ERROR;
+            {
+                const int hrc = parse_huffman_header<kCoop>(ws, br, type, lane);
+                if (hrc != ZK_OK) {
+                    res.status = hrc;
                     break;
                 }
-                const int hlit = (int)br.peek(5) + 257;
-                br.drop(5);
-                const int hdist = (int)br.peek(5) + 1;
-                br.drop(5);
-                const int hclen = (int)br.peek(4) + 4;
-                br.drop(4);
-                int clen[19];
-#pragma unroll
-                for (int i = 0; i < 19; ++i) clen[i] = 0;
-                int bad = 0;
-                for (int i = 0; i < hclen; ++i) {
-                    br.refill();
-                    if (br.held < 3) {
-                        bad = ZK_BUF_ERROR;
-                        break;
-                    }
-                    clen[i_cl_order[i]] = (int)br.peek(3);
-                    br.drop(3);
-                }
-                if (bad) {
-                    res.status = bad;
-                    break;
-                }
-                // code-length-code table exactly as CanonicalHuffman.buildFull makes it (CH:54-82): later
-                // symbols overwrite earlier ones when the lengths over-subscribe the code space
-                int cl_max = 0;
-                for (int i = 0; i < 19; ++i) cl_max = max(cl_max, clen[i]);
-                if (lane == 0) {
-                    ws.cl_max = cl_max;
-                    for (int i = 0; i < 128; ++i) ws.cl_bits[i] = 0;
-                    int per[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nextc[8];
-                    for (int i = 0; i < 19; ++i)
-                        if (clen[i]) per[clen[i]]++;
-                    int code = 0;
-                    nextc[0] = 0;
-                    for (int b = 1; b <= 7; ++b) {
-                        code = (code + per[b - 1]) << 1;
-                        nextc[b] = code;
-                    }
-                    for (int s = 0; s < 19; ++s) {
-                        const int l = clen[s];
-                        if (!l) continue;
-                        const uint32_t assigned = (uint32_t)nextc[l]++;
-                        for (uint32_t idx = rev_bits(assigned & ((1u << l) - 1u), l); idx < (1u << cl_max); idx += 1u << l) {
-                            ws.cl_bits[idx] = (uint8_t)l;
-                            ws.cl_vals[idx] = (uint8_t)s;
-                        }
-                    }
-                }
-                __syncwarp();
-                // IS:235-263, twice: literal/length lengths, then distance lengths, never merged
-                int fail = 0;
-                for (int pass = 0; pass < 2 && !fail; ++pass) {
-                    const int count = pass == 0 ? hlit : hdist;
-                    const int base = pass == 0 ? 0 : 288;
-                    int i = 0;
-                    while (i < count) {
-                        br.refill();
-                        if (cl_max == 0) {  // "Empty Huffman table": escapes in the reference (CH:127)
-                            fail = ZK_DATA_ERROR;
-                            break;
-                        }
-                        if (br.held < cl_max) {
-                            fail = ZK_BUF_ERROR;
-                            break;
-                        }
-                        const uint32_t look = br.peek(cl_max);
-                        const int l = ws.cl_bits[look];
-                        if (l == 0) {  // invalid prefix: escapes in the reference (CH:133)
-                            fail = ZK_DATA_ERROR;
-                            break;
-                        }
-                        const int s = ws.cl_vals[look];
-                        br.drop(l);
-                        if (s <= 15) {
-                            if (lane == 0) ws.lengths[base + i] = (uint8_t)s;
-                            ++i;
-                            continue;
-                        }
-                        if (s == 16 && i == 0) {  // IS:246: checked before the repeat count is read
-                            fail = ZK_DATA_ERROR;
-                            break;
-                        }
-                        const int nb = s == 16 ? 2 : s == 17 ? 3 : 7;
-                        br.refill();
-                        if (br.held < nb) {
-                            fail = ZK_BUF_ERROR;
-                            break;
-                        }
-                        const int rep = (s == 16 ? 3 : s == 17 ? 3 : 11) + (int)br.peek(nb);
-                        br.drop(nb);
-                        if (i + rep > count) {
-                            fail = ZK_DATA_ERROR;
-                            break;
-                        }
-                        __syncwarp();
-                        const uint8_t v = s == 16 ? ws.lengths[base + i - 1] : (uint8_t)0;
-                        __syncwarp();
-                        if (lane < rep) ws.lengths[base + i + lane] = v;
-                        if (lane + 32 < rep) ws.lengths[base + i + lane + 32] = v;
-                        if (lane + 64 < rep) ws.lengths[base + i + lane + 64] = v;
-                        if (lane + 96 < rep) ws.lengths[base + i + lane + 96] = v;
-                        if (lane + 128 < rep) ws.lengths[base + i + lane + 128] = v;
-                        i += rep;
-                    }
-                    __syncwarp();
-                }
-                if (fail) {
-                    res.status = fail;
-                    break;
-                }
-                // IS:102-152: EOB present, a distance code present, neither tree over-subscribed nor
-                // incomplete (a single code may be incomplete)
-                int ok = 1;
-                {
-                    int any = 0, used = 0, left = 1, maxl = 0;
-                    int per[16];
-                    for (int b = 0; b < 16; ++b) per[b] = 0;
-                    for (int i = 0; i < hlit; ++i) {
-                        const int l = ws.lengths[i];
-                        if (l) {
-                            any = 1;
-                            ++used;
-                            per[l]++;
-                            maxl = max(maxl, l);
-                        }
-                    }
-                    if (!any || ws.lengths[256] == 0) ok = 0;
-                    for (int b = 1; b <= maxl && ok; ++b) {
-                        left = (left << 1) - per[b];
-                        if (left < 0) ok = 0;
-                    }
-                    if (ok && left != 0 && used > 1) ok = 0;
-                    int dany = 0, dused = 0, dmax = 0;
-                    for (int b = 0; b < 16; ++b) per[b] = 0;
-                    for (int i = 0; i < hdist; ++i) {
-                        const int l = ws.lengths[288 + i];
-                        if (l) {
-                            dany = 1;
-                            ++dused;
-                            per[l]++;
-                            dmax = max(dmax, l);
-                        }
-                    }
-                    if (!dany) ok = 0;
-                    left = 1;
-                    for (int b = 1; b <= dmax && ok; ++b) {
-                        left = (left << 1) - per[b];
-                        if (left < 0) ok = 0;
-                    }
-                    if (ok && left != 0 && dused > 1) ok = 0;
-                }
-                if (!ok) {
-                    res.status = ZK_DATA_ERROR;
-                    break;
-                }
-                build_decoder(ws.lit, ws.lengths, hlit, kLitLutBits, lane);
-                build_decoder(ws.dist, ws.lengths + 288, hdist, kDistLutBits, lane);
             }
             // symbol loop, IS:276-295 / IS:350-369
             int err = 0;
@@ -431,7 +456,8 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
                             err = ZK_BUF_ERROR;
                             break;
                         }
-                        if (lane == 0) sym[out_begin + produced] = (uint16_t)s;
+                        if (kTokens) sym[out_begin + units++] = (uint16_t)s;
+                        else if (lane == 0) sym[out_begin + produced] = (uint16_t)s;
                     }
                     ++produced;
                     continue;
@@ -480,9 +506,14 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
                         err = ZK_BUF_ERROR;
                         break;
                     }
-                    __syncwarp();
+                    if (kTokens) {
+                        sym[out_begin + units] = (uint16_t)(0x8000u | (uint32_t)length);
+                        sym[out_begin + units + 1] = (uint16_t)(dist - 1);
+                        units += 2;
+                    }
+                    coop_sync<kCoop>();
                     uint16_t *dst = sym + out_begin + produced;
-                    for (int i = lane; i < length; i += 32) {
+                    for (int i = kTokens ? length : lane; i < length; i += kStep) {
                         const int k = dist >= length ? i : i % dist;
                         const int64_t rel = (int64_t)produced - dist + k;  // position inside this chunk
                         uint16_t v;
@@ -490,7 +521,7 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
                         else v = (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
                         dst[i] = v;
                     }
-                    __syncwarp();
+                    coop_sync<kCoop>();
                 }
                 produced += (uint64_t)length;
             }
@@ -522,6 +553,7 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
         }
     }
     res.out_len = produced;
+    if (units_out) *units_out = units;
     return res;
 }
 
@@ -592,7 +624,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) decode_kernel(const uint8_t *_
     ChunkInfo &ci = chunks[c];
     if (!kWrite && ci.out_len != ~0ull) return;  // sized in an earlier round
     const uint64_t room = kWrite ? (ci.out_begin <= out_cap ? out_cap - ci.out_begin : 0) : ~0ull;
-    const ChunkResult r = decode_chunk<kWrite>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0, sym, ci.out_begin, room, lane);
+    const ChunkResult r = decode_chunk<kWrite, true>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0, sym, ci.out_begin, room, lane);
     if (lane == 0) {
         ci.status = r.status;
         if (!kWrite) {
@@ -761,6 +793,435 @@ __global__ void set_result_kernel(uint64_t *result, uint64_t a, uint64_t b, int6
     }
 }
 
+
+// ===== lane-per-block path (streams with many marker-delimited blocks, i.e. this engine's own output) ===========
+// The warp-per-chunk decoder above runs the same serial decode on all 32 lanes.  When a stream has thousands of
+// blocks of at most 32 KiB, every LANE decodes its own block instead: tables live in global memory (one WarpState
+// per block), the latency of a table lookup is hidden by the other lanes and warps, and a warp retires 32 symbols
+// per pass through the loop instead of one.  One decode pass: a block writes into its own slot of 32768 symbols, its
+// size is known afterwards, and a per-coarse-chunk step moves the slots to their final place while resolving the
+// references between the blocks of a coarse chunk; references that reach before the coarse chunk stay symbolic and
+// go through the same window chain as above.
+constexpr uint32_t kSlotSyms = 32768;   // symbols a block may decode to on this path
+constexpr uint32_t kCoarse = 8;         // blocks per coarse chunk
+constexpr uint32_t kPieceBytes = 16384; // marker search: bytes per CTA
+
+__device__ __forceinline__ bool marker_at(const uint8_t *in, uint64_t m, uint64_t p) {
+    // a block may start at p: the four bytes before it are 00 00 FF FF and BTYPE != 3
+    return p >= 6 && p < m && in[p - 1] == 0xFF && in[p - 2] == 0xFF && in[p - 3] == 0 && in[p - 4] == 0 &&
+           ((in[p] >> 1) & 3) != 3;
+}
+
+// pass 1 (write == false): markers per piece.  pass 2: their positions, in order.
+template <bool kWritePass>
+__global__ void __launch_bounds__(256) marker_compact_kernel(const uint8_t *__restrict__ in, uint64_t m,
+                                                             uint32_t *__restrict__ counts,
+                                                             const uint64_t *__restrict__ piece_offset,
+                                                             uint64_t *__restrict__ positions, uint64_t max_positions) {
+    __shared__ uint32_t warp_tot[8];
+    const uint64_t base = (uint64_t)blockIdx.x * kPieceBytes + (uint64_t)threadIdx.x * (kPieceBytes / 256);
+    uint64_t found = 0;  // bit k: marker at base + k (64 positions per thread)
+    for (int k = 0; k < (int)(kPieceBytes / 256); ++k)
+        if (marker_at(in, m, base + k)) found |= 1ull << k;
+    const uint32_t mine = (uint32_t)__popcll(found);
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) before += warp_tot[w];
+        total += warp_tot[w];
+    }
+    if (!kWritePass) {
+        if (threadIdx.x == 0) counts[blockIdx.x] = total;
+    } else {
+        uint64_t at = piece_offset[blockIdx.x] + before + incl - mine;
+        while (found) {
+            const int k = __ffsll((long long)found) - 1;
+            found &= found - 1;
+            if (at < max_positions) positions[at] = base + (uint64_t)k;
+            ++at;
+        }
+    }
+}
+
+// exclusive scan of the piece counts (single CTA); total to out_total[0]
+__global__ void __launch_bounds__(1024) marker_scan_kernel(const uint32_t *__restrict__ counts, uint32_t n,
+                                                           uint64_t *__restrict__ offsets, uint64_t *out_total) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < n ? counts[i] : 0;
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint64_t before = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += warp_sum[w];
+        const uint64_t start = carry + before + incl - v;
+        if (i < n) offsets[i] = start;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = start + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_total[0] = carry;
+}
+
+struct LaneChunk {
+    uint64_t in_begin, in_end;
+    uint64_t out_begin;
+    uint32_t out_len;
+    int32_t status;
+    uint64_t end_byte;
+    int32_t final_seen;
+    uint32_t units;  // 16-bit units of the block's token stream
+    uint64_t stored_src;  // a chunk that is one stored block: byte offset of its payload in the stream ...
+    uint32_t stored_len;  // ... and its length (then units == 0)
+    uint32_t pad;
+};
+
+__global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32_t num_markers, uint64_t m,
+                                  LaneChunk *__restrict__ lc) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > num_markers) return;
+    lc[k].in_begin = k == 0 ? 2 : positions[k - 1];
+    lc[k].in_end = k < num_markers ? positions[k] : m;
+    lc[k].out_begin = 0;
+    lc[k].out_len = 0;
+    lc[k].status = ZK_OK;
+    lc[k].end_byte = 0;
+    lc[k].final_seen = 0;
+    lc[k].units = 0;
+    lc[k].stored_src = 0;
+    lc[k].stored_len = 0;
+}
+
+// one LANE per block.  The loop is warp-uniform: in every pass each lane that is still busy either reads one block
+// header (and builds its tables) or decodes exactly one token, then the lanes meet again at the vote -- without that
+// the lanes of a warp would run their data-dependent loops one after the other.
+__global__ void __launch_bounds__(32) decode_lanes_kernel(const uint8_t *__restrict__ in, uint64_t m, LaneChunk *lc,
+                                                          uint32_t num_chunks, WarpState *tables, uint16_t *slots) {
+    const uint32_t k = blockIdx.x * 32 + threadIdx.x;
+    const bool live = k < num_chunks;
+    enum { kHeader = 0, kSymbols = 1, kDone = 2 };
+    int state = live ? kHeader : kDone;
+    int status = ZK_OK, final_seen = 0, last = 0;
+    uint64_t end_byte = 0;
+    uint32_t units = 0, produced = 0, stored_len = 0;
+    uint64_t stored_src = 0;
+    const uint32_t kk = live ? k : 0;
+    WarpState &ws = tables[kk];
+    uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
+    const uint64_t in_end = lc[kk].in_end;
+    BitReader br{in, m, lc[kk].in_begin, 0, 0};
+    int lit_need = 0, dist_need = 0;
+    while (__any_sync(0xFFFFFFFFu, state != kDone)) {
+        if (state == kHeader) {
+            br.refill();
+            if (br.held < 3) {
+                status = ZK_BUF_ERROR;
+                state = kDone;
+            } else {
+                last = (int)br.peek(1);
+                br.drop(1);
+                const int type = (int)br.peek(2);
+                br.drop(2);
+                if (type == 3) {
+                    status = ZK_DATA_ERROR;
+                    state = kDone;
+                } else if (type == 0) {
+                    br.drop(br.held & 7);
+                    br.refill();
+                    if (br.held < 32) {
+                        status = ZK_BUF_ERROR;
+                        state = kDone;
+                    } else {
+                        const uint32_t len = br.peek(16);
+                        br.drop(16);
+                        const uint32_t nlen = br.peek(16);
+                        br.drop(16);
+                        const uint64_t src0 = br.next - (uint64_t)(br.held >> 3);
+                        if (((~len) & 0xFFFFu) != nlen) {
+                            status = ZK_DATA_ERROR;
+                            state = kDone;
+                        } else if (src0 + len > m || produced + len > kSlotSyms || (len && (produced || stored_len))) {
+                            // truncated, more than this path's slot holds, or a chunk that mixes a stored payload with
+                            // other data (not made by this engine): the warp-per-chunk path takes the stream
+                            status = ZK_BUF_ERROR;
+                            state = kDone;
+                        } else {
+                            if (len) {  // the payload is copied by the expansion kernel, in parallel
+                                stored_src = src0;
+                                stored_len = len;
+                            }
+                            produced += len;
+                            br.next = src0 + len;
+                            br.hold = 0;
+                            br.held = 0;
+                            // block boundary (a stored block ends on a byte)
+                            if (last) {
+                                final_seen = 1;
+                                end_byte = br.next;
+                                state = kDone;
+                            } else if (br.next == in_end) {
+                                end_byte = br.next;
+                                state = kDone;
+                            } else if (br.next > in_end) {
+                                status = ZK_DATA_ERROR;
+                                state = kDone;
+                            }
+                        }
+                    }
+                } else {
+                    const int hrc = stored_len ? ZK_BUF_ERROR : parse_huffman_header<false>(ws, br, type, 0);
+                    if (hrc != ZK_OK) {
+                        status = hrc;
+                        state = kDone;
+                    } else {
+                        lit_need = ws.lit.max_len;
+                        dist_need = ws.dist.max_len;
+                        state = kSymbols;
+                    }
+                }
+            }
+        } else if (state == kSymbols) {
+            br.refill();
+            int sym = -1;
+            if (br.held < lit_need) status = ZK_BUF_ERROR;
+            else {
+                sym = decode_sym(ws.lit, br);
+                if (sym < 0) status = ZK_DATA_ERROR;
+            }
+            if (status != ZK_OK) {
+                state = kDone;
+            } else if (sym < 256) {
+                if (produced >= kSlotSyms) {
+                    status = ZK_BUF_ERROR;
+                    state = kDone;
+                } else {
+                    out[units++] = (uint16_t)sym;
+                    ++produced;
+                }
+            } else if (sym == 256) {
+                const uint64_t bits = br.bit_pos();
+                if (last) {
+                    final_seen = 1;
+                    end_byte = (bits + 7) >> 3;
+                    state = kDone;
+                } else if ((bits & 7) == 0 && (bits >> 3) == in_end) {
+                    end_byte = bits >> 3;
+                    state = kDone;
+                } else if ((bits >> 3) >= in_end) {
+                    status = ZK_DATA_ERROR;
+                    state = kDone;
+                } else {
+                    state = kHeader;
+                }
+            } else {
+                const int lcode = sym - 257;
+                int length = 0, dist = 0;
+                if (lcode > 28) status = ZK_DATA_ERROR;
+                if (status == ZK_OK) {
+                    br.refill();
+                    const int le = i_len_extra[lcode];
+                    if (br.held < le + dist_need) status = ZK_BUF_ERROR;
+                    else {
+                        length = i_len_base[lcode] + (int)br.peek(le);
+                        br.drop(le);
+                        const int dsym = decode_sym(ws.dist, br);
+                        if (dsym < 0 || dsym > 29) status = ZK_DATA_ERROR;
+                        else {
+                            br.refill();
+                            const int de = i_dist_extra[dsym];
+                            if (br.held < de) status = ZK_BUF_ERROR;
+                            else {
+                                dist = i_dist_base[dsym] + (int)br.peek(de);
+                                br.drop(de);
+                            }
+                        }
+                    }
+                }
+                if (status == ZK_OK && (dist > kWindow || (k == 0 && (uint32_t)dist > produced))) status = ZK_DATA_ERROR;
+                if (status == ZK_OK && produced + (uint32_t)length > kSlotSyms) status = ZK_BUF_ERROR;
+                if (status != ZK_OK) {
+                    state = kDone;
+                } else {
+                    out[units] = (uint16_t)(0x8000u | (uint32_t)length);
+                    out[units + 1] = (uint16_t)(dist - 1);
+                    units += 2;
+                    produced += (uint32_t)length;
+                }
+            }
+        }
+    }
+    if (live) {
+        lc[k].units = units;
+        lc[k].stored_src = stored_src;
+        lc[k].stored_len = stored_len;
+        lc[k].status = status;
+        lc[k].out_len = produced;
+        lc[k].end_byte = end_byte;
+        lc[k].final_seen = final_seen;
+    }
+}
+
+// Verify the blocks, prefix-sum their sizes, build the coarse chunk table for the window chain.
+// verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen
+__global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_t n, ChunkInfo *coarse,
+                                                          uint32_t *num_coarse, uint64_t *verdict, uint64_t cap) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    __shared__ int bad;
+    if (threadIdx.x == 0) {
+        carry = 0;
+        bad = 0;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint64_t v = 0;
+        if (i < n) {
+            v = lc[i].out_len;
+            const bool last = i + 1 == n;
+            // every block but the last must end exactly on the next one; the last must close the stream
+            if (lc[i].status != ZK_OK || (last ? !lc[i].final_seen : (lc[i].final_seen || lc[i].end_byte != lc[i].in_end))) bad = 1;
+        }
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint64_t before = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += warp_sum[w];
+        const uint64_t start = carry + before + incl - v;
+        if (i < n) lc[i].out_begin = start;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = start + v;
+        __syncthreads();
+    }
+    const uint64_t total = carry;
+    const uint32_t nc = (n + kCoarse - 1) / kCoarse;
+    for (uint32_t c = threadIdx.x; c < nc; c += 1024) {
+        const uint32_t first = c * kCoarse, lastb = min(n, first + kCoarse) - 1;
+        coarse[c].in_begin = lc[first].in_begin;
+        coarse[c].in_end = lc[lastb].in_end;
+        coarse[c].out_begin = lc[first].out_begin;
+        coarse[c].out_len = lc[lastb].out_begin + lc[lastb].out_len - lc[first].out_begin;
+        coarse[c].end_byte = lc[lastb].end_byte;
+        coarse[c].status = ZK_OK;
+        coarse[c].final_seen = lc[lastb].final_seen;
+        coarse[c].retries = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        num_coarse[0] = nc;
+        verdict[0] = nc;
+        verdict[1] = (!bad && total <= cap) ? 1 : 0;
+        verdict[2] = (uint64_t)(int64_t)ZK_OK;
+        verdict[3] = total;
+        verdict[4] = lc[n - 1].end_byte;
+        verdict[5] = (uint64_t)lc[n - 1].final_seen;
+    }
+}
+
+// Expand the token stream of every block into the dense symbol array, one WARP per block.  32 units per pass: a warp
+// scan of the token lengths gives every token its position, the literals of the pass are stored by their lanes, the
+// matches are done in stream order with all 32 lanes copying.  A source before the block becomes 0x8000 | (index into the
+// 32 KiB before the block); resolve_coarse_kernel re-bases those afterwards.  Many warps per SM hide the L2 round trip
+// of each copy.
+constexpr int kExpandWarps = 8;
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const uint8_t *__restrict__ in,
+                                                                        const LaneChunk *__restrict__ lc, uint32_t n,
+                                                                        const uint16_t *__restrict__ slots, uint16_t *dense) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t j = blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
+    if (j >= n) return;
+    uint16_t *out = dense + lc[j].out_begin;
+    if (lc[j].stored_len) {  // a stored block: its payload is the output
+        const uint8_t *src = in + lc[j].stored_src;
+        for (uint32_t i = lane; i < lc[j].stored_len; i += 32) out[i] = src[i];
+        return;
+    }
+    const uint32_t units = lc[j].units;
+    const uint16_t *tok = slots + (uint64_t)j * kSlotSyms;
+    uint32_t base_out = 0;
+    uint32_t carry_prev = 0;  // last unit of the previous pass
+    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        const uint32_t me = u < units ? tok[u] : 0u;
+        const uint32_t nxt = u + 1 < units ? tok[u + 1] : 0u;
+        uint32_t prevu = __shfl_up_sync(0xFFFFFFFFu, me, 1);
+        if (lane == 0) prevu = carry_prev;
+        carry_prev = __shfl_sync(0xFFFFFFFFu, me, 31);
+        const bool is_dist = (prevu & 0x8000u) != 0 && u < units;
+        const bool is_match = !is_dist && (me & 0x8000u) != 0 && u < units;
+        const bool is_lit = !is_dist && !is_match && u < units;
+        const uint32_t len = is_match ? (me & 0x7FFFu) : (is_lit ? 1u : 0u);
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t off = base_out + incl - len;
+        if (is_lit) out[off] = (uint16_t)me;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, is_match);
+        __syncwarp();
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t moff = __shfl_sync(0xFFFFFFFFu, off, src_lane);
+            const uint32_t mlen = __shfl_sync(0xFFFFFFFFu, len, src_lane);
+            const uint32_t mdist = __shfl_sync(0xFFFFFFFFu, nxt, src_lane) + 1u;
+            for (uint32_t i = lane; i < mlen; i += 32) {
+                const uint32_t kk = mdist >= mlen ? i : i % mdist;
+                const int32_t rel = (int32_t)moff - (int32_t)mdist + (int32_t)kk;  // position inside this block
+                const uint16_t v = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
+                out[moff + i] = v;
+            }
+            __syncwarp();
+        }
+        base_out += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+}
+
+// Re-base the symbolic references of one coarse chunk in place, block by block: a reference into an earlier block of the
+// same coarse chunk becomes that block's (already final) symbol, the others are re-expressed relative to the 32 KiB before
+// the coarse chunk, which is what the window chain resolves.
+__global__ void __launch_bounds__(1024) resolve_coarse_kernel(const LaneChunk *__restrict__ lc, uint32_t n, uint16_t *dense) {
+    const uint32_t first = blockIdx.x * kCoarse, end = min(n, first + kCoarse);
+    const int64_t coarse_begin = (int64_t)lc[first].out_begin;
+    for (uint32_t j = first + 1; j < end; ++j) {
+        const int64_t ob = (int64_t)lc[j].out_begin;
+        const uint32_t len = lc[j].out_len;
+        for (uint32_t i = threadIdx.x; i < len; i += 1024) {
+            const uint16_t s16 = dense[ob + i];
+            if (s16 & 0x8000u) {
+                const int64_t pos = ob - kWindow + (int64_t)(s16 & 0x7FFFu);
+                dense[ob + i] = pos >= coarse_begin ? __ldcg(dense + pos)
+                                                    : (uint16_t)(0x8000u | (uint32_t)(pos - (coarse_begin - kWindow)));
+            }
+        }
+        __syncthreads();  // the next block may refer to what was just written
+    }
+}
+
 }  // namespace
 
 int run_inflate(zk_ctx *c, const InflateJob &job) {
@@ -770,10 +1231,17 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     uint32_t span_shift = 9;  // >= 512-byte spans, at most ~4096 spans
     while ((m >> span_shift) > 4096) ++span_shift;
     const uint32_t num_spans = (uint32_t)(m >> span_shift) + 1;
-    const uint32_t max_chunks = num_spans + 1;
+    // lane-per-block path: blocks the scratch is reserved for (this engine's blocks decode to 32 KiB; a block needs
+    // at least ~16 bytes of stream); below a few hundred blocks the warp-per-chunk path is used anyway
+    uint64_t lane_blocks_reserved = tmin<uint64_t>(job.cap / 16384 + 1024, m / 16 + 1);
+    if (lane_blocks_reserved < 512) lane_blocks_reserved = 0;
+    const uint32_t pieces_reserved = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
+    const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2);
     c->arena.reset();
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
-                        (size_t)max_chunks * kWindow + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192;
+                        (size_t)max_chunks * kWindow + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
+                        (size_t)pieces_reserved * 12 + 1024 +
+                        (size_t)lane_blocks_reserved * (8 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
     int32_t *d_header = static_cast<int32_t *>(c->arena.take(256));
     uint32_t *d_cand = static_cast<uint32_t *>(c->arena.take((size_t)num_spans * 4));
@@ -799,53 +1267,100 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
         ZK_CUDA(cudaGetLastError());
         return ZK_OK;
     }
-    // ---- candidates -> chunks -------------------------------------------------------------------------
-    fill_u32_kernel<<<32, 256, 0, st>>>(d_cand, num_spans, kNoCand);
     ZK_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
-    {
-        const uint32_t grid = (uint32_t)tmin<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
-        marker_kernel<<<grid ? grid : 1, 256, 0, st>>>(job.d_in, m, span_shift, d_cand);
-    }
-    chunk_list_kernel<<<1, 32, 0, st>>>(d_cand, num_spans, 1, m, d_chunks, d_num, max_chunks);
-    c->launches += 3;
-    // ---- size pass, repeated while candidates turn out to be false ----------------------------------------
+    // ---- lane-per-block path: every marker is a block start -------------------------------------------------
+    bool lane_path_done = false;
     uint64_t verdict[6] = {0, 0, 0, 0, 0, 0};
-    for (int round = 0; round < 64; ++round) {
-        const uint32_t grid = (max_chunks + kInfWarps - 1) / kInfWarps;
-        {
-            ScopedTimer t(c, 4);
-            decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0);
-        }
-        plan_chunks_kernel<<<1, 32, 0, st>>>(d_chunks, d_num, d_verdict);
-        c->launches += 2;
-        ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
-        ZK_CUDA(cudaStreamSynchronize(st));
-        if (!verdict[1]) break;
-    }
-    const uint64_t total = verdict[3];
-    int status = (int)(int64_t)verdict[2];
-    if (total > job.cap) {
-        set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, 0, ZK_BUF_ERROR, 1);
-        c->launches++;
-        ZK_CUDA(cudaGetLastError());
-        return ZK_OK;
-    }
-    // ---- write pass, window chain, bytes ------------------------------------------------------------------
     {
-        const uint32_t nchunks = (uint32_t)verdict[0];
-        const uint32_t grid = (nchunks + kInfWarps - 1) / kInfWarps;
+        const uint32_t pieces = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
+        uint32_t *d_counts = static_cast<uint32_t *>(c->arena.take((size_t)pieces * 4 + 16));
+        uint64_t *d_piece_off = static_cast<uint64_t *>(c->arena.take((size_t)pieces * 8 + 16));
+        uint64_t *d_total = static_cast<uint64_t *>(c->arena.take(256));
+        if (d_counts && d_piece_off && d_total) {
+            marker_compact_kernel<false><<<pieces, 256, 0, st>>>(job.d_in, m, d_counts, nullptr, nullptr, 0);
+            marker_scan_kernel<<<1, 1024, 0, st>>>(d_counts, pieces, d_piece_off, d_total);
+            c->launches += 2;
+            uint64_t num_markers = 0;
+            ZK_CUDA(cudaMemcpyAsync(&num_markers, d_total, 8, cudaMemcpyDeviceToHost, st));
+            ZK_CUDA(cudaStreamSynchronize(st));
+            const uint64_t n = num_markers + 1;
+            // worth it from a few hundred blocks on, and only if the scratch was reserved for it
+            if (num_markers >= 256 && n <= lane_blocks_reserved) {
+                uint64_t *d_pos = static_cast<uint64_t *>(c->arena.take((size_t)n * 8));
+                LaneChunk *d_lc = static_cast<LaneChunk *>(c->arena.take((size_t)n * sizeof(LaneChunk)));
+                WarpState *d_tables = static_cast<WarpState *>(c->arena.take((size_t)n * sizeof(WarpState)));
+                uint16_t *d_slots = static_cast<uint16_t *>(c->arena.take((size_t)n * kSlotSyms * 2));
+                if (d_pos && d_lc && d_tables && d_slots) {
+                    marker_compact_kernel<true><<<pieces, 256, 0, st>>>(job.d_in, m, nullptr, d_piece_off, d_pos, num_markers);
+                    lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc);
+                    {
+                        ScopedTimer t(c, 4);
+                        decode_lanes_kernel<<<(uint32_t)((n + 31) / 32), 32, 0, st>>>(job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots);
+                    }
+                    plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap);
+                    c->launches += 4;
+                    ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
+                    ZK_CUDA(cudaStreamSynchronize(st));
+                    if (verdict[1] == 1 && verdict[0] <= max_chunks) {
+                        ScopedTimer t(c, 5);
+                        expand_blocks_kernel<<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
+                            job.d_in, d_lc, (uint32_t)n, d_slots, d_sym);
+                        resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
+                        c->launches += 2;
+                        lane_path_done = true;
+                    }
+                }
+            }
+        }
+    }
+    uint64_t total = verdict[3];
+    if (!lane_path_done) {
+        // ---- candidates -> chunks -------------------------------------------------------------------------
+        fill_u32_kernel<<<32, 256, 0, st>>>(d_cand, num_spans, kNoCand);
         {
+            const uint32_t grid = (uint32_t)tmin<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
+            marker_kernel<<<grid ? grid : 1, 256, 0, st>>>(job.d_in, m, span_shift, d_cand);
+        }
+        chunk_list_kernel<<<1, 32, 0, st>>>(d_cand, num_spans, 1, m, d_chunks, d_num, max_chunks);
+        c->launches += 3;
+        // ---- size pass, repeated while candidates turn out to be false ----------------------------------------
+        for (int round = 0; round < 64; ++round) {
+            const uint32_t grid = (max_chunks + kInfWarps - 1) / kInfWarps;
+            {
+                ScopedTimer t(c, 4);
+                decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0);
+            }
+            plan_chunks_kernel<<<1, 32, 0, st>>>(d_chunks, d_num, d_verdict);
+            c->launches += 2;
+            ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
+            ZK_CUDA(cudaStreamSynchronize(st));
+            if (!verdict[1]) break;
+        }
+        total = verdict[3];
+        if (total > job.cap) {
+            set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, 0, ZK_BUF_ERROR, 1);
+            c->launches++;
+            ZK_CUDA(cudaGetLastError());
+            return ZK_OK;
+        }
+        // ---- write pass -------------------------------------------------------------------------------------------
+        {
+            const uint32_t nchunks = (uint32_t)verdict[0];
+            const uint32_t grid = (nchunks + kInfWarps - 1) / kInfWarps;
             ScopedTimer t(c, 4);
             decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap);
+            c->launches += 1;
         }
+    }
+    // ---- window chain over the (coarse) chunks, symbols -> bytes ------------------------------------------------
+    {
         ScopedTimer t(c, 5);
         ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
         window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(d_chunks, d_num, d_sym, d_windows, d_flag);
         const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
         if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag);
-        c->launches += 3;
+        c->launches += 2;
     }
-    (void)status;
     int rc = launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
     if (rc != ZK_OK) return rc;
     finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result);

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
         } else {
             for (uint32_t i = threadIdx.x; i < raw; i += kPackThreads) d[i] = src[i];
         }
+        if (threadIdx.x < 5) d[raw + threadIdx.x] = threadIdx.x >= 3 ? 0xFF : 0x00;  // sync marker: 00 | 0000 | FFFF
         return;
     }
 
