@@ -103,6 +103,84 @@ struct BitReader {
     __device__ __forceinline__ uint64_t bit_pos() const { return next * 8 - (uint64_t)held; }
 };
 
+// Bit reader of the lane-per-block decoder.  A lane that waits for DRAM stalls its whole warp (the decode loop is
+// warp-uniform), so the stream is fetched in aligned 16-byte chunks TWO chunks ahead of their use: `q` holds the words
+// of the current chunk, `pre0`/`pre1` the next two (their loads are in flight while ~30 tokens are decoded), and one
+// L2 prefetch runs further ahead.  Bytes outside [base, base + len) read as zero; `next` may run past `len`, the caller
+// bounds it (any anomaly on this path sends the stream to the warp-per-chunk decoder, which owns the error codes).
+struct LaneReader {
+    const uint8_t *base;
+    uint64_t len;
+    uint64_t next;  // stream offset just past the bits in `hold`
+    uint64_t hold;
+    int held;
+    uint32_t q0, q1, q2, q3;
+    int qn;          // words left in q
+    uint4 pre0, pre1;
+    uintptr_t pre_at;  // address of the chunk in pre1
+
+    __device__ __forceinline__ uint4 fetch(uintptr_t a) const {
+        const uintptr_t lo = (uintptr_t)base, hi = lo + len;
+        if (a >= lo && a + 16 <= hi) return __ldg(reinterpret_cast<const uint4 *>(a));
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 16; ++i) {
+            const uintptr_t b = a + i;
+            if (b >= lo && b < hi) w[i >> 2] |= (uint32_t)(*reinterpret_cast<const uint8_t *>(b)) << ((i & 3) * 8);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ __forceinline__ void shift() {
+        q0 = q1;
+        q1 = q2;
+        q2 = q3;
+        if (--qn == 0) {
+            q0 = pre0.x, q1 = pre0.y, q2 = pre0.z, q3 = pre0.w;
+            qn = 4;
+            pre0 = pre1;
+            pre_at += 16;
+            pre1 = fetch(pre_at);
+            const uintptr_t far = pre_at + 1024;
+            if (far < (uintptr_t)base + len) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
+        }
+    }
+    __device__ __forceinline__ void seek(uint64_t pos) {
+        const uintptr_t p = (uintptr_t)base + pos;
+        const uintptr_t a = p & ~(uintptr_t)15;
+        const uint4 c = fetch(a);
+        pre0 = fetch(a + 16);
+        pre1 = fetch(a + 32);
+        pre_at = a + 32;
+        q0 = c.x, q1 = c.y, q2 = c.z, q3 = c.w;
+        qn = 4;
+        const int skip = (int)((p - a) >> 2);
+        for (int i = 0; i < skip; ++i) shift();
+        const int sub = (int)(p & 3u);
+        hold = 0;
+        held = 0;
+        next = pos;
+        if (sub) {
+            hold = (uint64_t)(q0 >> (8 * sub));
+            held = 32 - 8 * sub;
+            next = pos + (uint64_t)(4 - sub);
+            shift();
+        }
+    }
+    __device__ __forceinline__ void refill() {
+        if (held <= 32) {
+            hold |= (uint64_t)q0 << held;
+            held += 32;
+            next += 4;
+            shift();
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(hold & ((1ull << n) - 1ull)); }
+    __device__ __forceinline__ void drop(int n) {
+        hold >>= n;
+        held -= n;
+    }
+    __device__ __forceinline__ uint64_t bit_pos() const { return next * 8 - (uint64_t)held; }
+};
+
 __device__ __forceinline__ uint32_t rev_bits(uint32_t v, int len) { return __brev(v) >> (32 - len); }
 
 // Build a canonical decoder from code lengths (already validated: complete or single-code).
@@ -162,7 +240,8 @@ __device__ void build_decoder(Decoder &d, const uint8_t *lens, int n, int lut_bi
 
 // Decode one symbol; returns -1 for an invalid prefix.  `br` holds at least max_len bits or the end of
 // the stream has been reached (missing bits read as zero; the caller checks availability first).
-__device__ __forceinline__ int decode_sym(const Decoder &d, BitReader &br) {
+template <class Reader>
+__device__ __forceinline__ int decode_sym(const Decoder &d, Reader &br) {
     const uint32_t e = d.lut[br.peek(d.lut_bits)];
     if (e) {
         br.drop((int)(e >> 12));
@@ -183,8 +262,8 @@ __device__ __forceinline__ int decode_sym(const Decoder &d, BitReader &br) {
 
 // Read the header of a fixed (type 1) or dynamic (type 2) block and build both decoders.  Returns ZK_OK or the
 // code the reference reports (IS:299-348).
-template <bool kCoop>
-__device__ int parse_huffman_header(WarpState &ws, BitReader &br, int type, int lane) {
+template <bool kCoop, class Reader>
+__device__ int parse_huffman_header(WarpState &ws, Reader &br, int type, int lane) {
     constexpr int kStep = kCoop ? 32 : 1;
     if (type == 1) {  // IS:154-173
         for (int i = lane; i < 288; i += kStep) ws.lengths[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
@@ -679,48 +758,113 @@ __global__ void plan_chunks_kernel(ChunkInfo *chunks, uint32_t *num_chunks, uint
     verdict[5] = w ? (uint64_t)chunks[w - 1].final_seen : 0;
 }
 
-// Resolve the last 32 KiB of every chunk in order.  windows[c][i] = byte at (chunk c's end - 32768 + i).
-// One CTA walks the chunks; the previous window lives in shared memory (ping-pong), so the dependent lookup of a
-// symbolic reference is a shared load, and the tail symbols of a chunk are fetched with independent loads.
-__global__ void __launch_bounds__(1024) window_chain_kernel(const ChunkInfo *chunks, const uint32_t *num_chunks,
-                                                            const uint16_t *__restrict__ sym, uint8_t *windows,
-                                                            uint32_t *error_flag) {
-    extern __shared__ __align__(16) uint8_t wsm[];  // two windows of 32 KiB
-    const uint32_t n = num_chunks[0];
-    constexpr int kPer = kWindow / 1024;  // window slots per thread, interleaved: thread t owns t, t+1024, ...
-    for (uint32_t c = 0; c < n; ++c) {
-        const uint64_t begin = chunks[c].out_begin, len = chunks[c].out_len;
-        const uint8_t *prev = wsm + ((c + 1) & 1) * kWindow;
-        uint8_t *cur = wsm + (c & 1) * kWindow;
-        const int64_t pos0 = (int64_t)(begin + len) - kWindow + threadIdx.x;
-        uint16_t sy[kPer];
+// Resolve the last 32 KiB of every chunk: windows[c][i] = byte at (chunk c's end - 32768 + i).
+// The tail of chunk c is a MAP over the window before it: slot i is a byte, or 0x8000 | (index into the window of
+// chunk c-1).  Maps compose (apply the map of c-1 to the references of c), and composition is associative, so the
+// chain over thousands of chunks is a two-level scan instead of one serial walk:
+//   A. window_compose_kernel: chunks are cut into groups of `group` consecutive chunks; one CTA per group composes
+//      its maps in order, so that every map refers to the window BEFORE THE GROUP.  The running map lives in shared
+//      memory (ping-pong), the symbols of the next chunk are fetched while the current one is composed.
+//   B. window_chain_kernel: one CTA resolves the last window of every group in stream order (n / group steps).
+//   C. window_apply_kernel: every other window = its composed map applied to its group's entry window, in parallel.
+constexpr int kPerThread = kWindow / 1024;  // window slots per thread, interleaved: thread t owns t, t+1024, ...
+
+// slot (threadIdx.x + k*1024) of the tail map of chunk c, relative to the window of chunk c-1
+__device__ __forceinline__ void load_tail_map(const ChunkInfo *chunks, uint32_t c, const uint16_t *__restrict__ sym,
+                                              uint16_t (&sy)[kPerThread], uint32_t *error_flag) {
+    const uint64_t begin = chunks[c].out_begin, len = chunks[c].out_len;
+    const int64_t pos0 = (int64_t)(begin + len) - kWindow + threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int64_t pos = pos0 + k * 1024;
-            sy[k] = pos >= (int64_t)begin ? sym[pos] : (uint16_t)0xFFFFu;  // 0xFFFF: not in this chunk
+    for (int k = 0; k < kPerThread; ++k) {
+        const int64_t pos = pos0 + k * 1024;
+        uint16_t s = 0;
+        if (pos >= (int64_t)begin) {
+            s = sym[pos];
+            if ((s & 0x8000u) && (c == 0 || (int64_t)begin - kWindow + (int64_t)(s & 0x7FFFu) < 0)) {
+                atomicExch(error_flag, 1u);  // distance reaches before the start of the output (IS:287-291)
+                s = 0;
+            }
+        } else if (c > 0 && pos >= 0) {
+            s = (uint16_t)(0x8000u | (uint32_t)((int64_t)kWindow - ((int64_t)begin - pos)));  // the chunk is shorter than the window
         }
+        sy[k] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024) window_compose_kernel(const ChunkInfo *chunks, uint32_t n, uint32_t group,
+                                                              const uint16_t *__restrict__ sym, uint16_t *maps,
+                                                              uint32_t *error_flag) {
+    extern __shared__ __align__(16) uint16_t msm[];  // two maps of 32768 slots
+    const uint32_t c0 = blockIdx.x * group, c1 = min(n, c0 + group);
+    uint16_t sy[kPerThread], nx[kPerThread];
+    load_tail_map(chunks, c0, sym, sy, error_flag);
+    for (uint32_t c = c0; c < c1; ++c) {
+        if (c + 1 < c1) load_tail_map(chunks, c + 1, sym, nx, error_flag);  // independent of the composition below
+        const uint16_t *prev = msm + ((c + 1) & 1) * kWindow;
+        uint16_t *cur = msm + (c & 1) * kWindow;
+        uint16_t *glob = maps + (uint64_t)c * kWindow;
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            const int i = threadIdx.x + k * 1024;
+            uint16_t s = sy[k];
+            if (c > c0 && (s & 0x8000u)) s = prev[s & 0x7FFFu];
+            cur[i] = s;
+            glob[i] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) sy[k] = nx[k];
+    }
+}
+
+__global__ void __launch_bounds__(1024) window_chain_kernel(uint32_t n, uint32_t group, const uint16_t *__restrict__ maps,
+                                                            uint8_t *windows) {
+    extern __shared__ __align__(16) uint8_t wsm[];  // two windows of 32 KiB
+    const uint32_t groups = (n + group - 1) / group;
+    uint16_t sy[kPerThread], nx[kPerThread];
+    {
+        const uint16_t *mp = maps + (uint64_t)(min(n, group) - 1) * kWindow + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) sy[k] = mp[k * 1024];
+    }
+    for (uint32_t g = 0; g < groups; ++g) {
+        const uint32_t c = min(n, (g + 1) * group) - 1;  // last chunk of the group
+        if (g + 1 < groups) {
+            const uint16_t *mp = maps + (uint64_t)(min(n, (g + 2) * group) - 1) * kWindow + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) nx[k] = mp[k * 1024];
+        }
+        const uint8_t *prev = wsm + ((g + 1) & 1) * kWindow;
+        uint8_t *cur = wsm + (g & 1) * kWindow;
         uint8_t *glob = windows + (uint64_t)c * kWindow;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
+        for (int k = 0; k < kPerThread; ++k) {
             const int i = threadIdx.x + k * 1024;
-            const int64_t pos = pos0 + k * 1024;
-            uint8_t v = 0;
-            const uint16_t s16 = sy[k];
-            if (pos >= (int64_t)begin) {
-                if (s16 & 0x8000u) {
-                    const uint32_t idx = s16 & 0x7FFFu;
-                    if (c == 0 || (int64_t)begin - kWindow + (int64_t)idx < 0) atomicExch(error_flag, 1u);
-                    else v = prev[idx];
-                } else {
-                    v = (uint8_t)s16;
-                }
-            } else if (c > 0 && pos >= 0) {
-                v = prev[(int64_t)kWindow - ((int64_t)begin - pos)];
-            }
+            const uint16_t s = sy[k];
+            // group 0 has no entry window: its references were reported by window_compose_kernel
+            const uint8_t v = (s & 0x8000u) ? (g ? prev[s & 0x7FFFu] : (uint8_t)0) : (uint8_t)s;
             cur[i] = v;
             glob[i] = v;
         }
         __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) sy[k] = nx[k];
+    }
+}
+
+__global__ void __launch_bounds__(1024) window_apply_kernel(uint32_t n, uint32_t group, const uint16_t *__restrict__ maps,
+                                                            uint8_t *windows) {
+    const uint32_t c = blockIdx.x;
+    const uint32_t g = c / group;
+    if (c >= n || c == min(n, (g + 1) * group) - 1) return;  // group-last windows come from window_chain_kernel
+    const uint8_t *entry = g ? windows + (uint64_t)(g * group - 1) * kWindow : nullptr;
+    const uint16_t *mp = maps + (uint64_t)c * kWindow;
+    uint8_t *glob = windows + (uint64_t)c * kWindow;
+#pragma unroll 8
+    for (int k = 0; k < kPerThread; ++k) {
+        const int i = threadIdx.x + k * 1024;
+        const uint16_t s = mp[i];
+        glob[i] = (s & 0x8000u) ? (entry ? entry[s & 0x7FFFu] : (uint8_t)0) : (uint8_t)s;
     }
 }
 
@@ -912,29 +1056,49 @@ __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32
 // one LANE per block.  The loop is warp-uniform: in every pass each lane that is still busy either reads one block
 // header (and builds its tables) or decodes exactly one token, then the lanes meet again at the vote -- without that
 // the lanes of a warp would run their data-dependent loops one after the other.
-__global__ void __launch_bounds__(32) decode_lanes_kernel(const uint8_t *__restrict__ in, uint64_t m, LaneChunk *lc,
-                                                          uint32_t num_chunks, WarpState *tables, uint16_t *slots) {
-    const uint32_t k = blockIdx.x * 32 + threadIdx.x;
-    const bool live = k < num_chunks;
-    enum { kHeader = 0, kSymbols = 1, kDone = 2 };
-    int state = live ? kHeader : kDone;
-    int status = ZK_OK, final_seen = 0, last = 0;
-    uint64_t end_byte = 0;
-    uint32_t units = 0, produced = 0, stored_len = 0;
-    uint64_t stored_src = 0;
-    const uint32_t kk = live ? k : 0;
-    WarpState &ws = tables[kk];
-    uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
-    const uint64_t in_end = lc[kk].in_end;
-    BitReader br{in, m, lc[kk].in_begin, 0, 0};
-    int lit_need = 0, dist_need = 0;
-    while (__any_sync(0xFFFFFFFFu, state != kDone)) {
-        if (state == kHeader) {
-            br.refill();
-            if (br.held < 3) {
-                status = ZK_BUF_ERROR;
+constexpr int kLaneLitBits = 9;   // literal/length codes up to 9 bits and ...
+constexpr int kLaneDistBits = 6;  // ... distance codes up to 6 bits decode from shared memory
+constexpr int kLaneWarps = 6;     // 6 x 36 KiB of tables: one persistent CTA per SM, 192 blocks in flight on it
+constexpr int kLaneWarpSmem = ((1 << kLaneLitBits) + (1 << kLaneDistBits)) * 32 * 2;
+__global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const uint8_t *__restrict__ in, uint64_t m,
+                                                                          LaneChunk *lc, uint32_t num_chunks,
+                                                                          WarpState *tables, uint16_t *slots,
+                                                                          uint32_t *next_task) {
+    // every lane's short-code tables, interleaved so that the lanes of a warp fall into different banks: entry i of
+    // lane l sits at [i * 32 + l].  Longer codes go through the lane's WarpState in global memory.
+    extern __shared__ __align__(16) uint16_t s_lut_all[];
+    uint16_t *s_lit = s_lut_all + (threadIdx.x >> 5) * (kLaneWarpSmem / 2);
+    uint16_t *s_dist = s_lit + (1 << kLaneLitBits) * 32;
+    const int lane = threadIdx.x & 31;
+    const uint32_t num_tasks = (num_chunks + 31) / 32;
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(next_task, 1u);
+        task = __shfl_sync(0xFFFFFFFFu, task, 0);
+        if (task >= num_tasks) break;
+        const uint32_t k = task * 32 + lane;
+        const bool live = k < num_chunks;
+        enum { kHeader = 0, kSymbols = 1, kDone = 2 };
+        int state = live ? kHeader : kDone;
+        int status = ZK_OK, final_seen = 0, last = 0;
+        uint64_t end_byte = 0;
+        uint32_t units = 0, produced = 0, stored_len = 0;
+        uint64_t stored_src = 0;
+        const uint32_t kk = live ? k : 0;
+        WarpState &ws = tables[kk];
+        uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
+        const uint64_t in_end = lc[kk].in_end;
+        LaneReader br;
+        br.base = in;
+        br.len = m;
+        br.seek(lc[kk].in_begin);
+        while (__any_sync(0xFFFFFFFFu, state != kDone)) {
+            if (state != kDone && br.next > in_end + 64) {  // ran away from its chunk: not a block of this path
+                status = ZK_DATA_ERROR;
                 state = kDone;
-            } else {
+            }
+            if (state == kHeader) {
+                br.refill();
                 last = (int)br.peek(1);
                 br.drop(1);
                 const int type = (int)br.peek(2);
@@ -945,44 +1109,39 @@ __global__ void __launch_bounds__(32) decode_lanes_kernel(const uint8_t *__restr
                 } else if (type == 0) {
                     br.drop(br.held & 7);
                     br.refill();
-                    if (br.held < 32) {
+                    const uint32_t len = br.peek(16);
+                    br.drop(16);
+                    const uint32_t nlen = br.peek(16);
+                    br.drop(16);
+                    const uint64_t src0 = br.next - (uint64_t)(br.held >> 3);
+                    if (((~len) & 0xFFFFu) != nlen) {
+                        status = ZK_DATA_ERROR;
+                        state = kDone;
+                    } else if (src0 + len > m || produced + len > kSlotSyms || (len && (produced || stored_len))) {
+                        // truncated, more than this path's slot holds, or a chunk that mixes a stored payload with
+                        // other data (not made by this engine): the warp-per-chunk path takes the stream
                         status = ZK_BUF_ERROR;
                         state = kDone;
                     } else {
-                        const uint32_t len = br.peek(16);
-                        br.drop(16);
-                        const uint32_t nlen = br.peek(16);
-                        br.drop(16);
-                        const uint64_t src0 = br.next - (uint64_t)(br.held >> 3);
-                        if (((~len) & 0xFFFFu) != nlen) {
+                        if (len) {  // the payload is copied by the expansion kernel, in parallel
+                            stored_src = src0;
+                            stored_len = len;
+                        }
+                        produced += len;
+                        const uint64_t at = src0 + len;
+                        // block boundary (a stored block ends on a byte)
+                        if (last) {
+                            final_seen = 1;
+                            end_byte = at;
+                            state = kDone;
+                        } else if (at == in_end) {
+                            end_byte = at;
+                            state = kDone;
+                        } else if (at > in_end) {
                             status = ZK_DATA_ERROR;
                             state = kDone;
-                        } else if (src0 + len > m || produced + len > kSlotSyms || (len && (produced || stored_len))) {
-                            // truncated, more than this path's slot holds, or a chunk that mixes a stored payload with
-                            // other data (not made by this engine): the warp-per-chunk path takes the stream
-                            status = ZK_BUF_ERROR;
-                            state = kDone;
                         } else {
-                            if (len) {  // the payload is copied by the expansion kernel, in parallel
-                                stored_src = src0;
-                                stored_len = len;
-                            }
-                            produced += len;
-                            br.next = src0 + len;
-                            br.hold = 0;
-                            br.held = 0;
-                            // block boundary (a stored block ends on a byte)
-                            if (last) {
-                                final_seen = 1;
-                                end_byte = br.next;
-                                state = kDone;
-                            } else if (br.next == in_end) {
-                                end_byte = br.next;
-                                state = kDone;
-                            } else if (br.next > in_end) {
-                                status = ZK_DATA_ERROR;
-                                state = kDone;
-                            }
+                            br.seek(at);
                         }
                     }
                 } else {
@@ -991,97 +1150,117 @@ __global__ void __launch_bounds__(32) decode_lanes_kernel(const uint8_t *__restr
                         status = hrc;
                         state = kDone;
                     } else {
-                        lit_need = ws.lit.max_len;
-                        dist_need = ws.dist.max_len;
+                        // short codes into this lane's columns of the shared tables (the global tables repeat with
+                        // the short period for codes that fit it; a longer code leaves its slot empty)
+                        for (int i = 0; i < (1 << kLaneLitBits); ++i) {
+                            const uint16_t e = ws.lit.lut[i];
+                            s_lit[i * 32 + lane] = (e >> 12) <= kLaneLitBits ? e : (uint16_t)0;
+                        }
+                        for (int i = 0; i < (1 << kLaneDistBits); ++i) {
+                            const uint16_t e = ws.dist.lut[i];
+                            s_dist[i * 32 + lane] = (e >> 12) <= kLaneDistBits ? e : (uint16_t)0;
+                        }
                         state = kSymbols;
                     }
                 }
-            }
-        } else if (state == kSymbols) {
-            br.refill();
-            int sym = -1;
-            if (br.held < lit_need) status = ZK_BUF_ERROR;
-            else {
-                sym = decode_sym(ws.lit, br);
-                if (sym < 0) status = ZK_DATA_ERROR;
-            }
-            if (status != ZK_OK) {
-                state = kDone;
-            } else if (sym < 256) {
-                if (produced >= kSlotSyms) {
-                    status = ZK_BUF_ERROR;
-                    state = kDone;
-                } else {
-                    out[units++] = (uint16_t)sym;
-                    ++produced;
-                }
-            } else if (sym == 256) {
-                const uint64_t bits = br.bit_pos();
-                if (last) {
-                    final_seen = 1;
-                    end_byte = (bits + 7) >> 3;
-                    state = kDone;
-                } else if ((bits & 7) == 0 && (bits >> 3) == in_end) {
-                    end_byte = bits >> 3;
-                    state = kDone;
-                } else if ((bits >> 3) >= in_end) {
-                    status = ZK_DATA_ERROR;
-                    state = kDone;
-                } else {
-                    state = kHeader;
-                }
-            } else {
-                const int lcode = sym - 257;
-                int length = 0, dist = 0;
-                if (lcode > 28) status = ZK_DATA_ERROR;
-                if (status == ZK_OK) {
-                    br.refill();
-                    const int le = i_len_extra[lcode];
-                    if (br.held < le + dist_need) status = ZK_BUF_ERROR;
-                    else {
-                        length = i_len_base[lcode] + (int)br.peek(le);
-                        br.drop(le);
-                        const int dsym = decode_sym(ws.dist, br);
-                        if (dsym < 0 || dsym > 29) status = ZK_DATA_ERROR;
-                        else {
-                            br.refill();
-                            const int de = i_dist_extra[dsym];
-                            if (br.held < de) status = ZK_BUF_ERROR;
-                            else {
-                                dist = i_dist_base[dsym] + (int)br.peek(de);
-                                br.drop(de);
-                            }
-                        }
+            } else if (state == kSymbols) {
+                br.refill();
+                int sym;
+                {
+                    const uint32_t e = s_lit[br.peek(kLaneLitBits) * 32 + lane];
+                    if (e) {
+                        br.drop((int)(e >> 12));
+                        sym = (int)(e & 0x0FFFu);
+                    } else {
+                        sym = decode_sym(ws.lit, br);
                     }
                 }
-                if (status == ZK_OK && (dist > kWindow || (k == 0 && (uint32_t)dist > produced))) status = ZK_DATA_ERROR;
-                if (status == ZK_OK && produced + (uint32_t)length > kSlotSyms) status = ZK_BUF_ERROR;
-                if (status != ZK_OK) {
+                if (sym < 0) {
+                    status = ZK_DATA_ERROR;
                     state = kDone;
+                } else if (sym < 256) {
+                    if (produced >= kSlotSyms) {
+                        status = ZK_BUF_ERROR;
+                        state = kDone;
+                    } else {
+                        out[units++] = (uint16_t)sym;
+                        ++produced;
+                    }
+                } else if (sym == 256) {
+                    const uint64_t bits = br.bit_pos();
+                    if (last) {
+                        final_seen = 1;
+                        end_byte = (bits + 7) >> 3;
+                        state = kDone;
+                    } else if ((bits & 7) == 0 && (bits >> 3) == in_end) {
+                        end_byte = bits >> 3;
+                        state = kDone;
+                    } else if ((bits >> 3) >= in_end) {
+                        status = ZK_DATA_ERROR;
+                        state = kDone;
+                    } else {
+                        state = kHeader;
+                    }
                 } else {
-                    out[units] = (uint16_t)(0x8000u | (uint32_t)length);
-                    out[units + 1] = (uint16_t)(dist - 1);
-                    units += 2;
-                    produced += (uint32_t)length;
+                    const int lcode = sym - 257;
+                    int length = 0, dist = 0;
+                    if (lcode > 28) status = ZK_DATA_ERROR;
+                    if (status == ZK_OK) {
+                        // one refill covers length extra (5) + distance code (15) + distance extra (13) = 33 bits
+                        br.refill();
+                        // RFC 1951 3.2.5 in arithmetic (a table indexed per lane would serialise in the constant cache)
+                        const int le = (lcode < 8 || lcode == 28) ? 0 : (lcode >> 2) - 1;
+                        const int lbase = lcode < 8 ? 3 + lcode : lcode == 28 ? 258 : 3 + ((4 + (lcode & 3)) << le);
+                        length = lbase + (int)br.peek(le);
+                        br.drop(le);
+                        int dsym;
+                        const uint32_t e = s_dist[br.peek(kLaneDistBits) * 32 + lane];
+                        if (e) {
+                            br.drop((int)(e >> 12));
+                            dsym = (int)(e & 0x0FFFu);
+                        } else {
+                            dsym = decode_sym(ws.dist, br);
+                        }
+                        if (dsym < 0 || dsym > 29) status = ZK_DATA_ERROR;
+                        else {
+                            const int de = dsym < 4 ? 0 : (dsym >> 1) - 1;
+                            const int dbase = dsym < 4 ? 1 + dsym : 1 + ((2 + (dsym & 1)) << de);
+                            dist = dbase + (int)br.peek(de);
+                            br.drop(de);
+                        }
+                    }
+                    if (status == ZK_OK && (dist > kWindow || (k == 0 && (uint32_t)dist > produced))) status = ZK_DATA_ERROR;
+                    if (status == ZK_OK && produced + (uint32_t)length > kSlotSyms) status = ZK_BUF_ERROR;
+                    if (status != ZK_OK) {
+                        state = kDone;
+                    } else {
+                        out[units] = (uint16_t)(0x8000u | (uint32_t)length);
+                        out[units + 1] = (uint16_t)(dist - 1);
+                        units += 2;
+                        produced += (uint32_t)length;
+                    }
                 }
             }
         }
-    }
-    if (live) {
-        lc[k].units = units;
-        lc[k].stored_src = stored_src;
-        lc[k].stored_len = stored_len;
-        lc[k].status = status;
-        lc[k].out_len = produced;
-        lc[k].end_byte = end_byte;
-        lc[k].final_seen = final_seen;
+        // a block that used bits past the end of the stream is not a block of this path
+        if (live && status == ZK_OK && end_byte > m) status = ZK_BUF_ERROR;
+        if (live) {
+            lc[k].units = units;
+            lc[k].stored_src = stored_src;
+            lc[k].stored_len = stored_len;
+            lc[k].status = status;
+            lc[k].out_len = produced;
+            lc[k].end_byte = end_byte;
+            lc[k].final_seen = final_seen;
+        }
+        __syncwarp();
     }
 }
 
 // Verify the blocks, prefix-sum their sizes, build the coarse chunk table for the window chain.
 // verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen
 __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_t n, ChunkInfo *coarse,
-                                                          uint32_t *num_coarse, uint64_t *verdict, uint64_t cap) {
+                                                          uint32_t *num_coarse, uint64_t *verdict, uint64_t cap, uint64_t m) {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
     __shared__ int bad;
@@ -1098,6 +1277,8 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
             const bool last = i + 1 == n;
             // every block but the last must end exactly on the next one; the last must close the stream
             if (lc[i].status != ZK_OK || (last ? !lc[i].final_seen : (lc[i].final_seen || lc[i].end_byte != lc[i].in_end))) bad = 1;
+            // a stream cut inside its trailer: the warp-per-chunk decoder reports what the reference reports (BR:48-57)
+            if (last && lc[i].end_byte + 4 > m) bad = 1;
         }
         uint64_t incl = v;
 #pragma unroll
@@ -1239,7 +1420,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2);
     c->arena.reset();
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
-                        (size_t)max_chunks * kWindow + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
+                        (size_t)max_chunks * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
                         (size_t)lane_blocks_reserved * (8 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
@@ -1252,6 +1433,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     uint32_t *d_adler = static_cast<uint32_t *>(c->arena.take(256));
     void *d_partials = c->arena.take(adler_partials_bytes(job.cap));
     uint8_t *d_windows = static_cast<uint8_t *>(c->arena.take((size_t)max_chunks * kWindow));
+    uint16_t *d_maps = static_cast<uint16_t *>(c->arena.take((size_t)max_chunks * kWindow * 2));
     uint16_t *d_sym = static_cast<uint16_t *>(c->arena.take((job.cap + 64) * 2));
 
     // ---- header -------------------------------------------------------------------------------------
@@ -1295,9 +1477,15 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc);
                     {
                         ScopedTimer t(c, 4);
-                        decode_lanes_kernel<<<(uint32_t)((n + 31) / 32), 32, 0, st>>>(job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots);
+                        const int lane_smem = kLaneWarps * kLaneWarpSmem;
+                        const uint32_t tasks = (uint32_t)((n + 31) / 32);
+                        const uint32_t grid = tmin<uint32_t>((tasks + kLaneWarps - 1) / kLaneWarps, (uint32_t)c->sm_count);
+                        ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
+                        ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
+                        decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
+                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total));
                     }
-                    plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap);
+                    plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m);
                     c->launches += 4;
                     ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
                     ZK_CUDA(cudaStreamSynchronize(st));
@@ -1355,8 +1543,18 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     // ---- window chain over the (coarse) chunks, symbols -> bytes ------------------------------------------------
     {
         ScopedTimer t(c, 5);
-        ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
-        window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(d_chunks, d_num, d_sym, d_windows, d_flag);
+        const uint32_t nch = (uint32_t)verdict[0];
+        if (nch) {
+            uint32_t group = 1;  // ~sqrt(n): phase A takes `group` dependent steps, phase B n / group
+            while (group * group < nch) group <<= 1;
+            const uint32_t groups = (nch + group - 1) / group;
+            ZK_CUDA(cudaFuncSetAttribute(window_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWindow));
+            ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
+            window_compose_kernel<<<groups, 1024, 4 * kWindow, st>>>(d_chunks, nch, group, d_sym, d_maps, d_flag);
+            window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(nch, group, d_maps, d_windows);
+            window_apply_kernel<<<nch, 1024, 0, st>>>(nch, group, d_maps, d_windows);
+            c->launches += 2;
+        }
         const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
         if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag);
         c->launches += 2;
