@@ -103,83 +103,87 @@ struct BitReader {
     __device__ __forceinline__ uint64_t bit_pos() const { return next * 8 - (uint64_t)held; }
 };
 
-// Bit reader of the lane-per-block decoder.  A lane that waits for DRAM stalls its whole warp (the decode loop is
-// warp-uniform), so the stream is fetched in aligned 16-byte chunks TWO chunks ahead of their use: `q` holds the words
-// of the current chunk, `pre0`/`pre1` the next two (their loads are in flight while ~30 tokens are decoded), and one
-// L2 prefetch runs further ahead.  Bytes outside [base, base + len) read as zero; `next` may run past `len`, the caller
-// bounds it (any anomaly on this path sends the stream to the warp-per-chunk decoder, which owns the error codes).
-struct LaneReader {
-    const uint8_t *base;
-    uint64_t len;
-    uint64_t next;  // stream offset just past the bits in `hold`
+// Bit reader of the lane-per-block decoder.  The decode loop is warp-uniform, so a lane that branches away to refill,
+// or waits for DRAM, stalls 31 others.  The refill is therefore straight-line predicated code, and the stream reaches
+// the lane through a ring of kRing 32-bit words in shared memory filled by cp.async: the word requested at one refill
+// is consumed kRing - 1 refills (~30 tokens) later, and no register waits on a load in between (in-order issue would
+// stall the warp at the first instruction that touches such a register).  An L2 prefetch runs half a KiB further on.
+// Words that are not entirely inside [base, base + len) read as zero in the hot path (that can only be the tail of the
+// Adler trailer); seek_bits() reads edge words byte by byte.
+constexpr int kRing = 8;
+struct FastReader {
     uint64_t hold;
     int held;
-    uint32_t q0, q1, q2, q3;
-    int qn;          // words left in q
-    uint4 pre0, pre1;
-    uintptr_t pre_at;  // address of the chunk in pre1
+    uint32_t w0;       // the stream word after the bits in `hold` (= ring slot rd)
+    uint32_t rd;       // ring slot of w0
+    uint32_t ring;     // shared-space address of this lane's slot 0; slot j at ring + j * 128
+    uintptr_t at;      // address of the next word to request (kRing words after w0)
+    uintptr_t lo, hi;  // [base, base + len)
 
-    __device__ __forceinline__ uint4 fetch(uintptr_t a) const {
-        const uintptr_t lo = (uintptr_t)base, hi = lo + len;
-        if (a >= lo && a + 16 <= hi) return __ldg(reinterpret_cast<const uint4 *>(a));
-        uint32_t w[4] = {0, 0, 0, 0};
-        for (int i = 0; i < 16; ++i) {
+    __device__ __forceinline__ uint32_t fetch_edge(uintptr_t a) const {
+        if (a >= lo && a + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t *>(a));
+        uint32_t w = 0;
+        for (int i = 0; i < 4; ++i) {
             const uintptr_t b = a + i;
-            if (b >= lo && b < hi) w[i >> 2] |= (uint32_t)(*reinterpret_cast<const uint8_t *>(b)) << ((i & 3) * 8);
+            if (b >= lo && b < hi) w |= (uint32_t)(*reinterpret_cast<const uint8_t *>(b)) << (i * 8);
         }
-        return make_uint4(w[0], w[1], w[2], w[3]);
+        return w;
     }
-    __device__ __forceinline__ void shift() {
-        q0 = q1;
-        q1 = q2;
-        q2 = q3;
-        if (--qn == 0) {
-            q0 = pre0.x, q1 = pre0.y, q2 = pre0.z, q3 = pre0.w;
-            qn = 4;
-            pre0 = pre1;
-            pre_at += 16;
-            pre1 = fetch(pre_at);
-            const uintptr_t far = pre_at + 1024;
-            if (far < (uintptr_t)base + len) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
+    __device__ __forceinline__ void seek_bits(uint64_t bitpos) {
+        asm volatile("cp.async.wait_all;" ::: "memory");  // nothing may land in the ring after it is rewritten
+        const uintptr_t p = lo + (bitpos >> 3);
+        const uintptr_t a = p & ~(uintptr_t)3;
+        const int sub = (int)(p & 3u) * 8 + (int)(bitpos & 7u);
+        hold = (uint64_t)(fetch_edge(a) >> sub);
+        held = 32 - sub;
+        for (int j = 0; j < kRing; ++j) {
+            const uint32_t w = fetch_edge(a + 4 + 4 * j);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring + j * 128), "r"(w) : "memory");
+            if (j == 0) w0 = w;
         }
+        rd = 0;
+        at = a + 4 + 4 * kRing;
     }
-    __device__ __forceinline__ void seek(uint64_t pos) {
-        const uintptr_t p = (uintptr_t)base + pos;
-        const uintptr_t a = p & ~(uintptr_t)15;
-        const uint4 c = fetch(a);
-        pre0 = fetch(a + 16);
-        pre1 = fetch(a + 32);
-        pre_at = a + 32;
-        q0 = c.x, q1 = c.y, q2 = c.z, q3 = c.w;
-        qn = 4;
-        const int skip = (int)((p - a) >> 2);
-        for (int i = 0; i < skip; ++i) shift();
-        const int sub = (int)(p & 3u);
-        hold = 0;
-        held = 0;
-        next = pos;
-        if (sub) {
-            hold = (uint64_t)(q0 >> (8 * sub));
-            held = 32 - 8 * sub;
-            next = pos + (uint64_t)(4 - sub);
-            shift();
-        }
+    // move w0 into `hold` when there is room (pred && held <= 32), request the word kRing further on; no branch
+    __device__ __forceinline__ void refill(bool pred) {
+        const bool take = pred && held <= 32;
+        const uint64_t add = (uint64_t)w0 << (held & 63);
+        hold |= take ? add : 0ull;
+        held += take ? 32 : 0;
+        const bool inside = at + 4 <= hi;
+        const uint32_t slot = ring + (rd & (kRing - 1)) * 128;
+        const uint32_t nslot = ring + ((rd + 1) & (kRing - 1)) * 128;
+        asm volatile(
+            "{\n\t.reg .pred p, q, t;\n\t"
+            "setp.ne.u32 t, %3, 0;\n\t"
+            "setp.ne.u32 p, %4, 0;\n\t"
+            "setp.ne.u32 q, %5, 0;\n\t"
+            "@p cp.async.ca.shared.global [%1], [%2], 4;\n\t"
+            "@q st.shared.u32 [%1], 0;\n\t"
+            "@t cp.async.commit_group;\n\t"
+            "@t cp.async.wait_group 7;\n\t"
+            "@t ld.shared.u32 %0, [%6];\n\t}"
+            : "+r"(w0)
+            : "r"(slot), "l"(at), "r"(take ? 1u : 0u), "r"((take && inside) ? 1u : 0u), "r"((take && !inside) ? 1u : 0u),
+              "r"(nslot)
+            : "memory");
+        const uint32_t far = (take && (at & 127u) == 0 && at + 640 <= hi) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.u32 p, %1, 0;\n\t"
+            "@p prefetch.global.L2 [%0];\n\t}" ::"l"(at + 512),
+            "r"(far));
+        rd += take ? 1u : 0u;
+        at += take ? 4 : 0;
     }
-    __device__ __forceinline__ void refill() {
-        if (held <= 32) {
-            hold |= (uint64_t)q0 << held;
-            held += 32;
-            next += 4;
-            shift();
-        }
-    }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(hold & ((1ull << n) - 1ull)); }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)hold & ((1u << n) - 1u); }  // n <= 16
     __device__ __forceinline__ void drop(int n) {
         hold >>= n;
         held -= n;
     }
-    __device__ __forceinline__ uint64_t bit_pos() const { return next * 8 - (uint64_t)held; }
+    __device__ __forceinline__ uint64_t bit_pos() const { return (uint64_t)(at - 4 * kRing - lo) * 8 - (uint64_t)held; }
 };
+static_assert(kRing == 8, "cp.async.wait_group immediate in FastReader::refill is kRing - 1");
 
 __device__ __forceinline__ uint32_t rev_bits(uint32_t v, int len) { return __brev(v) >> (32 - len); }
 
@@ -1056,14 +1060,42 @@ __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32
 // one LANE per block.  The loop is warp-uniform: in every pass each lane that is still busy either reads one block
 // header (and builds its tables) or decodes exactly one token, then the lanes meet again at the vote -- without that
 // the lanes of a warp would run their data-dependent loops one after the other.
+// Longest blocks first: the decode of a block is serial, so the kernel can not end before its longest block does, and a
+// warp waits for the slowest of its 32 lanes.  Blocks are bucketed by compressed size (a proxy for their token count)
+// in descending order; a warp then takes 32 blocks of similar size, the big ones start at once.
+__global__ void __launch_bounds__(1024) lane_order_kernel(const LaneChunk *__restrict__ lc, uint32_t n, uint32_t *perm) {
+    __shared__ uint32_t bucket[256];
+    if (threadIdx.x < 256) bucket[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < n; k += 1024) {
+        const uint64_t size = lc[k].in_end - lc[k].in_begin;
+        atomicAdd(&bucket[255u - (uint32_t)tmin<uint64_t>(size >> 7, 255)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < 256; ++b) {
+            const uint32_t c = bucket[b];
+            bucket[b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < n; k += 1024) {
+        const uint64_t size = lc[k].in_end - lc[k].in_begin;
+        perm[atomicAdd(&bucket[255u - (uint32_t)tmin<uint64_t>(size >> 7, 255)], 1u)] = k;
+    }
+}
+
 constexpr int kLaneLitBits = 9;   // literal/length codes up to 9 bits and ...
 constexpr int kLaneDistBits = 6;  // ... distance codes up to 6 bits decode from shared memory
 constexpr int kLaneWarps = 6;     // 6 x 36 KiB of tables: one persistent CTA per SM, 192 blocks in flight on it
-constexpr int kLaneWarpSmem = ((1 << kLaneLitBits) + (1 << kLaneDistBits)) * 32 * 2;
+constexpr int kLaneWarpSmem = ((1 << kLaneLitBits) + (1 << kLaneDistBits)) * 32 * 2 + kRing * 32 * 4;
 __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const uint8_t *__restrict__ in, uint64_t m,
                                                                           LaneChunk *lc, uint32_t num_chunks,
                                                                           WarpState *tables, uint16_t *slots,
-                                                                          uint32_t *next_task) {
+                                                                          uint32_t *next_task,
+                                                                          const uint32_t *__restrict__ perm) {
     // every lane's short-code tables, interleaved so that the lanes of a warp fall into different banks: entry i of
     // lane l sits at [i * 32 + l].  Longer codes go through the lane's WarpState in global memory.
     extern __shared__ __align__(16) uint16_t s_lut_all[];
@@ -1076,8 +1108,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         if (lane == 0) task = atomicAdd(next_task, 1u);
         task = __shfl_sync(0xFFFFFFFFu, task, 0);
         if (task >= num_tasks) break;
-        const uint32_t k = task * 32 + lane;
-        const bool live = k < num_chunks;
+        const bool live = task * 32 + lane < num_chunks;
+        const uint32_t k = live ? perm[task * 32 + lane] : 0u;
         enum { kHeader = 0, kSymbols = 1, kDone = 2 };
         int state = live ? kHeader : kDone;
         int status = ZK_OK, final_seen = 0, last = 0;
@@ -1088,106 +1120,110 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         WarpState &ws = tables[kk];
         uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
         const uint64_t in_end = lc[kk].in_end;
-        LaneReader br;
-        br.base = in;
-        br.len = m;
-        br.seek(lc[kk].in_begin);
+        const uint32_t dist_cap = (live && k == 0) ? 0u : (uint32_t)kWindow;  // block 0 has nothing before it (IS:287-291)
+        FastReader fr;
+        fr.ring = (uint32_t)__cvta_generic_to_shared(s_dist + (1 << kLaneDistBits) * 32) + lane * 4;
+        fr.lo = (uintptr_t)in;
+        fr.hi = fr.lo + m;
+        fr.seek_bits(lc[kk].in_begin * 8);
         while (__any_sync(0xFFFFFFFFu, state != kDone)) {
-            if (state != kDone && br.next > in_end + 64) {  // ran away from its chunk: not a block of this path
-                status = ZK_DATA_ERROR;
-                state = kDone;
-            }
             if (state == kHeader) {
+                // once or twice per block: the plain byte-wise reader parses the header, the fast one is re-seated after
+                const uint64_t bp = fr.bit_pos();
+                BitReader br{in, m, bp >> 3, 0, 0};
                 br.refill();
-                last = (int)br.peek(1);
-                br.drop(1);
-                const int type = (int)br.peek(2);
-                br.drop(2);
-                if (type == 3) {
-                    status = ZK_DATA_ERROR;
+                if (br.held < 3 + (int)(bp & 7)) {
+                    status = ZK_BUF_ERROR;
                     state = kDone;
-                } else if (type == 0) {
-                    br.drop(br.held & 7);
-                    br.refill();
-                    const uint32_t len = br.peek(16);
-                    br.drop(16);
-                    const uint32_t nlen = br.peek(16);
-                    br.drop(16);
-                    const uint64_t src0 = br.next - (uint64_t)(br.held >> 3);
-                    if (((~len) & 0xFFFFu) != nlen) {
+                } else {
+                    br.drop((int)(bp & 7));
+                    last = (int)br.peek(1);
+                    br.drop(1);
+                    const int type = (int)br.peek(2);
+                    br.drop(2);
+                    if (type == 3) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
-                    } else if (src0 + len > m || produced + len > kSlotSyms || (len && (produced || stored_len))) {
-                        // truncated, more than this path's slot holds, or a chunk that mixes a stored payload with
-                        // other data (not made by this engine): the warp-per-chunk path takes the stream
-                        status = ZK_BUF_ERROR;
-                        state = kDone;
-                    } else {
-                        if (len) {  // the payload is copied by the expansion kernel, in parallel
-                            stored_src = src0;
-                            stored_len = len;
-                        }
-                        produced += len;
-                        const uint64_t at = src0 + len;
-                        // block boundary (a stored block ends on a byte)
-                        if (last) {
-                            final_seen = 1;
-                            end_byte = at;
-                            state = kDone;
-                        } else if (at == in_end) {
-                            end_byte = at;
-                            state = kDone;
-                        } else if (at > in_end) {
-                            status = ZK_DATA_ERROR;
+                    } else if (type == 0) {
+                        br.drop(br.held & 7);
+                        br.refill();
+                        if (br.held < 32) {
+                            status = ZK_BUF_ERROR;
                             state = kDone;
                         } else {
-                            br.seek(at);
+                            const uint32_t len = br.peek(16);
+                            br.drop(16);
+                            const uint32_t nlen = br.peek(16);
+                            br.drop(16);
+                            const uint64_t src0 = br.next - (uint64_t)(br.held >> 3);
+                            if (((~len) & 0xFFFFu) != nlen) {
+                                status = ZK_DATA_ERROR;
+                                state = kDone;
+                            } else if (src0 + len > m || produced + len > kSlotSyms || (len && (produced || stored_len))) {
+                                // truncated, more than this path's slot holds, or a chunk that mixes a stored payload
+                                // with other data (not made by this engine): the warp-per-chunk path takes the stream
+                                status = ZK_BUF_ERROR;
+                                state = kDone;
+                            } else {
+                                if (len) {  // the payload is copied by the expansion kernel, in parallel
+                                    stored_src = src0;
+                                    stored_len = len;
+                                }
+                                produced += len;
+                                const uint64_t at = src0 + len;
+                                // block boundary (a stored block ends on a byte)
+                                if (last) {
+                                    final_seen = 1;
+                                    end_byte = at;
+                                    state = kDone;
+                                } else if (at == in_end) {
+                                    end_byte = at;
+                                    state = kDone;
+                                } else if (at > in_end) {
+                                    status = ZK_DATA_ERROR;
+                                    state = kDone;
+                                } else {
+                                    fr.seek_bits(at * 8);
+                                }
+                            }
                         }
-                    }
-                } else {
-                    const int hrc = stored_len ? ZK_BUF_ERROR : parse_huffman_header<false>(ws, br, type, 0);
-                    if (hrc != ZK_OK) {
-                        status = hrc;
-                        state = kDone;
                     } else {
-                        // short codes into this lane's columns of the shared tables (the global tables repeat with
-                        // the short period for codes that fit it; a longer code leaves its slot empty)
-                        for (int i = 0; i < (1 << kLaneLitBits); ++i) {
-                            const uint16_t e = ws.lit.lut[i];
-                            s_lit[i * 32 + lane] = (e >> 12) <= kLaneLitBits ? e : (uint16_t)0;
+                        const int hrc = stored_len ? ZK_BUF_ERROR : parse_huffman_header<false>(ws, br, type, 0);
+                        if (hrc != ZK_OK) {
+                            status = hrc;
+                            state = kDone;
+                        } else {
+                            // short codes into this lane's columns of the shared tables (the global tables repeat
+                            // with the short period for codes that fit it; a longer code leaves its slot empty)
+                            for (int i = 0; i < (1 << kLaneLitBits); ++i) {
+                                const uint16_t e = ws.lit.lut[i];
+                                s_lit[i * 32 + lane] = (e >> 12) <= kLaneLitBits ? e : (uint16_t)0;
+                            }
+                            for (int i = 0; i < (1 << kLaneDistBits); ++i) {
+                                const uint16_t e = ws.dist.lut[i];
+                                s_dist[i * 32 + lane] = (e >> 12) <= kLaneDistBits ? e : (uint16_t)0;
+                            }
+                            fr.seek_bits(br.bit_pos());
+                            state = kSymbols;
                         }
-                        for (int i = 0; i < (1 << kLaneDistBits); ++i) {
-                            const uint16_t e = ws.dist.lut[i];
-                            s_dist[i * 32 + lane] = (e >> 12) <= kLaneDistBits ? e : (uint16_t)0;
-                        }
-                        state = kSymbols;
                     }
                 }
             } else if (state == kSymbols) {
-                br.refill();
+                // ---- one token per lane, straight-line: literals and matches share the code, only long codes, the end
+                // of a block and errors branch away
+                fr.refill(true);
                 int sym;
                 {
-                    const uint32_t e = s_lit[br.peek(kLaneLitBits) * 32 + lane];
+                    const uint32_t e = s_lit[fr.peek(kLaneLitBits) * 32 + lane];
                     if (e) {
-                        br.drop((int)(e >> 12));
+                        fr.drop((int)(e >> 12));
                         sym = (int)(e & 0x0FFFu);
                     } else {
-                        sym = decode_sym(ws.lit, br);
+                        sym = decode_sym(ws.lit, fr);
                     }
                 }
-                if (sym < 0) {
-                    status = ZK_DATA_ERROR;
-                    state = kDone;
-                } else if (sym < 256) {
-                    if (produced >= kSlotSyms) {
-                        status = ZK_BUF_ERROR;
-                        state = kDone;
-                    } else {
-                        out[units++] = (uint16_t)sym;
-                        ++produced;
-                    }
-                } else if (sym == 256) {
-                    const uint64_t bits = br.bit_pos();
+                if (sym == 256) {
+                    const uint64_t bits = fr.bit_pos();
                     if (last) {
                         final_seen = 1;
                         end_byte = (bits + 7) >> 3;
@@ -1202,42 +1238,45 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         state = kHeader;
                     }
                 } else {
-                    const int lcode = sym - 257;
-                    int length = 0, dist = 0;
-                    if (lcode > 28) status = ZK_DATA_ERROR;
-                    if (status == ZK_OK) {
-                        // one refill covers length extra (5) + distance code (15) + distance extra (13) = 33 bits
-                        br.refill();
+                    const bool is_match = sym > 256;
+                    uint32_t length = 1, word1 = 0;
+                    bool bad = sym < 0;
+                    if (__any_sync(__activemask(), is_match)) {
+                        // length extra (5) + distance code (15) + distance extra (13) = 33 bits: one more refill
+                        fr.refill(is_match);
                         // RFC 1951 3.2.5 in arithmetic (a table indexed per lane would serialise in the constant cache)
-                        const int le = (lcode < 8 || lcode == 28) ? 0 : (lcode >> 2) - 1;
-                        const int lbase = lcode < 8 ? 3 + lcode : lcode == 28 ? 258 : 3 + ((4 + (lcode & 3)) << le);
-                        length = lbase + (int)br.peek(le);
-                        br.drop(le);
-                        int dsym;
-                        const uint32_t e = s_dist[br.peek(kLaneDistBits) * 32 + lane];
-                        if (e) {
-                            br.drop((int)(e >> 12));
-                            dsym = (int)(e & 0x0FFFu);
+                        const int lcode = is_match ? sym - 257 : 0;
+                        const int le = (lcode < 8 || lcode >= 28) ? 0 : (lcode >> 2) - 1;
+                        const int lbase = lcode < 8 ? 3 + lcode : lcode >= 28 ? 258 : 3 + ((4 + (lcode & 3)) << le);
+                        length = is_match ? (uint32_t)lbase + fr.peek(le) : 1u;
+                        fr.drop(le);
+                        int dsym = 0;
+                        const uint32_t e = s_dist[fr.peek(kLaneDistBits) * 32 + lane];
+                        if (is_match && e == 0) {
+                            dsym = decode_sym(ws.dist, fr);
                         } else {
-                            dsym = decode_sym(ws.dist, br);
+                            fr.drop(is_match ? (int)(e >> 12) : 0);
+                            dsym = (int)(e & 0x0FFFu);
                         }
-                        if (dsym < 0 || dsym > 29) status = ZK_DATA_ERROR;
-                        else {
-                            const int de = dsym < 4 ? 0 : (dsym >> 1) - 1;
-                            const int dbase = dsym < 4 ? 1 + dsym : 1 + ((2 + (dsym & 1)) << de);
-                            dist = dbase + (int)br.peek(de);
-                            br.drop(de);
-                        }
+                        const int de = dsym < 4 ? 0 : (dsym >> 1) - 1;
+                        const uint32_t dbase = dsym < 4 ? 1u + (uint32_t)dsym : 1u + ((2u + (uint32_t)(dsym & 1)) << de);
+                        const uint32_t dist = dbase + fr.peek(is_match ? de : 0);
+                        fr.drop(is_match ? de : 0);
+                        bad = bad || (is_match && (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow ||
+                                                   (dist_cap == 0u && dist > produced)));
+                        word1 = dist - 1u;
                     }
-                    if (status == ZK_OK && (dist > kWindow || (k == 0 && (uint32_t)dist > produced))) status = ZK_DATA_ERROR;
-                    if (status == ZK_OK && produced + (uint32_t)length > kSlotSyms) status = ZK_BUF_ERROR;
-                    if (status != ZK_OK) {
+                    if (bad) {
+                        status = ZK_DATA_ERROR;
+                        state = kDone;
+                    } else if (produced + length > kSlotSyms) {
+                        status = ZK_BUF_ERROR;
                         state = kDone;
                     } else {
-                        out[units] = (uint16_t)(0x8000u | (uint32_t)length);
-                        out[units + 1] = (uint16_t)(dist - 1);
-                        units += 2;
-                        produced += (uint32_t)length;
+                        out[units] = (uint16_t)(is_match ? (0x8000u | length) : (uint32_t)sym);
+                        if (is_match) out[units + 1] = (uint16_t)word1;
+                        units += is_match ? 2u : 1u;
+                        produced += length;
                     }
                 }
             }
@@ -1253,6 +1292,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
             lc[k].end_byte = end_byte;
             lc[k].final_seen = final_seen;
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
     }
 }
@@ -1422,7 +1462,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
                         (size_t)max_chunks * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
-                        (size_t)lane_blocks_reserved * (8 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
+                        (size_t)lane_blocks_reserved * (12 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
     int32_t *d_header = static_cast<int32_t *>(c->arena.take(256));
     uint32_t *d_cand = static_cast<uint32_t *>(c->arena.take((size_t)num_spans * 4));
@@ -1475,6 +1515,9 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                 if (d_pos && d_lc && d_tables && d_slots) {
                     marker_compact_kernel<true><<<pieces, 256, 0, st>>>(job.d_in, m, nullptr, d_piece_off, d_pos, num_markers);
                     lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc);
+                    uint32_t *d_perm = static_cast<uint32_t *>(c->arena.take((size_t)n * 4));
+                    lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
+                    c->launches += 1;
                     {
                         ScopedTimer t(c, 4);
                         const int lane_smem = kLaneWarps * kLaneWarpSmem;
@@ -1483,7 +1526,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                         ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
                         decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
-                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total));
+                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m);
                     c->launches += 4;
