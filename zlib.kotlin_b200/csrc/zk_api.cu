@@ -124,7 +124,8 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
 
     c->arena.reset();
     const bool stored_only = level <= 0;
-    const uint64_t slab = tmin<uint64_t>(n, kSlabBytes);
+    const uint64_t slab_bytes = job.slab_bytes ? tmin<uint64_t>(job.slab_bytes, kSlabBytes) : kSlabBytes;
+    const uint64_t slab = tmin<uint64_t>(n, slab_bytes);
     const uint32_t slab_blocks = (uint32_t)((slab + block_bytes - 1) / block_bytes) + 1;
     size_t need = 8192 + adler_partials_bytes(n);
     if (!stored_only)
@@ -136,13 +137,14 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     ZK_CUDA(cudaMemsetAsync(d_cursor, 0, 16, c->stream));
 
     int rc;
-    {
-        ScopedTimer t(c, 3);
-        rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
-    }
-    if (rc != ZK_OK) return rc;
-
     if (stored_only) {
+        if (job.before_slab)
+            for (uint32_t k = 0; (uint64_t)k * slab_bytes < n; ++k) job.before_slab(job.user, k);
+        {
+            ScopedTimer t(c, 3);
+            rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
+        }
+        if (rc != ZK_OK) return rc;
         // DS:331-373: 65535-byte stored blocks; an input that is a multiple of 65535 (0 included) ends with an
         // empty final block, exactly as the reference's loop does.
         const uint32_t nb = (uint32_t)(n / 65535u) + 1;
@@ -166,8 +168,10 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     uint64_t *d_offsets = static_cast<uint64_t *>(c->arena.take((size_t)slab_blocks * 8));
     if (!d_offsets) return ZK_MEM_ERROR;
 
-    for (uint64_t s0 = 0; s0 < n; s0 += kSlabBytes) {
-        const uint64_t sn = tmin<uint64_t>(kSlabBytes, n - s0);
+    uint32_t slab_index = 0;
+    for (uint64_t s0 = 0; s0 < n; s0 += slab_bytes, ++slab_index) {
+        const uint64_t sn = tmin<uint64_t>(slab_bytes, n - s0);
+        if (job.before_slab) job.before_slab(job.user, slab_index);
         const uint32_t nb = (uint32_t)((sn + block_bytes - 1) / block_bytes);
         const uint32_t unit = pick_unit_bytes(c, sn, block_bytes);
         const uint8_t *hist = s0 ? job.d_in + s0 - kWindow : job.d_hist;
@@ -192,7 +196,15 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
                              d_offsets, d_cursor, body);
         }
         if (rc != ZK_OK) return rc;
+        if (job.after_slab) job.after_slab(job.user, slab_index, d_cursor);
     }
+    // the checksum reads the whole input once more (0.2 ms per GiB); it runs last so that a pipelined host copy of the
+    // input only has to be complete here
+    {
+        ScopedTimer t(c, 3);
+        rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
+    }
+    if (rc != ZK_OK) return rc;
     return launch_frame(c, job.d_out, job.cap, level, job.framed, job.framed, d_cursor, -1, d_adler, n, job.d_result);
 }
 
@@ -255,6 +267,8 @@ void zk_ctx_destroy(zk_ctx *c) {
     }
     free(c->spans);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     delete c;
 }
 
@@ -435,6 +449,51 @@ uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len)
     return out;
 }
 
+// Pipelined host call: the input goes up in slabs on its own stream, slab k is compressed as soon as it has arrived,
+// and the bytes slab k produced come down on a third stream while slab k+1 is being compressed.
+namespace {
+constexpr uint64_t kHostSlab = 64ull << 20;
+constexpr uint32_t kMaxHostSlabs = 4096;
+struct HostPipe {
+    zk_ctx *c;
+    const uint8_t *d_out;  // device stream (2 header bytes, then the body)
+    uint8_t *out;          // caller's buffer
+    uint64_t *h_cursor;    // pinned: body bytes after slab k
+    cudaEvent_t *in_ready, *done;
+    uint32_t nslabs;
+    uint32_t flushed;      // slabs whose output has been sent down
+    uint64_t sent;         // body bytes sent down so far
+    cudaError_t err;
+};
+void pipe_flush(HostPipe *p, uint32_t upto) {  // send down the output of slabs [flushed, upto)
+    for (; p->flushed < upto; ++p->flushed) {
+        const uint32_t k = p->flushed;
+        cudaError_t e = cudaEventSynchronize(p->done[k]);
+        if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
+        const uint64_t cur = p->h_cursor[k];
+        if (cur > p->sent) {
+            e = cudaMemcpyAsync(p->out + 2 + p->sent, p->d_out + 2 + p->sent, cur - p->sent, cudaMemcpyDeviceToHost,
+                                p->c->copy_out);
+            if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
+            p->c->d2h_bytes += (int64_t)(cur - p->sent);
+            p->sent = cur;
+        }
+    }
+}
+void pipe_before(void *user, uint32_t k) {
+    HostPipe *p = static_cast<HostPipe *>(user);
+    const cudaError_t e = cudaStreamWaitEvent(p->c->stream, p->in_ready[k], 0);
+    if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
+}
+void pipe_after(void *user, uint32_t k, const uint64_t *d_cursor) {
+    HostPipe *p = static_cast<HostPipe *>(user);
+    cudaError_t e = cudaMemcpyAsync(&p->h_cursor[k], d_cursor, 8, cudaMemcpyDeviceToHost, p->c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(p->done[k], p->c->stream);
+    if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
+    if (k >= 1) pipe_flush(p, k);  // slab k is queued behind it: the device stays busy while the host waits here
+}
+}  // namespace
+
 int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
                     uint64_t *out_len, uint32_t *adler) {
     if (out_len) *out_len = 0;
@@ -450,20 +509,83 @@ int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
     uint64_t *d_result = reinterpret_cast<uint64_t *>(s->base);
     uint8_t *d_in = s->base + 256;
     uint8_t *d_out = d_in + in_room;
-    if (n) ZK_CUDA(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += (int64_t)n;
-    int rc = zk_deflate_zlib_device(c, d_in, n, level, strategy, d_out, dcap, d_result);
+    const uint32_t nslabs = (uint32_t)((n + kHostSlab - 1) / kHostSlab);
+    const bool piped = level > 0 && nslabs >= 2 && nslabs <= kMaxHostSlabs && dcap >= 8;
+    if (!piped) {
+        if (n) ZK_CUDA(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += (int64_t)n;
+        int rc = zk_deflate_zlib_device(c, d_in, n, level, strategy, d_out, dcap, d_result);
+        if (rc != ZK_OK) return rc;
+        uint64_t res[4];
+        ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += 32;
+        const int status = (int)(int64_t)res[2];
+        if (adler) *adler = (uint32_t)res[1];
+        if (status != ZK_OK) return status;
+        ZK_CUDA(cudaMemcpyAsync(out, d_out, res[0], cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += (int64_t)res[0];
+        *out_len = res[0];
+        return ZK_OK;
+    }
+    if (!c->copy_in) ZK_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    if (!c->copy_out) ZK_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> ev(2 * (size_t)nslabs, nullptr);
+    uint64_t *h_cursor = nullptr;
+    ZK_CUDA(cudaMallocHost(&h_cursor, (size_t)nslabs * 8 + 64));
+    int rc = ZK_OK;
+    HostPipe pipe{c, d_out, out, h_cursor, ev.data(), ev.data() + nslabs, nslabs, 0, 0, cudaSuccess};
+    for (auto &e : ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = ZK_ERRNO;
+    uint64_t res[4] = {0, 0, 0, 0};
+    if (rc == ZK_OK) {
+        // the staging buffer may still be in use by earlier work on the compute stream
+        cudaEvent_t fence = pipe.done[0];
+        cudaEventRecord(fence, c->stream);
+        cudaStreamWaitEvent(c->copy_in, fence, 0);
+        for (uint32_t k = 0; k < nslabs && pipe.err == cudaSuccess; ++k) {
+            const uint64_t off = (uint64_t)k * kHostSlab, len = tmin<uint64_t>(kHostSlab, n - off);
+            pipe.err = cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->copy_in);
+            if (pipe.err == cudaSuccess) pipe.err = cudaEventRecord(pipe.in_ready[k], c->copy_in);
+        }
+        c->h2d_bytes += (int64_t)n;
+        DeflateJob job{d_in, n, nullptr, 0, level, strategy, d_out, dcap, true, d_result};
+        job.slab_bytes = kHostSlab;
+        job.before_slab = pipe_before;
+        job.after_slab = pipe_after;
+        job.user = &pipe;
+        rc = run_deflate(c, job);
+        if (rc == ZK_OK && pipe.err == cudaSuccess) {
+            pipe.err = cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream);
+            pipe_flush(&pipe, nslabs);  // waits for the last slab; the trailer kernels are behind it
+            if (pipe.err == cudaSuccess) pipe.err = cudaStreamSynchronize(c->stream);
+            c->d2h_bytes += 32;
+            const int status = (int)(int64_t)res[2];
+            if (pipe.err == cudaSuccess && status == ZK_OK) {
+                // header, and whatever follows the last slab's bytes (final block + Adler-32)
+                pipe.err = cudaMemcpyAsync(out, d_out, 2, cudaMemcpyDeviceToHost, c->copy_out);
+                if (pipe.err == cudaSuccess && res[0] > 2 + pipe.sent)
+                    pipe.err = cudaMemcpyAsync(out + 2 + pipe.sent, d_out + 2 + pipe.sent, res[0] - 2 - pipe.sent,
+                                               cudaMemcpyDeviceToHost, c->copy_out);
+                c->d2h_bytes += (int64_t)(res[0] - pipe.sent);
+            }
+        }
+        cudaStreamSynchronize(c->copy_in);
+        cudaStreamSynchronize(c->copy_out);
+        cudaStreamSynchronize(c->stream);
+    }
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e);
+    cudaFreeHost(h_cursor);
     if (rc != ZK_OK) return rc;
-    uint64_t res[4];
-    ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
-    ZK_CUDA(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += 32;
+    if (pipe.err != cudaSuccess) {
+        set_last_error("zk_deflate_zlib(pipelined)", pipe.err);
+        return ZK_ERRNO;
+    }
     const int status = (int)(int64_t)res[2];
     if (adler) *adler = (uint32_t)res[1];
     if (status != ZK_OK) return status;
-    ZK_CUDA(cudaMemcpyAsync(out, d_out, res[0], cudaMemcpyDeviceToHost, c->stream));
-    ZK_CUDA(cudaStreamSynchronize(c->stream));
-    c->d2h_bytes += (int64_t)res[0];
     *out_len = res[0];
     return ZK_OK;
 }

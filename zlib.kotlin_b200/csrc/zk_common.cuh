@@ -79,6 +79,7 @@ struct zk_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer entry points: H2D / D2H overlap with compute
     zk::Arena arena;       // device scratch (tokens, histograms, plans, staging)
     uint8_t *pinned = nullptr; // pinned host staging for small results
     size_t pinned_cap = 0;
@@ -128,6 +129,13 @@ struct DeflateJob {
     uint64_t cap;
     bool framed;           // true: emit zlib header + final block + trailer around the body
     uint64_t *d_result;    // {out_len, adler, status, n}
+    // optional pipelining hooks of the host-buffer entry point: the input is processed in slabs of `slab_bytes`;
+    // before_slab(k) runs on the host before slab k's kernels are enqueued (wait for its H2D copy), after_slab(k,
+    // d_cursor) after they are (d_cursor[0] = body bytes written so far, final for every slab up to k)
+    uint64_t slab_bytes = 0;  // 0 = default
+    void (*before_slab)(void *user, uint32_t k) = nullptr;
+    void (*after_slab)(void *user, uint32_t k, const uint64_t *d_cursor) = nullptr;
+    void *user = nullptr;
 };
 int run_deflate(zk_ctx *c, const DeflateJob &job);
 

@@ -114,11 +114,12 @@ constexpr int kRing = 8;
 struct FastReader {
     uint64_t hold;
     int held;
-    uint32_t w0;       // the stream word after the bits in `hold` (= ring slot rd)
-    uint32_t rd;       // ring slot of w0
-    uint32_t ring;     // shared-space address of this lane's slot 0; slot j at ring + j * 128
-    uintptr_t at;      // address of the next word to request (kRing words after w0)
-    uintptr_t lo, hi;  // [base, base + len)
+    uint32_t w0;         // the stream word after the bits in `hold` (ring slot at byte offset roff)
+    uint32_t roff;       // byte offset of w0's slot in the lane's ring: slot * 128
+    uint32_t ring;       // shared-space address of this lane's slot 0
+    const uint8_t *at;   // address of the next word to request (kRing words after w0)
+    int32_t words_left;  // whole words of the stream at and after `at`
+    uintptr_t lo, hi;    // [base, base + len)
 
     __device__ __forceinline__ uint32_t fetch_edge(uintptr_t a) const {
         if (a >= lo && a + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t *>(a));
@@ -141,47 +142,52 @@ struct FastReader {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(ring + j * 128), "r"(w) : "memory");
             if (j == 0) w0 = w;
         }
-        rd = 0;
-        at = a + 4 + 4 * kRing;
+        roff = 0;
+        const uintptr_t nxt = a + 4 + 4 * kRing;
+        at = reinterpret_cast<const uint8_t *>(nxt);
+        const uint64_t left = hi > nxt ? (uint64_t)(hi - nxt) >> 2 : 0;
+        words_left = (int32_t)tmin<uint64_t>(left, 0x7FFFFFFFull);
     }
-    // move w0 into `hold` when there is room (pred && held <= 32), request the word kRing further on; no branch
+    // move w0 into `hold` when there is room (pred && held <= 32), request the word kRing further on.  Straight-line:
+    // every instruction is predicated, the commit / wait pair runs every time (an empty group is free, and the word
+    // consumed at a refill was requested at least kRing - 1 commits earlier, which is what wait_group guarantees).
     __device__ __forceinline__ void refill(bool pred) {
-        const bool take = pred && held <= 32;
-        const uint64_t add = (uint64_t)w0 << (held & 63);
-        hold |= take ? add : 0ull;
-        held += take ? 32 : 0;
-        const bool inside = at + 4 <= hi;
-        const uint32_t slot = ring + (rd & (kRing - 1)) * 128;
-        const uint32_t nslot = ring + ((rd + 1) & (kRing - 1)) * 128;
+        const uint32_t take = (pred && held <= 32) ? 1u : 0u;
+        const uint32_t nroff = (roff + 128u) & (uint32_t)((kRing - 1) * 128);
         asm volatile(
-            "{\n\t.reg .pred p, q, t;\n\t"
-            "setp.ne.u32 t, %3, 0;\n\t"
-            "setp.ne.u32 p, %4, 0;\n\t"
-            "setp.ne.u32 q, %5, 0;\n\t"
-            "@p cp.async.ca.shared.global [%1], [%2], 4;\n\t"
-            "@q st.shared.u32 [%1], 0;\n\t"
-            "@t cp.async.commit_group;\n\t"
-            "@t cp.async.wait_group 7;\n\t"
-            "@t ld.shared.u32 %0, [%6];\n\t}"
-            : "+r"(w0)
-            : "r"(slot), "l"(at), "r"(take ? 1u : 0u), "r"((take && inside) ? 1u : 0u), "r"((take && !inside) ? 1u : 0u),
-              "r"(nslot)
+            "{\n\t.reg .pred t, p, q, f;\n\t.reg .b64 tmp;\n\t.reg .b32 lowat;\n\t"
+            "setp.ne.u32 t, %6, 0;\n\t"
+            "cvt.u64.u32 tmp, %2;\n\t"
+            "shl.b64 tmp, tmp, %1;\n\t"
+            "@t or.b64 %0, %0, tmp;\n\t"
+            "@t add.s32 %1, %1, 32;\n\t"
+            "setp.gt.and.s32 p, %5, 0, t;\n\t"
+            "setp.le.and.s32 q, %5, 0, t;\n\t"
+            "@p cp.async.ca.shared.global [%7], [%4], 4;\n\t"
+            "@q st.shared.u32 [%7], 0;\n\t"
+            "cp.async.commit_group;\n\t"
+            "cp.async.wait_group 7;\n\t"
+            "@t ld.shared.u32 %2, [%8];\n\t"
+            "@t mov.u32 %3, %9;\n\t"
+            "cvt.u32.u64 lowat, %4;\n\t"
+            "and.b32 lowat, lowat, 127;\n\t"
+            "setp.eq.and.u32 f, lowat, 0, t;\n\t"
+            "setp.gt.and.s32 f, %5, 160, f;\n\t"
+            "@f prefetch.global.L2 [%4+512];\n\t"
+            "@t add.u64 %4, %4, 4;\n\t"
+            "@t add.s32 %5, %5, -1;\n\t}"
+            : "+l"(hold), "+r"(held), "+r"(w0), "+r"(roff), "+l"(at), "+r"(words_left)
+            : "r"(take), "r"(ring + roff), "r"(ring + nroff), "r"(nroff)
             : "memory");
-        const uint32_t far = (take && (at & 127u) == 0 && at + 640 <= hi) ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.u32 p, %1, 0;\n\t"
-            "@p prefetch.global.L2 [%0];\n\t}" ::"l"(at + 512),
-            "r"(far));
-        rd += take ? 1u : 0u;
-        at += take ? 4 : 0;
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)hold & ((1u << n) - 1u); }  // n <= 16
     __device__ __forceinline__ void drop(int n) {
         hold >>= n;
         held -= n;
     }
-    __device__ __forceinline__ uint64_t bit_pos() const { return (uint64_t)(at - 4 * kRing - lo) * 8 - (uint64_t)held; }
+    __device__ __forceinline__ uint64_t bit_pos() const {
+        return (uint64_t)((uintptr_t)at - 4 * kRing - lo) * 8 - (uint64_t)held;
+    }
 };
 static_assert(kRing == 8, "cp.async.wait_group immediate in FastReader::refill is kRing - 1");
 
@@ -1114,11 +1120,12 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         int state = live ? kHeader : kDone;
         int status = ZK_OK, final_seen = 0, last = 0;
         uint64_t end_byte = 0;
-        uint32_t units = 0, produced = 0, stored_len = 0;
+        uint32_t produced = 0, stored_len = 0;
         uint64_t stored_src = 0;
         const uint32_t kk = live ? k : 0;
         WarpState &ws = tables[kk];
         uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
+        uint16_t *optr = out;
         const uint64_t in_end = lc[kk].in_end;
         const uint32_t dist_cap = (live && k == 0) ? 0u : (uint32_t)kWindow;  // block 0 has nothing before it (IS:287-291)
         FastReader fr;
@@ -1209,8 +1216,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     }
                 }
             } else if (state == kSymbols) {
-                // ---- one token per lane, straight-line: literals and matches share the code, only long codes, the end
-                // of a block and errors branch away
+                // ---- one token per lane.  Literals leave through a few instructions; a match or the end of a block
+                // branches away (the lanes with a literal wait for them)
                 fr.refill(true);
                 int sym;
                 {
@@ -1222,7 +1229,18 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         sym = decode_sym(ws.lit, fr);
                     }
                 }
-                if (sym == 256) {
+                if (sym < 256) {
+                    if (sym < 0) {
+                        status = ZK_DATA_ERROR;
+                        state = kDone;
+                    } else if (produced >= kSlotSyms) {
+                        status = ZK_BUF_ERROR;
+                        state = kDone;
+                    } else {
+                        *optr++ = (uint16_t)sym;
+                        ++produced;
+                    }
+                } else if (sym == 256) {
                     const uint64_t bits = fr.bit_pos();
                     if (last) {
                         final_seen = 1;
@@ -1238,49 +1256,56 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         state = kHeader;
                     }
                 } else {
-                    const bool is_match = sym > 256;
-                    uint32_t length = 1, word1 = 0;
-                    bool bad = sym < 0;
-                    if (__any_sync(__activemask(), is_match)) {
-                        // length extra (5) + distance code (15) + distance extra (13) = 33 bits: one more refill
-                        fr.refill(is_match);
-                        // RFC 1951 3.2.5 in arithmetic (a table indexed per lane would serialise in the constant cache)
-                        const int lcode = is_match ? sym - 257 : 0;
-                        const int le = (lcode < 8 || lcode >= 28) ? 0 : (lcode >> 2) - 1;
-                        const int lbase = lcode < 8 ? 3 + lcode : lcode >= 28 ? 258 : 3 + ((4 + (lcode & 3)) << le);
-                        length = is_match ? (uint32_t)lbase + fr.peek(le) : 1u;
-                        fr.drop(le);
-                        int dsym = 0;
-                        const uint32_t e = s_dist[fr.peek(kLaneDistBits) * 32 + lane];
-                        if (is_match && e == 0) {
-                            dsym = decode_sym(ws.dist, fr);
-                        } else {
-                            fr.drop(is_match ? (int)(e >> 12) : 0);
-                            dsym = (int)(e & 0x0FFFu);
-                        }
-                        const int de = dsym < 4 ? 0 : (dsym >> 1) - 1;
-                        const uint32_t dbase = dsym < 4 ? 1u + (uint32_t)dsym : 1u + ((2u + (uint32_t)(dsym & 1)) << de);
-                        const uint32_t dist = dbase + fr.peek(is_match ? de : 0);
-                        fr.drop(is_match ? de : 0);
-                        bad = bad || (is_match && (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow ||
-                                                   (dist_cap == 0u && dist > produced)));
-                        word1 = dist - 1u;
+                    // length extra (5) + distance code (15) + distance extra (13) = 33 bits: one more refill
+                    fr.refill(true);
+                    // RFC 1951 3.2.5 in arithmetic (a table indexed per lane would serialise in the constant cache)
+                    const int lcode = sym - 257;
+                    const int le = (lcode < 8 || lcode >= 28) ? 0 : (lcode >> 2) - 1;
+                    const int lbase = lcode < 8 ? 3 + lcode : lcode >= 28 ? 258 : 3 + ((4 + (lcode & 3)) << le);
+                    const uint32_t length = (uint32_t)lbase + fr.peek(le);
+                    fr.drop(le);
+                    int dsym;
+                    const uint32_t e = s_dist[fr.peek(kLaneDistBits) * 32 + lane];
+                    if (e) {
+                        fr.drop((int)(e >> 12));
+                        dsym = (int)(e & 0x0FFFu);
+                    } else {
+                        dsym = decode_sym(ws.dist, fr);
                     }
-                    if (bad) {
+                    const int dcl = min(max(dsym, 0), 29);
+                    const int de = dcl < 4 ? 0 : (dcl >> 1) - 1;
+                    const uint32_t dbase = dcl < 4 ? 1u + (uint32_t)dcl : 1u + ((2u + (uint32_t)(dcl & 1)) << de);
+                    const uint32_t dist = dbase + fr.peek(de);
+                    fr.drop(de);
+                    if (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow || (dist_cap == 0u && dist > produced)) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
                     } else if (produced + length > kSlotSyms) {
                         status = ZK_BUF_ERROR;
                         state = kDone;
                     } else {
-                        out[units] = (uint16_t)(is_match ? (0x8000u | length) : (uint32_t)sym);
-                        if (is_match) out[units + 1] = (uint16_t)word1;
-                        units += is_match ? 2u : 1u;
+                        optr[0] = (uint16_t)(0x8000u | length);
+                        optr[1] = (uint16_t)(dist - 1u);
+                        optr += 2;
                         produced += length;
+                    }
+                }
+                // ---- up to three more literals while this lane's next code is a short literal code and its bits are
+                // already in `hold`: no refill, no votes, no state changes
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    const uint32_t e = s_lit[fr.peek(kLaneLitBits) * 32 + lane];
+                    const bool lit = state == kSymbols && e != 0u && (e & 0x0F00u) == 0u && fr.held >= kLaneLitBits &&
+                                     produced < kSlotSyms;
+                    if (lit) {
+                        fr.drop((int)(e >> 12));
+                        *optr++ = (uint16_t)(e & 0xFFu);
+                        ++produced;
                     }
                 }
             }
         }
+        const uint32_t units = (uint32_t)(optr - out);
         // a block that used bits past the end of the stream is not a block of this path
         if (live && status == ZK_OK && end_byte > m) status = ZK_BUF_ERROR;
         if (live) {
