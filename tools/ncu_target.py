@@ -12,7 +12,8 @@ mib = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 level = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 do_inflate = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 n = mib << 20
-host = corpus.text_like(n) if kind == "text" else corpus.mixed_entropy(n)
+seg = {"random": 1, "repeat4k": 2, "runs": 3, "counters": 4, "base64": 5}
+host = corpus.text_like(n) if kind == "text" else corpus.mixed_entropy(n) if kind == "mixed" else corpus._segment(seg[kind], n, 10)
 dev = torch.device("cuda", 0)
 eng = zlibk_b200.Engine(0)
 d_in = torch.from_numpy(host).to(dev)

@@ -1066,6 +1066,30 @@ __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32
 // one LANE per block.  The loop is warp-uniform: in every pass each lane that is still busy either reads one block
 // header (and builds its tables) or decodes exactly one token, then the lanes meet again at the vote -- without that
 // the lanes of a warp would run their data-dependent loops one after the other.
+// Token sink of the lane decoder.  A 2-byte store per token from 32 lanes is 32 sectors through the L1 tag stage, and
+// every shared-memory load of the warp queues behind it; tokens are therefore gathered four at a time in a register pair
+// and leave as one 8-byte store.
+struct TokenSink {
+    uint64_t acc;
+    uint32_t cnt;    // units in acc (0..3)
+    uint16_t *ptr;   // next 8-byte aligned group
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {  // n = 1: v = unit; n = 2: v = unit0 | unit1 << 16
+        acc |= (uint64_t)v << (16u * cnt);
+        const uint32_t spill = (cnt + n > 4u) ? (v >> 16) : 0u;  // cnt == 3 and n == 2: the second unit fell off the top
+        cnt += n;
+        if (cnt >= 4u) {
+            *reinterpret_cast<uint64_t *>(ptr) = acc;
+            ptr += 4;
+            acc = spill;
+            cnt -= 4u;
+        }
+    }
+    __device__ __forceinline__ uint32_t finish(const uint16_t *base) {  // -> units written in total
+        for (uint32_t i = 0; i < cnt; ++i) ptr[i] = (uint16_t)(acc >> (16u * i));
+        return (uint32_t)(ptr - base) + cnt;
+    }
+};
+
 // Longest blocks first: the decode of a block is serial, so the kernel can not end before its longest block does, and a
 // warp waits for the slowest of its 32 lanes.  Blocks are bucketed by compressed size (a proxy for their token count)
 // in descending order; a warp then takes 32 blocks of similar size, the big ones start at once.
@@ -1125,7 +1149,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         const uint32_t kk = live ? k : 0;
         WarpState &ws = tables[kk];
         uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
-        uint16_t *optr = out;
+        TokenSink sink{0ull, 0u, out};
         const uint64_t in_end = lc[kk].in_end;
         const uint32_t dist_cap = (live && k == 0) ? 0u : (uint32_t)kWindow;  // block 0 has nothing before it (IS:287-291)
         FastReader fr;
@@ -1237,7 +1261,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         status = ZK_BUF_ERROR;
                         state = kDone;
                     } else {
-                        *optr++ = (uint16_t)sym;
+                        sink.put((uint32_t)sym, 1u);
                         ++produced;
                     }
                 } else if (sym == 256) {
@@ -1284,9 +1308,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         status = ZK_BUF_ERROR;
                         state = kDone;
                     } else {
-                        optr[0] = (uint16_t)(0x8000u | length);
-                        optr[1] = (uint16_t)(dist - 1u);
-                        optr += 2;
+                        sink.put((0x8000u | length) | ((dist - 1u) << 16), 2u);
                         produced += length;
                     }
                 }
@@ -1299,13 +1321,13 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                                      produced < kSlotSyms;
                     if (lit) {
                         fr.drop((int)(e >> 12));
-                        *optr++ = (uint16_t)(e & 0xFFu);
+                        sink.put(e & 0xFFu, 1u);
                         ++produced;
                     }
                 }
             }
         }
-        const uint32_t units = (uint32_t)(optr - out);
+        const uint32_t units = sink.finish(out);
         // a block that used bits past the end of the stream is not a block of this path
         if (live && status == ZK_OK && end_byte > m) status = ZK_BUF_ERROR;
         if (live) {
@@ -1547,7 +1569,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         ScopedTimer t(c, 4);
                         const int lane_smem = kLaneWarps * kLaneWarpSmem;
                         const uint32_t tasks = (uint32_t)((n + 31) / 32);
-                        const uint32_t grid = tmin<uint32_t>((tasks + kLaneWarps - 1) / kLaneWarps, (uint32_t)c->sm_count);
+                        const uint32_t grid = tmin<uint32_t>(tasks, (uint32_t)c->sm_count);  // a warp per SM before a second one
                         ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                         ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
                         decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
