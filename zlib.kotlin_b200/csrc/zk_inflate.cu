@@ -878,35 +878,69 @@ __global__ void __launch_bounds__(1024) window_apply_kernel(uint32_t n, uint32_t
     }
 }
 
-// Symbols -> bytes.  One CTA per 16 KiB of output; the chunk of a position is found by binary search.
+// Symbols -> bytes.  One CTA per 16 KiB of output; a thread turns 8 consecutive symbols (one 16-byte load) into one
+// 8-byte store.  The chunk of the tile's first position is found once per CTA by binary search, every thread then walks
+// forward from it (chunks are almost always much longer than a tile).
 __global__ void __launch_bounds__(256) materialize_kernel(const ChunkInfo *__restrict__ chunks,
                                                           const uint32_t *__restrict__ num_chunks,
                                                           const uint16_t *__restrict__ sym,
                                                           const uint8_t *__restrict__ windows, uint8_t *__restrict__ out,
                                                           uint64_t total, uint32_t *error_flag) {
+    __shared__ uint32_t s_lo;
     const uint32_t n = num_chunks[0];
     const uint64_t tile0 = (uint64_t)blockIdx.x * 16384;
-    for (uint64_t p = tile0 + threadIdx.x; p < tile0 + 16384 && p < total; p += 256) {
-        const uint16_t s = sym[p];
-        uint8_t v;
-        if (s & 0x8000u) {
-            uint32_t lo = 0, hi = n;  // last chunk with out_begin <= p
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (chunks[mid].out_begin <= p) lo = mid;
-                else hi = mid;
-            }
-            const uint32_t idx = s & 0x7FFFu;
-            if (lo == 0 || (int64_t)chunks[lo].out_begin - kWindow + (int64_t)idx < 0) {
-                atomicExch(error_flag, 1u);
-                v = 0;
-            } else {
-                v = windows[(uint64_t)(lo - 1) * kWindow + idx];
-            }
-        } else {
-            v = (uint8_t)s;
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = n;  // last chunk with out_begin <= tile0
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (chunks[mid].out_begin <= tile0) lo = mid;
+            else hi = mid;
         }
-        out[p] = v;
+        s_lo = lo;
+    }
+    __syncthreads();
+    uint32_t c = s_lo;
+    uint64_t cbegin = chunks[c].out_begin;
+    uint64_t nbegin = c + 1 < n ? chunks[c + 1].out_begin : ~0ull;
+    const bool aligned8 = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    for (int step = 0; step < 8; ++step) {
+        const uint64_t p0 = tile0 + (uint64_t)step * 2048 + (uint64_t)threadIdx.x * 8;
+        if (p0 >= total) break;
+        const int cnt = (int)tmin<uint64_t>(8, total - p0);
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (cnt == 8) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(sym + p0);
+            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        } else {
+            for (int e = 0; e < cnt; ++e) w[e >> 1] |= (uint32_t)sym[p0 + e] << (16 * (e & 1));
+        }
+        uint64_t bytes = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t s16 = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+            uint32_t v = s16 & 0xFFu;
+            if ((s16 & 0x8000u) && e < cnt) {
+                const uint64_t p = p0 + e;
+                while (nbegin <= p) {  // next chunk (empty chunks are skipped by the loop)
+                    ++c;
+                    cbegin = nbegin;
+                    nbegin = c + 1 < n ? chunks[c + 1].out_begin : ~0ull;
+                }
+                const uint32_t idx = s16 & 0x7FFFu;
+                if (c == 0 || (int64_t)cbegin - kWindow + (int64_t)idx < 0) {
+                    atomicExch(error_flag, 1u);
+                    v = 0;
+                } else {
+                    v = windows[(uint64_t)(c - 1) * kWindow + idx];
+                }
+            }
+            bytes |= (uint64_t)v << (8 * e);
+        }
+        if (cnt == 8 && aligned8) {
+            *reinterpret_cast<uint64_t *>(out + p0) = bytes;
+        } else {
+            for (int e = 0; e < cnt; ++e) out[p0 + e] = (uint8_t)(bytes >> (8 * e));
+        }
     }
 }
 
@@ -975,8 +1009,26 @@ __global__ void __launch_bounds__(256) marker_compact_kernel(const uint8_t *__re
     __shared__ uint32_t warp_tot[8];
     const uint64_t base = (uint64_t)blockIdx.x * kPieceBytes + (uint64_t)threadIdx.x * (kPieceBytes / 256);
     uint64_t found = 0;  // bit k: marker at base + k (64 positions per thread)
-    for (int k = 0; k < (int)(kPieceBytes / 256); ++k)
-        if (marker_at(in, m, base + k)) found |= 1ull << k;
+    if (base >= 16 && base + 80 <= m && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+        // bytes [base - 16, base + 80) as 24 words; position base + k needs the four bytes before it and its own
+        const uint4 *v = reinterpret_cast<const uint4 *>(in + base - 16);
+        uint32_t w[24];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const uint4 x = __ldg(v + q);
+            w[4 * q] = x.x, w[4 * q + 1] = x.y, w[4 * q + 2] = x.z, w[4 * q + 3] = x.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const int o = 12 + k;  // window offset of the byte at base + k - 4
+            const uint32_t four = __funnelshift_r(w[o >> 2], w[(o >> 2) + 1], (o & 3) * 8);
+            const uint32_t self = (w[(o + 4) >> 2] >> (((o + 4) & 3) * 8)) & 0xFFu;
+            if (four == 0xFFFF0000u && ((self >> 1) & 3u) != 3u) found |= 1ull << k;
+        }
+    } else {
+        for (int k = 0; k < (int)(kPieceBytes / 256); ++k)
+            if (marker_at(in, m, base + k)) found |= 1ull << k;
+    }
     const uint32_t mine = (uint32_t)__popcll(found);
     uint32_t incl = mine;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1090,6 +1142,45 @@ struct TokenSink {
     }
 };
 
+// Codes longer than the shared-memory table of the lane decoder: six consecutive lengths (L0 .. L0+5) decode by canonical
+// arithmetic from six registers -- per length the left-justified 15-bit upper limit of its codes and (first index in the
+// canonical order - first code) -- plus ONE load from the decoder's symbol order.  The walk through the decoder in global
+// memory (several dependent loads) is left for lengths beyond that.
+struct LongCodes {
+    uint32_t lim[3];  // lim(L0 + 2i) | lim(L0 + 2i + 1) << 16, in units of 2^-15 (the last limit of a full code is 32768)
+    uint32_t off[3];  // the same packing of (first_index - first_code) as int16
+    __device__ void load(const Decoder &d, int l0) {
+        for (int i = 0; i < 3; ++i) {
+            uint32_t lm = 0, of = 0;
+            for (int h = 0; h < 2; ++h) {
+                const int l = l0 + 2 * i + h;
+                uint32_t v = 0, o = 0;
+                if (l <= 15) {
+                    v = ((uint32_t)d.first_code[l] + (uint32_t)d.count[l]) << (15 - l);
+                    o = ((uint32_t)d.first_index[l] - (uint32_t)d.first_code[l]) & 0xFFFFu;
+                }
+                if (v > 0xFFFFu) v = 0xFFFFu;  // 65535 > every 15-bit code: same verdicts as 32768
+                lm |= v << (16 * h);
+                of |= o << (16 * h);
+            }
+            lim[i] = lm;
+            off[i] = of;
+        }
+    }
+    // bits = the next (at least 15) stream bits, LSB first.  -> index into d.sorted and the code length, or len = 0
+    __device__ __forceinline__ void find(uint32_t bits, int l0, int &index, int &len) const {
+        const uint32_t c15 = __brev(bits) >> 17;
+        const uint32_t l_0 = lim[0] & 0xFFFFu, l_1 = lim[0] >> 16, l_2 = lim[1] & 0xFFFFu, l_3 = lim[1] >> 16,
+                       l_4 = lim[2] & 0xFFFFu, l_5 = lim[2] >> 16;
+        const int k = (c15 >= l_0) + (c15 >= l_1) + (c15 >= l_2) + (c15 >= l_3) + (c15 >= l_4) + (c15 >= l_5);
+        const uint32_t pair = k < 2 ? off[0] : k < 4 ? off[1] : off[2];
+        const int o = (int)(int16_t)((k & 1) ? (pair >> 16) : (pair & 0xFFFFu));
+        const int l = l0 + k;
+        len = (k < 6 && l <= 15) ? l : 0;
+        index = (int)(c15 >> (15 - min(l, 15))) + o;
+    }
+};
+
 // Longest blocks first: the decode of a block is serial, so the kernel can not end before its longest block does, and a
 // warp waits for the slowest of its 32 lanes.  Blocks are bucketed by compressed size (a proxy for their token count)
 // in descending order; a warp then takes 32 blocks of similar size, the big ones start at once.
@@ -1119,8 +1210,9 @@ __global__ void __launch_bounds__(1024) lane_order_kernel(const LaneChunk *__res
 
 constexpr int kLaneLitBits = 9;   // literal/length codes up to 9 bits and ...
 constexpr int kLaneDistBits = 6;  // ... distance codes up to 6 bits decode from shared memory
-constexpr int kLaneWarps = 6;     // 6 x 36 KiB of tables: one persistent CTA per SM, 192 blocks in flight on it
-constexpr int kLaneWarpSmem = ((1 << kLaneLitBits) + (1 << kLaneDistBits)) * 32 * 2 + kRing * 32 * 4;
+constexpr int kLaneWarps = 6;     // 6 x 37 KiB of tables and rings: one persistent CTA per SM, 192 blocks in flight on it
+constexpr int kLaneLitEntries = 1 << kLaneLitBits, kLaneDistEntries = 1 << kLaneDistBits;
+constexpr int kLaneWarpSmem = (kLaneLitEntries + kLaneDistEntries) * 32 * 2 + kRing * 32 * 4;
 __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const uint8_t *__restrict__ in, uint64_t m,
                                                                           LaneChunk *lc, uint32_t num_chunks,
                                                                           WarpState *tables, uint16_t *slots,
@@ -1130,7 +1222,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
     // lane l sits at [i * 32 + l].  Longer codes go through the lane's WarpState in global memory.
     extern __shared__ __align__(16) uint16_t s_lut_all[];
     uint16_t *s_lit = s_lut_all + (threadIdx.x >> 5) * (kLaneWarpSmem / 2);
-    uint16_t *s_dist = s_lit + (1 << kLaneLitBits) * 32;
+    uint16_t *s_dist = s_lit + kLaneLitEntries * 32;
     const int lane = threadIdx.x & 31;
     const uint32_t num_tasks = (num_chunks + 31) / 32;
     for (;;) {
@@ -1152,8 +1244,9 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         TokenSink sink{0ull, 0u, out};
         const uint64_t in_end = lc[kk].in_end;
         const uint32_t dist_cap = (live && k == 0) ? 0u : (uint32_t)kWindow;  // block 0 has nothing before it (IS:287-291)
+        LongCodes long_lit, long_dist;
         FastReader fr;
-        fr.ring = (uint32_t)__cvta_generic_to_shared(s_dist + (1 << kLaneDistBits) * 32) + lane * 4;
+        fr.ring = (uint32_t)__cvta_generic_to_shared(s_dist + kLaneDistEntries * 32) + lane * 4;
         fr.lo = (uintptr_t)in;
         fr.hi = fr.lo + m;
         fr.seek_bits(lc[kk].in_begin * 8);
@@ -1234,6 +1327,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                                 const uint16_t e = ws.dist.lut[i];
                                 s_dist[i * 32 + lane] = (e >> 12) <= kLaneDistBits ? e : (uint16_t)0;
                             }
+                            long_lit.load(ws.lit, kLaneLitBits + 1);
+                            long_dist.load(ws.dist, kLaneDistBits + 1);
                             fr.seek_bits(br.bit_pos());
                             state = kSymbols;
                         }
@@ -1250,7 +1345,14 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         fr.drop((int)(e >> 12));
                         sym = (int)(e & 0x0FFFu);
                     } else {
-                        sym = decode_sym(ws.lit, fr);
+                        int index, len;
+                        long_lit.find((uint32_t)fr.hold, kLaneLitBits + 1, index, len);
+                        if (len) {
+                            fr.drop(len);
+                            sym = ws.lit.sorted[index];
+                        } else {
+                            sym = decode_sym(ws.lit, fr);
+                        }
                     }
                 }
                 if (sym < 256) {
@@ -1294,7 +1396,14 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         fr.drop((int)(e >> 12));
                         dsym = (int)(e & 0x0FFFu);
                     } else {
-                        dsym = decode_sym(ws.dist, fr);
+                        int index, len;
+                        long_dist.find((uint32_t)fr.hold, kLaneDistBits + 1, index, len);
+                        if (len) {
+                            fr.drop(len);
+                            dsym = ws.dist.sorted[index];
+                        } else {
+                            dsym = decode_sym(ws.dist, fr);
+                        }
                     }
                     const int dcl = min(max(dsym, 0), 29);
                     const int de = dcl < 4 ? 0 : (dcl >> 1) - 1;
@@ -1635,8 +1744,9 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
         ScopedTimer t(c, 5);
         const uint32_t nch = (uint32_t)verdict[0];
         if (nch) {
-            uint32_t group = 1;  // ~sqrt(n): phase A takes `group` dependent steps, phase B n / group
-            while (group * group < nch) group <<= 1;
+            // phase A takes `group` dependent steps of ~18 us (64 KiB maps), phase B n / group steps of ~4 us
+            uint32_t group = 1;
+            while (group * group * 4 < nch) group <<= 1;
             const uint32_t groups = (nch + group - 1) / group;
             ZK_CUDA(cudaFuncSetAttribute(window_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWindow));
             ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
