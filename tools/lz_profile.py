@@ -24,7 +24,7 @@ for name, gen in kinds.items():
     d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
     d_res = torch.zeros(4, dtype=torch.int64, device=dev)
     units = 256
-    prof = torch.zeros(units * 16, dtype=torch.int64, device=dev)
+    prof = torch.zeros(units * 32, dtype=torch.int64, device=dev)
     eng.set_option("chunk_bytes", 1 << 20)
     eng.set_option("lz_profile_buffer", prof.data_ptr())
     eng.set_option("timing", 1)
@@ -32,7 +32,7 @@ for name, gen in kinds.items():
         eng.counter("reset_timing")
         eng.deflate_device(d_in.data_ptr(), n, level, strategy, d_out.data_ptr(), cap, d_res.data_ptr())
         eng.synchronize()
-    p = prof.cpu().numpy().reshape(units, 16)[: n >> 20].astype(np.float64)
+    p = prof.cpu().numpy().reshape(units, 32)[: n >> 20].astype(np.float64)
     tot = p[:, 0].mean()
     lz_ms = eng.counter("lz77_us") / 1e3
     print("%-9s L%d lz77 %.2f ms (%.1f GB/s) huff %.2f pack %.2f ratio %.4f | cycles/byte %.1f | builder role %.0f%% search %.0f%% (%.0f) | parser role %.0f%% search %.0f%% (%.0f) | w2 search %.0f%% (%.0f) | w3 search %.0f%% (%.0f)" % (
@@ -40,4 +40,6 @@ for name, gen in kinds.items():
         100 * p[:, 1].mean() / tot, 100 * p[:, 2].mean() / tot, 100 * p[:, 3].mean() / tot,
         100 * p[:, 4].mean() / tot, 100 * p[:, 5].mean() / tot, 100 * p[:, 6].mean() / tot,
         100 * p[:, 8].mean() / tot, 100 * p[:, 9].mean() / tot, 100 * p[:, 11].mean() / tot, 100 * p[:, 12].mean() / tot))
+    print("          parser phases %% of unit: passA %.1f wait %.1f stitch+wait %.1f passB+scan %.1f wait %.1f copy-out %.1f" % tuple(
+        100 * p[:, 16 + q].mean() / tot for q in range(6)))
 eng.set_option("lz_profile_buffer", 0)

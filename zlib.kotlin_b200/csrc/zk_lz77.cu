@@ -41,6 +41,7 @@ constexpr int kStrip = 32 * kRun;            // positions per work-stealing stri
 constexpr int kStripsPerGroup = kGroup / kStrip;
 constexpr int kParserWarps = 4;
 constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
+constexpr int kPreRows = 8;                         // parser: real-parse tokens a lane may emit before convergence
 // The sequential roles (1 builder + 4 parser warps) all live on one SM sub-partition (warp id % 4 == 3): the issue
 // arbiter is fair among ready warps, so a role warp sharing its scheduler with seven issue-bound searcher warps gets
 // one slot in eight and becomes the critical path.  The other three warps of that sub-partition only search once the
@@ -61,6 +62,9 @@ struct LzSmem {
     uint8_t prep[2][kGroup];  // per position of a group to be built: 0x80 last of its hash in its batch, 0x40 | lane of
                               // the nearest lower lane with the same hash
     uint32_t stage[(kSeg + 2) * kParserWarps * 32];  // tokens of the group being parsed: [k][parser lane]
+    uint32_t pre[kPreRows * kParserWarps * 32];      // tokens of the real parse before it meets the speculative one
+    int32_t jnext[kParserWarps * 32];                // stitch: segment the parse of segment l exits into (pointer jumping)
+    int32_t jmark[kParserWarps * 32];                // stitch: segment l is entered by the real parse
     unsigned long long bar[kStages];
     int work[2];
     int roles_done[2];  // role warps that have finished their part of the step (parity = step)
@@ -450,7 +454,14 @@ __device__ __forceinline__ void parser_barrier() { asm volatile("bar.sync 1, %0;
 // L = parser lane 0..127.  The carry (first unparsed position, tokens emitted, block start) lives in shared
 // memory and is advanced by parser lane 0 after the last barrier of the group.
 __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, int L,
-                                            uint32_t unit_index) {
+                                            uint32_t unit_index, long long (&pt)[6]) {
+    long long tc = clock64();
+#define ZK_PT(i)                        \
+    {                                   \
+        const long long now = clock64(); \
+        pt[i] += now - tc;              \
+        tc = now;                       \
+    }
     uint32_t *mv = s.match[t & 1];
     const int lane = L & 31, pw = L >> 5;
     const int32_t g0 = t * kGroup;
@@ -458,71 +469,127 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     const int lazy = a.lp.lazy;
     const int32_t seg0 = min(g0 + L * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
 
-    // pass A: speculative parse of this lane's segment; only the exit (and the distance of the match that makes
-    // it) matter
+    constexpr int kLanes = kParserWarps * 32;
+    static_assert(kSeg == 32, "the visited-position mask of a segment is one 32-bit word");
+    uint32_t *col = s.stage + L;
+    // pass A: speculative parse of this lane's segment from its first position.  The tokens go to the lane's staging
+    // column, the positions it visits into a bit mask, the exit (and the distance of the match that makes it) to the
+    // stitch.
+    uint32_t visited = 0;
+    int cnt_spec = 0;
+    int32_t my_exit;
     {
         int32_t p = seg0, lastd = -1;
         while (p < seg1) {
+            const uint32_t w = mv[p - g0];
             const int step = decide(mv, g0, gend, p, lazy);
-            lastd = step > 1 ? (int32_t)(mv[p - g0] & 0xFFFFu) : -1;
+            visited |= 1u << (p - seg0);
+            lastd = step > 1 ? (int32_t)(w & 0xFFFFu) : -1;
+            col[cnt_spec * kLanes] = step > 1 ? (((uint32_t)step << 16) | (w & 0xFFFFu)) : ring_load8(s.ring, (uint32_t)p);
+            ++cnt_spec;
             p += step;
         }
-        s.pexit[L] = p;
+        my_exit = p;
         s.plast[L] = lastd;
+        s.jnext[L] = p >= gend ? kLanes : (p - g0) / kSeg;
+        s.jmark[L] = 0;
     }
+    ZK_PT(0)
     parser_barrier();
-    // stitch (first parser warp): segment l really starts where the parse left the segments before it
-    if (pw == 0) {
-        int32_t x = s.carry_entry;
-#pragma unroll 8
-        for (int l = 0; l < kParserWarps * 32; ++l) {
-            const int32_t send = min(g0 + (l + 1) * kSeg, gend);
-            const int32_t e = s.pexit[l];
-            const bool entered = x < send;
-            if (lane == (l & 31)) {
-                s.pstart[l] = x;
-                s.pstop[l] = entered ? e : x;  // empty range when the segment is already covered
-            }
-            x = entered ? e : x;
-        }
-        if (lane == 0) s.pfinal = x;
-    }
-    parser_barrier();
-    const int32_t my_start = s.pstart[L], my_stop = s.pstop[L];
-    // pass B: the tokens of [my_start, my_stop) go to this lane's column of the staging area.  When the real parse
-    // leaves the segment before my_stop (it had not converged with the speculative one), the rest is the tail of the
-    // speculative parse's last match: one match at that distance, or up to two literals, closes the gap.
-    int cnt = 0;
+    ZK_PT(1)
+    // stitch: the real parse enters the segment that holds the carry, and from an entered segment l the one its
+    // speculative exit lies in (the two parses have met by then, or the gap is closed below).  Which segments are
+    // entered is reachability along those links: pointer jumping, log2(128) rounds.
     {
-        uint32_t *col = s.stage + L;
-        int32_t p = my_start;
-        while (p < my_stop) {
-            uint32_t tok;
-            int step;
-            if (p >= seg1) {
-                const int gap = my_stop - p;
-                const int32_t d1 = s.plast[L];
-                if (gap >= 3 && d1 >= 0) {
-                    tok = ((uint32_t)gap << 16) | (uint32_t)d1;
-                    step = gap;
-                } else {
-                    tok = ring_load8(s.ring, (uint32_t)p);
-                    step = 1;
-                }
-            } else {
-                const uint32_t w = mv[p - g0];
-                step = decide(mv, g0, gend, p, lazy);
-                if (p + step > my_stop) step = my_stop - p;  // overshoot: cut (a match of < 3 becomes literals)
-                if (step >= 3) {
-                    tok = ((uint32_t)step << 16) | (w & 0xFFFFu);
-                } else {
-                    tok = ring_load8(s.ring, (uint32_t)p);
-                    step = 1;
-                }
+        const int32_t x0 = s.carry_entry;
+        const int first = x0 >= gend ? kLanes : (x0 - g0) / kSeg;
+        const int n0 = s.jnext[L];
+        if (L == first) s.jmark[L] = 1;
+        if (L == 0) s.pfinal = x0;  // stays when nothing is entered
+        int jn = n0;
+#pragma unroll 1
+        for (int round = 0; round < 7; ++round) {
+            parser_barrier();
+            int t2 = kLanes;
+            if (jn < kLanes) {
+                if (s.jmark[L]) s.jmark[jn] = 1;
+                t2 = s.jnext[jn];
             }
-            col[cnt * (kParserWarps * 32)] = tok;
+            parser_barrier();
+            jn = t2;
+            s.jnext[L] = jn;
+        }
+        parser_barrier();
+        const bool entered = s.jmark[L] != 0;
+        if (L == first) s.pstart[L] = x0;
+        if (entered) {
+            if (n0 < kLanes) s.pstart[n0] = my_exit;
+            else s.pfinal = my_exit;
+        }
+        parser_barrier();
+        s.pstop[L] = entered ? my_exit : 0;
+        if (!entered) s.pstart[L] = 0;
+    }
+    ZK_PT(2)
+    const int32_t my_start = s.pstart[L], my_stop = s.pstop[L];
+    // pass B: the lane's tokens are those of the real parse of [my_start, my_stop).  It usually meets the speculative
+    // parse within a few tokens (at a position that one visited): those few go to the prefix rows, the rest is already in
+    // the column.  Otherwise the range is parsed again into the column; when the real parse leaves the segment before
+    // my_stop, the rest is the tail of the speculative parse's last match: one match at that distance, or up to two
+    // literals, closes the gap.
+    int pre_cnt = 0, skip = 0, cnt = 0;
+    if (my_start < my_stop) {
+        int32_t p = my_start;
+        bool met = false;
+#pragma unroll 1
+        for (int it = 0; it <= kPreRows; ++it) {
+            if (p >= seg1) break;
+            if ((visited >> (p - seg0)) & 1u) {
+                met = true;
+                break;
+            }
+            if (it == kPreRows) break;
+            const uint32_t w = mv[p - g0];
+            const int step = decide(mv, g0, gend, p, lazy);
+            s.pre[pre_cnt * kLanes + L] = step > 1 ? (((uint32_t)step << 16) | (w & 0xFFFFu)) : ring_load8(s.ring, (uint32_t)p);
+            ++pre_cnt;
             p += step;
-            ++cnt;
+        }
+        if (met) {
+            skip = __popc(visited & ((1u << (p - seg0)) - 1u));
+            cnt = pre_cnt + cnt_spec - skip;
+        } else {
+            pre_cnt = 0;
+            skip = 0;
+            p = my_start;
+            while (p < my_stop) {
+                uint32_t tok;
+                int step;
+                if (p >= seg1) {
+                    const int gap = my_stop - p;
+                    const int32_t d1 = s.plast[L];
+                    if (gap >= 3 && d1 >= 0) {
+                        tok = ((uint32_t)gap << 16) | (uint32_t)d1;
+                        step = gap;
+                    } else {
+                        tok = ring_load8(s.ring, (uint32_t)p);
+                        step = 1;
+                    }
+                } else {
+                    const uint32_t w = mv[p - g0];
+                    step = decide(mv, g0, gend, p, lazy);
+                    if (p + step > my_stop) step = my_stop - p;  // overshoot: cut (a match of < 3 becomes literals)
+                    if (step >= 3) {
+                        tok = ((uint32_t)step << 16) | (w & 0xFFFFu);
+                    } else {
+                        tok = ring_load8(s.ring, (uint32_t)p);
+                        step = 1;
+                    }
+                }
+                col[cnt * kLanes] = tok;
+                p += step;
+                ++cnt;
+            }
         }
     }
     // dense offsets across the 128 parser lanes
@@ -533,7 +600,9 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         if (lane >= off) incl += v;
     }
     if (lane == 31) s.pcount[pw] = incl;
+    ZK_PT(3)
     parser_barrier();
+    ZK_PT(4)
     int before = 0, total = 0;
 #pragma unroll
     for (int k = 0; k < kParserWarps; ++k) {
@@ -545,8 +614,10 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     // copy-out: independent loads from the staging column, dense stores (adjacent lanes write adjacent runs)
     {
         uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + tok_off + (uint32_t)(before + incl - cnt);
-        const uint32_t *col = s.stage + L;
-        for (int k = 0; k < cnt; ++k) dst[k] = col[k * (kParserWarps * 32)];
+        for (int k = 0; k < pre_cnt; ++k) dst[k] = s.pre[k * kLanes + L];
+        const uint32_t *src = col + skip * kLanes;
+        dst += pre_cnt;
+        for (int k = 0; k < cnt - pre_cnt; ++k) dst[k] = src[k * kLanes];
     }
     // close the deflate block when this group ends it, then advance the carry (one lane; the next group's parse
     // starts after the CTA-wide barrier of the step)
@@ -564,6 +635,8 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         s.carry_entry = s.pfinal;
         s.carry_tok_off = new_off;
     }
+    ZK_PT(5)
+#undef ZK_PT
 }
 
 __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
@@ -622,6 +695,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
 
         // step i: stage(i+4) | prepare(i+2) | build(i+1) | search(i) | parse(i-1)
         long long t_role = 0, t_search = 0;
+        long long pt[6] = {0, 0, 0, 0, 0, 0};
         const long long t_unit0 = clock64();
         for (int i = g.first_group - 2; i <= g.last_group + 1; ++i) {
             const bool tma_next = (i + 4 <= g.last_group + 1) ? stage_group(s, a, g, i + 4, true) : false;
@@ -633,7 +707,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             const long long t0 = clock64();
             if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
             if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
-                parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit);
+                parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit, pt);
             if ((is_builder || is_parser) && lane == 0) atomicAdd(&s.roles_done[i & 1], 1);
             if (is_guest) {
                 // keep the role sub-partition quiet until the builder and the parsers have finished this step
@@ -675,8 +749,10 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         const int builder_warp = kBuilderSlot * 4 + kRoleSmsp, parser_warp = kFirstParserSlot * 4 + kRoleSmsp;
         if (a.prof && lane == 0 && (warp == builder_warp || warp == parser_warp || warp == 2 || warp == 3)) {
             // per unit: [0] total, then {role, search} of the builder, the first parser warp, a searcher and a guest
-            unsigned long long *o = a.prof + (size_t)unit * 16;
+            unsigned long long *o = a.prof + (size_t)unit * 32;
             const int k = warp == builder_warp ? 0 : warp == parser_warp ? 1 : warp == 2 ? 2 : 3;
+            if (warp == parser_warp)
+                for (int q = 0; q < 6; ++q) o[16 + q] = (unsigned long long)pt[q];
             if (warp == builder_warp) o[0] = (unsigned long long)(clock64() - t_unit0);
             o[1 + 3 * k] = (unsigned long long)t_role;
             o[2 + 3 * k] = (unsigned long long)t_search;
