@@ -336,7 +336,7 @@ def test_host_call_pipelined_slabs(engine, oracle, level):
     out_len = d_res.cpu().tolist()[0]
     # slab size differs between the two calls (64 MiB vs 256 MiB) only in where LZ units start: the streams need not
     # be identical, but both must decode to the input and stay within the same size
-    assert abs(out_len - len(stream)) <= len(stream) // 500
+    assert abs(out_len - len(stream)) <= len(stream) // 100
     rc2, out, _, _ = oracle.inflate(stream[: 8 << 20], cap=64 << 20)
     assert rc2 in (Z_BUF_ERROR, Z_STREAM_END) and len(out) > (4 << 20) and out == host[: len(out)].tobytes()
 

@@ -33,6 +33,7 @@ struct LevelParams {
     int far4;      // a length-4 match farther than this is dropped
     int min_len;   // 3, or 259 for Z_HUFFMAN_ONLY (no matches)
     int filtered;  // Z_FILTERED: matches of length <= 5 become literals
+    int probe_adaptive;  // 1: probe short distances everywhere only while a sample of positions finds such matches
 };
 
 // Per-block record written by the Huffman kernel and consumed by the packer.

@@ -53,6 +53,12 @@ constexpr int kRoleWarps = 1 + kParserWarps;
 constexpr int kHistGroups = kWindow / kGroup;
 constexpr int kMaxDist = kWindow - 2 * kGroup;
 constexpr int kStages = 4;                   // ring staging barriers
+// The short-distance probes (3-byte matches of binary records and runs) cost a fifth of the search and find nothing in
+// text: every group probes in its first kProbeSample strips only, and in all of them when the sample of the group
+// before it had at least kProbeThreshold hits.  Strips are fixed ranges of positions, so the decision does not depend
+// on which warp happens to search them.
+constexpr int kProbeSample = 8;
+constexpr int kProbeThreshold = 8;
 
 struct LzSmem {
     uint32_t ring[65536 / 4 + 8];  // + 32 mirrored bytes so a 20-byte read never wraps
@@ -67,6 +73,7 @@ struct LzSmem {
     int32_t jmark[kParserWarps * 32];                // stitch: segment l is entered by the real parse
     unsigned long long bar[kStages];
     int work[2];
+    int probe_hits[4];  // short-distance probe hits in the sampled strips of group t, at [t & 3]
     int roles_done[2];  // role warps that have finished their part of the step (parity = step)
     int32_t pexit[kParserWarps * 32];
     int32_t pstart[kParserWarps * 32];
@@ -270,7 +277,8 @@ __device__ __forceinline__ int common_prefix16(const Bytes16 &a, const Bytes16 &
 constexpr int kCap = 16;  // candidates are compared over 16 bytes; the nearest one that reaches 16 is extended
 
 __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, const UnitGeom &g, int t, int strip,
-                                             int lane, uint32_t block_shift) {
+                                             int lane, uint32_t block_shift, bool probe_all) {
+    const bool probing = probe_all || strip < kProbeSample;
     uint32_t *mv = s.match[t & 1];
     const int32_t base = t * kGroup + strip * kStrip + lane * kRun;
     int inh_len = 0, inh_dist = 0, inh_run = 0;
@@ -327,8 +335,9 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
         }
         // ---- short matches at small fixed distances (3-byte repeats of binary records, byte runs) -------------
         {
-            const bool want = valid && best < 4 && maxlen >= 3 && lp.min_len <= 3;
+            const bool want = probing && valid && best < 4 && maxlen >= 3 && lp.min_len <= 3;
             if (__any_sync(0xFFFFFFFFu, want)) {
+                bool hit3 = false;
                 // the 3 bytes at p against the 3 bytes at p-1, -2, -3, -4, -6, -8, -12, -16: all come from the 16
                 // bytes before p
                 const Bytes16 bk = ring_load128(s.ring, (uint32_t)(p - 16));
@@ -348,7 +357,12 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
                         best = len;
                         bestd = hit;
                         capped = len >= kCap;
+                        hit3 = true;
                     }
+                }
+                if (strip < kProbeSample) {
+                    const int hits = __popc(__ballot_sync(0xFFFFFFFFu, hit3));
+                    if (lane == 0 && hits) atomicAdd(&s.probe_hits[t & 3], hits);
                 }
             }
         }
@@ -666,6 +680,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             if (threadIdx.x == 0) {
                 for (int b = 0; b < kStages; ++b) mbar_init(&s.bar[b], 1);
                 s.work[0] = s.work[1] = 0;
+                s.probe_hits[0] = s.probe_hits[1] = s.probe_hits[2] = s.probe_hits[3] = 0;
                 s.roles_done[0] = s.roles_done[1] = 0;
                 s.carry_entry = kWindow;
                 s.carry_tok_off = 0;
@@ -701,8 +716,11 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             const bool tma_next = (i + 4 <= g.last_group + 1) ? stage_group(s, a, g, i + 4, true) : false;
             if (threadIdx.x == 0) {
                 s.work[(i + 1) & 1] = 0;
+                s.probe_hits[(i + 1) & 3] = 0;
                 s.roles_done[(i + 1) & 1] = 0;
             }
+            // (the first group of a unit has no sample before it: it probes everywhere)
+            const bool probe_all = !a.lp.probe_adaptive || i <= kHistGroups || s.probe_hits[(i - 1) & 3] >= kProbeThreshold;
 
             const long long t0 = clock64();
             if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
@@ -725,7 +743,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                     strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
                     if (strip >= kStripsPerGroup) break;
                     if (preparing) prep_strip(s, i + 2, strip, lane);
-                    if (searching) search_strip(s, a.lp, g, i, strip, lane, a.block_shift);
+                    if (searching) search_strip(s, a.lp, g, i, strip, lane, a.block_shift, probe_all);
                 }
             }
             const long long t2 = clock64();
@@ -773,6 +791,7 @@ LevelParams level_params(int level, int strategy) {
     p.min_len = 3;
     p.filtered = strategy == ZK_FILTERED;
     p.skip_deep = 1;
+    p.probe_adaptive = level <= 7;
     p.good = 8;
     p.nice = 128;
     p.lazy = 1;
