@@ -291,17 +291,34 @@ def main():
 
     # ---- e2e through the host-buffer C-ABI call (pinned memory; H2D + D2H inside) ----------------------------
     e2e = None
-    if shard is None:
-        h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
-        e_steps = max(1, min(args.steps, 3))
-        eng.deflate(h_in, args.level, out=h_out)  # warm-up: staging allocation
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    e_steps = max(1, min(args.steps, 3))
+    h_hist = hist.cpu().pin_memory() if (world > 1 and rank > 0) else None
+
+    def e2e_step():
+        if shard is None:
             rc, s, _ = eng.deflate(h_in, args.level, out=h_out)
-        dt = (time.perf_counter() - t0) / e_steps
-        e2e = {"value": n / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(len(s)) + 32,
-               "ms_per_step": dt * 1e3}
+        else:
+            rc = shard.step_host(h_in, args.level, h_out, h_hist)
+            s = None
+        if rc != 0:
+            raise SystemExit("host deflate failed rc=%d %s" % (rc, eng.last_error()))
+        return s
+
+    e2e_step()  # warm-up: staging allocation
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        s = e2e_step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / e_steps
+    e2e_out = int(len(s)) if s is not None else int(shard.d_meta.cpu().tolist()[0])
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": n * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": e2e_out + 32,
+           "ms_per_step": dt * 1e3, "note": "per GPU bytes; wall clock around the host-buffer call (max over ranks)"}
 
     if rank != 0:
         if world > 1:
@@ -317,11 +334,20 @@ def main():
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # dominant kernel: lz77_kernel.  Algorithmic bytes of the launches timed = uncompressed + compressed bytes of
     # this rank's steps; duration = CUDA-event time around those launches on their stream.
+    traffic, traffic_source = None, None
+    try:  # DRAM bytes of one lz77_kernel launch from the committed ncu capture, scaled to this run's launch size
+        tr = json.load(open(os.path.join(ROOT, "profiles", "lz77_traffic.json")))
+        launch_bytes = n * args.steps / max(1, lz_spans)
+        traffic = tr["dram_bytes_per_input_byte"] * launch_bytes
+        traffic_source = tr["source"]
+    except Exception:
+        pass
     alg_bytes = (n + total_out / world) * args.steps
     lz_s = lz_us * 1e-6
     achieved = alg_bytes / lz_s / 1e9 if lz_s > 0 else None
     roofline = {"bound": "hbm", "kernel": "lz77_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "peak_source": peak_kind, "traffic": None,
+                "frac": achieved / peak if achieved else None, "peak_source": peak_kind, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_source,
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, lz_spans),
                 "launches_timed": lz_spans, "avg_launch_ms": lz_us / 1e3 / max(1, lz_spans),
                 "share_of_step": {"lz77": lz_us / 1e3 / args.steps / ms_per_step, "huffman+offsets": huff_us / 1e3 / args.steps / ms_per_step,
                                   "pack": pack_us / 1e3 / args.steps / ms_per_step, "adler": adler_us / 1e3 / args.steps / ms_per_step}}

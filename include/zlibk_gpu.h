@@ -128,6 +128,10 @@ int zk_inflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t m, uint8_t
  * zk_deflate_zlib_device's d_result. */
 int zk_deflate_shard_device(zk_ctx *ctx, const uint8_t *d_hist, uint32_t hist_len, const uint8_t *d_in, uint64_t n,
                             int level, int strategy, uint8_t *d_body, uint64_t cap, uint64_t *d_meta);
+/* The same with host buffers (pipelined H2D / compute / D2H like zk_deflate_zlib): `hist` = the up to 32 KiB of input
+ * before this shard (host), the body goes to out_body. */
+int zk_deflate_shard(zk_ctx *ctx, const uint8_t *hist, uint32_t hist_len, const uint8_t *in, uint64_t n, int level,
+                     int strategy, uint8_t *out_body, uint64_t cap, uint64_t *body_len, uint32_t *adler);
 /* zlib header for `level` (2 bytes, DS:35-50) and stream tail (final empty block + big-endian
  * Adler-32, 6 bytes) as host helpers for the rank that owns them. */
 void zk_zlib_header(int level, uint8_t out2[2]);

@@ -32,6 +32,7 @@ SIGNATURES = {
     "zk_deflate_zlib_device": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, c_void_p]),
     "zk_inflate_zlib_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p]),
     "zk_deflate_shard_device": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, c_void_p]),
+    "zk_deflate_shard": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
     "zk_zlib_header": (None, [c_int, POINTER(c_uint8)]),
     "zk_zlib_tail": (None, [c_uint32, POINTER(c_uint8)]),
     "zk_deflate_init": (c_void_p, [c_void_p, c_int, c_int]),
@@ -184,6 +185,19 @@ class Engine:
 
     def deflate_shard_device(self, d_hist, hist_len, d_in, n, level, strategy, d_body, cap, d_meta):
         return self.lib.zk_deflate_shard_device(self.ctx, d_hist, hist_len, d_in, n, level, strategy, d_body, cap, d_meta)
+
+    def deflate_shard(self, hist, data, level=6, strategy=Z_DEFAULT_STRATEGY, out=None):
+        """Host buffers: -> (rc, body bytes-like, adler of the shard).  `hist` = up to 32 KiB before the shard or None."""
+        import numpy as np
+
+        addr, n, keep = _as_buffer(data)
+        haddr, hn, hkeep = _as_buffer(hist) if hist is not None and len(hist) else (None, 0, None)
+        if out is None:
+            out = np.empty(self.lib.zk_compress_bound(n), dtype=np.uint8)
+        oaddr, ocap, okeep = _as_buffer(out)
+        out_len, adler = c_uint64(0), c_uint32(0)
+        rc = self.lib.zk_deflate_shard(self.ctx, haddr, hn, addr, n, level, strategy, oaddr, ocap, ctypes.byref(out_len), ctypes.byref(adler))
+        return rc, out[: out_len.value], adler.value
 
     def adler32_combine(self, a1, a2, len2):
         return self.lib.zk_adler32_combine(a1, a2, len2)

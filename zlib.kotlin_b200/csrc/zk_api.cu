@@ -458,6 +458,7 @@ struct HostPipe {
     zk_ctx *c;
     const uint8_t *d_out;  // device stream (2 header bytes, then the body)
     uint8_t *out;          // caller's buffer
+    uint64_t lead;         // bytes in front of the body (2 for a framed stream, 0 for a shard)
     uint64_t *h_cursor;    // pinned: body bytes after slab k
     cudaEvent_t *in_ready, *done;
     uint32_t nslabs;
@@ -472,8 +473,8 @@ void pipe_flush(HostPipe *p, uint32_t upto) {  // send down the output of slabs 
         if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
         const uint64_t cur = p->h_cursor[k];
         if (cur > p->sent) {
-            e = cudaMemcpyAsync(p->out + 2 + p->sent, p->d_out + 2 + p->sent, cur - p->sent, cudaMemcpyDeviceToHost,
-                                p->c->copy_out);
+            e = cudaMemcpyAsync(p->out + p->lead + p->sent, p->d_out + p->lead + p->sent, cur - p->sent,
+                                cudaMemcpyDeviceToHost, p->c->copy_out);
             if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
             p->c->d2h_bytes += (int64_t)(cur - p->sent);
             p->sent = cur;
@@ -494,27 +495,29 @@ void pipe_after(void *user, uint32_t k, const uint64_t *d_cursor) {
 }
 }  // namespace
 
-int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
-                    uint64_t *out_len, uint32_t *adler) {
-    if (out_len) *out_len = 0;
-    if (!c || !out_len || (!in && n) || (!out && cap)) return ZK_STREAM_ERROR;
-    if (level > 9) return ZK_STREAM_ERROR;  // DS:323-325: nothing written
-    if (strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+// Host buffers -> device -> host, framed (a whole zlib stream) or as a shard body primed with `hist`.
+static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const uint8_t *in, uint64_t n, int level,
+                        int strategy, uint8_t *out, uint64_t cap, bool framed, uint64_t *out_len, uint32_t *adler) {
     ZK_CUDA(cudaSetDevice(c->device));
     const uint64_t bound = zk_compress_bound(n);
     const uint64_t dcap = cap < bound ? cap : bound;
     const size_t in_room = ((size_t)n + 255) / 256 * 256;
-    Staging *s = staging_for(c, 256 + in_room + (size_t)dcap + 256);
+    Staging *s = staging_for(c, 256 + (size_t)kWindow + in_room + (size_t)dcap + 256);
     if (!s) return ZK_MEM_ERROR;
     uint64_t *d_result = reinterpret_cast<uint64_t *>(s->base);
-    uint8_t *d_in = s->base + 256;
+    uint8_t *d_hist = s->base + 256;
+    uint8_t *d_in = d_hist + kWindow;
     uint8_t *d_out = d_in + in_room;
+    const uint64_t lead = framed ? 2 : 0;  // bytes in front of the body in d_out
+    if (hist_len) ZK_CUDA(cudaMemcpyAsync(d_hist, hist, hist_len, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (int64_t)hist_len;
     const uint32_t nslabs = (uint32_t)((n + kHostSlab - 1) / kHostSlab);
     const bool piped = level > 0 && nslabs >= 2 && nslabs <= kMaxHostSlabs && dcap >= 8;
+    DeflateJob job{d_in, n, hist_len ? d_hist : nullptr, hist_len, level, strategy, d_out, dcap, framed, d_result};
     if (!piped) {
         if (n) ZK_CUDA(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, c->stream));
         c->h2d_bytes += (int64_t)n;
-        int rc = zk_deflate_zlib_device(c, d_in, n, level, strategy, d_out, dcap, d_result);
+        int rc = run_deflate(c, job);
         if (rc != ZK_OK) return rc;
         uint64_t res[4];
         ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
@@ -535,7 +538,7 @@ int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
     uint64_t *h_cursor = nullptr;
     ZK_CUDA(cudaMallocHost(&h_cursor, (size_t)nslabs * 8 + 64));
     int rc = ZK_OK;
-    HostPipe pipe{c, d_out, out, h_cursor, ev.data(), ev.data() + nslabs, nslabs, 0, 0, cudaSuccess};
+    HostPipe pipe{c, d_out, out, lead, h_cursor, ev.data(), ev.data() + nslabs, nslabs, 0, 0, cudaSuccess};
     for (auto &e : ev)
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = ZK_ERRNO;
     uint64_t res[4] = {0, 0, 0, 0};
@@ -550,7 +553,6 @@ int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
             if (pipe.err == cudaSuccess) pipe.err = cudaEventRecord(pipe.in_ready[k], c->copy_in);
         }
         c->h2d_bytes += (int64_t)n;
-        DeflateJob job{d_in, n, nullptr, 0, level, strategy, d_out, dcap, true, d_result};
         job.slab_bytes = kHostSlab;
         job.before_slab = pipe_before;
         job.after_slab = pipe_after;
@@ -564,9 +566,9 @@ int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
             const int status = (int)(int64_t)res[2];
             if (pipe.err == cudaSuccess && status == ZK_OK) {
                 // header, and whatever follows the last slab's bytes (final block + Adler-32)
-                pipe.err = cudaMemcpyAsync(out, d_out, 2, cudaMemcpyDeviceToHost, c->copy_out);
-                if (pipe.err == cudaSuccess && res[0] > 2 + pipe.sent)
-                    pipe.err = cudaMemcpyAsync(out + 2 + pipe.sent, d_out + 2 + pipe.sent, res[0] - 2 - pipe.sent,
+                if (lead) pipe.err = cudaMemcpyAsync(out, d_out, lead, cudaMemcpyDeviceToHost, c->copy_out);
+                if (pipe.err == cudaSuccess && res[0] > lead + pipe.sent)
+                    pipe.err = cudaMemcpyAsync(out + lead + pipe.sent, d_out + lead + pipe.sent, res[0] - lead - pipe.sent,
                                                cudaMemcpyDeviceToHost, c->copy_out);
                 c->d2h_bytes += (int64_t)(res[0] - pipe.sent);
             }
@@ -580,7 +582,7 @@ int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
     cudaFreeHost(h_cursor);
     if (rc != ZK_OK) return rc;
     if (pipe.err != cudaSuccess) {
-        set_last_error("zk_deflate_zlib(pipelined)", pipe.err);
+        set_last_error("host deflate (pipelined)", pipe.err);
         return ZK_ERRNO;
     }
     const int status = (int)(int64_t)res[2];
@@ -588,6 +590,25 @@ int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
     if (status != ZK_OK) return status;
     *out_len = res[0];
     return ZK_OK;
+}
+
+int zk_deflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
+                    uint64_t *out_len, uint32_t *adler) {
+    if (out_len) *out_len = 0;
+    if (!c || !out_len || (!in && n) || (!out && cap)) return ZK_STREAM_ERROR;
+    if (level > 9) return ZK_STREAM_ERROR;  // DS:323-325: nothing written
+    if (strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    return host_deflate(c, nullptr, 0, in, n, level, strategy, out, cap, true, out_len, adler);
+}
+
+int zk_deflate_shard(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const uint8_t *in, uint64_t n, int level,
+                     int strategy, uint8_t *out_body, uint64_t cap, uint64_t *body_len, uint32_t *adler) {
+    if (body_len) *body_len = 0;
+    if (!c || !body_len || (!in && n) || (!out_body && cap) || hist_len > (uint32_t)kWindow || (!hist && hist_len))
+        return ZK_STREAM_ERROR;
+    if (level > 9) return ZK_STREAM_ERROR;
+    if (strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    return host_deflate(c, hist, hist_len, in, n, level, strategy, out_body, cap, false, body_len, adler);
 }
 
 int zk_inflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,

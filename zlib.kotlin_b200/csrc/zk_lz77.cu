@@ -74,7 +74,6 @@ struct LzSmem {
     unsigned long long bar[kStages];
     int work[2];
     int probe_hits[4];  // short-distance probe hits in the sampled strips of group t, at [t & 3]
-    int roles_done[2];  // role warps that have finished their part of the step (parity = step)
     int32_t pexit[kParserWarps * 32];
     int32_t pstart[kParserWarps * 32];
     int32_t pstop[kParserWarps * 32];
@@ -681,7 +680,6 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                 for (int b = 0; b < kStages; ++b) mbar_init(&s.bar[b], 1);
                 s.work[0] = s.work[1] = 0;
                 s.probe_hits[0] = s.probe_hits[1] = s.probe_hits[2] = s.probe_hits[3] = 0;
-                s.roles_done[0] = s.roles_done[1] = 0;
                 s.carry_entry = kWindow;
                 s.carry_tok_off = 0;
                 s.carry_blk_begin = 0;
@@ -717,7 +715,6 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             if (threadIdx.x == 0) {
                 s.work[(i + 1) & 1] = 0;
                 s.probe_hits[(i + 1) & 3] = 0;
-                s.roles_done[(i + 1) & 1] = 0;
             }
             // (the first group of a unit has no sample before it: it probes everywhere)
             const bool probe_all = !a.lp.probe_adaptive || i <= kHistGroups || s.probe_hits[(i - 1) & 3] >= kProbeThreshold;
@@ -726,13 +723,10 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
             if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
                 parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit, pt);
-            if ((is_builder || is_parser) && lane == 0) atomicAdd(&s.roles_done[i & 1], 1);
-            if (is_guest) {
-                // keep the role sub-partition quiet until the builder and the parsers have finished this step
-                volatile int *done = &s.roles_done[i & 1];
-                uint32_t spins = 0;
-                while (*done < kRoleWarps && ++spins < (1u << 18)) __nanosleep(1500);
-            }
+            // the other warps of the role sub-partition stay off its issue port until the builder and the parsers have
+            // finished this step: a named barrier (roles arrive, guests wait), no polling
+            if (is_builder || is_parser) asm volatile("bar.arrive 2, %0;" ::"n"(8 * 32) : "memory");
+            if (is_guest) asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
             const long long t1 = clock64();
             const bool searching = i >= kHistGroups && i <= g.last_group;
             const bool preparing = i + 2 >= g.first_group && i + 2 <= g.last_group;

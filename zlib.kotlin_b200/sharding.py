@@ -73,6 +73,19 @@ class ShardedDeflate:
         self.gathered = exchange(self.d_meta, self.world)  # the only collective
         return 0
 
+    def step_host(self, h_in, level, h_body, h_hist=None):
+        """The same through host buffers (H2D + D2H inside, pipelined in slabs): the end-to-end leg of bench.py.  The
+        meta record is rebuilt on the host and exchanged with the same single all_gather."""
+        import torch
+
+        rc, body, adler = self.eng.deflate_shard(h_hist, h_in, level, 0, out=h_body)
+        if rc != 0:
+            return rc
+        meta = torch.tensor([len(body), adler, 0, int(h_in.numel() if hasattr(h_in, "numel") else len(h_in))], dtype=torch.int64)
+        self.d_meta.copy_(meta)
+        self.gathered = exchange(self.d_meta, self.world)
+        return 0
+
     def finish(self):
         """Host view after the timed region: offsets, total length, folded Adler-32."""
         g = self.gathered.cpu().tolist()
