@@ -117,6 +117,15 @@ int zk_deflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t n, int lev
 int zk_inflate_zlib_device(zk_ctx *ctx, const uint8_t *d_in, uint64_t m, uint8_t *d_out, uint64_t cap,
                            uint64_t *d_result);
 
+/* ---- preset dictionaries (zlib.h deflateSetDictionary / inflateSetDictionary) ----
+ * The reference only detects FDICT and returns Z_NEED_DICT (inflate/InflateStream.kt:36-43); these entry points take
+ * the stream further: deflate emits FDICT + DICTID (Adler-32 of the dictionary) and primes matching with the
+ * dictionary's last 32 KiB; inflate checks DICTID (ZK_DATA_ERROR on mismatch) and resolves references into it. */
+int zk_deflate_zlib_dict(zk_ctx *ctx, const uint8_t *dict, uint32_t dict_len, const uint8_t *in, uint64_t n, int level,
+                         int strategy, uint8_t *out, uint64_t cap, uint64_t *out_len, uint32_t *adler);
+int zk_inflate_zlib_dict(zk_ctx *ctx, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
+                         uint64_t cap, uint64_t *out_len, uint64_t *consumed);
+
 /* ---- sharded deflate across GPUs ------------------------------------
  * Each rank compresses a contiguous range of the input as a headerless, byte-aligned body
  * (every block ends with a sync marker).  Ranks exchange {body_len, adler, raw_len} with

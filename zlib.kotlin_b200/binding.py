@@ -32,6 +32,8 @@ SIGNATURES = {
     "zk_deflate_zlib_device": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, c_void_p]),
     "zk_inflate_zlib_device": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p]),
     "zk_deflate_shard_device": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, c_void_p]),
+    "zk_deflate_zlib_dict": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
+    "zk_inflate_zlib_dict": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
     "zk_deflate_shard": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
     "zk_zlib_header": (None, [c_int, POINTER(c_uint8)]),
     "zk_zlib_tail": (None, [c_uint32, POINTER(c_uint8)]),
@@ -185,6 +187,30 @@ class Engine:
 
     def deflate_shard_device(self, d_hist, hist_len, d_in, n, level, strategy, d_body, cap, d_meta):
         return self.lib.zk_deflate_shard_device(self.ctx, d_hist, hist_len, d_in, n, level, strategy, d_body, cap, d_meta)
+
+    def deflate_dict(self, dictionary, data, level=6, strategy=Z_DEFAULT_STRATEGY):
+        """zlib stream with FDICT: -> (rc, stream bytes-like, adler of the data)."""
+        import numpy as np
+
+        addr, n, keep = _as_buffer(data)
+        daddr, dn, dkeep = _as_buffer(dictionary)
+        out = np.empty(self.lib.zk_compress_bound(n) + 16, dtype=np.uint8)
+        oaddr, ocap, okeep = _as_buffer(out)
+        out_len, adler = c_uint64(0), c_uint32(0)
+        rc = self.lib.zk_deflate_zlib_dict(self.ctx, daddr, dn, addr, n, level, strategy, oaddr, ocap, ctypes.byref(out_len), ctypes.byref(adler))
+        return rc, out[: out_len.value], adler.value
+
+    def inflate_dict(self, stream, dictionary, cap):
+        """-> (rc, bytes-like out[:out_len], consumed) for a stream whose header has FDICT."""
+        import numpy as np
+
+        addr, m, keep = _as_buffer(stream)
+        daddr, dn, dkeep = _as_buffer(dictionary)
+        out = np.empty(max(int(cap), 1), dtype=np.uint8)
+        oaddr, ocap, okeep = _as_buffer(out)
+        out_len, used = c_uint64(0), c_uint64(0)
+        rc = self.lib.zk_inflate_zlib_dict(self.ctx, addr, m, daddr, dn, oaddr, min(int(cap), ocap), ctypes.byref(out_len), ctypes.byref(used))
+        return rc, out[: out_len.value], used.value
 
     def deflate_shard(self, hist, data, level=6, strategy=Z_DEFAULT_STRATEGY, out=None):
         """Host buffers: -> (rc, body bytes-like, adler of the shard).  `hist` = up to 32 KiB before the shard or None."""

@@ -611,21 +611,31 @@ int zk_deflate_shard(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const ui
     return host_deflate(c, hist, hist_len, in, n, level, strategy, out_body, cap, false, body_len, adler);
 }
 
-int zk_inflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
-                    uint64_t *consumed) {
+static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
+                        uint64_t cap, uint64_t *out_len, uint64_t *consumed) {
     if (out_len) *out_len = 0;
     if (consumed) *consumed = 0;
-    if (!c || !out_len || (!in && m) || (!out && cap)) return ZK_STREAM_ERROR;
+    if (!c || !out_len || (!in && m) || (!out && cap) || (!dict && dict_len)) return ZK_STREAM_ERROR;
     ZK_CUDA(cudaSetDevice(c->device));
-    const size_t in_room = ((size_t)m + 255) / 256 * 256;
-    Staging *s = staging_for(c, 256 + in_room + (size_t)cap + 256);
+    uint32_t dict_id = 0;
+    if (dict) dict_id = dict_len ? zk_adler32(c, 1u, dict, dict_len) : 1u;  // DICTID = Adler-32 of the dictionary
+    const size_t in_room = ((size_t)m + 255) / 256 * 256, dict_room = ((size_t)dict_len + 255) / 256 * 256 + 256;
+    Staging *s = staging_for(c, 256 + dict_room + in_room + (size_t)cap + 256);
     if (!s) return ZK_MEM_ERROR;
     uint64_t *d_result = reinterpret_cast<uint64_t *>(s->base);
-    uint8_t *d_in = s->base + 256;
+    uint8_t *d_dict = s->base + 256;
+    uint8_t *d_in = d_dict + dict_room;
     uint8_t *d_out = d_in + in_room;
+    if (dict_len) ZK_CUDA(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, c->stream));
     if (m) ZK_CUDA(cudaMemcpyAsync(d_in, in, m, cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += (int64_t)m;
-    int rc = zk_inflate_zlib_device(c, d_in, m, d_out, cap, d_result);
+    c->h2d_bytes += (int64_t)m + dict_len;
+    InflateJob job{d_in, m, d_out, cap, d_result};
+    if (dict) {
+        job.d_dict = d_dict;
+        job.dict_len = dict_len;
+        job.dict_id = dict_id;
+    }
+    int rc = run_inflate(c, job);
     if (rc != ZK_OK) return rc;
     uint64_t res[4];
     ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
@@ -640,6 +650,43 @@ int zk_inflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint
     *out_len = res[0] <= cap ? res[0] : 0;
     if (consumed) *consumed = res[1];
     return status;
+}
+
+int zk_inflate_zlib(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                    uint64_t *consumed) {
+    return host_inflate(c, in, m, nullptr, 0, out, cap, out_len, consumed);
+}
+
+int zk_inflate_zlib_dict(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
+                         uint64_t cap, uint64_t *out_len, uint64_t *consumed) {
+    if (!dict) return ZK_STREAM_ERROR;
+    return host_inflate(c, in, m, dict, dict_len, out, cap, out_len, consumed);
+}
+
+int zk_deflate_zlib_dict(zk_ctx *c, const uint8_t *dict, uint32_t dict_len, const uint8_t *in, uint64_t n, int level,
+                         int strategy, uint8_t *out, uint64_t cap, uint64_t *out_len, uint32_t *adler) {
+    // zlib.h deflateSetDictionary: FDICT in the header, DICTID = Adler-32 of the dictionary, matching primed with its last
+    // 32 KiB; the trailer covers the data only
+    if (out_len) *out_len = 0;
+    if (!c || !out_len || !dict || (!in && n) || !out) return ZK_STREAM_ERROR;
+    if (level > 9 || strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    if (cap < 12) return ZK_BUF_ERROR;
+    const uint32_t id = dict_len ? zk_adler32(c, 1u, dict, dict_len) : 1u;
+    const uint32_t keep = dict_len > (uint32_t)kWindow ? (uint32_t)kWindow : dict_len;
+    uint64_t body = 0;
+    uint32_t a = 1;
+    int rc = zk_deflate_shard(c, dict + (dict_len - keep), keep, in, n, level, strategy, out + 6, cap - 12, &body, &a);
+    if (rc != ZK_OK) return rc;
+    uint8_t h[2];
+    zk_zlib_header(level, h);
+    h[1] = (uint8_t)((h[1] & 0xC0) | 0x20);
+    h[1] = (uint8_t)(h[1] + (31 - ((h[0] << 8) | h[1]) % 31) % 31);
+    out[0] = h[0], out[1] = h[1];
+    out[2] = (uint8_t)(id >> 24), out[3] = (uint8_t)(id >> 16), out[4] = (uint8_t)(id >> 8), out[5] = (uint8_t)id;
+    zk_zlib_tail(a, out + 6 + body);
+    *out_len = 6 + body + 6;
+    if (adler) *adler = a;
+    return ZK_OK;
 }
 
 // ---- streaming handles (docs/API.md:205-281) ------------------------------------------------------------------
@@ -657,6 +704,9 @@ struct zk_stream {
     std::vector<uint8_t> history;      // last 32 KiB of compressed-so-far input (deflate) / dictionary
     std::vector<uint8_t> pending_out;  // produced, not yet handed to the caller
     size_t out_pos;
+    bool have_dict = false;            // deflate: emit FDICT + DICTID; inflate: a dictionary has been supplied
+    uint32_t dict_id = 0;
+    std::vector<uint8_t> dict;         // inflate: the supplied dictionary
 };
 
 static const size_t kStreamSlab = 8u << 20;
@@ -726,9 +776,14 @@ int zk_deflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
     *out_len = 0;
     if (s->finished && avail_in) return ZK_STREAM_ERROR;
     if (!s->header_done) {
-        uint8_t h[2];
+        uint8_t h[6];
         zk_zlib_header(s->level, h);
-        s->pending_out.insert(s->pending_out.end(), h, h + 2);
+        if (s->have_dict) {  // zlib.h deflateSetDictionary: FDICT, then the dictionary's Adler-32
+            h[1] = (uint8_t)((h[1] & 0xC0) | 0x20);
+            h[1] = (uint8_t)(h[1] + (31 - ((h[0] << 8) | h[1]) % 31) % 31);
+            h[2] = (uint8_t)(s->dict_id >> 24), h[3] = (uint8_t)(s->dict_id >> 16), h[4] = (uint8_t)(s->dict_id >> 8), h[5] = (uint8_t)s->dict_id;
+        }
+        s->pending_out.insert(s->pending_out.end(), h, h + (s->have_dict ? 6 : 2));
         s->header_done = true;
     }
     if (avail_in) {
@@ -790,11 +845,13 @@ int zk_deflate_params(zk_stream *s, int level, int strategy) {
 }
 
 int zk_deflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len) {
-    // Raw priming only: the zlib wrapper's FDICT/DICTID is not emitted (the reference refuses FDICT streams,
-    // IS:36-43), so this is accepted before any input and only affects match finding.
-    if (!s || s->mode != 0 || !dict || s->total_in) return ZK_STREAM_ERROR;
+    // zlib.h semantics: accepted before any input; the header then carries FDICT and the dictionary's Adler-32, and the
+    // last 32 KiB of the dictionary prime the match finder (the same mechanism as a shard's history)
+    if (!s || s->mode != 0 || !dict || s->total_in || s->header_done) return ZK_STREAM_ERROR;
     const uint32_t keep = len > 32768 ? 32768 : len;
     s->history.assign(dict + (len - keep), dict + len);
+    s->have_dict = true;
+    s->dict_id = len ? zk_adler32(s->ctx, 1u, dict, len) : 1u;
     return ZK_OK;
 }
 
@@ -829,7 +886,9 @@ int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
         for (;;) {
             std::vector<uint8_t> buf(cap);
             uint64_t got = 0, used = 0;
-            int rc = zk_inflate_zlib(s->ctx, s->pending_in.data(), s->pending_in.size(), buf.data(), cap, &got, &used);
+            int rc = host_inflate(s->ctx, s->pending_in.data(), s->pending_in.size(), s->have_dict ? s->dict.data() : nullptr,
+                                  s->have_dict ? (uint32_t)s->dict.size() : 0u, buf.data(), cap, &got, &used);
+            if (rc == ZK_NEED_DICT) return ZK_NEED_DICT;  // the input stays pending: zk_inflate_set_dictionary, then call again
             if (rc == ZK_STREAM_END) {
                 buf.resize(got);
                 s->pending_out.swap(buf);
@@ -888,12 +947,14 @@ int zk_inflate_reset(zk_stream *s) {
 }
 
 int zk_inflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len) {
-    // The reference has no dictionary API and answers FDICT streams with Z_NEED_DICT (IS:36-43); preset
-    // dictionaries are a SURVEY.md 8(f) "next" row.
-    (void)dict;
-    (void)len;
-    if (!s || s->mode != 1) return ZK_STREAM_ERROR;
-    return ZK_STREAM_ERROR;
+    // zlib.h inflateSetDictionary: called after zk_inflate returned ZK_NEED_DICT (or up front).  The reference itself has
+    // no dictionary API and stops at Z_NEED_DICT (IS:36-43); this is the SURVEY.md 8(f) row built on the same priming
+    // mechanism as the chunk halos.  A dictionary whose Adler-32 is not the stream's DICTID gives ZK_DATA_ERROR at decode.
+    if (!s || s->mode != 1 || (!dict && len)) return ZK_STREAM_ERROR;
+    s->dict.assign(dict, dict + len);
+    if (s->dict.empty()) s->dict.push_back(0), s->dict.clear();
+    s->have_dict = true;
+    return ZK_OK;
 }
 
 uint64_t zk_stream_total_in(const zk_stream *s) { return s ? s->total_in : 0; }

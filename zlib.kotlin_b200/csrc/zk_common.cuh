@@ -146,6 +146,9 @@ struct InflateJob {
     uint8_t *d_out;
     uint64_t cap;
     uint64_t *d_result; // {out_len, consumed, status, adler}
+    const uint8_t *d_dict = nullptr;  // preset dictionary (device) for a stream with FDICT, or nullptr
+    uint32_t dict_len = 0;
+    uint32_t dict_id = 0;             // Adler-32 of the whole dictionary: must equal the stream's DICTID
 };
 int run_inflate(zk_ctx *c, const InflateJob &job);
 

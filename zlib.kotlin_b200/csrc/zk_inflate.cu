@@ -455,7 +455,7 @@ struct ChunkResult {
 // units -- a literal is one unit (its byte), a match two (0x8000 | length, distance - 1); `units` counts them.
 template <bool kWrite, bool kCoop, bool kTokens = false>
 __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m, uint64_t in_begin, uint64_t in_end,
-                                    bool first_chunk, uint16_t *sym, uint64_t out_begin, uint64_t out_cap, int lane,
+                                    uint64_t reach_before, uint16_t *sym, uint64_t out_begin, uint64_t out_cap, int lane,
                                     uint32_t *units_out = nullptr) {
     constexpr int kStep = kCoop ? 32 : 1;
     uint32_t units = 0;
@@ -586,7 +586,8 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
                 // IS:287-291 / 361-365: distance bounded by min(bytes out, 32768).  For a later chunk the
                 // bytes before it exist (the predecessor decoded them); the bound is checked when the
                 // symbol is resolved.
-                if (dist > kWindow || (first_chunk && (uint64_t)dist > produced)) {
+                // (reach_before: bytes that exist before this chunk -- the preset dictionary for the first one)
+                if (dist > kWindow || (uint64_t)dist > produced + reach_before) {
                     err = ZK_DATA_ERROR;
                     break;
                 }
@@ -649,16 +650,29 @@ __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m
 // ---- kernels --------------------------------------------------------------------------------------------
 
 // zlib header (IS:28-45) -> header[0] = status (ZK_OK / ZK_DATA_ERROR / ZK_NEED_DICT / ZK_BUF_ERROR)
-__global__ void header_kernel(const uint8_t *in, uint64_t m, int32_t *header) {
+// header[1] = offset of the deflate data (2, or 6 behind a DICTID).  A stream with FDICT needs the caller's dictionary:
+// without one the answer is ZK_NEED_DICT (all the reference does, IS:36-43); with one its Adler-32 must be the DICTID.
+__global__ void header_kernel(const uint8_t *in, uint64_t m, int32_t *header, int have_dict, uint32_t dict_id) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int st = ZK_OK;
+    int st = ZK_OK, body = 2;
     if (m < 2) st = ZK_BUF_ERROR;
     else {
         const int cmf = in[0], flg = in[1];
         if ((cmf & 0x0F) != 8 || ((cmf >> 4) & 0x0F) > 7 || (((cmf << 8) | flg) % 31) != 0) st = ZK_DATA_ERROR;
-        else if (flg & 0x20) st = m >= 6 ? ZK_NEED_DICT : ZK_BUF_ERROR;
+        else if (flg & 0x20) {
+            if (m < 6) st = ZK_BUF_ERROR;
+            else if (!have_dict) st = ZK_NEED_DICT;
+            else {
+                const uint32_t id = ((uint32_t)in[2] << 24) | ((uint32_t)in[3] << 16) | ((uint32_t)in[4] << 8) | (uint32_t)in[5];
+                if (id != dict_id) st = ZK_DATA_ERROR;
+                body = 6;
+            }
+        } else if (have_dict) {
+            st = ZK_OK;  // zlib.h: a dictionary nobody asked for is ignored
+        }
     }
     header[0] = st;
+    header[1] = body;
 }
 
 // one candidate chunk start per span: the first byte offset p in the span with in[p-4..p) == 00 00 FF FF
@@ -675,10 +689,10 @@ __global__ void __launch_bounds__(256) marker_kernel(const uint8_t *__restrict__
 
 // candidates -> chunk list (keeps every `every`-th span's candidate); single thread, a few thousand spans
 __global__ void chunk_list_kernel(const uint32_t *cand, uint32_t num_spans, uint32_t every, uint64_t m,
-                                  ChunkInfo *chunks, uint32_t *num_chunks, uint32_t max_chunks) {
+                                  ChunkInfo *chunks, uint32_t *num_chunks, uint32_t max_chunks, uint32_t body_begin) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t n = 0;
-    chunks[0].in_begin = 2;
+    chunks[0].in_begin = body_begin;
     n = 1;
     uint32_t since = 0;
     for (uint32_t s = 0; s < num_spans && n < max_chunks; ++s) {
@@ -705,7 +719,7 @@ __global__ void chunk_list_kernel(const uint32_t *cand, uint32_t num_spans, uint
 template <bool kWrite>
 __global__ void __launch_bounds__(kInfWarps * 32) decode_kernel(const uint8_t *__restrict__ in, uint64_t m,
                                                                 ChunkInfo *chunks, const uint32_t *num_chunks,
-                                                                uint16_t *sym, uint64_t out_cap) {
+                                                                uint16_t *sym, uint64_t out_cap, uint32_t dict_len) {
     __shared__ WarpState state[kInfWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t c = blockIdx.x * kInfWarps + wid;
@@ -713,7 +727,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) decode_kernel(const uint8_t *_
     ChunkInfo &ci = chunks[c];
     if (!kWrite && ci.out_len != ~0ull) return;  // sized in an earlier round
     const uint64_t room = kWrite ? (ci.out_begin <= out_cap ? out_cap - ci.out_begin : 0) : ~0ull;
-    const ChunkResult r = decode_chunk<kWrite, true>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0, sym, ci.out_begin, room, lane);
+    const ChunkResult r = decode_chunk<kWrite, true>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0 ? (uint64_t)dict_len : (uint64_t)kWindow, sym, ci.out_begin, room, lane);
     if (lane == 0) {
         ci.status = r.status;
         if (!kWrite) {
@@ -781,7 +795,7 @@ constexpr int kPerThread = kWindow / 1024;  // window slots per thread, interlea
 
 // slot (threadIdx.x + k*1024) of the tail map of chunk c, relative to the window of chunk c-1
 __device__ __forceinline__ void load_tail_map(const ChunkInfo *chunks, uint32_t c, const uint16_t *__restrict__ sym,
-                                              uint16_t (&sy)[kPerThread], uint32_t *error_flag) {
+                                              uint16_t (&sy)[kPerThread], uint32_t *error_flag, uint32_t dict_len) {
     const uint64_t begin = chunks[c].out_begin, len = chunks[c].out_len;
     const int64_t pos0 = (int64_t)(begin + len) - kWindow + threadIdx.x;
 #pragma unroll
@@ -790,12 +804,14 @@ __device__ __forceinline__ void load_tail_map(const ChunkInfo *chunks, uint32_t 
         uint16_t s = 0;
         if (pos >= (int64_t)begin) {
             s = sym[pos];
-            if ((s & 0x8000u) && (c == 0 || (int64_t)begin - kWindow + (int64_t)(s & 0x7FFFu) < 0)) {
+            if ((s & 0x8000u) && (int64_t)begin - kWindow + (int64_t)(s & 0x7FFFu) < -(int64_t)dict_len) {
                 atomicExch(error_flag, 1u);  // distance reaches before the start of the output (IS:287-291)
                 s = 0;
             }
-        } else if (c > 0 && pos >= 0) {
-            s = (uint16_t)(0x8000u | (uint32_t)((int64_t)kWindow - ((int64_t)begin - pos)));  // the chunk is shorter than the window
+        } else if (pos >= -(int64_t)dict_len) {
+            // the chunk is shorter than the window: the slot shows through to the window before it (for the first
+            // chunk that is the preset dictionary, window -1)
+            s = (uint16_t)(0x8000u | (uint32_t)((int64_t)kWindow - ((int64_t)begin - pos)));
         }
         sy[k] = s;
     }
@@ -803,13 +819,13 @@ __device__ __forceinline__ void load_tail_map(const ChunkInfo *chunks, uint32_t 
 
 __global__ void __launch_bounds__(1024) window_compose_kernel(const ChunkInfo *chunks, uint32_t n, uint32_t group,
                                                               const uint16_t *__restrict__ sym, uint16_t *maps,
-                                                              uint32_t *error_flag) {
+                                                              uint32_t *error_flag, uint32_t dict_len) {
     extern __shared__ __align__(16) uint16_t msm[];  // two maps of 32768 slots
     const uint32_t c0 = blockIdx.x * group, c1 = min(n, c0 + group);
     uint16_t sy[kPerThread], nx[kPerThread];
-    load_tail_map(chunks, c0, sym, sy, error_flag);
+    load_tail_map(chunks, c0, sym, sy, error_flag, dict_len);
     for (uint32_t c = c0; c < c1; ++c) {
-        if (c + 1 < c1) load_tail_map(chunks, c + 1, sym, nx, error_flag);  // independent of the composition below
+        if (c + 1 < c1) load_tail_map(chunks, c + 1, sym, nx, error_flag, dict_len);  // independent of the composition below
         const uint16_t *prev = msm + ((c + 1) & 1) * kWindow;
         uint16_t *cur = msm + (c & 1) * kWindow;
         uint16_t *glob = maps + (uint64_t)c * kWindow;
@@ -832,6 +848,9 @@ __global__ void __launch_bounds__(1024) window_chain_kernel(uint32_t n, uint32_t
     extern __shared__ __align__(16) uint8_t wsm[];  // two windows of 32 KiB
     const uint32_t groups = (n + group - 1) / group;
     uint16_t sy[kPerThread], nx[kPerThread];
+    // window -1 (the preset dictionary right-aligned, zeros otherwise) sits in the slot before windows[0]
+    for (int k = 0; k < kPerThread; ++k) wsm[kWindow + threadIdx.x + k * 1024] = (windows - kWindow)[threadIdx.x + k * 1024];
+    __syncthreads();
     {
         const uint16_t *mp = maps + (uint64_t)(min(n, group) - 1) * kWindow + threadIdx.x;
 #pragma unroll
@@ -851,8 +870,7 @@ __global__ void __launch_bounds__(1024) window_chain_kernel(uint32_t n, uint32_t
         for (int k = 0; k < kPerThread; ++k) {
             const int i = threadIdx.x + k * 1024;
             const uint16_t s = sy[k];
-            // group 0 has no entry window: its references were reported by window_compose_kernel
-            const uint8_t v = (s & 0x8000u) ? (g ? prev[s & 0x7FFFu] : (uint8_t)0) : (uint8_t)s;
+            const uint8_t v = (s & 0x8000u) ? prev[s & 0x7FFFu] : (uint8_t)s;
             cur[i] = v;
             glob[i] = v;
         }
@@ -867,14 +885,14 @@ __global__ void __launch_bounds__(1024) window_apply_kernel(uint32_t n, uint32_t
     const uint32_t c = blockIdx.x;
     const uint32_t g = c / group;
     if (c >= n || c == min(n, (g + 1) * group) - 1) return;  // group-last windows come from window_chain_kernel
-    const uint8_t *entry = g ? windows + (uint64_t)(g * group - 1) * kWindow : nullptr;
+    const uint8_t *entry = windows + ((int64_t)g * group - 1) * kWindow;  // group 0: window -1
     const uint16_t *mp = maps + (uint64_t)c * kWindow;
     uint8_t *glob = windows + (uint64_t)c * kWindow;
 #pragma unroll 8
     for (int k = 0; k < kPerThread; ++k) {
         const int i = threadIdx.x + k * 1024;
         const uint16_t s = mp[i];
-        glob[i] = (s & 0x8000u) ? (entry ? entry[s & 0x7FFFu] : (uint8_t)0) : (uint8_t)s;
+        glob[i] = (s & 0x8000u) ? entry[s & 0x7FFFu] : (uint8_t)s;
     }
 }
 
@@ -885,7 +903,7 @@ __global__ void __launch_bounds__(256) materialize_kernel(const ChunkInfo *__res
                                                           const uint32_t *__restrict__ num_chunks,
                                                           const uint16_t *__restrict__ sym,
                                                           const uint8_t *__restrict__ windows, uint8_t *__restrict__ out,
-                                                          uint64_t total, uint32_t *error_flag) {
+                                                          uint64_t total, uint32_t *error_flag, uint32_t dict_len) {
     __shared__ uint32_t s_lo;
     const uint32_t n = num_chunks[0];
     const uint64_t tile0 = (uint64_t)blockIdx.x * 16384;
@@ -927,11 +945,11 @@ __global__ void __launch_bounds__(256) materialize_kernel(const ChunkInfo *__res
                     nbegin = c + 1 < n ? chunks[c + 1].out_begin : ~0ull;
                 }
                 const uint32_t idx = s16 & 0x7FFFu;
-                if (c == 0 || (int64_t)cbegin - kWindow + (int64_t)idx < 0) {
+                if ((int64_t)cbegin - kWindow + (int64_t)idx < -(int64_t)dict_len) {
                     atomicExch(error_flag, 1u);
                     v = 0;
                 } else {
-                    v = windows[(uint64_t)(c - 1) * kWindow + idx];
+                    v = windows[((int64_t)c - 1) * kWindow + idx];  // chunk 0: window -1, the preset dictionary
                 }
             }
             bytes |= (uint64_t)v << (8 * e);
@@ -1100,10 +1118,10 @@ struct LaneChunk {
 };
 
 __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32_t num_markers, uint64_t m,
-                                  LaneChunk *__restrict__ lc) {
+                                  LaneChunk *__restrict__ lc, uint32_t body_begin) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > num_markers) return;
-    lc[k].in_begin = k == 0 ? 2 : positions[k - 1];
+    lc[k].in_begin = k == 0 ? body_begin : positions[k - 1];
     lc[k].in_end = k < num_markers ? positions[k] : m;
     lc[k].out_begin = 0;
     lc[k].out_len = 0;
@@ -1217,7 +1235,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                                                                           LaneChunk *lc, uint32_t num_chunks,
                                                                           WarpState *tables, uint16_t *slots,
                                                                           uint32_t *next_task,
-                                                                          const uint32_t *__restrict__ perm) {
+                                                                          const uint32_t *__restrict__ perm, uint32_t dict_len) {
     // every lane's short-code tables, interleaved so that the lanes of a warp fall into different banks: entry i of
     // lane l sits at [i * 32 + l].  Longer codes go through the lane's WarpState in global memory.
     extern __shared__ __align__(16) uint16_t s_lut_all[];
@@ -1243,7 +1261,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
         TokenSink sink{0ull, 0u, out};
         const uint64_t in_end = lc[kk].in_end;
-        const uint32_t dist_cap = (live && k == 0) ? 0u : (uint32_t)kWindow;  // block 0 has nothing before it (IS:287-291)
+        // bytes that exist before the block: the preset dictionary for block 0 (IS:287-291), a full window otherwise
+        const uint32_t reach_before = (live && k == 0) ? dict_len : (uint32_t)kWindow;
         LongCodes long_lit, long_dist;
         FastReader fr;
         fr.ring = (uint32_t)__cvta_generic_to_shared(s_dist + kLaneDistEntries * 32) + lane * 4;
@@ -1410,7 +1429,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     const uint32_t dbase = dcl < 4 ? 1u + (uint32_t)dcl : 1u + ((2u + (uint32_t)(dcl & 1)) << de);
                     const uint32_t dist = dbase + fr.peek(de);
                     fr.drop(de);
-                    if (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow || (dist_cap == 0u && dist > produced)) {
+                    if (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow || dist > produced + reach_before) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
                     } else if (produced + length > kSlotSyms) {
@@ -1616,7 +1635,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2);
     c->arena.reset();
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
-                        (size_t)max_chunks * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
+                        (size_t)(max_chunks + 1) * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
                         (size_t)lane_blocks_reserved * (12 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
@@ -1628,16 +1647,23 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     uint32_t *d_flag = static_cast<uint32_t *>(c->arena.take(256));
     uint32_t *d_adler = static_cast<uint32_t *>(c->arena.take(256));
     void *d_partials = c->arena.take(adler_partials_bytes(job.cap));
-    uint8_t *d_windows = static_cast<uint8_t *>(c->arena.take((size_t)max_chunks * kWindow));
+    // windows[-1] is the window before the stream: the preset dictionary right-aligned, zeros otherwise
+    uint8_t *d_windows = static_cast<uint8_t *>(c->arena.take((size_t)(max_chunks + 1) * kWindow)) + kWindow;
     uint16_t *d_maps = static_cast<uint16_t *>(c->arena.take((size_t)max_chunks * kWindow * 2));
     uint16_t *d_sym = static_cast<uint16_t *>(c->arena.take((job.cap + 64) * 2));
 
     // ---- header -------------------------------------------------------------------------------------
-    header_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_header);
+    header_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_header, job.d_dict != nullptr, job.dict_id);
     c->launches++;
-    int32_t hst = 0;
-    ZK_CUDA(cudaMemcpyAsync(&hst, d_header, 4, cudaMemcpyDeviceToHost, st));
+    int32_t hdr[2] = {0, 2};
+    ZK_CUDA(cudaMemcpyAsync(hdr, d_header, 8, cudaMemcpyDeviceToHost, st));
     ZK_CUDA(cudaStreamSynchronize(st));
+    const int32_t hst = hdr[0];
+    const uint32_t body_begin = (uint32_t)hdr[1];
+    const uint32_t dict_len = (job.d_dict && body_begin == 6) ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow) : 0u;
+    ZK_CUDA(cudaMemsetAsync(d_windows - kWindow, 0, kWindow, st));
+    if (dict_len)
+        ZK_CUDA(cudaMemcpyAsync(d_windows - dict_len, job.d_dict + (job.dict_len - dict_len), dict_len, cudaMemcpyDeviceToDevice, st));
     if (hst != ZK_OK) {
         // (hdr, 0): nothing decoded; FDICT consumes the 4 DICTID bytes (IS:41)
         set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, hst == ZK_NEED_DICT ? 6 : (m < 2 ? m : 2), hst, 1);
@@ -1670,7 +1696,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                 uint16_t *d_slots = static_cast<uint16_t *>(c->arena.take((size_t)n * kSlotSyms * 2));
                 if (d_pos && d_lc && d_tables && d_slots) {
                     marker_compact_kernel<true><<<pieces, 256, 0, st>>>(job.d_in, m, nullptr, d_piece_off, d_pos, num_markers);
-                    lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc);
+                    lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc, body_begin);
                     uint32_t *d_perm = static_cast<uint32_t *>(c->arena.take((size_t)n * 4));
                     lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
                     c->launches += 1;
@@ -1682,7 +1708,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                         ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
                         decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
-                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm);
+                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm, dict_len);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m);
                     c->launches += 4;
@@ -1708,14 +1734,14 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             const uint32_t grid = (uint32_t)tmin<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
             marker_kernel<<<grid ? grid : 1, 256, 0, st>>>(job.d_in, m, span_shift, d_cand);
         }
-        chunk_list_kernel<<<1, 32, 0, st>>>(d_cand, num_spans, 1, m, d_chunks, d_num, max_chunks);
+        chunk_list_kernel<<<1, 32, 0, st>>>(d_cand, num_spans, 1, m, d_chunks, d_num, max_chunks, body_begin);
         c->launches += 3;
         // ---- size pass, repeated while candidates turn out to be false ----------------------------------------
         for (int round = 0; round < 64; ++round) {
             const uint32_t grid = (max_chunks + kInfWarps - 1) / kInfWarps;
             {
                 ScopedTimer t(c, 4);
-                decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0);
+                decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0, dict_len);
             }
             plan_chunks_kernel<<<1, 32, 0, st>>>(d_chunks, d_num, d_verdict);
             c->launches += 2;
@@ -1735,7 +1761,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             const uint32_t nchunks = (uint32_t)verdict[0];
             const uint32_t grid = (nchunks + kInfWarps - 1) / kInfWarps;
             ScopedTimer t(c, 4);
-            decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap);
+            decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap, dict_len);
             c->launches += 1;
         }
     }
@@ -1750,13 +1776,13 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             const uint32_t groups = (nch + group - 1) / group;
             ZK_CUDA(cudaFuncSetAttribute(window_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWindow));
             ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
-            window_compose_kernel<<<groups, 1024, 4 * kWindow, st>>>(d_chunks, nch, group, d_sym, d_maps, d_flag);
+            window_compose_kernel<<<groups, 1024, 4 * kWindow, st>>>(d_chunks, nch, group, d_sym, d_maps, d_flag, dict_len);
             window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(nch, group, d_maps, d_windows);
             window_apply_kernel<<<nch, 1024, 0, st>>>(nch, group, d_maps, d_windows);
             c->launches += 2;
         }
         const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
-        if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag);
+        if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag, dict_len);
         c->launches += 2;
     }
     int rc = launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
