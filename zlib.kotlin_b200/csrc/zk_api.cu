@@ -112,7 +112,7 @@ static uint32_t pick_unit_bytes(const zk_ctx *c, uint64_t n, uint32_t block_byte
     return (uint32_t)tmax<uint64_t>(u, block_bytes);
 }
 
-constexpr uint64_t kSlabBytes = 256ull << 20;  // tokens for one slab: 4 B per input byte
+constexpr uint64_t kSlabBytes = 1024ull << 20;  // tokens for one slab: 4 B per input byte (4 GiB of scratch at most)
 
 int run_deflate(zk_ctx *c, const DeflateJob &job) {
     const uint64_t n = job.n;

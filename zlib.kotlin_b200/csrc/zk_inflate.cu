@@ -1585,11 +1585,19 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
             const uint32_t moff = __shfl_sync(0xFFFFFFFFu, off, src_lane);
             const uint32_t mlen = __shfl_sync(0xFFFFFFFFu, len, src_lane);
             const uint32_t mdist = __shfl_sync(0xFFFFFFFFu, nxt, src_lane) + 1u;
-            for (uint32_t i = lane; i < mlen; i += 32) {
-                const uint32_t kk = mdist >= mlen ? i : i % mdist;
-                const int32_t rel = (int32_t)moff - (int32_t)mdist + (int32_t)kk;  // position inside this block
-                const uint16_t v = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
-                out[moff + i] = v;
+            if (mdist >= mlen && mlen <= 32u) {  // the common case: one pass, no overlap
+                if ((uint32_t)lane < mlen) {
+                    const int32_t rel = (int32_t)moff - (int32_t)mdist + lane;  // position inside this block
+                    out[moff + lane] = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t i = lane; i < mlen; i += 32) {
+                    const uint32_t kk = mdist >= mlen ? i : i % mdist;
+                    const int32_t rel = (int32_t)moff - (int32_t)mdist + (int32_t)kk;
+                    const uint16_t v = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
+                    out[moff + i] = v;
+                }
             }
             __syncwarp();
         }

@@ -29,6 +29,10 @@
 // The symbol histograms are built from the token stream by hist_kernel (zk_huffman.cu).
 #include "zk_common.cuh"
 
+#ifndef ZK_USE_MATCH_ANY
+#define ZK_USE_MATCH_ANY 1
+#endif
+
 namespace zk {
 
 namespace {
@@ -199,6 +203,9 @@ __device__ __forceinline__ void prep_strip(LzSmem &s, int t, int strip, int lane
 #pragma unroll
     for (int u = 0; u < kStrip / 32; ++u) {
         const uint32_t hv = hash4(ring_load32(s.ring, q0 + u * 32));
+#if ZK_USE_MATCH_ANY
+        const uint32_t eq = __match_any_sync(0xFFFFFFFFu, hv);
+#else
         uint32_t eq = 0xFFFFFFFFu;
 #pragma unroll
         for (int bit = 0; bit < kHashBits; ++bit) {
@@ -206,6 +213,7 @@ __device__ __forceinline__ void prep_strip(LzSmem &s, int t, int strip, int lane
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, one);
             eq &= one ? bal : ~bal;
         }
+#endif
         const uint32_t below = eq & ((1u << lane) - 1u);
         uint32_t info = below ? (0x40u | (uint32_t)(31 - __clz(below))) : 0u;
         if (((eq >> lane) >> 1) == 0u) info |= 0x80u;
