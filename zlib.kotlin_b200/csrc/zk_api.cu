@@ -125,6 +125,7 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     c->arena.reset();
     const bool stored_only = level <= 0;
     const uint64_t slab_bytes = job.slab_bytes ? tmin<uint64_t>(job.slab_bytes, kSlabBytes) : kSlabBytes;
+    const uint64_t first_bytes = (job.first_slab_bytes && job.first_slab_bytes < slab_bytes) ? job.first_slab_bytes : slab_bytes;
     const uint64_t slab = tmin<uint64_t>(n, slab_bytes);
     const uint32_t slab_blocks = (uint32_t)((slab + block_bytes - 1) / block_bytes) + 1;
     size_t need = 8192 + adler_partials_bytes(n);
@@ -139,7 +140,7 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     int rc;
     if (stored_only) {
         if (job.before_slab)
-            for (uint32_t k = 0; (uint64_t)k * slab_bytes < n; ++k) job.before_slab(job.user, k);
+            for (uint32_t k = 0; (k ? first_bytes + (uint64_t)(k - 1) * slab_bytes : 0) < n; ++k) job.before_slab(job.user, k);
         {
             ScopedTimer t(c, 3);
             rc = launch_adler32(c, 1u, job.d_in, n, d_partials, d_adler);
@@ -169,8 +170,8 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     if (!d_offsets) return ZK_MEM_ERROR;
 
     uint32_t slab_index = 0;
-    for (uint64_t s0 = 0; s0 < n; s0 += slab_bytes, ++slab_index) {
-        const uint64_t sn = tmin<uint64_t>(slab_bytes, n - s0);
+    for (uint64_t s0 = 0; s0 < n; s0 += (slab_index ? slab_bytes : first_bytes), ++slab_index) {
+        const uint64_t sn = tmin<uint64_t>(slab_index ? slab_bytes : first_bytes, n - s0);
         if (job.before_slab) job.before_slab(job.user, slab_index);
         const uint32_t nb = (uint32_t)((sn + block_bytes - 1) / block_bytes);
         const uint32_t unit = pick_unit_bytes(c, sn, block_bytes);
@@ -452,7 +453,8 @@ uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len)
 // Pipelined host call: the input goes up in slabs on its own stream, slab k is compressed as soon as it has arrived,
 // and the bytes slab k produced come down on a third stream while slab k+1 is being compressed.
 namespace {
-constexpr uint64_t kHostSlab = 64ull << 20;
+constexpr uint64_t kHostSlab = 256ull << 20;       // large slabs keep the LZ units long (less history re-priming) ...
+constexpr uint64_t kHostFirstSlab = 64ull << 20;   // ... a short first one lets compute start after 64 MiB have arrived
 constexpr uint32_t kMaxHostSlabs = 4096;
 struct HostPipe {
     zk_ctx *c;
@@ -511,7 +513,7 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
     const uint64_t lead = framed ? 2 : 0;  // bytes in front of the body in d_out
     if (hist_len) ZK_CUDA(cudaMemcpyAsync(d_hist, hist, hist_len, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += (int64_t)hist_len;
-    const uint32_t nslabs = (uint32_t)((n + kHostSlab - 1) / kHostSlab);
+    const uint32_t nslabs = n <= kHostFirstSlab ? 1u : 1u + (uint32_t)((n - kHostFirstSlab + kHostSlab - 1) / kHostSlab);
     const bool piped = level > 0 && nslabs >= 2 && nslabs <= kMaxHostSlabs && dcap >= 8;
     DeflateJob job{d_in, n, hist_len ? d_hist : nullptr, hist_len, level, strategy, d_out, dcap, framed, d_result};
     if (!piped) {
@@ -548,12 +550,14 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
         cudaEventRecord(fence, c->stream);
         cudaStreamWaitEvent(c->copy_in, fence, 0);
         for (uint32_t k = 0; k < nslabs && pipe.err == cudaSuccess; ++k) {
-            const uint64_t off = (uint64_t)k * kHostSlab, len = tmin<uint64_t>(kHostSlab, n - off);
+            const uint64_t off = k ? kHostFirstSlab + (uint64_t)(k - 1) * kHostSlab : 0;
+            const uint64_t len = tmin<uint64_t>(k ? kHostSlab : kHostFirstSlab, n - off);
             pipe.err = cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->copy_in);
             if (pipe.err == cudaSuccess) pipe.err = cudaEventRecord(pipe.in_ready[k], c->copy_in);
         }
         c->h2d_bytes += (int64_t)n;
         job.slab_bytes = kHostSlab;
+        job.first_slab_bytes = kHostFirstSlab;
         job.before_slab = pipe_before;
         job.after_slab = pipe_after;
         job.user = &pipe;

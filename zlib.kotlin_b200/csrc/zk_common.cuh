@@ -134,6 +134,7 @@ struct DeflateJob {
     // before_slab(k) runs on the host before slab k's kernels are enqueued (wait for its H2D copy), after_slab(k,
     // d_cursor) after they are (d_cursor[0] = body bytes written so far, final for every slab up to k)
     uint64_t slab_bytes = 0;  // 0 = default
+    uint64_t first_slab_bytes = 0;  // 0 = slab_bytes; a short first slab lets compute start before much has arrived
     void (*before_slab)(void *user, uint32_t k) = nullptr;
     void (*after_slab)(void *user, uint32_t k, const uint64_t *d_cursor) = nullptr;
     void *user = nullptr;
