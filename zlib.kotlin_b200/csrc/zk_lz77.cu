@@ -39,7 +39,7 @@ namespace {
 
 constexpr int kThreadsLz = 1024;
 constexpr int kWarpsLz = kThreadsLz / 32;
-constexpr int kHashBits = 13;  // 8192 buckets of 32-bit positions (atomicMax needs 32 bits)
+constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
 constexpr int kRun = 2;                      // consecutive positions per lane (strip = 64 positions)
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
 constexpr int kStripsPerGroup = kGroup / kStrip;
@@ -67,7 +67,7 @@ constexpr int kProbeThreshold = 8;
 struct LzSmem {
     uint32_t ring[65536 / 4 + 8];  // + 32 mirrored bytes so a 20-byte read never wraps
     uint16_t prev[32768];
-    uint32_t head[1 << kHashBits];  // most recent position (q) per hash, 0 = none
+    uint16_t head[1 << kHashBits];  // most recent position (q & 0xFFFF) per hash
     uint32_t match[2][kGroup + 4];  // + slack: the parser reads one word past the group
     uint8_t prep[2][kGroup];  // per position of a group to be built: 0x80 last of its hash in its batch, 0x40 | lane of
                               // the nearest lower lane with the same hash
@@ -228,7 +228,7 @@ __device__ __forceinline__ void prep_strip(LzSmem &s, int t, int strip, int lane
 // are consumed only after eight batches have been issued.  No votes, no branches, no read-backs.
 __device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
     const uint32_t q0 = (uint32_t)t * kGroup + lane;
-    volatile uint32_t *vhead = s.head;
+    volatile uint16_t *vhead = s.head;
     const uint8_t *pp = s.prep[t & 1] + lane;
 #pragma unroll 1
     for (int b = 0; b < kGroup / 32; b += 8) {
@@ -241,7 +241,7 @@ __device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             old[u] = vhead[h[u]];
-            if (info[u] & 0x80u) vhead[h[u]] = q0 + (b + u) * 32;
+            if (info[u] & 0x80u) vhead[h[u]] = (uint16_t)(q0 + (b + u) * 32);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -786,7 +786,8 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
 LevelParams level_params(int level, int strategy) {
     // chain / nice / good / lazy per level.  The reference only varies the chain length (8/16/32/64 for level
     // <=2/<=4/<=6/else, DS:603-609) and never parses lazily (DS:610); these are tuned with tools/lzmodel.cpp so that
-    // level 6 lands on libz level-6 sizes (4-byte hash chains make a chain step worth ~3 of the reference's).
+    // level 6 lands just below libz level-6 sizes (4-byte hashes in 16384 buckets make a chain step worth several of the
+    // reference's 3-byte ones).
     LevelParams p;
     p.far3 = 256;
     p.far4 = 1024;
@@ -801,10 +802,10 @@ LevelParams level_params(int level, int strategy) {
         case 1: p.chain = 1; p.lazy = 0; p.nice = 32; break;
         case 2: p.chain = 2; p.lazy = 0; p.nice = 32; break;
         case 3: p.chain = 2; p.nice = 64; break;
-        case 4: p.chain = 3; p.nice = 64; break;
-        case 5: p.chain = 4; break;
-        case 6: p.chain = 4; break;
-        case 7: p.chain = 8; break;
+        case 4: p.chain = 2; break;
+        case 5: p.chain = 3; p.nice = 64; break;
+        case 6: p.chain = 3; break;
+        case 7: p.chain = 6; break;
         case 8: p.chain = 16; p.good = 32; p.nice = 258; break;
         default: p.chain = 32; p.good = 32; p.nice = 258; p.skip_deep = 0; break;
     }
