@@ -496,23 +496,66 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     // pass A: speculative parse of this lane's segment from its first position.  The tokens go to the lane's staging
     // column, the positions it visits into a bit mask, the exit (and the distance of the match that makes it) to the
     // stitch.
+    // No dependent chain through shared memory: the 33 match words of the segment are loaded with independent
+    // 16-byte loads, the step of every position (the lazy rule) is packed 8 bits per position into registers, and
+    // "which positions does the parse visit" is 32 unrolled register operations.  Tokens are then written for the
+    // visited positions (independent, predicated).
     uint32_t visited = 0;
     int cnt_spec = 0;
-    int32_t my_exit;
+    int32_t my_exit = seg0;
     {
-        int32_t p = seg0, lastd = -1;
-        while (p < seg1) {
-            const uint32_t w = mv[p - g0];
-            const int step = decide(mv, g0, gend, p, lazy);
-            visited |= 1u << (p - seg0);
-            lastd = step > 1 ? (int32_t)(w & 0xFFFFu) : -1;
-            col[cnt_spec * kLanes] = step > 1 ? (((uint32_t)step << 16) | (w & 0xFFFFu)) : ring_load8(s.ring, (uint32_t)p);
-            ++cnt_spec;
-            p += step;
+        const int seg_len = seg1 - seg0;
+        int32_t lastd = -1;
+        if (seg_len > 0) {
+            const uint32_t *mp = mv + (seg0 - g0);
+            uint32_t st[8];
+            uint4 cur = *reinterpret_cast<const uint4 *>(mp);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 nxt;
+                if (c < 7) nxt = *reinterpret_cast<const uint4 *>(mp + 4 * c + 4);
+                else nxt = make_uint4(mp[32], 0u, 0u, 0u);
+                const uint32_t w[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+                uint32_t packed = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int len = tok_len(w[j]), nextlen = tok_len(w[j + 1]);
+                    const bool defer = lazy && seg0 + 4 * c + j + 1 < gend && nextlen > len;
+                    const uint32_t step = (len == 0 || defer) ? 1u : (uint32_t)min(len, 64);
+                    packed |= step << (8 * j);
+                }
+                st[c] = packed;
+                cur = nxt;
+            }
+            visited = 1u;
+#pragma unroll
+            for (int i = 0; i < 31; ++i) {
+                const uint32_t tgt = (uint32_t)i + ((st[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                if (((visited >> i) & 1u) && tgt < 32u) visited |= 1u << tgt;
+            }
+            if (seg_len < 32) visited &= (1u << seg_len) - 1u;
+            const int lastpos = 31 - __clz(visited);
+            {
+                const int step = decide(mv, g0, gend, seg0 + lastpos, lazy);
+                lastd = step > 1 ? (int32_t)(mp[lastpos] & 0xFFFFu) : -1;
+                my_exit = seg0 + lastpos + step;
+            }
+            cnt_spec = __popc(visited);
+            // the segment's 32 bytes (aligned in the ring) for the literal tokens
+            const uint4 *rp = reinterpret_cast<const uint4 *>(s.ring + (((uint32_t)seg0 >> 2) & 0x3FFFu));
+            const uint4 r0 = rp[0], r1 = rp[1];
+            const uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if ((visited >> i) & 1u) {
+                    const bool is_match = ((st[i >> 2] >> (8 * (i & 3))) & 0xFFu) > 1u;
+                    const uint32_t tok = is_match ? (mp[i] & 0x01FFFFFFu) : ((rb[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                    col[__popc(visited & ((1u << i) - 1u)) * kLanes] = tok;
+                }
+            }
         }
-        my_exit = p;
         s.plast[L] = lastd;
-        s.jnext[L] = p >= gend ? kLanes : (p - g0) / kSeg;
+        s.jnext[L] = my_exit >= gend ? kLanes : (my_exit - g0) / kSeg;
         s.jmark[L] = 0;
     }
     ZK_PT(0)
