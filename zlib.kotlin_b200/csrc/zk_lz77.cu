@@ -45,7 +45,7 @@ constexpr int kStrip = 32 * kRun;            // positions per work-stealing stri
 constexpr int kStripsPerGroup = kGroup / kStrip;
 constexpr int kParserWarps = 4;
 constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
-constexpr int kPreRows = 8;                         // parser: real-parse tokens a lane may emit before convergence
+constexpr int kPreRows = 4;                         // parser: real-parse tokens a lane may emit before convergence
 // The sequential roles (1 builder + 4 parser warps) all live on one SM sub-partition (warp id % 4 == 3): the issue
 // arbiter is fair among ready warps, so a role warp sharing its scheduler with seven issue-bound searcher warps gets
 // one slot in eight and becomes the critical path.  The other three warps of that sub-partition only search once the
@@ -68,7 +68,9 @@ struct LzSmem {
     uint32_t ring[65536 / 4 + 8];  // + 32 mirrored bytes so a 20-byte read never wraps
     uint16_t prev[32768];
     uint16_t head[1 << kHashBits];  // most recent position (q & 0xFFFF) per hash
-    uint32_t match[2][kGroup + 4];  // + slack: the parser reads one word past the group
+    // best match per position of a group, skewed: position i sits at mvi(i) = i + 4 * (i / 32), so that the parser lanes
+    // (one 32-position segment each) read their rows with conflict-free 16-byte loads; + slack: one word past the group
+    uint32_t match[2][kGroup + kGroup / 8 + 8];
     uint8_t prep[2][kGroup];  // per position of a group to be built: 0x80 last of its hash in its batch, 0x40 | lane of
                               // the nearest lower lane with the same hash
     uint32_t stage[(kSeg + 2) * kParserWarps * 32];  // tokens of the group being parsed: [k][parser lane]
@@ -78,7 +80,6 @@ struct LzSmem {
     unsigned long long bar[kStages];
     int work[2];
     int probe_hits[4];  // short-distance probe hits in the sampled strips of group t, at [t & 3]
-    int32_t pexit[kParserWarps * 32];
     int32_t pstart[kParserWarps * 32];
     int32_t pstop[kParserWarps * 32];
     int32_t pfinal;
@@ -116,6 +117,7 @@ __device__ __forceinline__ uint32_t ring_load32(const uint32_t *ring, uint32_t q
 __device__ __forceinline__ uint32_t ring_load8(const uint32_t *ring, uint32_t q) {
     return (ring[(q >> 2) & 0x3FFFu] >> ((q & 3u) << 3)) & 0xFFu;
 }
+__device__ __forceinline__ int mvi(int i) { return i + ((i >> 5) << 2); }
 __device__ __forceinline__ uint32_t hash4(uint32_t four_bytes) { return (four_bytes * 0x9E3779B1u) >> (32 - kHashBits); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
@@ -440,7 +442,7 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
         inh_dist = bestd;
         uint32_t word = 0;
         if (best >= lp.min_len && !(lp.filtered && best <= 5)) word = ((uint32_t)best << 16) | (uint32_t)(bestd - 1);
-        mv[p - t * kGroup] = word;
+        mv[mvi(p - t * kGroup)] = word;
     }
 }
 
@@ -464,8 +466,8 @@ __device__ __forceinline__ int dist_symbol(int dist_minus1) {  // 0..29
 __device__ __forceinline__ int decide(const uint32_t *mv, int32_t g0, int32_t gend, int32_t p, int lazy) {
     // both words are loaded unconditionally (one slot of slack behind the group keeps p + 1 in bounds): no
     // dependent second load, no branch
-    const int len = tok_len(mv[p - g0]);
-    const int next = tok_len(mv[p + 1 - g0]);
+    const int len = tok_len(mv[mvi(p - g0)]);
+    const int next = tok_len(mv[mvi(p + 1 - g0)]);
     const bool defer = lazy && p + 1 < gend && next > len;
     return (len == 0 || defer) ? 1 : len;
 }
@@ -507,14 +509,14 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         const int seg_len = seg1 - seg0;
         int32_t lastd = -1;
         if (seg_len > 0) {
-            const uint32_t *mp = mv + (seg0 - g0);
+            const uint32_t *mp = mv + mvi(seg0 - g0);  // the segment's 32 words are contiguous
             uint32_t st[8];
             uint4 cur = *reinterpret_cast<const uint4 *>(mp);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 uint4 nxt;
                 if (c < 7) nxt = *reinterpret_cast<const uint4 *>(mp + 4 * c + 4);
-                else nxt = make_uint4(mp[32], 0u, 0u, 0u);
+                else nxt = make_uint4(mv[mvi(seg0 - g0 + 32)], 0u, 0u, 0u);
                 const uint32_t w[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
                 uint32_t packed = 0;
 #pragma unroll
@@ -545,12 +547,21 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
             const uint4 *rp = reinterpret_cast<const uint4 *>(s.ring + (((uint32_t)seg0 >> 2) & 0x3FFFu));
             const uint4 r0 = rp[0], r1 = rp[1];
             const uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            // eight positions at a time: the match words first (two 16-byte loads), then the stores -- a store to the
+            // staging column could alias the match array as far as the compiler knows, so one load per store would wait
+            // for shared memory 32 times in a row
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if ((visited >> i) & 1u) {
-                    const bool is_match = ((st[i >> 2] >> (8 * (i & 3))) & 0xFFu) > 1u;
-                    const uint32_t tok = is_match ? (mp[i] & 0x01FFFFFFu) : ((rb[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-                    col[__popc(visited & ((1u << i) - 1u)) * kLanes] = tok;
+            for (int c = 0; c < 4; ++c) {
+                const uint4 wa = *reinterpret_cast<const uint4 *>(mp + 8 * c), wb = *reinterpret_cast<const uint4 *>(mp + 8 * c + 4);
+                const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = 8 * c + j;
+                    if ((visited >> i) & 1u) {
+                        const bool is_match = ((st[i >> 2] >> (8 * (i & 3))) & 0xFFu) > 1u;
+                        const uint32_t tok = is_match ? (w8[j] & 0x01FFFFFFu) : ((rb[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                        col[__popc(visited & ((1u << i) - 1u)) * kLanes] = tok;
+                    }
                 }
             }
         }
@@ -613,7 +624,7 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
                 break;
             }
             if (it == kPreRows) break;
-            const uint32_t w = mv[p - g0];
+            const uint32_t w = mv[mvi(p - g0)];
             const int step = decide(mv, g0, gend, p, lazy);
             s.pre[pre_cnt * kLanes + L] = step > 1 ? (((uint32_t)step << 16) | (w & 0xFFFFu)) : ring_load8(s.ring, (uint32_t)p);
             ++pre_cnt;
@@ -640,7 +651,7 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
                         step = 1;
                     }
                 } else {
-                    const uint32_t w = mv[p - g0];
+                    const uint32_t w = mv[mvi(p - g0)];
                     step = decide(mv, g0, gend, p, lazy);
                     if (p + step > my_stop) step = my_stop - p;  // overshoot: cut (a match of < 3 becomes literals)
                     if (step >= 3) {
@@ -681,7 +692,13 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         for (int k = 0; k < pre_cnt; ++k) dst[k] = s.pre[k * kLanes + L];
         const uint32_t *src = col + skip * kLanes;
         dst += pre_cnt;
-        for (int k = 0; k < cnt - pre_cnt; ++k) dst[k] = src[k * kLanes];
+        const int rest = cnt - pre_cnt;
+        int k = 0;
+        for (; k + 4 <= rest; k += 4) {  // four loads in flight before the first store needs its value
+            const uint32_t t0 = src[k * kLanes], t1 = src[(k + 1) * kLanes], t2 = src[(k + 2) * kLanes], t3 = src[(k + 3) * kLanes];
+            dst[k] = t0, dst[k + 1] = t1, dst[k + 2] = t2, dst[k + 3] = t3;
+        }
+        for (; k < rest; ++k) dst[k] = src[k * kLanes];
     }
     // close the deflate block when this group ends it, then advance the carry (one lane; the next group's parse
     // starts after the CTA-wide barrier of the step)
