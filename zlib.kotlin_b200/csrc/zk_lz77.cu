@@ -29,6 +29,9 @@
 // The symbol histograms are built from the token stream by hist_kernel (zk_huffman.cu).
 #include "zk_common.cuh"
 
+#ifndef ZK_SPREAD_ROLES
+#define ZK_SPREAD_ROLES 1
+#endif
 #ifndef ZK_USE_MATCH_ANY
 #define ZK_USE_MATCH_ANY 1
 #endif
@@ -566,36 +569,44 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
             }
         }
         s.plast[L] = lastd;
-        s.jnext[L] = my_exit >= gend ? kLanes : (my_exit - g0) / kSeg;
-        s.jmark[L] = 0;
+    }
+    // stitch.  The real parse enters the segment that holds the carry, and from an entered segment l the one its
+    // speculative exit lies in (the two parses have met by then, or the gap is closed below): which segments are entered
+    // is reachability along those links.  Level 1, inside each parser warp with shuffles (pointer doubling, 5 rounds): for
+    // every segment of the warp the set of the warp's segments visited from it (a 32-bit mask) and the first segment
+    // after the warp it leads to.  Level 2, after one barrier: every lane walks the at most four hops from warp to warp.
+    const int n0 = my_exit >= gend ? kLanes : (my_exit - g0) / kSeg;
+    {
+        const int wbase = pw * 32;
+        int jl = n0;
+        uint32_t vm = 1u << lane;
+#pragma unroll
+        for (int round = 0; round < 5; ++round) {
+            const bool local = jl < wbase + 32;
+            const uint32_t vn = __shfl_sync(0xFFFFFFFFu, vm, jl & 31);
+            const int jn = __shfl_sync(0xFFFFFFFFu, jl, jl & 31);
+            if (local) {
+                vm |= vn;
+                jl = jn;
+            }
+        }
+        s.jnext[L] = jl;
+        s.jmark[L] = (int32_t)vm;
     }
     ZK_PT(0)
+    const int32_t x0 = s.carry_entry;
+    const int first = x0 >= gend ? kLanes : (x0 - g0) / kSeg;
+    if (L == 0) s.pfinal = x0;  // stays when nothing is entered
     parser_barrier();
     ZK_PT(1)
-    // stitch: the real parse enters the segment that holds the carry, and from an entered segment l the one its
-    // speculative exit lies in (the two parses have met by then, or the gap is closed below).  Which segments are
-    // entered is reachability along those links: pointer jumping, log2(128) rounds.
     {
-        const int32_t x0 = s.carry_entry;
-        const int first = x0 >= gend ? kLanes : (x0 - g0) / kSeg;
-        const int n0 = s.jnext[L];
-        if (L == first) s.jmark[L] = 1;
-        if (L == 0) s.pfinal = x0;  // stays when nothing is entered
-        int jn = n0;
+        bool entered = false;
+        int cur = first;
 #pragma unroll 1
-        for (int round = 0; round < 7; ++round) {
-            parser_barrier();
-            int t2 = kLanes;
-            if (jn < kLanes) {
-                if (s.jmark[L]) s.jmark[jn] = 1;
-                t2 = s.jnext[jn];
-            }
-            parser_barrier();
-            jn = t2;
-            s.jnext[L] = jn;
+        while (cur < kLanes) {
+            if ((cur >> 5) == pw) entered = (((uint32_t)s.jmark[cur]) >> lane) & 1u;
+            cur = s.jnext[cur];
         }
-        parser_barrier();
-        const bool entered = s.jmark[L] != 0;
         if (L == first) s.pstart[L] = x0;
         if (entered) {
             if (n0 < kLanes) s.pstart[n0] = my_exit;
@@ -694,9 +705,11 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         dst += pre_cnt;
         const int rest = cnt - pre_cnt;
         int k = 0;
-        for (; k + 4 <= rest; k += 4) {  // four loads in flight before the first store needs its value
+        // a lane's tokens are one contiguous run in global memory: scalar up to a 16-byte boundary, then four at a time
+        for (; k < rest && ((reinterpret_cast<uintptr_t>(dst + k)) & 15u) != 0; ++k) dst[k] = src[k * kLanes];
+        for (; k + 4 <= rest; k += 4) {
             const uint32_t t0 = src[k * kLanes], t1 = src[(k + 1) * kLanes], t2 = src[(k + 2) * kLanes], t3 = src[(k + 3) * kLanes];
-            dst[k] = t0, dst[k + 1] = t1, dst[k + 2] = t2, dst[k + 3] = t3;
+            *reinterpret_cast<uint4 *>(dst + k) = make_uint4(t0, t1, t2, t3);
         }
         for (; k < rest; ++k) dst[k] = src[k * kLanes];
     }
@@ -726,9 +739,18 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool on_role_smsp = (warp & 3) == kRoleSmsp;
     const int slot = warp >> 2;
+#if ZK_SPREAD_ROLES
+    // one parser warp per sub-partition (warps 24..27), the builder on warp 31; nobody waits
+    const bool is_builder = warp == 31;
+    const bool is_parser = warp >= 24 && warp < 28;
+    const bool is_guest = false;
+    const int parser_index = warp - 24;
+#else
     const bool is_builder = on_role_smsp && slot == kBuilderSlot;
     const bool is_parser = on_role_smsp && slot >= kFirstParserSlot && slot < kFirstParserSlot + kParserWarps;
     const bool is_guest = on_role_smsp && !is_builder && !is_parser;  // searches only after the roles are done
+    const int parser_index = slot - kFirstParserSlot;
+#endif
 
     for (uint32_t unit = blockIdx.x; unit < a.num_units; unit += gridDim.x) {
         UnitGeom g;
@@ -790,11 +812,13 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             const long long t0 = clock64();
             if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
             if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
-                parse_group(s, a, g, i - 1, (slot - kFirstParserSlot) * 32 + lane, unit, pt);
+                parse_group(s, a, g, i - 1, parser_index * 32 + lane, unit, pt);
             // the other warps of the role sub-partition stay off its issue port until the builder and the parsers have
             // finished this step: a named barrier (roles arrive, guests wait), no polling
+#if !ZK_SPREAD_ROLES
             if (is_builder || is_parser) asm volatile("bar.arrive 2, %0;" ::"n"(8 * 32) : "memory");
             if (is_guest) asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
+#endif
             const long long t1 = clock64();
             const bool searching = i >= kHistGroups && i <= g.last_group;
             const bool preparing = i + 2 >= g.first_group && i + 2 <= g.last_group;
@@ -826,7 +850,11 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             __syncthreads();
         }
         __syncthreads();
+#if ZK_SPREAD_ROLES
+        const int builder_warp = 31, parser_warp = 24;
+#else
         const int builder_warp = kBuilderSlot * 4 + kRoleSmsp, parser_warp = kFirstParserSlot * 4 + kRoleSmsp;
+#endif
         if (a.prof && lane == 0 && (warp == builder_warp || warp == parser_warp || warp == 2 || warp == 3)) {
             // per unit: [0] total, then {role, search} of the builder, the first parser warp, a searcher and a guest
             unsigned long long *o = a.prof + (size_t)unit * 32;
