@@ -126,6 +126,22 @@ int zk_deflate_zlib_dict(zk_ctx *ctx, const uint8_t *dict, uint32_t dict_len, co
 int zk_inflate_zlib_dict(zk_ctx *ctx, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
                          uint64_t cap, uint64_t *out_len, uint64_t *consumed);
 
+/* ---- CRC-32 and the gzip / raw-deflate containers ----------------
+ * The reference has neither (only a logging stub, common/ZlibLogger.kt:115-118); pigz's default format is gzip.
+ * zlib.h semantics: crc32(crc, buf, len), crc32_combine; RFC 1952 members, RFC 1951 raw streams. */
+uint32_t zk_crc32(zk_ctx *ctx, uint32_t crc, const uint8_t *buf, uint64_t len);
+int zk_crc32_device(zk_ctx *ctx, uint32_t crc, const uint8_t *d_buf, uint64_t len, uint32_t *d_out);
+uint32_t zk_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+int zk_deflate_gzip(zk_ctx *ctx, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
+                    uint64_t *out_len, uint32_t *crc);
+/* every member of the file is decoded, outputs concatenated (RFC 1952 2.2) */
+int zk_inflate_gzip(zk_ctx *ctx, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                    uint64_t *consumed);
+int zk_deflate_raw(zk_ctx *ctx, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
+                   uint64_t *out_len);
+int zk_inflate_raw(zk_ctx *ctx, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                   uint64_t *consumed);
+
 /* ---- sharded deflate across GPUs ------------------------------------
  * Each rank compresses a contiguous range of the input as a headerless, byte-aligned body
  * (every block ends with a sync marker).  Ranks exchange {body_len, adler, raw_len} with

@@ -34,6 +34,13 @@ SIGNATURES = {
     "zk_deflate_shard_device": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, c_void_p]),
     "zk_deflate_zlib_dict": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
     "zk_inflate_zlib_dict": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
+    "zk_crc32": (c_uint32, [c_void_p, c_uint32, c_void_p, c_uint64]),
+    "zk_crc32_device": (c_int, [c_void_p, c_uint32, c_void_p, c_uint64, c_void_p]),
+    "zk_crc32_combine": (c_uint32, [c_uint32, c_uint32, c_uint64]),
+    "zk_deflate_gzip": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
+    "zk_inflate_gzip": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
+    "zk_deflate_raw": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64)]),
+    "zk_inflate_raw": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
     "zk_deflate_shard": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
     "zk_zlib_header": (None, [c_int, POINTER(c_uint8)]),
     "zk_zlib_tail": (None, [c_uint32, POINTER(c_uint8)]),
@@ -187,6 +194,39 @@ class Engine:
 
     def deflate_shard_device(self, d_hist, hist_len, d_in, n, level, strategy, d_body, cap, d_meta):
         return self.lib.zk_deflate_shard_device(self.ctx, d_hist, hist_len, d_in, n, level, strategy, d_body, cap, d_meta)
+
+    def crc32(self, data, crc=0):
+        addr, n, keep = _as_buffer(data)
+        return self.lib.zk_crc32(self.ctx, crc, addr, n) if n else crc
+
+    def crc32_combine(self, crc1, crc2, len2):
+        return self.lib.zk_crc32_combine(crc1, crc2, len2)
+
+    def deflate_container(self, data, level=6, container="gzip", strategy=Z_DEFAULT_STRATEGY):
+        """-> (rc, stream bytes-like, crc32 or None) as a gzip member or a raw deflate stream."""
+        import numpy as np
+
+        addr, n, keep = _as_buffer(data)
+        out = np.empty(self.lib.zk_compress_bound(n) + 32, dtype=np.uint8)
+        oaddr, ocap, okeep = _as_buffer(out)
+        out_len, crc = c_uint64(0), c_uint32(0)
+        if container == "gzip":
+            rc = self.lib.zk_deflate_gzip(self.ctx, addr, n, level, strategy, oaddr, ocap, ctypes.byref(out_len), ctypes.byref(crc))
+            return rc, out[: out_len.value], crc.value
+        rc = self.lib.zk_deflate_raw(self.ctx, addr, n, level, strategy, oaddr, ocap, ctypes.byref(out_len))
+        return rc, out[: out_len.value], None
+
+    def inflate_container(self, stream, cap, container="gzip"):
+        """-> (rc, bytes-like out[:out_len], consumed)."""
+        import numpy as np
+
+        addr, m, keep = _as_buffer(stream)
+        out = np.empty(max(int(cap), 1), dtype=np.uint8)
+        oaddr, ocap, okeep = _as_buffer(out)
+        out_len, used = c_uint64(0), c_uint64(0)
+        fn = self.lib.zk_inflate_gzip if container == "gzip" else self.lib.zk_inflate_raw
+        rc = fn(self.ctx, addr, m, oaddr, min(int(cap), ocap), ctypes.byref(out_len), ctypes.byref(used))
+        return rc, out[: out_len.value], used.value
 
     def deflate_dict(self, dictionary, data, level=6, strategy=Z_DEFAULT_STRATEGY):
         """zlib stream with FDICT: -> (rc, stream bytes-like, adler of the data)."""

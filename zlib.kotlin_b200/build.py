@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libzlibk_b200.so")
-SOURCES = ["zk_adler.cu", "zk_lz77.cu", "zk_huffman.cu", "zk_pack.cu", "zk_inflate.cu", "zk_api.cu"]
+SOURCES = ["zk_adler.cu", "zk_crc32.cu", "zk_lz77.cu", "zk_huffman.cu", "zk_pack.cu", "zk_inflate.cu", "zk_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -499,17 +499,21 @@ void pipe_after(void *user, uint32_t k, const uint64_t *d_cursor) {
 
 // Host buffers -> device -> host, framed (a whole zlib stream) or as a shard body primed with `hist`.
 static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const uint8_t *in, uint64_t n, int level,
-                        int strategy, uint8_t *out, uint64_t cap, bool framed, uint64_t *out_len, uint32_t *adler) {
+                        int strategy, uint8_t *out, uint64_t cap, bool framed, uint64_t *out_len, uint32_t *adler,
+                        uint32_t *crc = nullptr) {
     ZK_CUDA(cudaSetDevice(c->device));
     const uint64_t bound = zk_compress_bound(n);
     const uint64_t dcap = cap < bound ? cap : bound;
     const size_t in_room = ((size_t)n + 255) / 256 * 256;
-    Staging *s = staging_for(c, 256 + (size_t)kWindow + in_room + (size_t)dcap + 256);
+    const size_t out_room = ((size_t)dcap + 255) / 256 * 256 + 256;
+    Staging *s = staging_for(c, 256 + (size_t)kWindow + in_room + out_room + crc_partials_bytes(n) + 256);
     if (!s) return ZK_MEM_ERROR;
     uint64_t *d_result = reinterpret_cast<uint64_t *>(s->base);
     uint8_t *d_hist = s->base + 256;
     uint8_t *d_in = d_hist + kWindow;
     uint8_t *d_out = d_in + in_room;
+    uint32_t *d_crc = reinterpret_cast<uint32_t *>(s->base + 128);  // second half of the result record
+    void *d_crc_partials = d_out + out_room;
     const uint64_t lead = framed ? 2 : 0;  // bytes in front of the body in d_out
     if (hist_len) ZK_CUDA(cudaMemcpyAsync(d_hist, hist, hist_len, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += (int64_t)hist_len;
@@ -520,9 +524,11 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
         if (n) ZK_CUDA(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, c->stream));
         c->h2d_bytes += (int64_t)n;
         int rc = run_deflate(c, job);
+        if (rc == ZK_OK && crc) rc = launch_crc32(c, 0u, d_in, n, d_crc_partials, d_crc);
         if (rc != ZK_OK) return rc;
         uint64_t res[4];
         ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+        if (crc) ZK_CUDA(cudaMemcpyAsync(crc, d_crc, 4, cudaMemcpyDeviceToHost, c->stream));
         ZK_CUDA(cudaStreamSynchronize(c->stream));
         c->d2h_bytes += 32;
         const int status = (int)(int64_t)res[2];
@@ -562,8 +568,10 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
         job.after_slab = pipe_after;
         job.user = &pipe;
         rc = run_deflate(c, job);
+        if (rc == ZK_OK && crc) rc = launch_crc32(c, 0u, d_in, n, d_crc_partials, d_crc);  // behind every slab's kernels
         if (rc == ZK_OK && pipe.err == cudaSuccess) {
             pipe.err = cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream);
+            if (crc && pipe.err == cudaSuccess) pipe.err = cudaMemcpyAsync(crc, d_crc, 4, cudaMemcpyDeviceToHost, c->stream);
             pipe_flush(&pipe, nslabs);  // waits for the last slab; the trailer kernels are behind it
             if (pipe.err == cudaSuccess) pipe.err = cudaStreamSynchronize(c->stream);
             c->d2h_bytes += 32;
@@ -616,7 +624,8 @@ int zk_deflate_shard(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const ui
 }
 
 static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
-                        uint64_t cap, uint64_t *out_len, uint64_t *consumed) {
+                        uint64_t cap, uint64_t *out_len, uint64_t *consumed, int container = 0, uint32_t body_begin = 0,
+                        uint32_t *check = nullptr) {
     if (out_len) *out_len = 0;
     if (consumed) *consumed = 0;
     if (!c || !out_len || (!in && m) || (!out && cap) || (!dict && dict_len)) return ZK_STREAM_ERROR;
@@ -639,6 +648,8 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
         job.dict_len = dict_len;
         job.dict_id = dict_id;
     }
+    job.container = container;
+    job.body_begin = body_begin;
     int rc = run_inflate(c, job);
     if (rc != ZK_OK) return rc;
     uint64_t res[4];
@@ -646,6 +657,7 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
     ZK_CUDA(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += 32;
     const int status = (int)(int64_t)res[2];
+    if (check) *check = (uint32_t)res[3];
     if (res[0] && res[0] <= cap) {
         ZK_CUDA(cudaMemcpyAsync(out, d_out, res[0], cudaMemcpyDeviceToHost, c->stream));
         ZK_CUDA(cudaStreamSynchronize(c->stream));
@@ -691,6 +703,130 @@ int zk_deflate_zlib_dict(zk_ctx *c, const uint8_t *dict, uint32_t dict_len, cons
     *out_len = 6 + body + 6;
     if (adler) *adler = a;
     return ZK_OK;
+}
+
+// ---- CRC-32 and the gzip / raw containers (RFC 1952 / RFC 1951) -------------------------------
+uint32_t zk_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { return crc32_combine(crc1, crc2, len2); }
+
+int zk_crc32_device(zk_ctx *c, uint32_t crc, const uint8_t *d_buf, uint64_t len, uint32_t *d_out) {
+    if (!c || !d_out || (!d_buf && len)) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    c->arena.reset();
+    if (c->arena.reserve(crc_partials_bytes(len) + 1024) != ZK_OK) return ZK_MEM_ERROR;
+    void *d_partials = c->arena.take(crc_partials_bytes(len));
+    return launch_crc32(c, crc, d_buf, len, d_partials, d_out);
+}
+
+uint32_t zk_crc32(zk_ctx *c, uint32_t crc, const uint8_t *buf, uint64_t len) {
+    if (buf == nullptr) return 0u;  // zlib.h: crc32(0, Z_NULL, 0) is the initial value
+    if (!c || len == 0) return crc;
+    if (cudaSetDevice(c->device) != cudaSuccess) return 0u;
+    Staging *s = staging_for(c, (size_t)len + 512);
+    if (!s) return 0u;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(s->base);
+    uint8_t *d_buf = s->base + 256;
+    if (cudaMemcpyAsync(d_buf, buf, len, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return 0u;
+    c->h2d_bytes += (int64_t)len;
+    if (zk_crc32_device(c, crc, d_buf, len, d_out) != ZK_OK) return 0u;
+    uint32_t out = 0;
+    if (cudaMemcpyAsync(&out, d_out, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return 0u;
+    cudaStreamSynchronize(c->stream);
+    c->d2h_bytes += 4;
+    return out;
+}
+
+int zk_deflate_raw(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
+                   uint64_t *out_len) {
+    // a complete raw deflate stream (RFC 1951): the shard body and the final empty fixed block
+    if (out_len) *out_len = 0;
+    if (!c || !out_len || (!in && n) || !out) return ZK_STREAM_ERROR;
+    if (level > 9 || strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    if (cap < 2) return ZK_BUF_ERROR;
+    uint64_t body = 0;
+    int rc = host_deflate(c, nullptr, 0, in, n, level < 1 ? 1 : level, strategy, out, cap - 2, false, &body, nullptr);
+    if (rc != ZK_OK) return rc;
+    out[body] = 0x03, out[body + 1] = 0x00;
+    *out_len = body + 2;
+    return ZK_OK;
+}
+
+int zk_deflate_gzip(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
+                    uint64_t *out_len, uint32_t *crc) {
+    // one gzip member (RFC 1952): 10-byte header without optional fields, raw deflate, CRC-32 and ISIZE (little-endian)
+    if (out_len) *out_len = 0;
+    if (!c || !out_len || (!in && n) || !out) return ZK_STREAM_ERROR;
+    if (level > 9 || strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
+    if (cap < 20) return ZK_BUF_ERROR;
+    const uint8_t head[10] = {0x1F, 0x8B, 8, 0, 0, 0, 0, 0, (uint8_t)(level >= 9 ? 2 : level <= 1 ? 4 : 0), 3 /* Unix */};
+    uint64_t body = 0;
+    uint32_t cr = 0;
+    int rc = host_deflate(c, nullptr, 0, in, n, level < 1 ? 1 : level, strategy, out + 10, cap - 20, false, &body, nullptr, &cr);
+    if (rc != ZK_OK) return rc;
+    memcpy(out, head, 10);
+    uint8_t *t = out + 10 + body;
+    t[0] = 0x03, t[1] = 0x00;
+    for (int i = 0; i < 4; ++i) {
+        t[2 + i] = (uint8_t)(cr >> (8 * i));
+        t[6 + i] = (uint8_t)((uint32_t)n >> (8 * i));
+    }
+    *out_len = 10 + body + 10;
+    if (crc) *crc = cr;
+    return ZK_OK;
+}
+
+int zk_inflate_raw(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                   uint64_t *consumed) {
+    return host_inflate(c, in, m, nullptr, 0, out, cap, out_len, consumed, 1, 0);
+}
+
+// RFC 1952 member header -> offset of the deflate data, or 0 (bad header) / ~0u (truncated)
+static uint32_t gzip_header_len(const uint8_t *p, uint64_t m) {
+    if (m < 10) return ~0u;
+    if (p[0] != 0x1F || p[1] != 0x8B || p[2] != 8 || (p[3] & 0xE0)) return 0;
+    const int flg = p[3];
+    uint64_t at = 10;
+    if (flg & 4) {  // FEXTRA
+        if (at + 2 > m) return ~0u;
+        at += 2 + ((uint64_t)p[at] | ((uint64_t)p[at + 1] << 8));
+    }
+    for (int bit = 8; bit <= 16; bit <<= 1)  // FNAME, FCOMMENT: zero-terminated
+        if (flg & bit) {
+            while (at < m && p[at]) ++at;
+            ++at;
+        }
+    if (flg & 2) at += 2;  // FHCRC
+    if (at > m) return ~0u;
+    return at > 0x7FFFFFFFull ? 0 : (uint32_t)at;
+}
+
+int zk_inflate_gzip(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                    uint64_t *consumed) {
+    // all members of the file (RFC 1952 2.2: a gzip file is a series of members), outputs concatenated
+    if (out_len) *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (!c || !out_len || (!in && m) || (!out && cap)) return ZK_STREAM_ERROR;
+    uint64_t at = 0, made = 0;
+    int members = 0;
+    while (at < m) {
+        const uint32_t h = gzip_header_len(in + at, m - at);
+        if (h == 0) {
+            if (members) break;  // trailing bytes that are not a member are left unread
+            return ZK_DATA_ERROR;
+        }
+        if (h == ~0u) return members ? ZK_STREAM_END : ZK_BUF_ERROR;
+        uint64_t got = 0, used = 0;
+        const int rc = host_inflate(c, in + at, m - at, nullptr, 0, out + made, cap - made, &got, &used, 2, h);
+        made += got;
+        *out_len = made;
+        if (rc != ZK_STREAM_END) {
+            if (consumed) *consumed = at + used;
+            return rc;
+        }
+        at += used;
+        ++members;
+        if (consumed) *consumed = at;
+    }
+    return members ? ZK_STREAM_END : ZK_BUF_ERROR;
 }
 
 // ---- streaming handles (docs/API.md:205-281) ------------------------------------------------------------------

@@ -150,8 +150,15 @@ struct InflateJob {
     const uint8_t *d_dict = nullptr;  // preset dictionary (device) for a stream with FDICT, or nullptr
     uint32_t dict_len = 0;
     uint32_t dict_id = 0;             // Adler-32 of the whole dictionary: must equal the stream's DICTID
+    int container = 0;                // 0 zlib, 1 raw deflate, 2 gzip member (header already parsed by the host)
+    uint32_t body_begin = 0;          // raw / gzip: offset of the deflate data in d_in
 };
 int run_inflate(zk_ctx *c, const InflateJob &job);
+
+// CRC-32 (gzip): same calling convention as launch_adler32
+size_t crc_partials_bytes(uint64_t n);
+int launch_crc32(zk_ctx *c, uint32_t seed, const uint8_t *d_buf, uint64_t n, void *d_partials, uint32_t *d_out);
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
 
 LevelParams level_params(int level, int strategy);
 uint32_t adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);

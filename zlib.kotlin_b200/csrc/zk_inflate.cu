@@ -962,28 +962,40 @@ __global__ void __launch_bounds__(256) materialize_kernel(const ChunkInfo *__res
     }
 }
 
-// Trailer check and result record.  result = {out_len, consumed, status, adler}
-__global__ void finish_inflate_kernel(const uint8_t *in, uint64_t m, const uint64_t *verdict, const uint32_t *adler,
-                                      const uint32_t *error_flag, uint64_t *result) {
+// Trailer check and result record.  result = {out_len, consumed, status, checksum}.  container: 0 zlib (big-endian
+// Adler-32, IS:414-424), 1 raw deflate (no trailer), 2 gzip (little-endian CRC-32 and ISIZE, RFC 1952).
+__global__ void finish_inflate_kernel(const uint8_t *in, uint64_t m, const uint64_t *verdict, const uint32_t *check,
+                                      const uint32_t *error_flag, uint64_t *result, int container) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int status = (int)(int64_t)verdict[2];
     const uint64_t total = verdict[3], end_byte = verdict[4];
     uint64_t consumed = end_byte;
     if (status == ZK_OK && error_flag[0]) status = ZK_DATA_ERROR;  // distance too far back (IS:287-291)
     if (status == ZK_OK) {
+        const uint64_t need = container == 0 ? 4 : container == 2 ? 8 : 0;
         if (!verdict[5]) status = ZK_BUF_ERROR;  // ran out of input before a final block
-        else if (end_byte + 4 > m) status = ZK_BUF_ERROR;  // IS:414-418 trailer bytes missing
-        else {
+        else if (end_byte + need > m) status = ZK_BUF_ERROR;  // IS:414-418 trailer bytes missing
+        else if (container == 0) {
             const uint32_t t = ((uint32_t)in[end_byte] << 24) | ((uint32_t)in[end_byte + 1] << 16) |
                                ((uint32_t)in[end_byte + 2] << 8) | (uint32_t)in[end_byte + 3];
             consumed = end_byte + 4;
-            status = t == adler[0] ? ZK_STREAM_END : ZK_DATA_ERROR;  // IS:419-424
+            status = t == check[0] ? ZK_STREAM_END : ZK_DATA_ERROR;  // IS:419-424
+        } else if (container == 2) {
+            uint32_t t = 0, sz = 0;
+            for (int i = 0; i < 4; ++i) {
+                t |= (uint32_t)in[end_byte + i] << (8 * i);
+                sz |= (uint32_t)in[end_byte + 4 + i] << (8 * i);
+            }
+            consumed = end_byte + 8;
+            status = (t == check[0] && sz == (uint32_t)total) ? ZK_STREAM_END : ZK_DATA_ERROR;
+        } else {
+            status = ZK_STREAM_END;
         }
     }
     result[0] = total;
     result[1] = consumed;
     result[2] = (uint64_t)(int64_t)status;
-    result[3] = adler[0];
+    result[3] = check[0];
 }
 
 __global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v) {
@@ -1475,7 +1487,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
 // Verify the blocks, prefix-sum their sizes, build the coarse chunk table for the window chain.
 // verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen
 __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_t n, ChunkInfo *coarse,
-                                                          uint32_t *num_coarse, uint64_t *verdict, uint64_t cap, uint64_t m) {
+                                                          uint32_t *num_coarse, uint64_t *verdict, uint64_t cap, uint64_t m,
+                                                          uint32_t trailer) {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
     __shared__ int bad;
@@ -1493,7 +1506,7 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
             // every block but the last must end exactly on the next one; the last must close the stream
             if (lc[i].status != ZK_OK || (last ? !lc[i].final_seen : (lc[i].final_seen || lc[i].end_byte != lc[i].in_end))) bad = 1;
             // a stream cut inside its trailer: the warp-per-chunk decoder reports what the reference reports (BR:48-57)
-            if (last && lc[i].end_byte + 4 > m) bad = 1;
+            if (last && lc[i].end_byte + trailer > m) bad = 1;
         }
         uint64_t incl = v;
 #pragma unroll
@@ -1643,7 +1656,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2);
     c->arena.reset();
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
-                        (size_t)(max_chunks + 1) * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + 8192 +
+                        (size_t)(max_chunks + 1) * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + crc_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
                         (size_t)lane_blocks_reserved * (12 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
@@ -1654,18 +1667,20 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     uint64_t *d_verdict = static_cast<uint64_t *>(c->arena.take(256));
     uint32_t *d_flag = static_cast<uint32_t *>(c->arena.take(256));
     uint32_t *d_adler = static_cast<uint32_t *>(c->arena.take(256));
-    void *d_partials = c->arena.take(adler_partials_bytes(job.cap));
+    void *d_partials = c->arena.take(tmax(adler_partials_bytes(job.cap), crc_partials_bytes(job.cap)));
     // windows[-1] is the window before the stream: the preset dictionary right-aligned, zeros otherwise
     uint8_t *d_windows = static_cast<uint8_t *>(c->arena.take((size_t)(max_chunks + 1) * kWindow)) + kWindow;
     uint16_t *d_maps = static_cast<uint16_t *>(c->arena.take((size_t)max_chunks * kWindow * 2));
     uint16_t *d_sym = static_cast<uint16_t *>(c->arena.take((job.cap + 64) * 2));
 
     // ---- header -------------------------------------------------------------------------------------
-    header_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_header, job.d_dict != nullptr, job.dict_id);
-    c->launches++;
-    int32_t hdr[2] = {0, 2};
-    ZK_CUDA(cudaMemcpyAsync(hdr, d_header, 8, cudaMemcpyDeviceToHost, st));
-    ZK_CUDA(cudaStreamSynchronize(st));
+    int32_t hdr[2] = {ZK_OK, (int32_t)job.body_begin};
+    if (job.container == 0) {
+        header_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_header, job.d_dict != nullptr, job.dict_id);
+        c->launches++;
+        ZK_CUDA(cudaMemcpyAsync(hdr, d_header, 8, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(cudaStreamSynchronize(st));
+    }
     const int32_t hst = hdr[0];
     const uint32_t body_begin = (uint32_t)hdr[1];
     const uint32_t dict_len = (job.d_dict && body_begin == 6) ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow) : 0u;
@@ -1718,7 +1733,8 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
                             job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm, dict_len);
                     }
-                    plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m);
+                    plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
+                                                          job.container == 0 ? 4u : job.container == 2 ? 8u : 0u);
                     c->launches += 4;
                     ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
                     ZK_CUDA(cudaStreamSynchronize(st));
@@ -1793,9 +1809,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
         if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag, dict_len);
         c->launches += 2;
     }
-    int rc = launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
+    int rc = job.container == 2 ? launch_crc32(c, 0u, job.d_out, total, d_partials, d_adler)
+                                : launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
     if (rc != ZK_OK) return rc;
-    finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result);
+    finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result, job.container);
     c->launches++;
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
