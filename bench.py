@@ -349,6 +349,9 @@ def main():
                 "frac": achieved / peak if achieved else None, "peak_source": peak_kind, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_source,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, lz_spans),
                 "launches_timed": lz_spans, "avg_launch_ms": lz_us / 1e3 / max(1, lz_spans),
+                # the one kernel of the path that IS bandwidth-bound: Adler-32 over the input (N algorithmic bytes)
+                "adler32_kernels": {"achieved": (n * args.steps) / (adler_us * 1e-6) / 1e9 if adler_us > 0 else None,
+                                    "frac": (n * args.steps) / (adler_us * 1e-6) / 1e9 / peak if adler_us > 0 else None, "unit": "GB/s"},
                 "share_of_step": {"lz77": lz_us / 1e3 / args.steps / ms_per_step, "huffman+offsets": huff_us / 1e3 / args.steps / ms_per_step,
                                   "pack": pack_us / 1e3 / args.steps / ms_per_step, "adler": adler_us / 1e3 / args.steps / ms_per_step}}
     line = {

@@ -125,16 +125,36 @@ __global__ void __launch_bounds__(kThreads) adler_spans_kernel(const uint8_t *__
 }
 
 // Fold the partials in order, starting from the seed.  One warp; the list is a few hundred long.
+// One warp: lane l folds a contiguous run of partials (independent loads), the lanes are combined pairwise in order with
+// shuffles (the combine is associative), lane 0 puts the seed in front.  The serial loop this replaces took as long as
+// the span kernel itself at 1 GiB.
 __global__ void adler_fold_kernel(const AdlerPartial *__restrict__ partials, int count, uint32_t seed,
                                   uint32_t *__restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t a = seed & 0xFFFFu, b = (seed >> 16) & 0xFFFFu;
-    for (int i = 0; i < count; ++i) {
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int run = (count + 31) / 32;
+    uint64_t a = 0, b = 0, len = 0;
+    for (int i = lane * run; i < min(count, (lane + 1) * run); ++i) {
         const AdlerPartial p = partials[i];
         b = (b + (p.len % kBase) * a + p.b) % kBase;
         a = (a + p.a) % kBase;
+        len += p.len;
     }
-    out[0] = (uint32_t)((b << 16) | a);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint64_t a2 = __shfl_down_sync(0xFFFFFFFFu, a, off), b2 = __shfl_down_sync(0xFFFFFFFFu, b, off);
+        const uint64_t l2 = __shfl_down_sync(0xFFFFFFFFu, len, off);
+        if (lane + off < 32) {
+            b = (b + (l2 % kBase) * a + b2) % kBase;
+            a = (a + a2) % kBase;
+            len += l2;
+        }
+    }
+    if (lane == 0) {
+        const uint64_t sa = seed & 0xFFFFu, sb = (seed >> 16) & 0xFFFFu;
+        const uint64_t rb = (sb + (len % kBase) * sa + b) % kBase, ra = (sa + a) % kBase;
+        out[0] = (uint32_t)((rb << 16) | ra);
+    }
 }
 
 int adler_grid(const zk_ctx *c, uint64_t n) {
