@@ -45,7 +45,12 @@ constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
 constexpr int kRun = 2;                      // consecutive positions per lane (strip = 64 positions)
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
-constexpr int kStripsPerGroup = kGroup / kStrip;
+// Work-stealing strips of a group: the first kBigStrips cover 64 positions each (two per lane: the second inherits from the
+// first), the rest of the group is cut into strips of 32 positions.  A step ends one strip after the last role warp has
+// joined the search, so the strips handed out last are the short ones.
+constexpr int kBigStrips = 40;
+constexpr int kSmallStrips = (kGroup - kBigStrips * kStrip) / 32;
+constexpr int kStripsPerGroup = kBigStrips + kSmallStrips;
 constexpr int kParserWarps = 4;
 constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
 constexpr int kPreRows = 4;                         // parser: real-parse tokens a lane may emit before convergence
@@ -202,11 +207,11 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
 // the batch.  The lane groups are an exact match.any, emulated with one ballot per hash bit (MATCH.ANY itself was
 // measured at several hundred cycles per call on B200); it is a pure function of the batch, so it runs in parallel
 // on the searcher warps and the serial builder is left with table updates only.
-__device__ __forceinline__ void prep_strip(LzSmem &s, int t, int strip, int lane) {
-    uint8_t *pp = s.prep[t & 1] + strip * kStrip;
-    const uint32_t q0 = (uint32_t)t * kGroup + strip * kStrip + lane;
-#pragma unroll
-    for (int u = 0; u < kStrip / 32; ++u) {
+__device__ __forceinline__ void prep_strip(LzSmem &s, int t, int pos0, int batches, int lane) {
+    uint8_t *pp = s.prep[t & 1] + pos0;
+    const uint32_t q0 = (uint32_t)t * kGroup + pos0 + lane;
+#pragma unroll 1
+    for (int u = 0; u < batches; ++u) {
         const uint32_t hv = hash4(ring_load32(s.ring, q0 + u * 32));
 #if ZK_USE_MATCH_ANY
         const uint32_t eq = __match_any_sync(0xFFFFFFFFu, hv);
@@ -289,13 +294,13 @@ __device__ __forceinline__ int common_prefix16(const Bytes16 &a, const Bytes16 &
 constexpr int kCap = 16;  // candidates are compared over 16 bytes; the nearest one that reaches 16 is extended
 
 __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, const UnitGeom &g, int t, int strip,
-                                             int lane, uint32_t block_shift, bool probe_all) {
+                                             int pos0, int run, int lane, uint32_t block_shift, bool probe_all) {
     const bool probing = probe_all || strip < kProbeSample;
     uint32_t *mv = s.match[t & 1];
-    const int32_t base = t * kGroup + strip * kStrip + lane * kRun;
+    const int32_t base = t * kGroup + pos0 + lane * run;
     int inh_len = 0, inh_dist = 0, inh_run = 0;
 #pragma unroll 1
-    for (int r = 0; r < kRun; ++r) {
+    for (int r = 0; r < run; ++r) {
         const int32_t p = base + r;
         const bool valid = p < g.data_end_q;
         // matches never cross the end of their deflate block
@@ -385,7 +390,7 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
         {
             bool ext = capped && best < maxlen;
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, ext);
-            const uint32_t scan0 = ((uint32_t)(t * kGroup + strip * kStrip + r) + kCap) & ~3u;  // word aligned
+            const uint32_t scan0 = ((uint32_t)(t * kGroup + pos0 + r) + kCap) & ~3u;  // word aligned
             while (pending) {
                 const int leader = __ffs(pending) - 1;
                 const uint32_t d = (uint32_t)__shfl_sync(0xFFFFFFFFu, bestd, leader);
@@ -828,8 +833,10 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                     if (lane == 0) strip = atomicAdd(&s.work[i & 1], 1);
                     strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
                     if (strip >= kStripsPerGroup) break;
-                    if (preparing) prep_strip(s, i + 2, strip, lane);
-                    if (searching) search_strip(s, a.lp, g, i, strip, lane, a.block_shift, probe_all);
+                    const int pos0 = strip < kBigStrips ? strip * kStrip : kBigStrips * kStrip + (strip - kBigStrips) * 32;
+                    const int run = strip < kBigStrips ? kRun : 1;
+                    if (preparing) prep_strip(s, i + 2, pos0, run, lane);  // run batches of 32 positions
+                    if (searching) search_strip(s, a.lp, g, i, strip, pos0, run, lane, a.block_shift, probe_all);
                 }
             }
             const long long t2 = clock64();
