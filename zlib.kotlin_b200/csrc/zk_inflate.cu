@@ -794,16 +794,27 @@ __global__ void plan_chunks_kernel(ChunkInfo *chunks, uint32_t *num_chunks, uint
 constexpr int kPerThread = kWindow / 1024;  // window slots per thread, interleaved: thread t owns t, t+1024, ...
 
 // slot (threadIdx.x + k*1024) of the tail map of chunk c, relative to the window of chunk c-1
-__device__ __forceinline__ void load_tail_map(const ChunkInfo *chunks, uint32_t c, const uint16_t *__restrict__ sym,
-                                              uint16_t (&sy)[kPerThread], uint32_t *error_flag, uint32_t dict_len) {
-    const uint64_t begin = chunks[c].out_begin, len = chunks[c].out_len;
+// Slot (threadIdx.x + k*1024) of the tail map of a chunk, relative to the window of the chunk before it, in two steps so
+// that the 32 loads of a thread are issued back to back and nothing waits for them until they are needed: raw symbols
+// first (fetch_tail), their interpretation when they are consumed (finish_tail).
+__device__ __forceinline__ void fetch_tail(uint64_t begin, uint64_t len, const uint16_t *__restrict__ sym,
+                                           uint16_t (&raw)[kPerThread]) {
+    const int64_t pos0 = (int64_t)(begin + len) - kWindow + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+        const int64_t pos = pos0 + k * 1024;
+        raw[k] = sym[pos >= (int64_t)begin ? pos : (int64_t)begin];  // clamped: always a valid address (len >= 0 slack: see host)
+    }
+}
+__device__ __forceinline__ void finish_tail(uint64_t begin, uint64_t len, uint16_t (&sy)[kPerThread], uint32_t *error_flag,
+                                            uint32_t dict_len) {
     const int64_t pos0 = (int64_t)(begin + len) - kWindow + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
         const int64_t pos = pos0 + k * 1024;
         uint16_t s = 0;
         if (pos >= (int64_t)begin) {
-            s = sym[pos];
+            s = sy[k];
             if ((s & 0x8000u) && (int64_t)begin - kWindow + (int64_t)(s & 0x7FFFu) < -(int64_t)dict_len) {
                 atomicExch(error_flag, 1u);  // distance reaches before the start of the output (IS:287-291)
                 s = 0;
@@ -823,9 +834,16 @@ __global__ void __launch_bounds__(1024) window_compose_kernel(const ChunkInfo *c
     extern __shared__ __align__(16) uint16_t msm[];  // two maps of 32768 slots
     const uint32_t c0 = blockIdx.x * group, c1 = min(n, c0 + group);
     uint16_t sy[kPerThread], nx[kPerThread];
-    load_tail_map(chunks, c0, sym, sy, error_flag, dict_len);
+    uint64_t begin = chunks[c0].out_begin, len = chunks[c0].out_len;
+    fetch_tail(begin, len, sym, sy);
+    finish_tail(begin, len, sy, error_flag, dict_len);
+    uint64_t nbegin = 0, nlen = 0;
+    if (c0 + 1 < c1) nbegin = chunks[c0 + 1].out_begin, nlen = chunks[c0 + 1].out_len;
     for (uint32_t c = c0; c < c1; ++c) {
-        if (c + 1 < c1) load_tail_map(chunks, c + 1, sym, nx, error_flag, dict_len);  // independent of the composition below
+        // the next chunk's symbols are requested now and interpreted after the barrier; the sizes of the one after it too
+        if (c + 1 < c1) fetch_tail(nbegin, nlen, sym, nx);
+        uint64_t nnbegin = 0, nnlen = 0;
+        if (c + 2 < c1) nnbegin = chunks[c + 2].out_begin, nnlen = chunks[c + 2].out_len;
         const uint16_t *prev = msm + ((c + 1) & 1) * kWindow;
         uint16_t *cur = msm + (c & 1) * kWindow;
         uint16_t *glob = maps + (uint64_t)c * kWindow;
@@ -838,8 +856,12 @@ __global__ void __launch_bounds__(1024) window_compose_kernel(const ChunkInfo *c
             glob[i] = s;
         }
         __syncthreads();
+        if (c + 1 < c1) {
 #pragma unroll
-        for (int k = 0; k < kPerThread; ++k) sy[k] = nx[k];
+            for (int k = 0; k < kPerThread; ++k) sy[k] = nx[k];
+            finish_tail(nbegin, nlen, sy, error_flag, dict_len);
+        }
+        nbegin = nnbegin, nlen = nnlen;
     }
 }
 
@@ -1627,12 +1649,40 @@ __global__ void __launch_bounds__(1024) resolve_coarse_kernel(const LaneChunk *_
     for (uint32_t j = first + 1; j < end; ++j) {
         const int64_t ob = (int64_t)lc[j].out_begin;
         const uint32_t len = lc[j].out_len;
-        for (uint32_t i = threadIdx.x; i < len; i += 1024) {
-            const uint16_t s16 = dense[ob + i];
+        // eight symbols per thread and step (one 16-byte load; most vectors hold no reference and are left alone);
+        // the unaligned head and the tail go one by one
+        const uint32_t head = tmin<uint32_t>(len, (uint32_t)((8 - (ob & 7)) & 7));
+        const uint32_t nvec = (len - head) >> 3;
+        for (uint32_t v = threadIdx.x; v < nvec; v += 1024) {
+            uint16_t *p = dense + ob + head + (uint64_t)v * 8;
+            uint4 w = *reinterpret_cast<const uint4 *>(p);
+            if (((w.x | w.y | w.z | w.w) & 0x80008000u) == 0) continue;
+            uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            uint16_t got[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {  // the loads first ...
+                const uint32_t s16 = (ws[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+                const int64_t pos = ob - kWindow + (int64_t)(s16 & 0x7FFFu);
+                got[e] = ((s16 & 0x8000u) && pos >= coarse_begin) ? __ldcg(dense + pos) : (uint16_t)0;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {  // ... then the symbols
+                const uint32_t s16 = (ws[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+                if (s16 & 0x8000u) {
+                    const int64_t pos = ob - kWindow + (int64_t)(s16 & 0x7FFFu);
+                    const uint32_t r = pos >= coarse_begin ? (uint32_t)got[e] : (0x8000u | (uint32_t)(pos - (coarse_begin - kWindow)));
+                    ws[e >> 1] = (ws[e >> 1] & ~(0xFFFFu << (16 * (e & 1)))) | (r << (16 * (e & 1)));
+                }
+            }
+            *reinterpret_cast<uint4 *>(p) = make_uint4(ws[0], ws[1], ws[2], ws[3]);
+        }
+        for (uint32_t i = threadIdx.x; i < head + ((len - head) & 7u); i += 1024) {
+            const uint32_t at = i < head ? i : head + nvec * 8 + (i - head);
+            const uint16_t s16 = dense[ob + at];
             if (s16 & 0x8000u) {
                 const int64_t pos = ob - kWindow + (int64_t)(s16 & 0x7FFFu);
-                dense[ob + i] = pos >= coarse_begin ? __ldcg(dense + pos)
-                                                    : (uint16_t)(0x8000u | (uint32_t)(pos - (coarse_begin - kWindow)));
+                dense[ob + at] = pos >= coarse_begin ? __ldcg(dense + pos)
+                                                     : (uint16_t)(0x8000u | (uint32_t)(pos - (coarse_begin - kWindow)));
             }
         }
         __syncthreads();  // the next block may refer to what was just written
