@@ -33,7 +33,10 @@ struct WarpScratch {
     uint32_t freq[kMaxSyms];      // working copy of the counts (>= 1 for coded symbols)
     uint16_t order[kMaxSyms];     // symbols sorted by ascending (freq, symbol)
     uint32_t weight[2 * kMaxSyms];
-    uint16_t parent[2 * kMaxSyms];
+    union {
+        uint16_t parent[2 * kMaxSyms];
+        uint32_t parent32[16];
+    };
     uint8_t depth[2 * kMaxSyms];
     uint8_t lit_len[kMaxSyms];
     uint8_t dist_len[32];
@@ -70,16 +73,28 @@ __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, in
     }
     used = __shfl_sync(0xFFFFFFFFu, used, 0);
     __syncwarp();
-    // 2. rank sort of the coded symbols by (freq, symbol)
-    for (int i = lane; i < n; i += 32) {
-        const uint32_t f = w.freq[i];
-        if (f == 0) continue;
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const uint32_t g = w.freq[j];
-            rank += (g != 0) && (g < f || (g == f && j < i));
+    // 2. rank sort of the coded symbols by (freq, symbol): one key per symbol (freq << 9 | symbol; counts are below
+    // 2^22), every lane ranks its up to nine symbols against all keys, which are read as broadcasts
+    {
+        uint32_t *key = w.weight;  // free until step 3
+        for (int i = lane; i < n; i += 32) key[i] = w.freq[i] ? ((w.freq[i] << 9) | (uint32_t)i) : 0xFFFFFFFFu;
+        __syncwarp();
+        uint32_t mykey[9];
+        int rank[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            mykey[t] = lane + 32 * t < n ? key[lane + 32 * t] : 0xFFFFFFFFu;
+            rank[t] = 0;
         }
-        w.order[rank] = (uint16_t)i;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t kj = key[j];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) rank[t] += kj < mykey[t];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+            if (mykey[t] != 0xFFFFFFFFu) w.order[rank[t]] = (uint16_t)(lane + 32 * t);
     }
     __syncwarp();
     // 3. tree with two queues (leaves in sorted order, internal nodes in creation order)
@@ -135,31 +150,37 @@ __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, in
 }
 
 // Canonical codes for `len`, bit-reversed for LSB-first emission; packed as code | len << 16.
-__device__ void assign_codes(const uint8_t *len, int n, int maxbits, uint32_t *packed, int lane) {
-    // every lane computes the tiny per-length table; symbols are then handled in parallel with a rank
-    int count[16];
-#pragma unroll
-    for (int b = 0; b < 16; ++b) count[b] = 0;
-    for (int i = 0; i < n; ++i) count[len[i]]++;
-    count[0] = 0;
-    int next[16];
-    int code = 0;
-    next[0] = 0;
-    for (int b = 1; b <= maxbits; ++b) {
-        code = (code + count[b - 1]) << 1;
-        next[b] = code;
-    }
-    for (int i = lane; i < n; i += 32) {
-        const int l = len[i];
-        uint32_t v = 0;
-        if (l) {
-            int rank = 0;
-            for (int j = 0; j < i; ++j) rank += len[j] == l;
-            v = bit_reverse((uint32_t)(next[l] + rank), l) | ((uint32_t)l << 16);
+__device__ void assign_codes(WarpScratch &w, const uint8_t *len, int n, int maxbits, uint32_t *packed, int lane) {
+    // symbols per length with shared atomics, first code of each length by lane 0, then the symbols in chunks of 32 in
+    // symbol order: a symbol's rank among the codes of its length is the running count of that length plus the number
+    // of lower lanes of the chunk with the same length (match.any)
+    uint32_t *count = w.cl_freq;   // 16 counters; the code-length frequencies are not needed any more when this runs ...
+    uint32_t *next = w.parent32;   // ... and neither is the tree
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32)
+        if (len[i]) atomicAdd(&count[len[i]], 1u);
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t code = 0;
+        next[0] = 0;
+        for (int b = 1; b <= maxbits; ++b) {
+            code = (code + (b > 1 ? count[b - 1] : 0u)) << 1;
+            next[b] = code;
         }
-        packed[i] = v;
     }
     __syncwarp();
+    for (int c = 0; c * 32 < n; ++c) {
+        const int i = c * 32 + lane;
+        const int l = i < n ? len[i] : 0;
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, l);
+        uint32_t v = 0;
+        if (l) v = bit_reverse(next[l] + (uint32_t)__popc(same & ((1u << lane) - 1u)), l) | ((uint32_t)l << 16);
+        __syncwarp();
+        if (l && (same & ((1u << lane) - 1u)) == 0u) next[l] += (uint32_t)__popc(same);
+        if (i < n) packed[i] = v;
+        __syncwarp();
+    }
 }
 
 struct BitSink {
@@ -257,14 +278,21 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint32_t *__re
     const uint32_t *tok = tokens + block_tok_begin[blk];
     const uint32_t n = block_tok_count[blk];
     uint32_t *mine = copy[wid];
-    for (uint32_t i = threadIdx.x; i < n; i += kHistThreads) {
-        const uint32_t t = tok[i];
-        const int len = (int)(t >> 16);
-        if (len == 0) {
-            atomicAdd(&mine[t & 0xFFu], 1u);
-        } else {
-            atomicAdd(&mine[hist_length_symbol(len)], 1u);
-            atomicAdd(&mine[kDistHistBase + hist_dist_symbol((int)(t & 0xFFFFu))], 1u);
+    // four tokens per thread and trip, the loads first: a load followed at once by its use waits for DRAM every time
+    for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 4 * kHistThreads) {
+        uint32_t t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = i0 + k * kHistThreads < n ? __ldg(tok + i0 + k * kHistThreads) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (t[k] == 0xFFFFFFFFu) continue;  // not a token: length field 0xFFFF does not occur
+            const int len = (int)(t[k] >> 16);
+            if (len == 0) {
+                atomicAdd(&mine[t[k] & 0xFFu], 1u);
+            } else {
+                atomicAdd(&mine[hist_length_symbol(len)], 1u);
+                atomicAdd(&mine[kDistHistBase + hist_dist_symbol((int)(t[k] & 0xFFFFu))], 1u);
+            }
         }
     }
     __syncthreads();
@@ -310,7 +338,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
     ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
     __syncwarp();
     build_lengths(w, w.cl_freq, 19, 7, w.cl_len, lane);
-    assign_codes(w.cl_len, 19, 7, w.cl_code, lane);
+    assign_codes(w, w.cl_len, 19, 7, w.cl_code, lane);
 
     // exact sizes of the three encodings
     uint64_t dyn_bits = 0, fix_bits = 0;
@@ -359,8 +387,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
     if (type != 0 && (type == 2 ? dyn_bytes : fix_bytes) > sto_bytes + 256) type = 0;
 
     if (type == 2) {
-        assign_codes(w.lit_len, kNumLitLen, 15, plan.litlen_code, lane);
-        assign_codes(w.dist_len, kNumDist, 15, plan.dist_code, lane);
+        assign_codes(w, w.lit_len, kNumLitLen, 15, plan.litlen_code, lane);
+        assign_codes(w, w.dist_len, kNumDist, 15, plan.dist_code, lane);
     } else {
         // fixed codes (RFC 1951 3.2.6); also filled for stored blocks so the plan is always defined
         for (int i = lane; i < kNumLitLen; i += 32) w.lit_len[i] = (uint8_t)fixed_litlen_bits(i);
