@@ -341,6 +341,20 @@ def test_host_call_pipelined_slabs(engine, oracle, level):
     assert rc2 in (Z_BUF_ERROR, Z_STREAM_END) and len(out) > (4 << 20) and out == host[: len(out)].tobytes()
 
 
+def test_host_call_pipelined_output_too_small(engine):
+    """The pipelined host call with an output buffer that can not hold the stream: Z_BUF_ERROR, nothing written past the
+    buffer (a guard band behind it stays intact)."""
+    import numpy as np
+
+    n = (160 << 20) + 7
+    data = np.random.default_rng(5).integers(0, 256, n, dtype=np.uint8)  # incompressible: the stream is larger than n
+    cap = n // 2
+    out = np.full(cap + 4096, 0xA5, dtype=np.uint8)
+    rc, stream, _ = engine.deflate(data, 6, out=out[:cap])
+    assert rc == Z_BUF_ERROR and len(stream) == 0
+    assert (out[cap:] == 0xA5).all()
+
+
 def test_api_mirror_reads_like_the_reference_tests(engine):
     """InflateBasicTests.kt:13-29 and DeflateParameterValidationTest.kt, through the reference-shaped API."""
     import zlibk_b200 as zk

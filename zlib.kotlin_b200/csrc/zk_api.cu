@@ -461,6 +461,7 @@ struct HostPipe {
     const uint8_t *d_out;  // device stream (2 header bytes, then the body)
     uint8_t *out;          // caller's buffer
     uint64_t lead;         // bytes in front of the body (2 for a framed stream, 0 for a shard)
+    uint64_t body_cap;     // the body may not grow past this (an overflowing cursor is reported, not copied)
     uint64_t *h_cursor;    // pinned: body bytes after slab k
     cudaEvent_t *in_ready, *done;
     uint32_t nslabs;
@@ -473,7 +474,7 @@ void pipe_flush(HostPipe *p, uint32_t upto) {  // send down the output of slabs 
         const uint32_t k = p->flushed;
         cudaError_t e = cudaEventSynchronize(p->done[k]);
         if (e != cudaSuccess && p->err == cudaSuccess) p->err = e;
-        const uint64_t cur = p->h_cursor[k];
+        const uint64_t cur = p->h_cursor[k] < p->body_cap ? p->h_cursor[k] : p->body_cap;
         if (cur > p->sent) {
             e = cudaMemcpyAsync(p->out + p->lead + p->sent, p->d_out + p->lead + p->sent, cur - p->sent,
                                 cudaMemcpyDeviceToHost, p->c->copy_out);
@@ -546,7 +547,8 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
     uint64_t *h_cursor = nullptr;
     ZK_CUDA(cudaMallocHost(&h_cursor, (size_t)nslabs * 8 + 64));
     int rc = ZK_OK;
-    HostPipe pipe{c, d_out, out, lead, h_cursor, ev.data(), ev.data() + nslabs, nslabs, 0, 0, cudaSuccess};
+    const uint64_t frame = framed ? 2 + 2 + 4 : 0;
+    HostPipe pipe{c, d_out, out, lead, dcap > frame ? dcap - frame : 0, h_cursor, ev.data(), ev.data() + nslabs, nslabs, 0, 0, cudaSuccess};
     for (auto &e : ev)
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = ZK_ERRNO;
     uint64_t res[4] = {0, 0, 0, 0};
