@@ -206,3 +206,57 @@ class ZStream {
         return ZK_OK
     }
 }
+
+/**
+ * gzip members and CRC-32 (SURVEY.md 8f row 4).  The reference has neither (only a logging stub,
+ * common/ZlibLogger.kt:115-118); the shapes follow zlib.h / RFC 1952 so that `pigz` output (gzip by default) can be
+ * read and written next to the zlib path.
+ */
+object Gzip {
+    fun compress(data: ByteArray, level: Int = 6): ByteArray {
+        val out = ByteArray(zk_compress_bound(data.size.toULong()).toInt() + 32)
+        memScoped {
+            val n = alloc<ULongVar>()
+            val rc = data.usePinned { i ->
+                out.usePinned { o ->
+                    zk_deflate_gzip(engine.ctx, if (data.isEmpty()) null else i.addressOf(0).reinterpret(), data.size.toULong(), level,
+                                    ZK_DEFAULT_STRATEGY, o.addressOf(0).reinterpret(), out.size.toULong(), n.ptr, null)
+                }
+            }
+            if (rc != ZK_OK) throw ZStreamException("gzip compress failed: $rc")
+            return out.copyOf(n.value.toInt())
+        }
+    }
+
+    /** All members of the file, outputs concatenated (RFC 1952 2.2). */
+    fun decompress(data: ByteArray, sizeHint: Int = data.size * 8 + 65536): ByteArray {
+        var cap = sizeHint
+        while (true) {
+            val out = ByteArray(cap)
+            memScoped {
+                val n = alloc<ULongVar>()
+                val used = alloc<ULongVar>()
+                val rc = data.usePinned { i ->
+                    out.usePinned { o ->
+                        zk_inflate_gzip(engine.ctx, i.addressOf(0).reinterpret(), data.size.toULong(), o.addressOf(0).reinterpret(),
+                                        cap.toULong(), n.ptr, used.ptr)
+                    }
+                }
+                if (rc == ZK_STREAM_END) return out.copyOf(n.value.toInt())
+                if (rc != ZK_BUF_ERROR || cap >= Int.MAX_VALUE / 4) throw ZStreamException("gzip decompress failed: $rc")
+            }
+            cap *= 4
+        }
+    }
+}
+
+object Crc32 {
+    /** zlib.h crc32(crc, buf, len); a null buffer gives the initial value 0. */
+    fun crc32(crc: Long, buf: ByteArray?, index: Int = 0, len: Int = buf?.size ?: 0): Long {
+        if (buf == null) return 0L
+        if (len == 0) return crc
+        return buf.usePinned { p -> zk_crc32(engine.ctx, crc.toUInt(), p.addressOf(index).reinterpret(), len.toULong()).toLong() }
+    }
+
+    fun combine(crc1: Long, crc2: Long, len2: Long): Long = zk_crc32_combine(crc1.toUInt(), crc2.toUInt(), len2.toULong()).toLong()
+}
