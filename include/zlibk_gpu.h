@@ -173,6 +173,11 @@ int zk_deflate_params(zk_stream *s, int level, int strategy);
 int zk_deflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len);
 /* inflateInit(windowBits=15) */
 zk_stream *zk_inflate_init(zk_ctx *ctx);
+/* zlib.h deflateInit2 / inflateInit2 windowBits variants: container 0 = zlib (windowBits 8..15), 1 = raw deflate
+ * (windowBits < 0), 2 = gzip (windowBits + 16).  zk_deflate_copy = deflateCopy (docs/API.md:253). */
+zk_stream *zk_deflate_init2(zk_ctx *ctx, int level, int strategy, int container);
+zk_stream *zk_inflate_init2(zk_ctx *ctx, int container);
+zk_stream *zk_deflate_copy(const zk_stream *src);
 int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush);
 int zk_inflate_reset(zk_stream *s);
 int zk_inflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len);

@@ -97,3 +97,71 @@ def test_gzip_large_through_the_lane_decoder(engine):
     assert gzip.decompress(bytes(stream)) == data.tobytes()
     rc, out, used = engine.inflate_container(stream, data.size, "gzip")
     assert rc == Z_STREAM_END and used == len(stream) and np.array_equal(np.asarray(out), data)
+
+
+def _zstream_deflate(zk, data_pieces, windowBits, level=6, copy_after=None):
+    z = zk.ZStream()
+    assert z.deflateInit(level, 8, windowBits) == zk.Z_OK
+    out, twin = bytearray(), None
+    for i, piece in enumerate(data_pieces):
+        z.next_in, z.next_in_index, z.avail_in = piece, 0, len(piece)
+        last = i == len(data_pieces) - 1
+        while True:
+            z.next_out, z.next_out_index, z.avail_out = bytearray(1 << 16), 0, 1 << 16
+            rc = z.deflate(zk.Z_FINISH if last else zk.Z_SYNC_FLUSH)
+            out += z.next_out[: z.next_out_index]
+            if rc == zk.Z_STREAM_END or (not last and z.avail_in == 0 and z.avail_out > 0):
+                break
+            assert rc in (zk.Z_OK, zk.Z_BUF_ERROR)
+        if copy_after == i:
+            twin = zk.ZStream()
+            assert z.deflateCopy(twin) == zk.Z_OK
+    z.deflateEnd()
+    return bytes(out), twin
+
+
+def test_zstream_window_bits_select_the_container(engine):
+    """docs/API.md:239-281 with zlib.h's windowBits convention: negative = raw deflate, +16 = gzip."""
+    import zlibk_b200 as zk
+
+    data = _text(7, 400_000)
+    pieces = [data[:1000], data[1000:250_000], data[250_000:]]
+    gz, _ = _zstream_deflate(zk, pieces, 31)
+    assert gz[:2] == b"\x1f\x8b" and gzip.decompress(gz) == data
+    raw, _ = _zstream_deflate(zk, pieces, -15)
+    assert zlib.decompress(raw, -15) == data
+    zl, _ = _zstream_deflate(zk, pieces, 15)
+    assert zlib.decompress(zl) == data
+    for stream, wbits in ((gzip.compress(data, 6, mtime=0), 31), (raw, -15), (zlib.compress(data, 6), 15)):
+        y = zk.ZStream()
+        assert y.inflateInit(wbits) == zk.Z_OK
+        y.next_in, y.next_in_index, y.avail_in = stream, 0, len(stream)
+        y.next_out, y.next_out_index, y.avail_out = bytearray(len(data)), 0, len(data)
+        assert y.inflate(zk.Z_FINISH) == zk.Z_STREAM_END
+        assert bytes(y.next_out[: y.next_out_index]) == data
+        y.inflateEnd()
+    assert zk.ZStream().deflateInit(6, 8, 7) == zk.Z_STREAM_ERROR
+    assert zk.ZStream().inflateInit(40) == zk.Z_STREAM_ERROR
+
+
+def test_zstream_deflate_copy(engine):
+    """docs/API.md:253: after deflateCopy both streams continue independently from the same state."""
+    import zlibk_b200 as zk
+
+    head, tail_a, tail_b = _text(8, 200_000), _text(9, 100_000), _text(10, 50_000)
+    a, twin = _zstream_deflate(zk, [head, tail_a], 15, copy_after=0)
+    assert zlib.decompress(a) == head + tail_a
+    twin.next_in, twin.next_in_index, twin.avail_in = tail_b, 0, len(tail_b)
+    twin.next_out, twin.next_out_index, twin.avail_out = bytearray(1 << 20), 0, 1 << 20
+    assert twin.deflate(zk.Z_FINISH) == zk.Z_STREAM_END
+    stream_b = bytes(twin.next_out[: twin.next_out_index])
+    twin.deflateEnd()
+    # the twin's output continues the original's output at the copy point: header + first piece come from the original
+    z = zk.ZStream()
+    assert z.deflateInit(6) == zk.Z_OK
+    z.next_in, z.next_in_index, z.avail_in = head, 0, len(head)
+    z.next_out, z.next_out_index, z.avail_out = bytearray(1 << 20), 0, 1 << 20
+    assert z.deflate(zk.Z_SYNC_FLUSH) == zk.Z_OK
+    prefix = bytes(z.next_out[: z.next_out_index])
+    z.deflateEnd()
+    assert zlib.decompress(prefix + stream_b) == head + tail_b

@@ -156,13 +156,37 @@ class ZStream:
         self._lib = _b.library()
 
     # -- deflate ---------------------------------------------------------------------------------
+    @staticmethod
+    def _container(windowBits):
+        """zlib.h: 8..15 zlib, -8..-15 raw deflate, 24..31 gzip -> container id, or None."""
+        if 8 <= windowBits <= 15:
+            return 0
+        if -15 <= windowBits <= -8:
+            return 1
+        if 24 <= windowBits <= 31:
+            return 2
+        return None
+
     def deflateInit(self, level=6, method=8, windowBits=15, memLevel=8, strategy=_b.Z_DEFAULT_STRATEGY):
-        if method != 8 or not (8 <= windowBits <= 15) or level > 9:
+        container = self._container(windowBits)
+        if method != 8 or container is None or level > 9:
             return _b.Z_STREAM_ERROR
         self._end()
-        self._h = self._lib.zk_deflate_init(default_engine().ctx, level, strategy)
+        self._h = self._lib.zk_deflate_init2(default_engine().ctx, level, strategy, container)
         self._mode = "deflate"
         return _b.Z_OK if self._h else _b.Z_STREAM_ERROR
+
+    def deflateCopy(self, dest):
+        """docs/API.md:253: dest becomes an independent copy of this deflate stream."""
+        if self._mode != "deflate" or not self._h or not isinstance(dest, ZStream):
+            return _b.Z_STREAM_ERROR
+        dest._end()
+        dest._h = self._lib.zk_deflate_copy(self._h)
+        dest._mode = "deflate"
+        for f in ("next_in", "next_in_index", "avail_in", "total_in", "next_out_index", "avail_out", "total_out", "adler", "data_type", "msg"):
+            setattr(dest, f, getattr(self, f))
+        dest.next_out = bytearray(self.next_out)
+        return _b.Z_OK if dest._h else _b.Z_MEM_ERROR
 
     def deflate(self, flush=_b.Z_NO_FLUSH):
         return self._run(self._lib.zk_deflate, "deflate", flush)
@@ -183,10 +207,11 @@ class ZStream:
 
     # -- inflate ---------------------------------------------------------------------------------
     def inflateInit(self, windowBits=15):
-        if not (8 <= windowBits <= 15):
+        container = self._container(windowBits)
+        if container is None:
             return _b.Z_STREAM_ERROR
         self._end()
-        self._h = self._lib.zk_inflate_init(default_engine().ctx)
+        self._h = self._lib.zk_inflate_init2(default_engine().ctx, container)
         self._mode = "inflate"
         return _b.Z_OK if self._h else _b.Z_STREAM_ERROR
 

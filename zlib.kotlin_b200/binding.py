@@ -46,6 +46,9 @@ SIGNATURES = {
     "zk_zlib_tail": (None, [c_uint32, POINTER(c_uint8)]),
     "zk_deflate_init": (c_void_p, [c_void_p, c_int, c_int]),
     "zk_deflate": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_void_p, POINTER(c_uint64), c_int]),
+    "zk_deflate_init2": (c_void_p, [c_void_p, c_int, c_int, c_int]),
+    "zk_inflate_init2": (c_void_p, [c_void_p, c_int]),
+    "zk_deflate_copy": (c_void_p, [c_void_p]),
     "zk_deflate_reset": (c_int, [c_void_p]),
     "zk_deflate_params": (c_int, [c_void_p, c_int, c_int]),
     "zk_deflate_set_dictionary": (c_int, [c_void_p, c_void_p, c_uint32]),

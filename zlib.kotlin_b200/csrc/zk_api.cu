@@ -846,6 +846,8 @@ struct zk_stream {
     std::vector<uint8_t> history;      // last 32 KiB of compressed-so-far input (deflate) / dictionary
     std::vector<uint8_t> pending_out;  // produced, not yet handed to the caller
     size_t out_pos;
+    int container = 0;                 // 0 zlib, 1 raw deflate (windowBits < 0), 2 gzip (windowBits + 16)
+    uint32_t crc = 0;                  // gzip deflate: CRC-32 of the input so far
     bool have_dict = false;            // deflate: emit FDICT + DICTID; inflate: a dictionary has been supplied
     uint32_t dict_id = 0;
     std::vector<uint8_t> dict;         // inflate: the supplied dictionary
@@ -898,6 +900,7 @@ static int stream_flush_slab(zk_stream *s) {
     ZK_CUDA(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += (int64_t)meta[0] + 32;
     s->adler = adler32_combine(s->adler, (uint32_t)meta[1], n);
+    if (s->container == 2) s->crc = zk_crc32(c, s->crc, s->pending_in.data(), n);
     // keep the last 32 KiB as the next slab's dictionary
     std::vector<uint8_t> h;
     if (n >= 32768) h.assign(s->pending_in.end() - 32768, s->pending_in.end());
@@ -918,14 +921,15 @@ int zk_deflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
     *out_len = 0;
     if (s->finished && avail_in) return ZK_STREAM_ERROR;
     if (!s->header_done) {
-        uint8_t h[6];
-        zk_zlib_header(s->level, h);
-        if (s->have_dict) {  // zlib.h deflateSetDictionary: FDICT, then the dictionary's Adler-32
+        uint8_t h[10] = {0x1F, 0x8B, 8, 0, 0, 0, 0, 0, (uint8_t)(s->level >= 9 ? 2 : s->level <= 1 ? 4 : 0), 3};
+        if (s->container == 0) zk_zlib_header(s->level, h);
+        if (s->container == 0 && s->have_dict) {  // zlib.h deflateSetDictionary: FDICT, then the dictionary's Adler-32
             h[1] = (uint8_t)((h[1] & 0xC0) | 0x20);
             h[1] = (uint8_t)(h[1] + (31 - ((h[0] << 8) | h[1]) % 31) % 31);
             h[2] = (uint8_t)(s->dict_id >> 24), h[3] = (uint8_t)(s->dict_id >> 16), h[4] = (uint8_t)(s->dict_id >> 8), h[5] = (uint8_t)s->dict_id;
         }
-        s->pending_out.insert(s->pending_out.end(), h, h + (s->have_dict ? 6 : 2));
+        const int hl = s->container == 2 ? 10 : s->container == 1 ? 0 : s->have_dict ? 6 : 2;
+        s->pending_out.insert(s->pending_out.end(), h, h + hl);
         s->header_done = true;
     }
     if (avail_in) {
@@ -940,9 +944,18 @@ int zk_deflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
         if (flush == ZK_FULL_FLUSH) s->history.clear();  // later data may not refer to earlier data
     }
     if (flush == ZK_FINISH && !s->finished) {
-        uint8_t t[6];
-        zk_zlib_tail(s->adler, t);
-        s->pending_out.insert(s->pending_out.end(), t, t + 6);
+        uint8_t t[10];
+        int tl = 6;
+        zk_zlib_tail(s->adler, t);  // final empty block + big-endian Adler-32
+        if (s->container == 1) tl = 2;
+        if (s->container == 2) {
+            for (int i = 0; i < 4; ++i) {
+                t[2 + i] = (uint8_t)(s->crc >> (8 * i));
+                t[6 + i] = (uint8_t)((uint32_t)s->total_in >> (8 * i));
+            }
+            tl = 10;
+        }
+        s->pending_out.insert(s->pending_out.end(), t, t + tl);
         s->finished = true;
     }
     const size_t have = s->pending_out.size() - s->out_pos;
@@ -968,11 +981,33 @@ int zk_deflate_reset(zk_stream *s) {
     s->header_done = s->finished = false;
     s->total_in = s->total_out = 0;
     s->adler = 1;
+    s->crc = 0;
+    s->have_dict = false;
     s->pending_in.clear();
     s->history.clear();
     s->pending_out.clear();
     s->out_pos = 0;
     return ZK_OK;
+}
+
+zk_stream *zk_deflate_init2(zk_ctx *ctx, int level, int strategy, int container) {
+    if (container < 0 || container > 2) return nullptr;
+    zk_stream *s = zk_deflate_init(ctx, level, strategy);
+    if (s) s->container = container;
+    return s;
+}
+
+zk_stream *zk_inflate_init2(zk_ctx *ctx, int container) {
+    if (container < 0 || container > 2) return nullptr;
+    zk_stream *s = zk_inflate_init(ctx);
+    if (s) s->container = container;
+    return s;
+}
+
+zk_stream *zk_deflate_copy(const zk_stream *src) {
+    // zlib.h deflateCopy: an independent stream with the same state (pending input and output, history, checksums)
+    if (!src || src->mode != 0) return nullptr;
+    return new (std::nothrow) zk_stream(*src);
 }
 
 int zk_deflate_params(zk_stream *s, int level, int strategy) {
@@ -1028,8 +1063,11 @@ int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
         for (;;) {
             std::vector<uint8_t> buf(cap);
             uint64_t got = 0, used = 0;
-            int rc = host_inflate(s->ctx, s->pending_in.data(), s->pending_in.size(), s->have_dict ? s->dict.data() : nullptr,
-                                  s->have_dict ? (uint32_t)s->dict.size() : 0u, buf.data(), cap, &got, &used);
+            int rc;
+            if (s->container == 2) rc = zk_inflate_gzip(s->ctx, s->pending_in.data(), s->pending_in.size(), buf.data(), cap, &got, &used);
+            else if (s->container == 1) rc = zk_inflate_raw(s->ctx, s->pending_in.data(), s->pending_in.size(), buf.data(), cap, &got, &used);
+            else rc = host_inflate(s->ctx, s->pending_in.data(), s->pending_in.size(), s->have_dict ? s->dict.data() : nullptr,
+                                   s->have_dict ? (uint32_t)s->dict.size() : 0u, buf.data(), cap, &got, &used);
             if (rc == ZK_NEED_DICT) return ZK_NEED_DICT;  // the input stays pending: zk_inflate_set_dictionary, then call again
             if (rc == ZK_STREAM_END) {
                 buf.resize(got);
@@ -1038,7 +1076,7 @@ int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
                 s->finished = true;
                 s->adler = 0;
                 // Adler-32 of the output is the stream's trailer
-                if (used >= 4) {
+                if (used >= 4 && s->container == 0) {
                     const uint8_t *t = s->pending_in.data() + used - 4;
                     s->adler = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
                 }

@@ -146,7 +146,8 @@ class ZStream {
     fun deflateInit(level: Int = 6, method: Int = 8, windowBits: Int = 15, memLevel: Int = 8, strategy: Int = 0): Int {
         if (method != 8 || windowBits !in 8..15 || level > 9) return ZK_STREAM_ERROR
         end()
-        handle = zk_deflate_init(engine.ctx, level, strategy)
+        val container = when (windowBits) { in 8..15 -> 0; in -15..-8 -> 1; in 24..31 -> 2; else -> return ZK_STREAM_ERROR }
+        handle = zk_deflate_init2(engine.ctx, level, strategy, container)
         deflating = true
         return if (handle != null) ZK_OK else ZK_STREAM_ERROR
     }
@@ -154,7 +155,8 @@ class ZStream {
     fun inflateInit(windowBits: Int = 15): Int {
         if (windowBits !in 8..15) return ZK_STREAM_ERROR
         end()
-        handle = zk_inflate_init(engine.ctx)
+        val container = when (windowBits) { in 8..15 -> 0; in -15..-8 -> 1; in 24..31 -> 2; else -> return ZK_STREAM_ERROR }
+        handle = zk_inflate_init2(engine.ctx, container)
         deflating = false
         return if (handle != null) ZK_OK else ZK_STREAM_ERROR
     }
@@ -168,6 +170,17 @@ class ZStream {
     fun inflateSetDictionary(dictionary: ByteArray, dictLength: Int = dictionary.size): Int =
         handle?.let { h -> dictionary.usePinned { zk_inflate_set_dictionary(h, it.addressOf(0).reinterpret(), dictLength.toUInt()) } }
             ?: ZK_STREAM_ERROR
+    fun deflateCopy(dest: ZStream): Int {
+        val h = handle ?: return ZK_STREAM_ERROR
+        if (!deflating) return ZK_STREAM_ERROR
+        dest.end()
+        dest.handle = zk_deflate_copy(h) ?: return ZK_MEM_ERROR
+        dest.deflating = true
+        dest.next_in = next_in; dest.next_in_index = next_in_index; dest.avail_in = avail_in; dest.total_in = total_in
+        dest.next_out = next_out.copyOf(); dest.next_out_index = next_out_index; dest.avail_out = avail_out; dest.total_out = total_out
+        dest.adler = adler
+        return ZK_OK
+    }
     fun deflateReset(): Int = handle?.let { zk_deflate_reset(it) } ?: ZK_STREAM_ERROR
     fun inflateReset(): Int = handle?.let { zk_inflate_reset(it) } ?: ZK_STREAM_ERROR
     fun inflateSync(): Int = ZK_DATA_ERROR
