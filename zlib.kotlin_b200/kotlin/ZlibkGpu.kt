@@ -144,7 +144,7 @@ class ZStream {
     private var deflating = false
 
     fun deflateInit(level: Int = 6, method: Int = 8, windowBits: Int = 15, memLevel: Int = 8, strategy: Int = 0): Int {
-        if (method != 8 || windowBits !in 8..15 || level > 9) return ZK_STREAM_ERROR
+        if (method != 8 || level > 9) return ZK_STREAM_ERROR
         end()
         val container = when (windowBits) { in 8..15 -> 0; in -15..-8 -> 1; in 24..31 -> 2; else -> return ZK_STREAM_ERROR }
         handle = zk_deflate_init2(engine.ctx, level, strategy, container)
@@ -153,7 +153,6 @@ class ZStream {
     }
 
     fun inflateInit(windowBits: Int = 15): Int {
-        if (windowBits !in 8..15) return ZK_STREAM_ERROR
         end()
         val container = when (windowBits) { in 8..15 -> 0; in -15..-8 -> 1; in 24..31 -> 2; else -> return ZK_STREAM_ERROR }
         handle = zk_inflate_init2(engine.ctx, container)
