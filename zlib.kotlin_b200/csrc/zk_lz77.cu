@@ -5,23 +5,25 @@
 // with a design that maps to an SM instead of a scalar loop.  It is not a port: the reference's
 // look-ahead/window arrays, its pre-seeded chains and its stale-window compare do not exist here.
 //
-// Layout in shared memory (one CTA per SM, ~198 KB):
+// Layout in shared memory (one CTA per SM, ~224 KB):
 //   ring  u8 [65536]   input bytes at (q & 0xFFFF); q = unit-relative position, history first
 //   prev  u16[32768]   hash-chain links at (q & 32767): previous position with the same 4-byte hash
-//   head  u16[16384]   most recent position per hash
-//   match u32[2][4096] per-position best match of the group in flight / the group being parsed
-//   stage u32[34][128] tokens of the group being parsed, one column per parser lane
+//   head  u16[16384]   most recent position (q & 0xFFFF) per 14-bit hash
+//   match u32[2][4608] per-position best match of the group in flight / the group being parsed (rows of 32 skewed)
+//   prep  u8 [2][4096] per position of a group to be built: lower lane of its batch with the same hash
+//   stage u32[34][128], pre u32[4][128]  tokens of the group being parsed, one column per parser lane
 //
 // Software pipeline over groups of 4096 positions, one __syncthreads per step.  In step i
 //   - one elected thread stages group i+4 into the ring with a TMA bulk copy (mbarrier-tracked),
-//   - warp 31 inserts group i+1 into the 4-byte hash chains, 32 positions per instruction sequence
-//     (a shared atomicMax per hash; match.any only resolves duplicates inside a batch: exact, deterministic),
-//   - warps 15/19/23/27 parse group i-1: a speculative pass finds the exit of every 32-byte lane segment,
-//     the exits are stitched, a second pass marks the tokens, a third emits them densely + histograms,
-//   - every warp (the role warps join when done) steals 128-position strips of group i; a lane walks 4
-//     consecutive positions, inherits (len-1, dist) from the last, and the chain loop is uniform across
-//     the warp: each candidate is compared over 16 bytes with no inner loop, the nearest one that
-//     fills them is extended afterwards, 3-byte matches come from probes at small fixed distances.
+//   - whichever warp takes a strip prepares the same strip of group i+2 (match.any over the hashes of each batch),
+//   - warp 31 inserts group i+1 into the hash chains: table updates only, 32 positions per instruction sequence,
+//   - warps 24..27 (one per SM sub-partition) parse group i-1: a register-only speculative pass per 32-byte lane
+//     segment, a two-level stitch with shuffles, a short real pass up to the point where it meets the speculative
+//     one, then the tokens leave densely with 16-byte stores,
+//   - every warp (the role warps join when done) steals strips of group i: 40 of 64 positions (a lane walks 2
+//     consecutive positions, the second inherits (len-1, dist) from the first), then 48 of 32; the chain loop is
+//     uniform across the warp: each candidate is compared over 16 bytes with no inner loop, the nearest one that
+//     fills them is extended afterwards, 3-byte matches come from probes at small fixed distances (adaptive).
 // A search only follows links of candidates within 32768 - 2*4096 bytes, which the builder (one
 // group ahead) can not have overwritten: results do not depend on warp timing.
 //
@@ -193,20 +195,11 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
     return tma;
 }
 
-// ---- builder: one warp inserts group t into the hash chains ----------------------------------
-// Exact, deterministic chains at LSU issue rate.  Per batch of 32 positions: read head[h] (the link), store the
-// position, read head[h] back.  The three accesses of a batch follow each other in program order and the LSU keeps
-// that order, so four batches are issued back to back and the loaded values are consumed afterwards.  A lane that
-// does not read its own position back shares its hash with another lane of the batch (the store picked one of
-// them): those hashes are resolved with one ballot round each -- every lane of the hash links to the nearest lower
-// lane with it and the highest one stays in head[].  (MATCH.ANY would do this in one instruction but was measured at
-// ~500 cycles per call on B200.)  Links of later batches that were read while head[] held an arbitrary duplicate
-// are corrected from the group masks, so the result never depends on which lane the hardware let win.
-// Preparation of four batches (one strip) of group t, done by whichever warp searches the matching strip: for every
-// position, which lower lane of its 32-position batch has the same hash, and whether it is the last of its hash in
-// the batch.  The lane groups are an exact match.any, emulated with one ballot per hash bit (MATCH.ANY itself was
-// measured at several hundred cycles per call on B200); it is a pure function of the batch, so it runs in parallel
-// on the searcher warps and the serial builder is left with table updates only.
+// ---- preparation of a strip of group t, done by whichever warp searches the matching strip ------------------
+// For every position: which lower lane of its 32-position batch has the same hash, and whether it is the last of its
+// hash in the batch (an exact match.any; cheap here because 26 warps share its latency, unlike in the serial builder
+// where it was first tried).  It is a pure function of the batch, so it runs in parallel on the searcher warps and the
+// serial builder is left with table updates only.
 __device__ __forceinline__ void prep_strip(LzSmem &s, int t, int pos0, int batches, int lane) {
     uint8_t *pp = s.prep[t & 1] + pos0;
     const uint32_t q0 = (uint32_t)t * kGroup + pos0 + lane;
