@@ -1,21 +1,28 @@
-// zk_inflate.cu -- K5: zlib inflate, parallel across chunks, one warp per chunk.
+// zk_inflate.cu -- K5: inflate (zlib / gzip / raw), parallel across blocks and chunks.
 //
 // Replaces InflateStream.inflateZlib (inflate/InflateStream.kt:376-438) with its block decoders
 // (copyStored IS:47-74, decodeFixed IS:265-297, decodeDynamic IS:299-371, readCodeLengths IS:235-263,
 // validation IS:102-152), CanonicalHuffman.buildFull/decodeOne (inflate/CanonicalHuffman.kt:54-82,123-138)
 // and StreamingBitReader (inflate/StreamingBitReader.kt:9-58).
 //
-// A DEFLATE stream has no entry points, but streams made by this engine (and by pigz) end every chunk with
-// an empty stored block: the bytes 00 00 FF FF, after which a block starts on a byte boundary.  The engine
-//   1. scans the stream for that pattern and keeps at most one candidate start per span of input,
-//   2. decodes every candidate chunk with one warp, first only to SIZE it (it must end exactly on the next
-//      candidate), then -- once a prefix sum has given every chunk its output offset -- to WRITE it as 16-bit
-//      symbols: a byte, or 0x8000 | i for "byte i of the 32 KiB that precede this chunk" (the chunk's
-//      dictionary is not known yet, so references into it are carried symbolically, copies included),
-//   3. resolves the last 32 KiB of every chunk in stream order (a short dependent chain),
-//   4. turns all symbols into bytes in parallel and checks the Adler-32 trailer.
-// A candidate that is not a real block start fails step 2 and is merged into its predecessor; a stream
-// with no candidates (reference or libz output) is one chunk decoded by one warp -- "replicas only".
+// A DEFLATE stream has no entry points, but streams made by this engine (and by pigz) end every block / chunk with an
+// empty stored block: the bytes 00 00 FF FF, after which a block starts on a byte boundary.  The engine
+//   1. collects the positions of that pattern (marker_compact_kernel);
+//   2. when there are hundreds of them (this engine's own streams): decodes one block per LANE to a token stream
+//      (decode_lanes_kernel: tables in shared memory, cp.async input ring, longest blocks first), checks that every
+//      block ended exactly on the next marker, prefix-sums the sizes, and expands the tokens with one warp per block to
+//      16-bit symbols -- a byte, or 0x8000 | i for "byte i of the 32 KiB that precede this block" (the dictionary of a
+//      block is not known yet, so references into it are carried symbolically, copies included); eight blocks are
+//      re-based into one coarse chunk (resolve_coarse_kernel);
+//      otherwise (pigz chunks, foreign streams): one WARP per candidate chunk, first only to SIZE it (it must end
+//      exactly on the next candidate; a false candidate fails and is merged into its predecessor), then to WRITE its
+//      symbols (decode_kernel);
+//   3. resolves the last 32 KiB of every chunk: the tail of a chunk is a map over the window before it, maps compose,
+//      and the chain becomes a two-level scan (window_compose / window_chain / window_apply kernels);
+//   4. turns all symbols into bytes in parallel (materialize_kernel) and checks the trailer (Adler-32 for zlib,
+//      CRC-32 + ISIZE for gzip, nothing for raw deflate).
+// A preset dictionary is "window -1" in front of the first chunk.  A stream with no candidates (reference or libz
+// output) is one chunk decoded by one warp -- "replicas only".
 //
 // Error behaviour follows the reference: Z_STREAM_END on success (IS:424), Z_NEED_DICT for FDICT (IS:36-43),
 // Z_DATA_ERROR for bad headers / block type 3 / LEN-NLEN / invalid codes / distance too far back
