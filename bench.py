@@ -267,27 +267,54 @@ def main():
     ms_per_step = ms / args.steps
     value = (n * world) / (ms_per_step * 1e-3) / 1e9
 
-    # ---- inflate of the produced stream (rank-local stream, device-resident) -------------------------------
+    # ---- inflate (device-resident).  N = 1: the stream just produced.  N > 1: every rank inflates a complete zlib stream of
+    # its own range (made outside the timed region) -- independent streams per GPU, the "replicas" form of SURVEY.md 8e;
+    # the aggregate is all ranks' bytes over the slowest rank's time.
     inflate = None
-    if shard is None:
+    if shard is not None:
+        if eng.deflate_device(d_in.data_ptr(), n, args.level, 0, d_out.data_ptr(), cap, d_res.data_ptr()) != 0:
+            raise SystemExit("deflate for the inflate leg failed: %s" % eng.last_error())
+        eng.synchronize()
+        m = int(d_res.cpu().tolist()[0])
+    else:
         m = int(out_len)
-        for _ in range(min(args.warmup, 2)):
-            eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
-        torch.cuda.synchronize(dev)
-        eng.counter("reset_timing")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        isteps = max(1, min(args.steps, 3))
-        e0.record(stream)
-        for _ in range(isteps):
-            eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ims = e0.elapsed_time(e1) / isteps
-        r2 = d_res2.cpu().tolist()
-        ok = r2[2] == 1 and r2[0] == n and bool(torch.equal(d_back, d_in))
-        inflate = {"value": n / (ims * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ims, "status": r2[2], "bit_exact": ok,
-                   "decode_kernel_ms": eng.counter("inflate_decode_us") / 1e3 / isteps,
-                   "other_kernels_ms": eng.counter("inflate_other_us") / 1e3 / isteps}
+    for _ in range(min(args.warmup, 2)):
+        eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
+    barrier()
+    eng.counter("reset_timing")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    isteps = max(1, min(args.steps, 3))
+    e0.record(stream)
+    for _ in range(isteps):
+        eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
+    e1.record(stream)
+    barrier()
+    ims = e0.elapsed_time(e1) / isteps
+    r2 = d_res2.cpu().tolist()
+    ok = r2[2] == 1 and r2[0] == n and bool(torch.equal(d_back, d_in))
+    if world > 1:
+        t = torch.tensor([ims, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ims, ok = float(t[0].item()), float(t[1].item()) == 0.0
+    inflate = {"value": n * world / (ims * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ims, "status": r2[2], "bit_exact": ok,
+               "decode_kernel_ms": eng.counter("inflate_decode_us") / 1e3 / isteps,
+               "other_kernels_ms": eng.counter("inflate_other_us") / 1e3 / isteps,
+               "streams": "one stream" if world == 1 else "one independent stream per GPU"}
+    # end to end through the host-buffer call (pinned memory, H2D of the stream and D2H of the output inside)
+    h_stream = d_out[:m].cpu().pin_memory()
+    h_back = torch.empty(n, dtype=torch.uint8).pin_memory()
+    eng.inflate(h_stream, n, out=h_back)  # warm-up: staging allocation
+    barrier()
+    t0 = time.perf_counter()
+    rc_i, back_i, _ = eng.inflate(h_stream, n, out=h_back)
+    torch.cuda.synchronize(dev)
+    idt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([idt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        idt = float(t.item())
+    inflate["e2e"] = {"value": n * world / idt / 1e9, "unit": UNIT, "h2d_bytes_per_step": m, "d2h_bytes_per_step": n, "status": rc_i}
+    del h_stream, h_back
 
     # ---- e2e through the host-buffer C-ABI call (pinned memory; H2D + D2H inside) ----------------------------
     e2e = None
