@@ -267,39 +267,55 @@ def main():
     ms_per_step = ms / args.steps
     value = (n * world) / (ms_per_step * 1e-3) / 1e9
 
-    # ---- inflate (device-resident).  N = 1: the stream just produced.  N > 1: every rank inflates a complete zlib stream of
-    # its own range (made outside the timed region) -- independent streams per GPU, the "replicas" form of SURVEY.md 8e;
-    # the aggregate is all ranks' bytes over the slowest rank's time.
+    # ---- inflate (device-resident).  N = 1: the stream just produced.  N > 1: the SAME sharded stream -- every rank holds
+    # the body of its chunk range and ends up with the bytes of that range; the only collective is one all_gather of the
+    # 64 KiB tail maps (zlibk_b200.sharding.ShardedInflate).
     inflate = None
+    isteps = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if shard is not None:
-        if eng.deflate_device(d_in.data_ptr(), n, args.level, 0, d_out.data_ptr(), cap, d_res.data_ptr()) != 0:
-            raise SystemExit("deflate for the inflate leg failed: %s" % eng.last_error())
-        eng.synchronize()
-        m = int(d_res.cpu().tolist()[0])
+        m = int(shard.last_body_len)
+        sinf = sharding.ShardedInflate(eng, rank, world, dev)
+
+        def inflate_step():
+            rc = sinf.step(d_out, m, d_back, n)
+            if rc != 0:
+                raise SystemExit("sharded inflate failed rc=%d %s" % (rc, eng.last_error()))
     else:
         m = int(out_len)
+
+        def inflate_step():
+            eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
     for _ in range(min(args.warmup, 2)):
-        eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
+        inflate_step()
     barrier()
     eng.counter("reset_timing")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    isteps = max(1, min(args.steps, 3))
     e0.record(stream)
     for _ in range(isteps):
-        eng.inflate_device(d_out.data_ptr(), m, d_back.data_ptr(), n, d_res2.data_ptr())
+        inflate_step()
     e1.record(stream)
     barrier()
     ims = e0.elapsed_time(e1) / isteps
-    r2 = d_res2.cpu().tolist()
-    ok = r2[2] == 1 and r2[0] == n and bool(torch.equal(d_back, d_in))
+    if shard is not None:
+        got_len, istatus, _, _ = sinf.finish()
+        ok = istatus == 1 and got_len == n and bool(torch.equal(d_back, d_in))
+    else:
+        r2 = d_res2.cpu().tolist()
+        istatus = r2[2]
+        ok = r2[2] == 1 and r2[0] == n and bool(torch.equal(d_back, d_in))
     if world > 1:
         t = torch.tensor([ims, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ims, ok = float(t[0].item()), float(t[1].item()) == 0.0
-    inflate = {"value": n * world / (ims * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ims, "status": r2[2], "bit_exact": ok,
+    inflate = {"value": n * world / (ims * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ims, "status": istatus, "bit_exact": ok,
                "decode_kernel_ms": eng.counter("inflate_decode_us") / 1e3 / isteps,
                "other_kernels_ms": eng.counter("inflate_other_us") / 1e3 / isteps,
-               "streams": "one stream" if world == 1 else "one independent stream per GPU"}
+               "streams": "one stream" if world == 1 else "one stream across %d GPUs (chunk ranges; one all_gather of 64 KiB tail maps)" % world}
+    if shard is not None:  # the host-buffer leg below inflates a complete stream of this rank's range
+        if eng.deflate_device(d_in.data_ptr(), n, args.level, 0, d_out.data_ptr(), cap, d_res.data_ptr()) != 0:
+            raise SystemExit("deflate for the inflate end-to-end leg failed: %s" % eng.last_error())
+        eng.synchronize()
+        m = int(d_res.cpu().tolist()[0])
     # end to end through the host-buffer call (pinned memory, H2D of the stream and D2H of the output inside)
     h_stream = d_out[:m].cpu().pin_memory()
     h_back = torch.empty(n, dtype=torch.uint8).pin_memory()

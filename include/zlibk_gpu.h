@@ -157,6 +157,16 @@ int zk_deflate_shard_device(zk_ctx *ctx, const uint8_t *d_hist, uint32_t hist_le
  * before this shard (host), the body goes to out_body. */
 int zk_deflate_shard(zk_ctx *ctx, const uint8_t *hist, uint32_t hist_len, const uint8_t *in, uint64_t n, int level,
                      int strategy, uint8_t *out_body, uint64_t cap, uint64_t *body_len, uint32_t *adler);
+/* One stream inflated across GPUs: every rank decodes the body of its chunk range (phase 1), the ranks all_gather their
+ * 64 KiB tail maps (the only collective), each composes the maps of the ranks before it into the 32 KiB in front of its
+ * shard, and phase 2 resolves the shard and writes its bytes.  hist_len = how far back the shard may refer (0 for the
+ * first rank, 32768 otherwise).  d_result (uint64_t[4]) = {out_len, consumed, status, Adler-32 of the shard's output};
+ * phase 1 reports ZK_OK when the body decoded, phase 2 ZK_STREAM_END.  Phase 2 uses scratch phase 1 left in the
+ * context: no other call on the context in between. */
+int zk_inflate_shard_prepare_device(zk_ctx *ctx, const uint8_t *d_body, uint64_t m, uint32_t hist_len, uint64_t cap,
+                                    uint16_t *d_tail_map, uint64_t *d_result);
+int zk_window_from_maps_device(zk_ctx *ctx, const uint16_t *d_maps, uint64_t stride_bytes, uint32_t count, uint8_t *d_window);
+int zk_inflate_shard_finish_device(zk_ctx *ctx, const uint8_t *d_entry_window, uint8_t *d_out, uint64_t *d_result);
 /* zlib header for `level` (2 bytes, DS:35-50) and stream tail (final empty block + big-endian
  * Adler-32, 6 bytes) as host helpers for the rank that owns them. */
 void zk_zlib_header(int level, uint8_t out2[2]);

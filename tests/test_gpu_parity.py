@@ -401,3 +401,67 @@ def test_zstream_streaming_surface(engine):
     zi = zk.ZInputStream(io.BytesIO(bytes(produced)))
     assert zi.read() == data
     zi.close()
+
+
+@pytest.mark.parametrize("world,n", [(4, (40 << 20) + 123), (3, 200_000), (2, 70_000)])
+def test_sharded_inflate_with_emulated_ranks(engine, world, n):
+    """SURVEY.md 8e, inflate: one stream cut into chunk ranges, every "rank" (its own context on this GPU) decodes its body
+    with references into the earlier ranks' output kept symbolic, the 64 KiB tail maps are exchanged (here: a tensor), and
+    every rank resolves its range.  Bytes per range and the folded Adler-32 must match; small inputs take the
+    warp-per-chunk decoder, the large one the lane-per-block decoder."""
+    import torch
+
+    import zlibk_b200
+    from zlibk_b200 import corpus, sharding
+
+    dev = torch.device("cuda", 0)
+    host = corpus.mixed_entropy(n) if n > (1 << 20) else np.frombuffer(
+        (b"the quick brown fox jumps over the lazy dog. " * (n // 45 + 1))[:n], dtype=np.uint8).copy()
+    ranges = sharding.plan_shards(n, world)
+    engines = [zlibk_b200.Engine(0) for _ in range(world)]
+    bodies, metas = [], []
+    for r, (a, b) in enumerate(ranges):
+        d_in = torch.from_numpy(host[a:b].copy()).to(dev)
+        hist = torch.from_numpy(host[max(0, a - 32768):a].copy()).to(dev) if a else None
+        cap = engine.compress_bound(b - a)
+        d_body = torch.empty(max(cap, 1), dtype=torch.uint8, device=dev)
+        d_meta = torch.zeros(4, dtype=torch.int64, device=dev)
+        assert engines[r].deflate_shard_device(hist.data_ptr() if hist is not None else None, int(hist.numel()) if hist is not None else 0,
+                                               d_in.data_ptr() if b > a else None, b - a, 6, 0, d_body.data_ptr(), cap, d_meta.data_ptr()) == 0
+        engines[r].synchronize()
+        body_len, adler, status, raw = d_meta.cpu().tolist()
+        assert status == 0 and raw == b - a
+        bodies.append(d_body[:body_len].clone())
+        metas.append((body_len, adler, status, raw))
+    # the assembled stream is a valid zlib stream (checked by libz)
+    offsets, total, folded = sharding.assemble(metas)
+    stream = engine.zlib_header(6) + b"".join(x.cpu().numpy().tobytes() for x in bodies) + engine.zlib_tail(folded)
+    assert len(stream) == total and zlib.decompress(stream) == host.tobytes()
+    # phase 1 on every rank, "all_gather" of the records, phase 2 on every rank
+    RECORD = sharding.ShardedInflate.RECORD
+    d_all = torch.zeros(world * RECORD, dtype=torch.uint8, device=dev)
+    results = []
+    for r, (a, b) in enumerate(ranges):
+        d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+        rc = engines[r].inflate_shard_prepare_device(bodies[r].data_ptr() if bodies[r].numel() else None, int(bodies[r].numel()),
+                                                     0 if r == 0 else 32768, b - a, d_all[r * RECORD:].data_ptr(), d_res.data_ptr())
+        assert rc == 0
+        engines[r].synchronize()
+        out_len, consumed, status, _ = d_res.cpu().tolist()
+        assert (out_len, consumed, status) == (b - a, int(bodies[r].numel()), 0), (r, out_len, consumed, status)
+    adler = 1
+    for r, (a, b) in enumerate(ranges):
+        d_entry = torch.zeros(32768, dtype=torch.uint8, device=dev)
+        d_out = torch.empty(max(b - a, 1), dtype=torch.uint8, device=dev)
+        d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+        assert engines[r].window_from_maps_device(d_all.data_ptr(), RECORD, r, d_entry.data_ptr()) == 0
+        if a >= 32768:
+            engines[r].synchronize()
+            assert d_entry.cpu().numpy().tobytes() == host[a - 32768:a].tobytes()  # the composed maps ARE the previous 32 KiB
+        assert engines[r].inflate_shard_finish_device(d_entry.data_ptr(), d_out.data_ptr(), d_res.data_ptr()) == 0
+        engines[r].synchronize()
+        out_len, _, status, a32 = d_res.cpu().tolist()
+        assert status == Z_STREAM_END and out_len == b - a
+        assert d_out[: b - a].cpu().numpy().tobytes() == host[a:b].tobytes()
+        adler = engine.adler32_combine(adler, a32 & 0xFFFFFFFF, b - a)
+    assert adler == zlib.adler32(host.tobytes()) == folded

@@ -40,5 +40,23 @@ if rank == 0:
     rc, back, used = one.inflate(stream, n)
     assert rc == 1 and bytes(back) == whole.tobytes()
     print("mgpu ok: world %d, %d -> %d bytes (%.4f), offsets %s" % (world, n, total, total / n, offsets))
+# sharded inflate of the same stream: every rank decodes its body, one all_gather of tail maps, every rank gets its range
+d_back = torch.empty(b - a, dtype=torch.uint8, device=dev)
+si = sharding.ShardedInflate(eng, rank, world, dev)
+assert si.step(d_body, lens[rank], d_back, b - a) == 0
+torch.cuda.synchronize(dev)
+got, status, a32, metas = si.finish()
+assert status == 1 and got == b - a and all(st == 0 for _, st in metas), (rank, status, got, metas)
+assert torch.equal(d_back, d_in)
+parts = torch.tensor([a32, b - a], dtype=torch.int64, device=dev)
+allp = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+dist.all_gather(allp, parts)
+folded = 1
+for t in allp:
+    x = t.cpu().tolist()
+    folded = sharding.adler32_combine(folded, x[0] & 0xFFFFFFFF, x[1])
+assert folded == adler
+if rank == 0:
+    print("mgpu inflate ok: world %d, every rank reproduced its range, folded Adler-32 %08x" % (world, folded))
 dist.barrier()
 dist.destroy_process_group()

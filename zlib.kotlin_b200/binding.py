@@ -42,6 +42,9 @@ SIGNATURES = {
     "zk_deflate_raw": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64)]),
     "zk_inflate_raw": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
     "zk_deflate_shard": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64, c_int, c_int, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint32)]),
+    "zk_inflate_shard_prepare_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint64, c_void_p, c_void_p]),
+    "zk_window_from_maps_device": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_void_p]),
+    "zk_inflate_shard_finish_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_zlib_header": (None, [c_int, POINTER(c_uint8)]),
     "zk_zlib_tail": (None, [c_uint32, POINTER(c_uint8)]),
     "zk_deflate_init": (c_void_p, [c_void_p, c_int, c_int]),
@@ -267,6 +270,15 @@ class Engine:
         out_len, adler = c_uint64(0), c_uint32(0)
         rc = self.lib.zk_deflate_shard(self.ctx, haddr, hn, addr, n, level, strategy, oaddr, ocap, ctypes.byref(out_len), ctypes.byref(adler))
         return rc, out[: out_len.value], adler.value
+
+    def inflate_shard_prepare_device(self, d_body, m, hist_len, cap, d_tail_map, d_result):
+        return self.lib.zk_inflate_shard_prepare_device(self.ctx, d_body, m, hist_len, cap, d_tail_map, d_result)
+
+    def window_from_maps_device(self, d_maps, stride_bytes, count, d_window):
+        return self.lib.zk_window_from_maps_device(self.ctx, d_maps, stride_bytes, count, d_window)
+
+    def inflate_shard_finish_device(self, d_entry_window, d_out, d_result):
+        return self.lib.zk_inflate_shard_finish_device(self.ctx, d_entry_window, d_out, d_result)
 
     def adler32_combine(self, a1, a2, len2):
         return self.lib.zk_adler32_combine(a1, a2, len2)

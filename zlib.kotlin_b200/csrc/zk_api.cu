@@ -398,6 +398,37 @@ int zk_inflate_zlib_device(zk_ctx *c, const uint8_t *d_in, uint64_t m, uint8_t *
     return run_inflate(c, job);
 }
 
+// ---- one stream inflated across GPUs ("Partitioning (inflate)") -------------------------------------
+// Every rank holds the body of a chunk range (what zk_deflate_shard_device made).  Phase 1 decodes it with references
+// into the preceding ranks' output kept symbolic and hands out the shard's total tail map (u16[32768]: slot = a byte of
+// the shard's last 32 KiB, or 0x8000 | index into the window in front of the shard).  The ranks exchange these maps with
+// ONE all_gather (64 KiB each); zk_window_from_maps_device composes the maps of the ranks before this one into the 32 KiB
+// in front of its shard; phase 2 resolves the shard with it and writes the bytes.  d_result = {out_len, consumed, status,
+// Adler-32 of the shard's output} -- fold the checksums with zk_adler32_combine and compare with the stream's trailer.
+int zk_inflate_shard_prepare_device(zk_ctx *c, const uint8_t *d_body, uint64_t m, uint32_t hist_len, uint64_t cap,
+                                    uint16_t *d_tail_map, uint64_t *d_result) {
+    if (!c || !d_tail_map || !d_result || (!d_body && m) || hist_len > (uint32_t)kWindow) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    InflateJob job{d_body, m, nullptr, cap, d_result};
+    job.container = 3;
+    job.dict_len = hist_len;
+    job.d_tail_map = d_tail_map;
+    c->shard.valid = false;
+    return run_inflate(c, job);
+}
+
+int zk_window_from_maps_device(zk_ctx *c, const uint16_t *d_maps, uint64_t stride_bytes, uint32_t count, uint8_t *d_window) {
+    if (!c || !d_window || (!d_maps && count) || (stride_bytes & 1)) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    return launch_window_from_maps(c, d_maps, stride_bytes / 2, count, d_window);
+}
+
+int zk_inflate_shard_finish_device(zk_ctx *c, const uint8_t *d_entry_window, uint8_t *d_out, uint64_t *d_result) {
+    if (!c || !d_entry_window || !d_result) return ZK_STREAM_ERROR;
+    ZK_CUDA(cudaSetDevice(c->device));
+    return run_inflate_shard_finish(c, d_entry_window, d_out, d_result);
+}
+
 // ---- host-buffer entry points ----------------------------------------------------------------------------------
 // Device staging for host calls: one grow-only buffer per context, separate from the kernel arena.
 struct Staging {

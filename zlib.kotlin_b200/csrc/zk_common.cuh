@@ -87,6 +87,17 @@ struct zk_ctx {
     int64_t opt_chunk_bytes = 0; // 0 = auto
     int64_t opt_block_bytes = zk::kBlockBytesDefault;
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    // scratch of a sharded inflate between its two phases (pointers into the arena)
+    struct ShardState {
+        bool valid;
+        void *d_chunks, *d_num, *d_verdict, *d_flag, *d_adler, *d_partials, *d_windows, *d_maps, *d_sym;
+        uint32_t nch, group;
+        uint64_t total;
+        uint32_t dict_len;
+        const uint8_t *d_in;
+        uint64_t m;
+    };
+    ShardState shard = {false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0};
     // optional per-kernel-class device timing (option "timing"): event pairs recorded around launches
     int64_t opt_timing = 0;
     unsigned long long *lz_prof = nullptr;  // debug: per-unit cycle counters of lz77_kernel
@@ -150,10 +161,13 @@ struct InflateJob {
     const uint8_t *d_dict = nullptr;  // preset dictionary (device) for a stream with FDICT, or nullptr
     uint32_t dict_len = 0;
     uint32_t dict_id = 0;             // Adler-32 of the whole dictionary: must equal the stream's DICTID
-    int container = 0;                // 0 zlib, 1 raw deflate, 2 gzip member (header already parsed by the host)
+    int container = 0;                // 0 zlib, 1 raw deflate, 2 gzip member (header already parsed by the host), 3 shard body
+    uint16_t *d_tail_map = nullptr;   // shard body: receives the shard's total tail map (u16[32768])
     uint32_t body_begin = 0;          // raw / gzip: offset of the deflate data in d_in
 };
 int run_inflate(zk_ctx *c, const InflateJob &job);
+int run_inflate_shard_finish(zk_ctx *c, const uint8_t *d_entry_window, uint8_t *d_out, uint64_t *d_result);
+int launch_window_from_maps(zk_ctx *c, const uint16_t *d_maps, uint64_t stride_u16, uint32_t count, uint8_t *d_window);
 
 // CRC-32 (gzip): same calling convention as launch_adler32
 size_t crc_partials_bytes(uint64_t n);

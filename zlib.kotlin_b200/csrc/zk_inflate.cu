@@ -925,6 +925,53 @@ __global__ void __launch_bounds__(1024) window_apply_kernel(uint32_t n, uint32_t
     }
 }
 
+// Sharded inflate (one stream cut into chunk ranges across GPUs): the total tail map of a shard relative to the window
+// before the shard -- the group-end maps composed in order, in the map domain (a reference stays a reference).
+__global__ void __launch_bounds__(1024) window_chain_maps_kernel(uint32_t n, uint32_t group, const uint16_t *__restrict__ maps,
+                                                                 uint16_t *__restrict__ total_map) {
+    extern __shared__ __align__(16) uint16_t cms[];  // two maps of 32768 slots
+    const uint32_t groups = (n + group - 1) / group;
+    for (int k = 0; k < kPerThread; ++k) cms[kWindow + threadIdx.x + k * 1024] = (uint16_t)(0x8000u | (threadIdx.x + k * 1024));
+    __syncthreads();
+    for (uint32_t g = 0; g < groups; ++g) {
+        const uint32_t c = min(n, (g + 1) * group) - 1;
+        const uint16_t *mp = maps + (uint64_t)c * kWindow;
+        const uint16_t *prev = cms + ((g + 1) & 1) * kWindow;
+        uint16_t *cur = cms + (g & 1) * kWindow;
+        uint16_t sy[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) sy[k] = mp[threadIdx.x + k * 1024];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            const uint16_t s = sy[k];
+            cur[threadIdx.x + k * 1024] = (s & 0x8000u) ? prev[s & 0x7FFFu] : s;
+        }
+        __syncthreads();
+    }
+    const uint16_t *last = cms + ((groups + 1) & 1) * kWindow;  // groups == 0: the identity
+    for (int k = 0; k < kPerThread; ++k) total_map[threadIdx.x + k * 1024] = last[threadIdx.x + k * 1024];
+}
+
+// The window in front of shard r: the tail maps of shards 0 .. r-1 applied in order to an empty window.
+__global__ void __launch_bounds__(1024) window_from_maps_kernel(const uint16_t *__restrict__ maps, uint64_t stride_u16,
+                                                                uint32_t count, uint8_t *__restrict__ window) {
+    extern __shared__ __align__(16) uint8_t wfm[];  // two windows
+    for (int k = 0; k < kPerThread; ++k) wfm[kWindow + threadIdx.x + k * 1024] = 0;
+    __syncthreads();
+    for (uint32_t q = 0; q < count; ++q) {
+        const uint16_t *mp = maps + (uint64_t)q * stride_u16;
+        const uint8_t *prev = wfm + ((q + 1) & 1) * kWindow;
+        uint8_t *cur = wfm + (q & 1) * kWindow;
+        for (int k = 0; k < kPerThread; ++k) {
+            const uint16_t s = mp[threadIdx.x + k * 1024];
+            cur[threadIdx.x + k * 1024] = (s & 0x8000u) ? prev[s & 0x7FFFu] : (uint8_t)s;
+        }
+        __syncthreads();
+    }
+    const uint8_t *last = wfm + ((count + 1) & 1) * kWindow;
+    for (int k = 0; k < kPerThread; ++k) window[threadIdx.x + k * 1024] = last[threadIdx.x + k * 1024];
+}
+
 // Symbols -> bytes.  One CTA per 16 KiB of output; a thread turns 8 consecutive symbols (one 16-byte load) into one
 // 8-byte store.  The chunk of the tile's first position is found once per CTA by binary search, every thread then walks
 // forward from it (chunks are almost always much longer than a tile).
@@ -1002,7 +1049,10 @@ __global__ void finish_inflate_kernel(const uint8_t *in, uint64_t m, const uint6
     if (status == ZK_OK && error_flag[0]) status = ZK_DATA_ERROR;  // distance too far back (IS:287-291)
     if (status == ZK_OK) {
         const uint64_t need = container == 0 ? 4 : container == 2 ? 8 : 0;
-        if (!verdict[5]) status = ZK_BUF_ERROR;  // ran out of input before a final block
+        if (container == 3) {
+            // a shard body: it carries no final block and must end exactly on the end of its range
+            status = (!verdict[5] && end_byte == m) ? ZK_STREAM_END : ZK_DATA_ERROR;
+        } else if (!verdict[5]) status = ZK_BUF_ERROR;  // ran out of input before a final block
         else if (end_byte + need > m) status = ZK_BUF_ERROR;  // IS:414-418 trailer bytes missing
         else if (container == 0) {
             const uint32_t t = ((uint32_t)in[end_byte] << 24) | ((uint32_t)in[end_byte + 1] << 16) |
@@ -1517,7 +1567,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
 // verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen
 __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_t n, ChunkInfo *coarse,
                                                           uint32_t *num_coarse, uint64_t *verdict, uint64_t cap, uint64_t m,
-                                                          uint32_t trailer) {
+                                                          uint32_t trailer, bool shard_body) {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
     __shared__ int bad;
@@ -1533,7 +1583,8 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
             v = lc[i].out_len;
             const bool last = i + 1 == n;
             // every block but the last must end exactly on the next one; the last must close the stream
-            if (lc[i].status != ZK_OK || (last ? !lc[i].final_seen : (lc[i].final_seen || lc[i].end_byte != lc[i].in_end))) bad = 1;
+            const bool last_ok = shard_body ? (!lc[i].final_seen && lc[i].end_byte == lc[i].in_end) : (lc[i].final_seen != 0);
+            if (lc[i].status != ZK_OK || (last ? !last_ok : (lc[i].final_seen || lc[i].end_byte != lc[i].in_end))) bad = 1;
             // a stream cut inside its trailer: the warp-per-chunk decoder reports what the reference reports (BR:48-57)
             if (last && lc[i].end_byte + trailer > m) bad = 1;
         }
@@ -1740,9 +1791,12 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     }
     const int32_t hst = hdr[0];
     const uint32_t body_begin = (uint32_t)hdr[1];
-    const uint32_t dict_len = (job.d_dict && body_begin == 6) ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow) : 0u;
+    // a shard body may reach hist_len bytes back into the output of the shards before it: the same mechanism as a preset
+    // dictionary, except that the window's CONTENT arrives later (run_inflate_shard_finish)
+    const uint32_t dict_len = job.container == 3 ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow)
+                              : (job.d_dict && body_begin == 6) ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow) : 0u;
     ZK_CUDA(cudaMemsetAsync(d_windows - kWindow, 0, kWindow, st));
-    if (dict_len)
+    if (dict_len && job.container != 3)
         ZK_CUDA(cudaMemcpyAsync(d_windows - dict_len, job.d_dict + (job.dict_len - dict_len), dict_len, cudaMemcpyDeviceToDevice, st));
     if (hst != ZK_OK) {
         // (hdr, 0): nothing decoded; FDICT consumes the 4 DICTID bytes (IS:41)
@@ -1791,7 +1845,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                             job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm, dict_len);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
-                                                          job.container == 0 ? 4u : job.container == 2 ? 8u : 0u);
+                                                          job.container == 0 ? 4u : job.container == 2 ? 8u : 0u, job.container == 3);
                     c->launches += 4;
                     ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
                     ZK_CUDA(cudaStreamSynchronize(st));
@@ -1858,9 +1912,29 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             ZK_CUDA(cudaFuncSetAttribute(window_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWindow));
             ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
             window_compose_kernel<<<groups, 1024, 4 * kWindow, st>>>(d_chunks, nch, group, d_sym, d_maps, d_flag, dict_len);
+            if (job.container == 3) {
+                // phase 1 of a sharded inflate ends here: hand out the shard's total tail map, keep the rest for phase 2
+                ZK_CUDA(cudaFuncSetAttribute(window_chain_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWindow));
+                window_chain_maps_kernel<<<1, 1024, 4 * kWindow, st>>>(nch, group, d_maps, job.d_tail_map);
+                c->launches += 2;
+                c->shard = {true, d_chunks, d_num, d_verdict, d_flag, d_adler, d_partials, d_windows, d_maps, d_sym, nch, group, total, dict_len, job.d_in, m};
+                set_result_kernel<<<1, 32, 0, st>>>(job.d_result, total, verdict[4], (int64_t)verdict[2], 0);
+                c->launches++;
+                ZK_CUDA(cudaGetLastError());
+                return ZK_OK;
+            }
             window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(nch, group, d_maps, d_windows);
             window_apply_kernel<<<nch, 1024, 0, st>>>(nch, group, d_maps, d_windows);
             c->launches += 2;
+        }
+        if (job.container == 3) {  // a shard without output: the identity map
+            ZK_CUDA(cudaFuncSetAttribute(window_chain_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWindow));
+            window_chain_maps_kernel<<<1, 1024, 4 * kWindow, st>>>(0, 1, d_maps, job.d_tail_map);
+            c->shard = {true, d_chunks, d_num, d_verdict, d_flag, d_adler, d_partials, d_windows, d_maps, d_sym, 0, 1, total, dict_len, job.d_in, m};
+            set_result_kernel<<<1, 32, 0, st>>>(job.d_result, total, verdict[4], (int64_t)verdict[2], 0);
+            c->launches += 2;
+            ZK_CUDA(cudaGetLastError());
+            return ZK_OK;
         }
         const uint32_t tiles = (uint32_t)((total + 16383) / 16384);
         if (tiles) materialize_kernel<<<tiles, 256, 0, st>>>(d_chunks, d_num, d_sym, d_windows, job.d_out, total, d_flag, dict_len);
@@ -1870,6 +1944,47 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                                 : launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
     if (rc != ZK_OK) return rc;
     finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result, job.container);
+    c->launches++;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+// Phase 2 of a sharded inflate: the window in front of the shard is known now (the tail maps of the shards before it,
+// composed): resolve the shard's windows, turn its symbols into bytes, checksum them.  Uses the scratch phase 1 left in
+// the context's arena: no other call on this context may come between the two.
+int run_inflate_shard_finish(zk_ctx *c, const uint8_t *d_entry_window, uint8_t *d_out, uint64_t *d_result) {
+    if (!c->shard.valid) return ZK_STREAM_ERROR;
+    const zk_ctx::ShardState sh = c->shard;
+    c->shard.valid = false;
+    cudaStream_t st = c->stream;
+    uint8_t *windows = static_cast<uint8_t *>(sh.d_windows);
+    ZK_CUDA(cudaMemcpyAsync(windows - kWindow, d_entry_window, kWindow, cudaMemcpyDeviceToDevice, st));
+    {
+        ScopedTimer t(c, 5);
+        if (sh.nch) {
+            ZK_CUDA(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
+            window_chain_kernel<<<1, 1024, 2 * kWindow, st>>>(sh.nch, sh.group, static_cast<const uint16_t *>(sh.d_maps), windows);
+            window_apply_kernel<<<sh.nch, 1024, 0, st>>>(sh.nch, sh.group, static_cast<const uint16_t *>(sh.d_maps), windows);
+        }
+        const uint32_t tiles = (uint32_t)((sh.total + 16383) / 16384);
+        if (tiles)
+            materialize_kernel<<<tiles, 256, 0, st>>>(static_cast<const ChunkInfo *>(sh.d_chunks), static_cast<const uint32_t *>(sh.d_num),
+                                                      static_cast<const uint16_t *>(sh.d_sym), windows, d_out, sh.total,
+                                                      static_cast<uint32_t *>(sh.d_flag), sh.dict_len);
+        c->launches += 3;
+    }
+    int rc = launch_adler32(c, 1u, d_out, sh.total, sh.d_partials, static_cast<uint32_t *>(sh.d_adler));
+    if (rc != ZK_OK) return rc;
+    finish_inflate_kernel<<<1, 32, 0, st>>>(sh.d_in, sh.m, static_cast<const uint64_t *>(sh.d_verdict), static_cast<const uint32_t *>(sh.d_adler),
+                                            static_cast<const uint32_t *>(sh.d_flag), d_result, 3);
+    c->launches++;
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+int launch_window_from_maps(zk_ctx *c, const uint16_t *d_maps, uint64_t stride_u16, uint32_t count, uint8_t *d_window) {
+    ZK_CUDA(cudaFuncSetAttribute(window_from_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kWindow));
+    window_from_maps_kernel<<<1, 1024, 2 * kWindow, c->stream>>>(d_maps, stride_u16, count, d_window);
     c->launches++;
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;

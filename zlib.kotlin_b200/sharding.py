@@ -96,3 +96,45 @@ class ShardedDeflate:
     @property
     def ready(self):
         return self.gathered is not None
+
+
+class ShardedInflate:
+    """One stream inflated across GPUs.  Rank r holds the body of its chunk range (what ShardedDeflate made) and ends up
+    with the bytes of that range.  The only collective is one all_gather of a 64 KiB + 32 B record per rank: the shard's
+    tail map (see include/zlibk_gpu.h) and {out_len, adler, status, consumed}."""
+
+    RECORD = 65536 + 32
+
+    def __init__(self, engine, rank, world, device):
+        import torch
+
+        self.eng, self.rank, self.world, self.dev = engine, rank, world, device
+        self.d_record = torch.zeros(self.RECORD, dtype=torch.uint8, device=device)   # tail map | meta of this rank
+        self.d_all = torch.zeros(world * self.RECORD, dtype=torch.uint8, device=device)
+        self.d_entry = torch.zeros(32768, dtype=torch.uint8, device=device)
+        self.d_res = torch.zeros(4, dtype=torch.int64, device=device)
+
+    def step(self, d_body, m, d_out, cap):
+        """-> zlib code of the C ABI calls (0 = launched); results via finish()."""
+        import torch
+        import torch.distributed as dist
+
+        hist_len = 0 if self.rank == 0 else 32768
+        rc = self.eng.inflate_shard_prepare_device(d_body.data_ptr(), m, hist_len, cap, self.d_record.data_ptr(), self.d_res.data_ptr())
+        if rc != 0:
+            return rc
+        # the one collective: every rank's tail map (the meta words ride along for the host)
+        self.d_record[65536:].view(torch.int64).copy_(self.d_res)
+        dist.all_gather_into_tensor(self.d_all, self.d_record)
+        rc = self.eng.window_from_maps_device(self.d_all.data_ptr(), self.RECORD, self.rank, self.d_entry.data_ptr())
+        if rc != 0:
+            return rc
+        return self.eng.inflate_shard_finish_device(self.d_entry.data_ptr(), d_out.data_ptr(), self.d_res.data_ptr())
+
+    def finish(self):
+        """-> (this rank's out_len, status, adler of its output, [(out_len, status) of every rank after phase 1])."""
+        import torch
+
+        out_len, _, status, adler = self.d_res.cpu().tolist()
+        metas = self.d_all.view(self.world, self.RECORD)[:, 65536:].contiguous().view(torch.int64).view(self.world, 4).cpu().tolist()
+        return out_len, status, adler & 0xFFFFFFFF, [(mm[0], mm[2]) for mm in metas]
