@@ -123,6 +123,7 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     const uint64_t body_cap = job.cap > frame_bytes ? job.cap - frame_bytes : 0;
 
     c->arena.reset();
+    c->shard.valid = false;  // the scratch of a pending sharded inflate is gone
     const bool stored_only = level <= 0;
     const uint64_t slab_bytes = job.slab_bytes ? tmin<uint64_t>(job.slab_bytes, kSlabBytes) : kSlabBytes;
     const uint64_t first_bytes = (job.first_slab_bytes && job.first_slab_bytes < slab_bytes) ? job.first_slab_bytes : slab_bytes;
@@ -256,10 +257,13 @@ zk_ctx *zk_ctx_create(int device) {
     return c;
 }
 
+static void staging_release(zk_ctx *c);
+
 void zk_ctx_destroy(zk_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    staging_release(c);
     c->arena.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < c->span_cap; ++i) {
@@ -365,6 +369,7 @@ int zk_adler32_device(zk_ctx *c, uint32_t adler, const uint8_t *d_buf, uint64_t 
     if (!c || !d_out || (!d_buf && len)) return ZK_STREAM_ERROR;
     ZK_CUDA(cudaSetDevice(c->device));
     c->arena.reset();
+    c->shard.valid = false;  // the scratch of a pending sharded inflate is gone
     if (c->arena.reserve(adler_partials_bytes(len) + 1024) != ZK_OK) return ZK_MEM_ERROR;
     void *partials = c->arena.take(adler_partials_bytes(len));
     return launch_adler32(c, adler, d_buf, len, partials, d_out);
@@ -461,6 +466,16 @@ static Staging *staging_for(zk_ctx *c, size_t bytes) {
         }
     }
     return s;
+}
+
+// the calling thread's staging buffer of a context that is being destroyed
+static void staging_release(zk_ctx *c) {
+    for (size_t i = 0; i < g_staging.size(); ++i)
+        if (g_staging[i].first == c) {
+            if (g_staging[i].second.base) cudaFree(g_staging[i].second.base);
+            g_staging.erase(g_staging.begin() + (long)i);
+            return;
+        }
 }
 
 uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len) {
@@ -745,6 +760,7 @@ int zk_crc32_device(zk_ctx *c, uint32_t crc, const uint8_t *d_buf, uint64_t len,
     if (!c || !d_out || (!d_buf && len)) return ZK_STREAM_ERROR;
     ZK_CUDA(cudaSetDevice(c->device));
     c->arena.reset();
+    c->shard.valid = false;  // the scratch of a pending sharded inflate is gone
     if (c->arena.reserve(crc_partials_bytes(len) + 1024) != ZK_OK) return ZK_MEM_ERROR;
     void *d_partials = c->arena.take(crc_partials_bytes(len));
     return launch_crc32(c, crc, d_buf, len, d_partials, d_out);

@@ -1763,6 +1763,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const uint32_t pieces_reserved = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2);
     c->arena.reset();
+    if (job.container != 3) c->shard.valid = false;
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
                         (size_t)(max_chunks + 1) * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + crc_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
