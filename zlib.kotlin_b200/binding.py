@@ -71,7 +71,8 @@ class EngineError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libzlibk_b200.so")
+    # ZLIBK_LIB: an experimental build of the same C ABI (tools/variants.sh), never a different implementation
+    return os.environ.get("ZLIBK_LIB") or os.path.join(_HERE, "libzlibk_b200.so")
 
 
 def library():

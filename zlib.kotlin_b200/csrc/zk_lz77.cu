@@ -31,9 +31,6 @@
 // The symbol histograms are built from the token stream by hist_kernel (zk_huffman.cu).
 #include "zk_common.cuh"
 
-#ifndef ZK_SPREAD_ROLES
-#define ZK_SPREAD_ROLES 1
-#endif
 #ifndef ZK_USE_MATCH_ANY
 #define ZK_USE_MATCH_ANY 1
 #endif
@@ -43,27 +40,24 @@ namespace zk {
 namespace {
 
 constexpr int kThreadsLz = 1024;
-constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
 constexpr int kRun = 2;                      // consecutive positions per lane (strip = 64 positions)
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
 // Work-stealing strips of a group: the first kBigStrips cover 64 positions each (two per lane: the second inherits from the
 // first), the rest of the group is cut into strips of 32 positions.  A step ends one strip after the last role warp has
 // joined the search, so the strips handed out last are the short ones.
-constexpr int kBigStrips = 40;
+#ifndef ZK_BIG_STRIPS
+#define ZK_BIG_STRIPS 40
+#endif
+constexpr int kBigStrips = ZK_BIG_STRIPS;
 constexpr int kSmallStrips = (kGroup - kBigStrips * kStrip) / 32;
 constexpr int kStripsPerGroup = kBigStrips + kSmallStrips;
 constexpr int kParserWarps = 4;
 constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
 constexpr int kPreRows = 4;                         // parser: real-parse tokens a lane may emit before convergence
-// The sequential roles (1 builder + 4 parser warps) all live on one SM sub-partition (warp id % 4 == 3): the issue
-// arbiter is fair among ready warps, so a role warp sharing its scheduler with seven issue-bound searcher warps gets
-// one slot in eight and becomes the critical path.  The other three warps of that sub-partition only search once the
-// roles of the step are done.
-constexpr int kRoleSmsp = 3;
-constexpr int kBuilderSlot = 7;        // slot = warp id / 4 among the warps of the role sub-partition
-constexpr int kFirstParserSlot = 3;    // slots 3..6
-constexpr int kRoleWarps = 1 + kParserWarps;
+// The sequential roles: one parser warp per SM sub-partition (warps 24..27) and the builder on warp 31.  With the heavy
+// roles of the first version all five had to share one sub-partition whose other warps waited; with today's lean roles
+// that one issue port had become the bottleneck.
 constexpr int kHistGroups = kWindow / kGroup;
 constexpr int kMaxDist = kWindow - 2 * kGroup;
 constexpr int kStages = 4;                   // ring staging barriers
@@ -450,19 +444,6 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const LevelParams &lp, c
 // ---- parser: four warps turn the per-position matches of group t into tokens -------------------------------
 __device__ __forceinline__ int tok_len(uint32_t w) { return (int)((w >> 16) & 0x1FFu); }
 
-__device__ __forceinline__ int length_symbol(int len) {  // 257..285
-    const int y = len - 3;
-    if (y < 8) return 257 + y;
-    if (len == 258) return 285;
-    const int b = 31 - __clz(y);
-    return 257 + 4 * (b - 1) + ((y >> (b - 2)) & 3);
-}
-__device__ __forceinline__ int dist_symbol(int dist_minus1) {  // 0..29
-    if (dist_minus1 < 4) return dist_minus1;
-    const int b = 31 - __clz(dist_minus1);
-    return 2 * b + ((dist_minus1 >> (b - 1)) & 1);
-}
-
 // Decide the token at p: returns the step (1 for a literal, len for a match).
 __device__ __forceinline__ int decide(const uint32_t *mv, int32_t g0, int32_t gend, int32_t p, int lazy) {
     // both words are loaded unconditionally (one slot of slack behind the group keeps p + 1 in bounds): no
@@ -735,20 +716,10 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LzSmem &s = *reinterpret_cast<LzSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool on_role_smsp = (warp & 3) == kRoleSmsp;
-    const int slot = warp >> 2;
-#if ZK_SPREAD_ROLES
     // one parser warp per sub-partition (warps 24..27), the builder on warp 31; nobody waits
     const bool is_builder = warp == 31;
     const bool is_parser = warp >= 24 && warp < 28;
-    const bool is_guest = false;
     const int parser_index = warp - 24;
-#else
-    const bool is_builder = on_role_smsp && slot == kBuilderSlot;
-    const bool is_parser = on_role_smsp && slot >= kFirstParserSlot && slot < kFirstParserSlot + kParserWarps;
-    const bool is_guest = on_role_smsp && !is_builder && !is_parser;  // searches only after the roles are done
-    const int parser_index = slot - kFirstParserSlot;
-#endif
 
     for (uint32_t unit = blockIdx.x; unit < a.num_units; unit += gridDim.x) {
         UnitGeom g;
@@ -813,10 +784,6 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                 parse_group(s, a, g, i - 1, parser_index * 32 + lane, unit, pt);
             // the other warps of the role sub-partition stay off its issue port until the builder and the parsers have
             // finished this step: a named barrier (roles arrive, guests wait), no polling
-#if !ZK_SPREAD_ROLES
-            if (is_builder || is_parser) asm volatile("bar.arrive 2, %0;" ::"n"(8 * 32) : "memory");
-            if (is_guest) asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
-#endif
             const long long t1 = clock64();
             const bool searching = i >= kHistGroups && i <= g.last_group;
             const bool preparing = i + 2 >= g.first_group && i + 2 <= g.last_group;
@@ -850,11 +817,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             __syncthreads();
         }
         __syncthreads();
-#if ZK_SPREAD_ROLES
         const int builder_warp = 31, parser_warp = 24;
-#else
-        const int builder_warp = kBuilderSlot * 4 + kRoleSmsp, parser_warp = kFirstParserSlot * 4 + kRoleSmsp;
-#endif
         if (a.prof && lane == 0 && (warp == builder_warp || warp == parser_warp || warp == 2 || warp == 3)) {
             // per unit: [0] total, then {role, search} of the builder, the first parser warp, a searcher and a guest
             unsigned long long *o = a.prof + (size_t)unit * 32;
