@@ -1531,10 +1531,12 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                         produced += length;
                     }
                 }
-                // ---- up to three more literals while this lane's next code is a short literal code and its bits are
-                // already in `hold`: no refill, no votes, no state changes
+                // ---- up to two more literals while this lane's next code is a short literal code and its bits are
+                // already in `hold`: no refill, no votes, no state changes.  (Measured at 1 GiB mixed: 0 / 1 / 2 / 3 / 4
+                // extra literals per trip -> 8.1 / 6.3 / 5.9 / 6.5 / 7.0 ms: every attempt that fails -- the next token is
+                // a match -- costs its dozen instructions, and the longest blocks alternate literals and matches.)
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
+                for (int b = 0; b < 2; ++b) {
                     const uint32_t e = s_lit[fr.peek(kLaneLitBits) * 32 + lane];
                     const bool lit = state == kSymbols && e != 0u && (e & 0x0F00u) == 0u && fr.held >= kLaneLitBits &&
                                      produced < kSlotSyms;
