@@ -28,6 +28,9 @@ for name, gen in kinds.items():
     eng.set_option("chunk_bytes", 1 << 20)
     eng.set_option("lz_profile_buffer", prof.data_ptr())
     eng.set_option("timing", 1)
+    for knob in ("lz_chain", "lz_good", "lz_nice"):
+        if os.environ.get(knob.upper()):
+            eng.set_option(knob, int(os.environ[knob.upper()]))
     for it in range(2):
         eng.counter("reset_timing")
         eng.deflate_device(d_in.data_ptr(), n, level, strategy, d_out.data_ptr(), cap, d_res.data_ptr())

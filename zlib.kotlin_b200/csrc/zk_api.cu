@@ -161,7 +161,10 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
                             job.d_result);
     }
 
-    const LevelParams lp = level_params(level, job.strategy);
+    LevelParams lp = level_params(level, job.strategy);
+    if (c->opt_lz_chain >= 0) lp.chain = (int)c->opt_lz_chain;
+    if (c->opt_lz_good >= 0) lp.good = (int)c->opt_lz_good;
+    if (c->opt_lz_nice >= 0) lp.nice = (int)c->opt_lz_nice;
     uint32_t *d_tokens = static_cast<uint32_t *>(c->arena.take((size_t)slab * 4));
     uint32_t *d_tok_begin = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
     uint32_t *d_tok_count = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
@@ -298,6 +301,11 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
     }
     if (!strcmp(name, "lz_profile_buffer")) {  // device pointer to u64[units][16] cycle counters, 0 = off
         c->lz_prof = reinterpret_cast<unsigned long long *>(static_cast<uintptr_t>(value));
+        return ZK_OK;
+    }
+    if (!strcmp(name, "lz_chain") || !strcmp(name, "lz_good") || !strcmp(name, "lz_nice")) {  // tuning (tools/lz_profile.py)
+        if (value < -1 || value > 258) return ZK_STREAM_ERROR;
+        (name[3] == 'c' ? c->opt_lz_chain : name[3] == 'g' ? c->opt_lz_good : c->opt_lz_nice) = value;
         return ZK_OK;
     }
     if (!strcmp(name, "timing")) {

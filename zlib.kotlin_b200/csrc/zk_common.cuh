@@ -86,6 +86,7 @@ struct zk_ctx {
     size_t pinned_cap = 0;
     int64_t opt_chunk_bytes = 0; // 0 = auto
     int64_t opt_block_bytes = zk::kBlockBytesDefault;
+    int64_t opt_lz_chain = -1, opt_lz_good = -1, opt_lz_nice = -1;  // tuning overrides of the level table (-1 = off)
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     // scratch of a sharded inflate between its two phases (pointers into the arena)
     struct ShardState {
