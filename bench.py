@@ -129,6 +129,13 @@ def cpu_baseline(kind, level, sample_mib, cores_note=""):
     }
 
 
+def workload_config(args, world):
+    """The `config` object both arms print: the workload the metric is quoted on."""
+    return {"workload": "%d MiB %s corpus per GPU (seed 0x5EED000%d), level %d, zlib stream, 32 KiB blocks; input larger than L2 (no flush needed)" % (
+                args.size_mib, "mixed-entropy" if args.workload == "mixed" else "text-like", 2 if args.workload == "mixed" else 1, args.level),
+            "parallelism": "chunk ranges per GPU x%d" % world}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the Kotlin reference can
     not be compiled here), one host thread -- the reference is single-threaded -- on a bounded sample per step."""
@@ -155,8 +162,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%d GiB-class %s corpus, level %d (bounded sample: first %d MiB per step)" % (
-            max(1, args.size_mib >> 10), args.workload, args.level, sample_mib)},
+        "config": dict(workload_config(args, args.gpus), sample="each step deflates the first %d MiB of that corpus on one host core "
+                       "(the reference is single-threaded)" % sample_mib),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "first %d MiB of the %s corpus per step" % (sample_mib, args.workload)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -401,9 +408,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "%d MiB %s corpus per GPU (seed 0x5EED000%d), level %d, zlib stream, 32 KiB blocks; input larger than L2 (no flush needed)" % (
-            args.size_mib, "mixed-entropy" if args.workload == "mixed" else "text-like", 2 if args.workload == "mixed" else 1, args.level),
-            "parallelism": "chunk ranges per GPU x%d" % world},
+        "config": workload_config(args, world),
         "compressed_ratio": total_out / (n * world),
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "inflate": inflate, "e2e": e2e,
