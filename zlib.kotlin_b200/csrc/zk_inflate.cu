@@ -1639,10 +1639,14 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
 constexpr int kExpandWarps = 8;
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const uint8_t *__restrict__ in,
                                                                         const LaneChunk *__restrict__ lc, uint32_t n,
-                                                                        const uint16_t *__restrict__ slots, uint16_t *dense) {
+                                                                        const uint16_t *__restrict__ slots, uint16_t *dense,
+                                                                        const uint32_t *__restrict__ perm) {
     const int lane = threadIdx.x & 31;
-    const uint32_t j = blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
-    if (j >= n) return;
+    const uint32_t slot = blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
+    if (slot >= n) return;
+    // longest blocks first and blocks of similar size in one CTA (the order the lane decoder used): a CTA keeps its
+    // slot until its slowest warp is done
+    const uint32_t j = perm[slot];
     uint16_t *out = dense + lc[j].out_begin;
     if (lc[j].stored_len) {  // a stored block: its payload is the output
         const uint8_t *src = in + lc[j].stored_src;
@@ -1855,7 +1859,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     if (verdict[1] == 1 && verdict[0] <= max_chunks) {
                         ScopedTimer t(c, 5);
                         expand_blocks_kernel<<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
-                            job.d_in, d_lc, (uint32_t)n, d_slots, d_sym);
+                            job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm);
                         resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
                         c->launches += 2;
                         lane_path_done = true;
