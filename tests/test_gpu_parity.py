@@ -341,6 +341,38 @@ def test_host_call_pipelined_slabs(engine, oracle, level):
     assert rc2 in (Z_BUF_ERROR, Z_STREAM_END) and len(out) > (4 << 20) and out == host[: len(out)].tobytes()
 
 
+def test_host_call_many_small_slabs_overlap(engine):
+    """Slabs of a multi-slab deflate alternate between two streams with their own scratch (the next slab's LZ kernel
+    fills the tail of the current one).  With small slabs (1 MiB first, then 2 MiB: 20 slabs, scratch sets reused ten
+    times) and the unit size pinned, the overlapped run must give exactly the bytes of the strictly serial run."""
+    from zlibk_b200 import corpus
+
+    n = (37 << 20) + 999
+    host = corpus.mixed_entropy(n)
+    try:
+        engine.set_option("host_slab_bytes", 2 << 20)
+        engine.set_option("host_first_slab_bytes", 1 << 20)
+        with pytest.raises(ValueError):
+            engine.set_option("host_slab_bytes", 12345)  # not a multiple of 64 KiB
+        engine.set_option("chunk_bytes", 128 << 10)
+        streams = []
+        for overlap in (1, 0, 1):
+            engine.set_option("slab_overlap", overlap)
+            rc, stream, adler = engine.deflate(host, 6)
+            assert rc == Z_OK, engine.last_error()
+            assert adler == zlib.adler32(host)
+            streams.append(bytes(stream))
+        assert streams[0] == streams[1] == streams[2]
+        assert zlib.decompress(streams[0]) == host.tobytes()
+        # automatic unit sizes (larger units in slabs that have a successor): still a valid stream of the same data
+        engine.set_option("chunk_bytes", 0)
+        rc, stream, _ = engine.deflate(host, 6)
+        assert rc == Z_OK and zlib.decompress(bytes(stream)) == host.tobytes()
+    finally:
+        for name, value in (("host_slab_bytes", 0), ("host_first_slab_bytes", 0), ("chunk_bytes", 0), ("slab_overlap", 1)):
+            engine.set_option(name, value)
+
+
 def test_host_call_pipelined_output_too_small(engine):
     """The pipelined host call with an output buffer that can not hold the stream: Z_BUF_ERROR, nothing written past the
     buffer (a guard band behind it stays intact)."""

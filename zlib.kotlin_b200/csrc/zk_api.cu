@@ -100,14 +100,31 @@ void Arena::release() {
 }
 
 // ---- deflate orchestration ---------------------------------------------------------------------------------
-static uint32_t pick_unit_bytes(const zk_ctx *c, uint64_t n, uint32_t block_bytes) {
+enum UnitMode { kUnitSingle, kUnitTailFilled, kUnitLastOfMany };
+static uint32_t pick_unit_bytes(const zk_ctx *c, uint64_t n, uint32_t block_bytes, UnitMode mode = kUnitSingle) {
     if (c->opt_chunk_bytes > 0) {
         uint64_t u = (uint64_t)c->opt_chunk_bytes / block_bytes * block_bytes;
         return (uint32_t)tmax<uint64_t>(u, block_bytes);
     }
+    uint64_t u = 512u << 10;
+    if (mode == kUnitTailFilled) {
+        // the next slab's LZ kernel fills the tail: large units, as long as two slabs in flight cover every SM
+        while (u > block_bytes && n / u < (uint64_t)c->sm_count / 2) u >>= 1;
+        return (uint32_t)tmax<uint64_t>(u, block_bytes);
+    }
+    if (mode == kUnitLastOfMany) {
+        // short last slab of a pipelined job: fewest waves x (unit + what a unit pays for its 32 KiB of history and for
+        // filling its software pipeline, ~52 KiB worth of steps)
+        uint64_t best = u, best_cost = ~0ull;
+        for (uint64_t v = u; v >= tmax<uint64_t>(block_bytes, 32u << 10); v >>= 1) {
+            const uint64_t units = (n + v - 1) / v;
+            const uint64_t cost = ((units + c->sm_count - 1) / c->sm_count) * (v + (52u << 10));
+            if (cost < best_cost) best = v, best_cost = cost;
+        }
+        return (uint32_t)tmax<uint64_t>(best, block_bytes);
+    }
     // at least ~4 units per SM so the tail wave is short (units differ a lot in cost: a unit of long repeats takes
     // twice as long as a unit of text); history re-priming costs 32 KiB per unit
-    uint64_t u = 512u << 10;
     while (u > block_bytes && n / u < (uint64_t)c->sm_count * 4) u >>= 1;
     return (uint32_t)tmax<uint64_t>(u, block_bytes);
 }
@@ -129,9 +146,12 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     const uint64_t first_bytes = (job.first_slab_bytes && job.first_slab_bytes < slab_bytes) ? job.first_slab_bytes : slab_bytes;
     const uint64_t slab = tmin<uint64_t>(n, slab_bytes);
     const uint32_t slab_blocks = (uint32_t)((slab + block_bytes - 1) / block_bytes) + 1;
-    size_t need = 8192 + adler_partials_bytes(n);
+    const uint64_t nslabs = n <= first_bytes ? 1 : 1 + (n - first_bytes + slab_bytes - 1) / slab_bytes;
+    // two sets of scratch when there is more than one slab: slab k+1 starts while slab k is still running (below)
+    const int nsets = (!stored_only && nslabs >= 2 && c->opt_slab_overlap) ? 2 : 1;
+    size_t need = 8192 + adler_partials_bytes(n) + (size_t)nslabs * 8 + 256;
     if (!stored_only)
-        need += (size_t)slab * 4 + (size_t)slab_blocks * (8 + kHistStride * 4 + sizeof(BlockPlan) + 8) + 4096;
+        need += ((size_t)slab * 4 + (size_t)slab_blocks * (8 + kHistStride * 4 + sizeof(BlockPlan) + 8) + 4096) * nsets;
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
     uint64_t *d_cursor = static_cast<uint64_t *>(c->arena.take(256));
     uint32_t *d_adler = static_cast<uint32_t *>(c->arena.take(256));
@@ -165,43 +185,89 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     if (c->opt_lz_chain >= 0) lp.chain = (int)c->opt_lz_chain;
     if (c->opt_lz_good >= 0) lp.good = (int)c->opt_lz_good;
     if (c->opt_lz_nice >= 0) lp.nice = (int)c->opt_lz_nice;
-    uint32_t *d_tokens = static_cast<uint32_t *>(c->arena.take((size_t)slab * 4));
-    uint32_t *d_tok_begin = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
-    uint32_t *d_tok_count = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
-    uint32_t *d_hist = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * kHistStride * 4));
-    BlockPlan *d_plans = static_cast<BlockPlan *>(c->arena.take((size_t)slab_blocks * sizeof(BlockPlan)));
-    uint64_t *d_offsets = static_cast<uint64_t *>(c->arena.take((size_t)slab_blocks * 8));
-    if (!d_offsets) return ZK_MEM_ERROR;
+    struct Scratch {
+        uint32_t *tokens, *tok_begin, *tok_count, *hist;
+        BlockPlan *plans;
+        uint64_t *offsets;
+    } sets[2];
+    for (int i = 0; i < nsets; ++i) {
+        sets[i].tokens = static_cast<uint32_t *>(c->arena.take((size_t)slab * 4));
+        sets[i].tok_begin = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
+        sets[i].tok_count = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * 4));
+        sets[i].hist = static_cast<uint32_t *>(c->arena.take((size_t)slab_blocks * kHistStride * 4));
+        sets[i].plans = static_cast<BlockPlan *>(c->arena.take((size_t)slab_blocks * sizeof(BlockPlan)));
+        sets[i].offsets = static_cast<uint64_t *>(c->arena.take((size_t)slab_blocks * 8));
+        if (!sets[i].offsets) return ZK_MEM_ERROR;
+    }
+    uint64_t *d_snap = static_cast<uint64_t *>(c->arena.take((size_t)nslabs * 8));  // the cursor after each slab
+    if (!d_snap) return ZK_MEM_ERROR;
+
+    // Slabs alternate between the caller's stream and alt_stream.  Everything of a slab is ordered on its stream; the
+    // only cross-slab dependency is the output cursor, which plan_offsets of slab k+1 continues from slab k.  The LZ
+    // kernel holds one CTA per SM, so the next slab's CTAs are dispatched exactly as the current slab's last units
+    // finish: no SM idles in a slab's tail wave, and the units of a slab that has a successor can be large.
+    struct Fork {
+        zk_ctx *c;
+        cudaStream_t main;
+        bool on;
+        ~Fork() {
+            c->stream = main;
+            if (on && cudaEventRecord(c->slab_ev[3], c->alt_stream) == cudaSuccess)
+                cudaStreamWaitEvent(main, c->slab_ev[3], 0);  // later work on the caller's stream sees every slab done
+        }
+    } fork{c, c->stream, false};
+    if (nsets == 2) {
+        if (!c->alt_stream) ZK_CUDA(cudaStreamCreateWithFlags(&c->alt_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : c->slab_ev)
+            if (!e) ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ZK_CUDA(cudaEventRecord(c->slab_ev[2], c->stream));
+        ZK_CUDA(cudaStreamWaitEvent(c->alt_stream, c->slab_ev[2], 0));
+        fork.on = true;
+    }
 
     uint32_t slab_index = 0;
     for (uint64_t s0 = 0; s0 < n; s0 += (slab_index ? slab_bytes : first_bytes), ++slab_index) {
         const uint64_t sn = tmin<uint64_t>(slab_index ? slab_bytes : first_bytes, n - s0);
+        const Scratch &w = sets[slab_index % nsets];
+        c->stream = (slab_index % nsets) ? c->alt_stream : fork.main;
         if (job.before_slab) job.before_slab(job.user, slab_index);
         const uint32_t nb = (uint32_t)((sn + block_bytes - 1) / block_bytes);
-        const uint32_t unit = pick_unit_bytes(c, sn, block_bytes);
+        const uint32_t unit = pick_unit_bytes(c, sn, block_bytes, nsets == 1 ? kUnitSingle : s0 + sn < n ? kUnitTailFilled : kUnitLastOfMany);
         const uint8_t *hist = s0 ? job.d_in + s0 - kWindow : job.d_hist;
         const uint32_t hist_len = s0 ? (uint32_t)kWindow : (job.d_hist ? job.hist_len : 0);
         {
             ScopedTimer t(c, 0);
-            rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, d_tokens, d_tok_begin,
-                             d_tok_count, c->lz_prof);
+            rc = launch_lz77(c, job.d_in + s0, sn, hist, hist_len, unit, block_bytes, lp, w.tokens, w.tok_begin,
+                             w.tok_count, c->lz_prof);
         }
         if (rc != ZK_OK) return rc;
         {
             ScopedTimer t(c, 1);
-            rc = launch_hist(c, d_tokens, d_tok_begin, d_tok_count, nb, d_hist);
-            if (rc == ZK_OK) rc = launch_huffman(c, d_hist, sn, block_bytes, nb, -1, d_plans);
+            rc = launch_hist(c, w.tokens, w.tok_begin, w.tok_count, nb, w.hist);
+            if (rc == ZK_OK) rc = launch_huffman(c, w.hist, sn, block_bytes, nb, -1, w.plans);
+            if (rc == ZK_OK && nsets == 2 && slab_index)
+                ZK_CUDA(cudaStreamWaitEvent(c->stream, c->slab_ev[(slab_index - 1) & 1], 0));
             // offsets continue from the previous slab: the cursor lives on the device, no host round trip
-            if (rc == ZK_OK) rc = launch_plan_offsets(c, d_plans, nb, d_offsets, d_cursor, body_cap);
+            if (rc == ZK_OK) rc = launch_plan_offsets(c, w.plans, nb, w.offsets, d_cursor, body_cap);
+            if (rc == ZK_OK) {
+                ZK_CUDA(cudaMemcpyAsync(d_snap + slab_index, d_cursor, 8, cudaMemcpyDeviceToDevice, c->stream));
+                if (nsets == 2) ZK_CUDA(cudaEventRecord(c->slab_ev[slab_index & 1], c->stream));
+            }
         }
         if (rc != ZK_OK) return rc;
         {
             ScopedTimer t(c, 2);
-            rc = launch_pack(c, job.d_in + s0, sn, block_bytes, nb, d_tokens, d_tok_begin, d_tok_count, d_plans,
-                             d_offsets, d_cursor, body);
+            rc = launch_pack(c, job.d_in + s0, sn, block_bytes, nb, w.tokens, w.tok_begin, w.tok_count, w.plans,
+                             w.offsets, d_cursor, body);
         }
         if (rc != ZK_OK) return rc;
-        if (job.after_slab) job.after_slab(job.user, slab_index, d_cursor);
+        if (job.after_slab) job.after_slab(job.user, slab_index, d_snap + slab_index);
+    }
+    c->stream = fork.main;
+    if (fork.on) {
+        fork.on = false;
+        ZK_CUDA(cudaEventRecord(c->slab_ev[3], c->alt_stream));
+        ZK_CUDA(cudaStreamWaitEvent(c->stream, c->slab_ev[3], 0));
     }
     // the checksum reads the whole input once more (0.2 ms per GiB); it runs last so that a pipelined host copy of the
     // input only has to be complete here
@@ -277,6 +343,9 @@ void zk_ctx_destroy(zk_ctx *c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
+    if (c->alt_stream) cudaStreamDestroy(c->alt_stream);
+    for (cudaEvent_t e : c->slab_ev)
+        if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -306,6 +375,15 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
     if (!strcmp(name, "lz_chain") || !strcmp(name, "lz_good") || !strcmp(name, "lz_nice")) {  // tuning (tools/lz_profile.py)
         if (value < -1 || value > 258) return ZK_STREAM_ERROR;
         (name[3] == 'c' ? c->opt_lz_chain : name[3] == 'g' ? c->opt_lz_good : c->opt_lz_nice) = value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "slab_overlap")) {  // 0: slabs of a multi-slab deflate run strictly one after the other
+        c->opt_slab_overlap = value != 0;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "host_slab_bytes") || !strcmp(name, "host_first_slab_bytes")) {  // 0 = built-in
+        if (value < 0 || (value && (value < (1 << 20) || value % 65536))) return ZK_STREAM_ERROR;
+        (name[5] == 's' ? c->opt_host_slab : c->opt_host_first_slab) = value;
         return ZK_OK;
     }
     if (!strcmp(name, "timing")) {
@@ -507,8 +585,11 @@ uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len)
 // Pipelined host call: the input goes up in slabs on its own stream, slab k is compressed as soon as it has arrived,
 // and the bytes slab k produced come down on a third stream while slab k+1 is being compressed.
 namespace {
-constexpr uint64_t kHostSlab = 128ull << 20;       // measured at 1 GiB: 64 / 96 / 128 / 160 / 256 / 512 MiB -> 25.8 / 28.0 / 29.0 / 28.1 / 28.2 / 24.6 GB/s
-constexpr uint64_t kHostFirstSlab = 64ull << 20;   // ... a short first one lets compute start after 64 MiB have arrived
+// Slab sizes, measured at 1 GiB with the slabs overlapping on two streams (tools/e2e_sweep.py, profiles/e2e_sweep_r1.md):
+// small slabs cost nothing any more (the next slab fills the tail of the LZ kernel), and they shorten the two exposed
+// ends of the pipeline: the first slab's way up and the last slab's way down.
+constexpr uint64_t kHostSlab = 64ull << 20;
+constexpr uint64_t kHostFirstSlab = 32ull << 20;
 constexpr uint32_t kMaxHostSlabs = 4096;
 struct HostPipe {
     zk_ctx *c;
@@ -572,7 +653,10 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
     const uint64_t lead = framed ? 2 : 0;  // bytes in front of the body in d_out
     if (hist_len) ZK_CUDA(cudaMemcpyAsync(d_hist, hist, hist_len, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += (int64_t)hist_len;
-    const uint32_t nslabs = n <= kHostFirstSlab ? 1u : 1u + (uint32_t)((n - kHostFirstSlab + kHostSlab - 1) / kHostSlab);
+    const uint64_t slab_bytes = c->opt_host_slab ? (uint64_t)c->opt_host_slab : kHostSlab;
+    const uint64_t first_bytes = tmin<uint64_t>(c->opt_host_first_slab ? (uint64_t)c->opt_host_first_slab : kHostFirstSlab, slab_bytes);
+    const uint64_t nslabs64 = n <= first_bytes ? 1 : 1 + (n - first_bytes + slab_bytes - 1) / slab_bytes;
+    const uint32_t nslabs = (uint32_t)tmin<uint64_t>(nslabs64, kMaxHostSlabs + 1);
     const bool piped = level > 0 && nslabs >= 2 && nslabs <= kMaxHostSlabs && dcap >= 8;
     DeflateJob job{d_in, n, hist_len ? d_hist : nullptr, hist_len, level, strategy, d_out, dcap, framed, d_result};
     if (!piped) {
@@ -598,8 +682,13 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
     if (!c->copy_in) ZK_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     if (!c->copy_out) ZK_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     std::vector<cudaEvent_t> ev(2 * (size_t)nslabs, nullptr);
+    // pinned words for the per-slab cursors: the context's small pinned block when they fit in it
     uint64_t *h_cursor = nullptr;
-    ZK_CUDA(cudaMallocHost(&h_cursor, (size_t)nslabs * 8 + 64));
+    const bool own_pinned = !c->pinned || (size_t)nslabs * 8 > c->pinned_cap;
+    if (own_pinned)
+        ZK_CUDA(cudaMallocHost(&h_cursor, (size_t)nslabs * 8));
+    else
+        h_cursor = reinterpret_cast<uint64_t *>(c->pinned);
     int rc = ZK_OK;
     const uint64_t frame = framed ? 2 + 2 + 4 : 0;
     HostPipe pipe{c, d_out, out, lead, dcap > frame ? dcap - frame : 0, h_cursor, ev.data(), ev.data() + nslabs, nslabs, 0, 0, cudaSuccess};
@@ -612,14 +701,14 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
         cudaEventRecord(fence, c->stream);
         cudaStreamWaitEvent(c->copy_in, fence, 0);
         for (uint32_t k = 0; k < nslabs && pipe.err == cudaSuccess; ++k) {
-            const uint64_t off = k ? kHostFirstSlab + (uint64_t)(k - 1) * kHostSlab : 0;
-            const uint64_t len = tmin<uint64_t>(k ? kHostSlab : kHostFirstSlab, n - off);
+            const uint64_t off = k ? first_bytes + (uint64_t)(k - 1) * slab_bytes : 0;
+            const uint64_t len = tmin<uint64_t>(k ? slab_bytes : first_bytes, n - off);
             pipe.err = cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->copy_in);
             if (pipe.err == cudaSuccess) pipe.err = cudaEventRecord(pipe.in_ready[k], c->copy_in);
         }
         c->h2d_bytes += (int64_t)n;
-        job.slab_bytes = kHostSlab;
-        job.first_slab_bytes = kHostFirstSlab;
+        job.slab_bytes = slab_bytes;
+        job.first_slab_bytes = first_bytes;
         job.before_slab = pipe_before;
         job.after_slab = pipe_after;
         job.user = &pipe;
@@ -647,7 +736,7 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
     }
     for (auto &e : ev)
         if (e) cudaEventDestroy(e);
-    cudaFreeHost(h_cursor);
+    if (own_pinned) cudaFreeHost(h_cursor);
     if (rc != ZK_OK) return rc;
     if (pipe.err != cudaSuccess) {
         set_last_error("host deflate (pipelined)", pipe.err);

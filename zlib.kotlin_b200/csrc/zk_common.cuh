@@ -81,6 +81,12 @@ struct zk_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer entry points: H2D / D2H overlap with compute
+    // deflate over several slabs: odd slabs run on alt_stream with their own scratch, so that the LZ kernel of the next
+    // slab fills the SMs the tail of the current one leaves idle; slab_ev = {plan done (even, odd), fork, join}
+    cudaStream_t alt_stream = nullptr;
+    cudaEvent_t slab_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t opt_slab_overlap = 1;
+    int64_t opt_host_slab = 0, opt_host_first_slab = 0;  // 0 = the built-in sizes of the pipelined host call
     zk::Arena arena;       // device scratch (tokens, histograms, plans, staging)
     uint8_t *pinned = nullptr; // pinned host staging for small results
     size_t pinned_cap = 0;
