@@ -69,10 +69,17 @@ void zk_ctx_destroy(zk_ctx *ctx);
  * stream) instead of its own; pass NULL to restore the private stream. */
 int zk_ctx_set_stream(zk_ctx *ctx, void *cuda_stream);
 int zk_ctx_synchronize(zk_ctx *ctx);
-/* Tunables: "chunk_bytes" (LZ unit, default auto), "block_bytes" (deflate block span,
- * default 32768), "inflate_index" (emit/consume the side index, default 1). */
+/* Tunables (0 restores the built-in value unless noted): "chunk_bytes" (LZ unit, default auto),
+ * "block_bytes" (deflate block span, a power of two in [4096, 32768], default 32768),
+ * "slab_bytes" (slab of a device-resident deflate; default: two equal slabs from 512 MiB to 2 GiB, 1 GiB beyond),
+ * "host_slab_bytes" / "host_first_slab_bytes" (slabs of the pipelined host-buffer deflate, default 64 MiB / 32 MiB;
+ * multiples of 64 KiB, at least 1 MiB), "slab_overlap" (default 1: slabs alternate between two streams; 0: in series),
+ * "lz_chain" / "lz_good" / "lz_nice" (override the level table, -1 = off),
+ * "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
+ * overlap about a tenth of its throughput). */
 int zk_ctx_set_option(zk_ctx *ctx, const char *name, int64_t value);
-/* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes"}. */
+/* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes"}; with "timing" on also
+ * {"lz77","huffman","pack","adler","inflate_decode","inflate_other"} + "_us" / "_spans"; "reset_timing" clears those. */
 int64_t zk_ctx_get_counter(zk_ctx *ctx, const char *name);
 
 /* ---- Adler-32 ------------------------------------------------------------------ */

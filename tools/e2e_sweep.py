@@ -42,7 +42,9 @@ def run(label, **opts):
 M = 1 << 20
 run("default")
 run("overlap off", slab_overlap=0)
-for slab, first in ((128, 64), (64, 32), (64, 16), (48, 16), (32, 16), (32, 32), (16, 16)):
+run("per-kernel timing events on", timing=1)
+run("default again")
+for slab, first in ((128, 64), (64, 32), (48, 24), (32, 16), (16, 16)):
     run("slab %d first %d" % (slab, first), host_slab_bytes=slab * M, host_first_slab_bytes=first * M)
 for unit in (256, 512):
     run("unit %d KiB (every slab)" % unit, chunk_bytes=unit << 10)

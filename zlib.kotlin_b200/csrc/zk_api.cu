@@ -142,7 +142,15 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     c->arena.reset();
     c->shard.valid = false;  // the scratch of a pending sharded inflate is gone
     const bool stored_only = level <= 0;
-    const uint64_t slab_bytes = job.slab_bytes ? tmin<uint64_t>(job.slab_bytes, kSlabBytes) : kSlabBytes;
+    // A device-resident job of 512 MiB .. 2 GiB runs as two equal slabs: the LZ kernel of the second fills the tail wave
+    // of the first, and the histogram / Huffman / pack kernels of the first run in its shadow (1 GiB: 36.1 -> 37.4 GB/s,
+    // profiles/e2e_sweep_r1.md; more, smaller slabs measured worse: their small kernels take SMs from the LZ kernel).
+    uint64_t own_slab = kSlabBytes;
+    if (c->opt_slab_bytes)
+        own_slab = (uint64_t)c->opt_slab_bytes;
+    else if (n >= (512ull << 20) && n < 2 * kSlabBytes && c->opt_slab_overlap)
+        own_slab = ((n + 1) / 2 + (1u << 20) - 1) >> 20 << 20;
+    const uint64_t slab_bytes = job.slab_bytes ? tmin<uint64_t>(job.slab_bytes, kSlabBytes) : own_slab;
     const uint64_t first_bytes = (job.first_slab_bytes && job.first_slab_bytes < slab_bytes) ? job.first_slab_bytes : slab_bytes;
     const uint64_t slab = tmin<uint64_t>(n, slab_bytes);
     const uint32_t slab_blocks = (uint32_t)((slab + block_bytes - 1) / block_bytes) + 1;
@@ -379,6 +387,11 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
     }
     if (!strcmp(name, "slab_overlap")) {  // 0: slabs of a multi-slab deflate run strictly one after the other
         c->opt_slab_overlap = value != 0;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "slab_bytes")) {  // slab of a device-resident deflate, 0 = built-in
+        if (value < 0 || value > (int64_t)kSlabBytes || (value && (value < (1 << 20) || value % 65536))) return ZK_STREAM_ERROR;
+        c->opt_slab_bytes = value;
         return ZK_OK;
     }
     if (!strcmp(name, "host_slab_bytes") || !strcmp(name, "host_first_slab_bytes")) {  // 0 = built-in

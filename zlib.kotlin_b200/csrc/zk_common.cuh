@@ -86,6 +86,7 @@ struct zk_ctx {
     cudaStream_t alt_stream = nullptr;
     cudaEvent_t slab_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t opt_slab_overlap = 1;
+    int64_t opt_slab_bytes = 0;                           // 0 = the built-in slab of a device-resident deflate
     int64_t opt_host_slab = 0, opt_host_first_slab = 0;  // 0 = the built-in sizes of the pipelined host call
     zk::Arena arena;       // device scratch (tokens, histograms, plans, staging)
     uint8_t *pinned = nullptr; // pinned host staging for small results
