@@ -43,7 +43,8 @@ def run(label, **opts):
         eng.set_option(k, 1 if k == "slab_overlap" else 0)
 
 
-run("one slab (default)")
+run("default (two equal slabs from 512 MiB)")
+run("one slab", slab_bytes=1024 * M)
 for slab in (512, 384, 256, 192, 128, 96, 64):
     run("slab %d MiB" % slab, slab_bytes=slab * M)
 run("slab 256 MiB, overlap off", slab_bytes=256 * M, slab_overlap=0)
