@@ -45,7 +45,9 @@ def run(label, **opts):
 
 run("default (two equal slabs from 512 MiB)")
 run("one slab", slab_bytes=1024 * M)
-for slab in (512, 384, 256, 192, 128, 96, 64):
+for slab in (896, 832, 768, 704, 640, 576, 512, 384, 256, 192, 128, 96, 64):
+    if slab * M >= n:
+        continue
     run("slab %d MiB" % slab, slab_bytes=slab * M)
 run("slab 256 MiB, overlap off", slab_bytes=256 * M, slab_overlap=0)
 for unit in (256, 512):
