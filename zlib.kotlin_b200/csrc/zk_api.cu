@@ -143,8 +143,8 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
     c->shard.valid = false;  // the scratch of a pending sharded inflate is gone
     const bool stored_only = level <= 0;
     // A device-resident job of 512 MiB .. 2 GiB runs as two equal slabs: the LZ kernel of the second fills the tail wave
-    // of the first, and the histogram / Huffman / pack kernels of the first run in its shadow (1 GiB: 36.1 -> 37.4 GB/s,
-    // profiles/e2e_sweep_r1.md; more, smaller slabs measured worse: their small kernels take SMs from the LZ kernel).
+    // of the first, and the histogram / Huffman / pack kernels of the first fill the tail wave of the second (1 GiB:
+    // 36.1 -> 37.4 GB/s, profiles/e2e_sweep_r1.md; more, smaller slabs measured slightly worse).
     uint64_t own_slab = kSlabBytes;
     if (c->opt_slab_bytes)
         own_slab = (uint64_t)c->opt_slab_bytes;
