@@ -312,9 +312,9 @@ def test_config2_1gib_mixed_level6_device_round_trip(engine, oracle):
 
 @pytest.mark.parametrize("level", [1, 6])
 def test_host_call_pipelined_slabs(engine, oracle, level):
-    """The host-buffer entry point overlaps H2D, compute and D2H in 64 MiB slabs: a 200 MiB + 12345 B input (four
-    slabs, ragged tail) must give the same bytes as the device-resident call, decode with libz, and a prefix must
-    decode with the reference inflate."""
+    """The host-buffer entry point overlaps H2D, compute and D2H in slabs (32 MiB, then 64 MiB each, alternating between
+    two streams): a 200 MiB + 12345 B input (four slabs, ragged tail) must decode with libz to the input, stay within 1 %
+    of the device-resident call's size, and a prefix must decode with the reference inflate."""
     import torch
 
     from zlibk_b200 import corpus
@@ -334,7 +334,7 @@ def test_host_call_pipelined_slabs(engine, oracle, level):
     assert engine.deflate_device(d_in.data_ptr(), n, level, 0, d_out.data_ptr(), cap, d_res.data_ptr()) == 0
     engine.synchronize()
     out_len = d_res.cpu().tolist()[0]
-    # slab size differs between the two calls (64 MiB vs 256 MiB) only in where LZ units start: the streams need not
+    # the two calls cut the input into different slabs and LZ units: the streams need not
     # be identical, but both must decode to the input and stay within the same size
     assert abs(out_len - len(stream)) <= len(stream) // 100
     rc2, out, _, _ = oracle.inflate(stream[: 8 << 20], cap=64 << 20)
