@@ -74,7 +74,7 @@ int zk_ctx_synchronize(zk_ctx *ctx);
  * "slab_bytes" (slab of a device-resident deflate; default: two equal slabs from 512 MiB to 2 GiB, 1 GiB beyond),
  * "host_slab_bytes" / "host_first_slab_bytes" (slabs of the pipelined host-buffer deflate, default 64 MiB / 32 MiB;
  * multiples of 64 KiB, at least 1 MiB), "slab_overlap" (default 1: slabs alternate between two streams; 0: in series),
- * "lz_chain" / "lz_good" / "lz_nice" (override the level table, -1 = off),
+ * "lz_chain" / "lz_max_lazy" / "lz_nice" (override the level table, -1 = off),
  * "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
  * overlap about a tenth of its throughput). */
 int zk_ctx_set_option(zk_ctx *ctx, const char *name, int64_t value);

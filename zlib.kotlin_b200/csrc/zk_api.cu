@@ -191,7 +191,7 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
 
     LevelParams lp = level_params(level, job.strategy);
     if (c->opt_lz_chain >= 0) lp.chain = (int)c->opt_lz_chain;
-    if (c->opt_lz_good >= 0) lp.good = (int)c->opt_lz_good;
+    if (c->opt_lz_max_lazy >= 0) lp.max_lazy = (int)c->opt_lz_max_lazy;
     if (c->opt_lz_nice >= 0) lp.nice = (int)c->opt_lz_nice;
     struct Scratch {
         uint32_t *tokens, *tok_begin, *tok_count, *hist;
@@ -249,6 +249,11 @@ int run_deflate(zk_ctx *c, const DeflateJob &job) {
                              w.tok_count, c->lz_prof);
         }
         if (rc != ZK_OK) return rc;
+        if (c->lz_dump_tokens && c->lz_dump_blocks && nslabs == 1) {  // tests compare the token stream with the CPU model
+            ZK_CUDA(cudaMemcpyAsync(c->lz_dump_tokens, w.tokens, (size_t)sn * 4, cudaMemcpyDeviceToDevice, c->stream));
+            ZK_CUDA(cudaMemcpyAsync(c->lz_dump_blocks, w.tok_begin, (size_t)nb * 4, cudaMemcpyDeviceToDevice, c->stream));
+            ZK_CUDA(cudaMemcpyAsync(c->lz_dump_blocks + nb, w.tok_count, (size_t)nb * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
         {
             ScopedTimer t(c, 1);
             rc = launch_hist(c, w.tokens, w.tok_begin, w.tok_count, nb, w.hist);
@@ -380,9 +385,13 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         c->lz_prof = reinterpret_cast<unsigned long long *>(static_cast<uintptr_t>(value));
         return ZK_OK;
     }
-    if (!strcmp(name, "lz_chain") || !strcmp(name, "lz_good") || !strcmp(name, "lz_nice")) {  // tuning (tools/lz_profile.py)
+    if (!strcmp(name, "lz_dump_tokens") || !strcmp(name, "lz_dump_blocks")) {  // device pointers, 0 = off (tests)
+        (name[8] == 't' ? c->lz_dump_tokens : c->lz_dump_blocks) = reinterpret_cast<uint32_t *>(static_cast<uintptr_t>(value));
+        return ZK_OK;
+    }
+    if (!strcmp(name, "lz_chain") || !strcmp(name, "lz_max_lazy") || !strcmp(name, "lz_nice")) {  // tuning (tools/lz_profile.py)
         if (value < -1 || value > 258) return ZK_STREAM_ERROR;
-        (name[3] == 'c' ? c->opt_lz_chain : name[3] == 'g' ? c->opt_lz_good : c->opt_lz_nice) = value;
+        (name[3] == 'c' ? c->opt_lz_chain : name[3] == 'm' ? c->opt_lz_max_lazy : c->opt_lz_nice) = value;
         return ZK_OK;
     }
     if (!strcmp(name, "slab_overlap")) {  // 0: slabs of a multi-slab deflate run strictly one after the other

@@ -26,9 +26,8 @@ constexpr uint32_t kTokLiteral = 0x40000000u; // parser mark: emit the byte alth
 struct LevelParams {
     int chain;     // hash-chain steps per search
     int nice;      // stop searching once a match this long is found
-    int good;      // quarter the chain when the inherited match is at least this long
     int lazy;      // one-step lazy evaluation
-    int skip_deep; // 1: from the 3rd inherited position on, do not search
+    int max_lazy;  // a match at least this long is taken without looking at the next position (zlib's max_lazy)
     int far3;      // a length-3 match farther than this is dropped
     int far4;      // a length-4 match farther than this is dropped
     int min_len;   // 3, or 259 for Z_HUFFMAN_ONLY (no matches)
@@ -93,7 +92,7 @@ struct zk_ctx {
     size_t pinned_cap = 0;
     int64_t opt_chunk_bytes = 0; // 0 = auto
     int64_t opt_block_bytes = zk::kBlockBytesDefault;
-    int64_t opt_lz_chain = -1, opt_lz_good = -1, opt_lz_nice = -1;  // tuning overrides of the level table (-1 = off)
+    int64_t opt_lz_chain = -1, opt_lz_max_lazy = -1, opt_lz_nice = -1;  // tuning overrides of the level table (-1 = off)
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     // scratch of a sharded inflate between its two phases (pointers into the arena)
     struct ShardState {
@@ -109,6 +108,8 @@ struct zk_ctx {
     // optional per-kernel-class device timing (option "timing"): event pairs recorded around launches
     int64_t opt_timing = 0;
     unsigned long long *lz_prof = nullptr;  // debug: per-unit cycle counters of lz77_kernel
+    uint32_t *lz_dump_tokens = nullptr;     // debug: receives the token array of the (single) slab, u32[n]
+    uint32_t *lz_dump_blocks = nullptr;     // debug: receives tok_begin[nb] then tok_count[nb]
     static constexpr int kTimedClasses = 6;  // 0 lz77, 1 huffman, 2 pack, 3 adler, 4 inflate-decode, 5 inflate-other
     struct TimedSpan {
         cudaEvent_t a, b;
