@@ -1,8 +1,8 @@
 """lz77_kernel against its CPU model (tools/lzmodel2.cpp), token for token.
 
-The model restates the kernel's algorithm decision for decision (exact hash chains with 16-bit links, one speculative
-parse per 16-byte segment, the stitch, the real prefix, the probe rule per warp round), checks that its own parse
-reproduces the input, and is what the ratio parameters were tuned with.  Equality of the two token streams means the
+The model restates the kernel's algorithm decision for decision (exact hash chains with 16-bit links, the best match of
+every position, one speculative parse per 16-byte segment, the stitch, the real prefix, the adaptive probe rule), checks
+that its own parse reproduces the input, and is what the ratio parameters were tuned with.  Equality of the two token streams means the
 kernel's result is a function of the data alone (no dependence on warp timing) and is the parse that was designed.
 Parity of the STREAM with the reference is tests/test_gpu_parity.py's business; this file pins the tokeniser.
 """
@@ -20,14 +20,14 @@ MODEL_SO = os.path.join(ROOT, "tools", "liblzmodel2.so")
 # zlib.kotlin_b200/csrc/zk_lz77.cu level_params(): chain, nice, lazy, max_lazy, probe_adaptive
 LEVELS = {
     1: (1, 32, 0, 16, 1),
-    2: (2, 32, 0, 16, 1),
-    3: (2, 64, 1, 8, 1),
-    4: (2, 128, 1, 16, 1),
-    5: (3, 64, 1, 16, 1),
-    6: (3, 128, 1, 16, 1),
-    7: (6, 128, 1, 32, 1),
-    8: (16, 258, 1, 128, 0),
-    9: (32, 258, 1, 258, 0),
+    2: (1, 32, 1, 8, 1),
+    3: (1, 64, 1, 16, 1),
+    4: (2, 64, 1, 8, 1),
+    5: (2, 64, 1, 16, 1),
+    6: (2, 128, 1, 16, 1),
+    7: (4, 128, 1, 32, 1),
+    8: (8, 258, 1, 128, 0),
+    9: (16, 258, 1, 258, 0),
 }
 
 
@@ -50,7 +50,7 @@ def model_tokens(lib, data, level, unit, block=32768, strategy=0):
         filtered = 1
     if strategy == 2:
         chain, min_len = 0, 259
-    params = np.array([chain, nice, lazy, max_lazy, 256, 1024, min_len, filtered, adaptive, 2, 2, 16, block, unit], dtype=np.int32)
+    params = np.array([chain, nice, lazy, max_lazy, 256, 1024, min_len, filtered, adaptive, 4, 8, 16, block, unit], dtype=np.int32)
     n = len(data)
     buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     buf = np.ascontiguousarray(buf)
@@ -127,7 +127,7 @@ def corpus_cases():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("level", [1, 6, 9])
+@pytest.mark.parametrize("level", [1, 2, 6, 7, 9])
 def test_kernel_tokens_equal_model(engine, level):
     import zlib
 

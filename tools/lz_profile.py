@@ -38,10 +38,9 @@ for name, gen in kinds.items():
     p = prof.cpu().numpy().reshape(units, 32)[: n >> 20].astype(np.float64)
     tot = p[:, 0].mean()
     lz_ms = eng.counter("lz77_us") / 1e3
-    groups = (1 << 20) / 4096
-    print("%-9s L%d lz77 %.2f ms (%.1f GB/s) huff %.2f pack %.2f ratio %.4f | cycles/byte %.2f | busy: builder %.0f%% prep %.0f%% search team %.0f%%" % (
+    print("%-9s L%d lz77 %.2f ms (%.1f GB/s) huff %.2f pack %.2f ratio %.4f | cycles/byte %.2f | builder role %.0f%% search %.0f%% | parser role %.0f%% search %.0f%% | searcher search %.0f%%" % (
         name, level, lz_ms, n / lz_ms / 1e6, eng.counter("huffman_us") / 1e3, eng.counter("pack_us") / 1e3, d_res.cpu().tolist()[0] / n, tot / (1 << 20),
-        100 * p[:, 1].mean() / tot, 100 * p[:, 2].mean() / tot, 100 * p[:, 3].mean() / tot))
-    print("          search team phases %% of unit: speculative %.1f stitch %.1f real prefix %.1f wait %.1f copy-out %.1f | rounds per group: speculative %.1f real %.1f | cycles per speculative round %.0f" % (
-        tuple(100 * p[:, 4 + q].mean() / tot for q in range(5)) + (p[:, 9].mean() / groups, p[:, 10].mean() / groups, p[:, 4].mean() / max(p[:, 9].mean(), 1))))
+        100 * p[:, 1].mean() / tot, 100 * p[:, 2].mean() / tot, 100 * p[:, 3].mean() / tot, 100 * p[:, 4].mean() / tot, 100 * p[:, 6].mean() / tot))
+    print("          parser phases %% of unit: pass A + stitch 1 %.1f wait %.1f stitch 2 %.1f pass B + count %.1f wait %.1f copy-out %.1f" % tuple(
+        100 * p[:, 8 + q].mean() / tot for q in range(6)))
 eng.set_option("lz_profile_buffer", 0)

@@ -1,9 +1,13 @@
-// lzmodel2.cpp -- CPU model of lz77_kernel (zk_lz77.cu, round-2 design): exact hash chains, one lane per input segment
-// parsing speculatively from the segment start with a search only where the parse lands (+ one lazy look-ahead), a
-// stitch over the segment exits, and a short real parse from the true entry of every entered segment up to the point
-// where it meets the speculative one.  The model follows the kernel decision for decision (same hash, same 16-bit
-// links, same candidate order, same probe rule per warp round), so that the kernel's token stream can be compared with
-// it token for token (tests/test_lz_model.py) and the ratio parameters can be tuned without a GPU.
+// lzmodel2.cpp -- CPU model of lz77_kernel (zk_lz77.cu, round-2 design).  It follows the kernel decision for decision:
+//   * exact hash chains over 4-byte hashes with 16-bit links, built one group ahead of the search;
+//   * the best match M(p) of EVERY position: up to `chain` candidates that pass a one-byte test, compared over 16 bytes,
+//     the longest (nearest on a tie) wins; 3-byte probes at small fixed distances where nothing was found (adaptive per
+//     group); a match that fills the 16 bytes is extended exactly.  M(p) is a pure function of the data;
+//   * the parse over M: greedy with one-step lazy evaluation, run speculatively from the first byte of every 16-byte
+//     segment, stitched over the segment exits, with a short real parse from the true entry of every entered segment up
+//     to the point where it meets the speculative one (or a cut / gap token when it does not).
+// The kernel's token stream is compared with the model's token for token (tests/test_lz_model.py), and the ratio
+// parameters are tuned here without a GPU.
 //
 // Test / design infrastructure only: nothing under zlib.kotlin_b200/ uses it.
 //
@@ -27,8 +31,8 @@ constexpr int kMaxMatch = 258;
 
 struct Params {
     int chain = 3, nice = 128, lazy = 1, max_lazy = 16, far3 = 256, far4 = 1024, min_len = 3, filtered = 0;
-    int probe_adaptive = 1, probe_rounds = 2, probe_thresh = 2;
-    int seg = 32;
+    int probe_adaptive = 1, probe_sample = 4, probe_thresh = 8;  // strips of 128 positions sampled per group / hits that switch probing on
+    int seg = 16;
     int block = 32768;
     int unit = 524288;
 };
@@ -91,6 +95,9 @@ struct Unit {
                 c16 = prev[c];
                 ++st->chain_steps;
                 if (base[c + tidx] == base[q + tidx]) {
+                    // a candidate that differs at index `best` cannot be longer than the best so far: skipped without a
+                    // compare (the kernel does the same; it does not change the result)
+                    if (best >= 4 && base[c + best] != base[q + best]) continue;
                     ++st->compares;
                     const int lim = std::min(kCap, maxlen);
                     int len = 0;
@@ -139,86 +146,23 @@ struct Unit {
     }
 };
 
-// state of one lane's parse (speculative or real)
-struct Lane {
-    int32_t p = 0, limit = 0, stop = 0;  // current position, end of the segment, position the parse may not pass
-    int phase = 0;
-    int curlen = 0, curdist = 0;
-    uint32_t visited = 0, ismatch = 0;
-    std::vector<uint32_t> mt;  // match tokens in order
-    int32_t lastd = -1;        // distance of the last emitted match
-    bool active = false;
-    bool met = false;
-};
-
 struct SegRec {
     int32_t seg0 = 0, seg1 = 0, exit = 0, lastd = -1;
-    uint32_t visited = 0, ismatch = 0;
-    std::vector<uint32_t> mt;
-    // real prefix (pass B)
+    uint32_t visited = 0, ismatch = 0;  // speculative parse: positions where a token starts / where it is a match
+    // real prefix
     bool entered = false;
     int32_t entry = 0, meet = 0;
     uint32_t visited2 = 0, ismatch2 = 0;
-    std::vector<uint32_t> mt2;
+    int cut_len = 0;  // > 0: the last match of the real prefix was cut to this length
     int gap_len = 0;
 };
-
-// one round of one lane: one search, then the decision.  `real`: the parse of an entered segment from its true entry; it
-// may not pass `stop` (the speculative exit of the segment).
-void lane_round(const Unit &U, Lane &L, int32_t seg0, int32_t gend, bool probing, bool real, uint32_t &hits) {
-    const Params &P = *U.P;
-    const int32_t q = L.p + L.phase;
-    const Match R = U.search(q, L.phase ? L.curlen : 0, probing);
-    if (R.probe_hit) ++hits;
-    auto emit_match = [&](int len, int dist) {
-        if (real && L.p + len > L.stop) {
-            len = L.stop - L.p;
-            if (len < 3) {  // cut below a match: a literal, the parse goes on behind it
-                L.visited |= 1u << (L.p - seg0);
-                L.p += 1;
-                L.phase = 0;
-                return;
-            }
-        }
-        L.visited |= 1u << (L.p - seg0);
-        L.ismatch |= 1u << (L.p - seg0);
-        L.mt.push_back(((uint32_t)len << 16) | (uint32_t)(dist - 1));
-        L.lastd = dist;
-        L.p += len;
-        L.phase = 0;
-    };
-    if (L.phase == 0) {
-        if (R.len == 0) {
-            L.visited |= 1u << (L.p - seg0);
-            L.p += 1;
-        } else if (P.lazy && R.len < P.max_lazy && L.p + 1 < gend) {
-            L.curlen = R.len;
-            L.curdist = R.dist;
-            L.phase = 1;
-        } else {
-            emit_match(R.len, R.dist);
-        }
-    } else {
-        if (R.len > L.curlen) {
-            L.visited |= 1u << (L.p - seg0);
-            L.p += 1;
-            L.curlen = R.len;
-            L.curdist = R.dist;
-            if (L.p >= L.limit) {
-                L.phase = 0;  // the pending match belongs to the next segment
-            } else if (!(R.len < P.max_lazy && L.p + 1 < gend)) {
-                emit_match(L.curlen, L.curdist);
-            }
-        } else {
-            emit_match(L.curlen, L.curdist);
-        }
-    }
-}
 
 struct Out {
     std::vector<uint32_t> tokens;
     std::vector<uint32_t> blk_begin, blk_count;
 };
+
+constexpr int kStrip = 128;  // positions per search strip (the unit of the adaptive probe decision)
 
 void run_unit(const uint8_t *base, int32_t h0q, uint32_t ulen, const Params &P, Stats &st, Out &out) {
     Unit U;
@@ -233,55 +177,48 @@ void run_unit(const uint8_t *base, int32_t h0q, uint32_t ulen, const Params &P, 
     const int nseg = kGroup / S;
     int32_t carry = kWindow;
     uint32_t blk_begin = (uint32_t)out.tokens.size();
-    std::vector<uint32_t> prev_hits(nseg / 32, 1u << 30);  // first group of a unit: probe everywhere
+    uint32_t prev_hits = 1u << 30;  // first group of a unit: probe everywhere
+    std::vector<Match> M(kGroup + 1);
     for (int32_t g0 = kWindow; g0 < U.data_end_q; g0 += kGroup) {
         const int32_t gend = std::min(g0 + kGroup, U.data_end_q);
-        std::vector<SegRec> rec(nseg);
-        std::vector<bool> batch_probing(nseg / 32);
-        // ---- speculative parse, one warp = 32 consecutive segments in lockstep rounds ----
-        for (int b = 0; b < nseg / 32; ++b) {
-            Lane lanes[32];
-            for (int l = 0; l < 32; ++l) {
-                const int s = b * 32 + l;
-                SegRec &r = rec[s];
-                r.seg0 = std::min(g0 + s * S, gend);
-                r.seg1 = std::min(r.seg0 + S, gend);
-                lanes[l].p = r.seg0;
-                lanes[l].limit = r.seg1;
-                lanes[l].stop = 1 << 30;
-            }
-            uint32_t hits = 0;
-            int round = 0;
-            ++st.batches;
-            for (;;) {
-                bool any = false;
-                for (int l = 0; l < 32; ++l) any = any || lanes[l].p < lanes[l].limit;
-                if (!any) break;
-                const bool probing = !P.probe_adaptive || round < P.probe_rounds || hits >= (uint32_t)P.probe_thresh ||
-                                     prev_hits[b] >= (uint32_t)P.probe_thresh;
-                if (probing) ++st.probe_rounds;
-                uint32_t h = 0;
-                for (int l = 0; l < 32; ++l) {
-                    if (lanes[l].p >= lanes[l].limit) continue;
-                    ++st.spec_searches;
-                    lane_round(U, lanes[l], rec[b * 32 + l].seg0, gend, probing, false, h);
-                }
-                hits += h;
-                st.probe_hits += h;
-                ++round;
-            }
-            st.spec_rounds += round;
-            prev_hits[b] = hits;
-            batch_probing[b] = !P.probe_adaptive || hits >= (uint32_t)P.probe_thresh;
-            for (int l = 0; l < 32; ++l) {
-                SegRec &r = rec[b * 32 + l];
-                r.visited = lanes[l].visited;
-                r.ismatch = lanes[l].ismatch;
-                r.mt = lanes[l].mt;
-                r.exit = lanes[l].p;
-                r.lastd = lanes[l].lastd;
-            }
+        // ---- the best match of every position ----
+        uint32_t hits = 0;
+        for (int32_t p = g0; p < gend; ++p) {
+            const int strip = (p - g0) / kStrip;
+            const bool probing = !P.probe_adaptive || strip < P.probe_sample || prev_hits >= (uint32_t)P.probe_thresh;
+            M[p - g0] = U.search(p, 0, probing);
+            ++st.spec_searches;
+            if (M[p - g0].probe_hit && strip < P.probe_sample) ++hits;
+            if (M[p - g0].probe_hit) ++st.probe_hits;
         }
+        M[gend - g0] = Match{0, 0, false};
+        prev_hits = hits;
+        // the step of the parse at p: 1 for a literal, the match length otherwise
+        auto step_at = [&](int32_t p) {
+            const int len = M[p - g0].len;
+            if (len == 0) return 1;
+            if (P.lazy && len < P.max_lazy && p + 1 < gend && M[p + 1 - g0].len > len) return 1;
+            return len;
+        };
+        std::vector<SegRec> rec(nseg);
+        // ---- speculative parse of every segment from its first byte ----
+        for (int s = 0; s < nseg; ++s) {
+            SegRec &r = rec[s];
+            r.seg0 = std::min(g0 + s * S, gend);
+            r.seg1 = std::min(r.seg0 + S, gend);
+            int32_t p = r.seg0;
+            while (p < r.seg1) {
+                const int stp = step_at(p);
+                r.visited |= 1u << (p - r.seg0);
+                if (stp > 1) {
+                    r.ismatch |= 1u << (p - r.seg0);
+                    r.lastd = M[p - g0].dist;
+                }
+                p += stp;
+            }
+            r.exit = p;
+        }
+        ++st.batches;
         // ---- stitch: which segments does the real parse enter, and where ----
         int32_t pfinal = carry;
         if (carry < gend) {
@@ -300,61 +237,40 @@ void run_unit(const uint8_t *base, int32_t h0q, uint32_t ulen, const Params &P, 
                 }
             }
         }
-        // ---- pass B: the real parse of every entered segment from its entry up to where it meets the speculative one ----
-        for (int b = 0; b < nseg / 32; ++b) {
-            Lane lanes[32];
-            bool act[32];
-            for (int l = 0; l < 32; ++l) {
-                SegRec &r = rec[b * 32 + l];
-                act[l] = r.entered && r.entry > r.seg0;
-                r.meet = r.seg0;
-                if (r.entered) ++st.entered;
-                if (!act[l]) continue;
-                ++st.mid_entries;
-                lanes[l].p = r.entry;
-                lanes[l].limit = r.seg1;
-                lanes[l].stop = r.exit;
-                lanes[l].met = false;
+        // ---- real prefix: from the entry until the parse lands on a position the speculative parse visited; it may not
+        // pass the speculative exit of its segment ----
+        for (int s = 0; s < nseg; ++s) {
+            SegRec &r = rec[s];
+            r.meet = r.seg0;
+            if (!r.entered) continue;
+            ++st.entered;
+            if (r.entry == r.seg0) continue;
+            ++st.mid_entries;
+            int32_t p = r.entry;
+            bool met = false;
+            while (p < r.seg1) {
+                if ((r.visited >> (p - r.seg0)) & 1u) {
+                    met = true;
+                    break;
+                }
+                ++st.real_searches;
+                int stp = step_at(p);
+                const uint32_t bit = 1u << (p - r.seg0);
+                if (stp > 1 && p + stp > r.exit) {
+                    stp = r.exit - p;
+                    if (stp < 3) stp = 1;  // cut below a match: a literal, the parse goes on behind it
+                    else r.cut_len = stp;
+                }
+                r.visited2 |= bit;
+                if (stp > 1) r.ismatch2 |= bit;
+                p += stp;
             }
-            int round = 0;
-            for (;;) {
-                bool any = false;
-                for (int l = 0; l < 32; ++l) {
-                    if (!act[l]) continue;
-                    Lane &L = lanes[l];
-                    SegRec &r = rec[b * 32 + l];
-                    if (L.p >= L.limit) {
-                        act[l] = false;
-                    } else if ((r.visited >> (L.p - r.seg0)) & 1u) {
-                        L.met = true;
-                        act[l] = false;
-                    }
-                    any = any || act[l];
-                }
-                if (!any) break;
-                uint32_t h = 0;
-                for (int l = 0; l < 32; ++l) {
-                    if (!act[l]) continue;
-                    ++st.real_searches;
-                    lane_round(U, lanes[l], rec[b * 32 + l].seg0, gend, batch_probing[b], true, h);
-                }
-                ++round;
-            }
-            st.real_rounds += round;
-            for (int l = 0; l < 32; ++l) {
-                SegRec &r = rec[b * 32 + l];
-                if (!(r.entered && r.entry > r.seg0)) continue;
-                Lane &L = lanes[l];
-                r.visited2 = L.visited;
-                r.ismatch2 = L.ismatch;
-                r.mt2 = L.mt;
-                if (L.met) {
-                    r.meet = L.p;
-                } else {
-                    ++st.not_met;
-                    r.meet = r.seg1;  // nothing of the speculative parse is used
-                    r.gap_len = r.exit - L.p;
-                }
+            if (met) {
+                r.meet = p;
+            } else {
+                ++st.not_met;
+                r.meet = r.seg1;  // nothing of the speculative parse is used
+                r.gap_len = r.exit - p;
             }
         }
         // ---- copy-out in segment order ----
@@ -364,17 +280,22 @@ void run_unit(const uint8_t *base, int32_t h0q, uint32_t ulen, const Params &P, 
                 st.wasted_tokens += __builtin_popcount(r.visited);
                 continue;
             }
-            size_t k2 = 0;
+            const int last2 = r.ismatch2 ? 31 - __builtin_clz(r.ismatch2) : -1;
             for (int i = 0; i < S; ++i)
                 if ((r.visited2 >> i) & 1u) {
-                    if ((r.ismatch2 >> i) & 1u) out.tokens.push_back(r.mt2[k2++]);
-                    else out.tokens.push_back(base[r.seg0 + i]);
+                    const Match &m = M[r.seg0 + i - g0];
+                    if ((r.ismatch2 >> i) & 1u) {
+                        const int len = (i == last2 && r.cut_len) ? r.cut_len : m.len;
+                        out.tokens.push_back(((uint32_t)len << 16) | (uint32_t)(m.dist - 1));
+                    } else {
+                        out.tokens.push_back(base[r.seg0 + i]);
+                    }
                 }
-            const int m = r.meet - r.seg0;
-            size_t k = m >= 32 ? r.mt.size() : (size_t)__builtin_popcount(r.ismatch & ((1u << m) - 1u));
-            for (int i = m; i < S; ++i)
+            const int m0 = r.meet - r.seg0;
+            for (int i = m0; i < S; ++i)
                 if ((r.visited >> i) & 1u) {
-                    if ((r.ismatch >> i) & 1u) out.tokens.push_back(r.mt[k++]);
+                    const Match &m = M[r.seg0 + i - g0];
+                    if ((r.ismatch >> i) & 1u) out.tokens.push_back(((uint32_t)m.len << 16) | (uint32_t)(m.dist - 1));
                     else out.tokens.push_back(base[r.seg0 + i]);
                 }
             if (r.gap_len >= 3) {
@@ -480,7 +401,7 @@ extern "C" long long lzm2_tokens(const uint8_t *in, unsigned long long n, unsign
                                  uint32_t *tokens, uint32_t *blk_begin, uint32_t *blk_count, unsigned long long *nblocks) {
     Params P;
     int *fields[] = {&P.chain, &P.nice, &P.lazy, &P.max_lazy, &P.far3, &P.far4, &P.min_len, &P.filtered, &P.probe_adaptive,
-                     &P.probe_rounds, &P.probe_thresh, &P.seg, &P.block, &P.unit};
+                     &P.probe_sample, &P.probe_thresh, &P.seg, &P.block, &P.unit};
     for (int i = 0; i < nparams && i < (int)(sizeof(fields) / sizeof(fields[0])); ++i) *fields[i] = params[i];
     Stats st;
     Out out;
@@ -504,7 +425,7 @@ int main(int argc, char **argv) {
         if (k == "chain") P.chain = v; else if (k == "nice") P.nice = v; else if (k == "lazy") P.lazy = v;
         else if (k == "max_lazy") P.max_lazy = v; else if (k == "far3") P.far3 = v; else if (k == "far4") P.far4 = v;
         else if (k == "min_len") P.min_len = v; else if (k == "probe_adaptive") P.probe_adaptive = v;
-        else if (k == "probe_rounds") P.probe_rounds = v; else if (k == "probe_thresh") P.probe_thresh = v;
+        else if (k == "probe_sample") P.probe_sample = v; else if (k == "probe_thresh") P.probe_thresh = v;
         else if (k == "seg") P.seg = v; else if (k == "block") P.block = v; else if (k == "unit") P.unit = v;
         else { fprintf(stderr, "unknown key %s\n", k.c_str()); return 1; }
     }
@@ -532,11 +453,8 @@ int main(int argc, char **argv) {
     printf("  searches/B spec=%.3f real=%.3f | chain steps/search=%.2f compares/search=%.2f | ext bytes/B=%.3f\n", st.spec_searches / N,
            st.real_searches / N, (double)st.chain_steps / (st.spec_searches + st.real_searches),
            (double)st.compares / (st.spec_searches + st.real_searches), st.ext_bytes / N);
-    printf("  rounds/batch spec=%.2f (lane efficiency %.2f) real=%.2f | probing rounds %.2f of spec, hits/B=%.4f\n",
-           (double)st.spec_rounds / st.batches, (double)st.spec_searches / (32.0 * st.spec_rounds), (double)st.real_rounds / st.batches,
-           (double)st.probe_rounds / st.spec_rounds, st.probe_hits / N);
     printf("  entered=%.3f of segments, mid entries=%.3f of entered, not met=%.4f of mid, wasted spec tokens/B=%.3f\n",
-           (double)st.entered / (st.batches * 32.0), (double)st.mid_entries / st.entered, (double)st.not_met / std::max<uint64_t>(1, st.mid_entries),
+           (double)st.entered / (st.batches * (double)(kGroup / P.seg)), (double)st.mid_entries / st.entered, (double)st.not_met / std::max<uint64_t>(1, st.mid_entries),
            st.wasted_tokens / N);
     return ok ? 0 : 2;
 }

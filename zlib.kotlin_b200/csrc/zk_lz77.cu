@@ -5,32 +5,36 @@
 // with a design that maps to an SM instead of a scalar loop.  It is not a port: the reference's
 // look-ahead/window arrays, its pre-seeded chains and its stale-window compare do not exist here.
 //
-// Round-2 design: the parse drives the search.  Round 1 searched every position and parsed the match array
-// afterwards (17.5 warp instructions per input byte); here a lane owns a short segment of the input and walks it
-// the way a scalar compressor would -- search where the parse lands, one look-ahead search for the lazy rule,
-// jump over the match -- so that positions inside a match cost nothing.
-//
-// Layout in shared memory (one CTA per SM, ~200 KB):
+// Layout in shared memory (one CTA per SM, ~226 KB):
 //   ring  u8 [65536]   input bytes at (q & 0xFFFF); q = unit-relative position, history first
 //   prev  u16[32768]   hash-chain links at (q & 32767): previous position with the same 4-byte hash
 //   head  u16[16384]   most recent position (q & 0xFFFF) per 14-bit hash
-//   ph/pi [2][4096]    per position of a group to be built: its hash, and which lower lane of its batch shares it
-//   mt/mt2 u32[6][256] match tokens of every segment: speculative parse / real prefix
+//   match u32[2][4608] per-position best match of the group in flight / the group being parsed (rows of 32 skewed)
+//   prep  u8 [2][4096] per position of a group to be built: lower lane of its batch with the same hash
+//   tq    u32[32][128] per warp: compare tasks (position, distance) of the strip in flight
 //
 // Software pipeline over groups of 4096 positions, one __syncthreads per step.  In step i
 //   - one elected thread stages group i+4 into the ring with a TMA bulk copy (mbarrier-tracked),
-//   - the prep warps hash group i+2 and resolve equal hashes inside every batch of 32 positions (match.any),
-//   - the builder warp inserts group i+1 into the hash chains: table updates only, eight batches in flight,
-//   - the eight search warps turn group i into tokens.  Lane L owns segment L (16 bytes):
-//       speculative parse  from the first byte of the segment, in warp-lockstep rounds of one search per lane;
-//       stitch             the real parse enters the segment the carry points into and, from an entered segment, the
-//                          one its speculative exit lies in: pointer doubling with shuffles, two team barriers;
-//       real prefix        an entered lane whose entry is not its first byte parses from the entry until it lands on a
-//                          position the speculative parse visited (usually at once: every literal is such a position);
-//       copy-out           prefix sum of the token counts, tokens leave in order.
-// A search only follows links of candidates within 32768 - 2*4096 bytes, which the builder (one group ahead) can
-// not have overwritten: results do not depend on warp timing.  tools/lzmodel2.cpp is a CPU model of exactly this
-// algorithm; tests compare the two token for token.
+//   - whichever warp takes a strip prepares the same strip of group i+2 (match.any over the hashes of each batch),
+//   - warp 31 inserts group i+1 into the hash chains: table updates only, 32 positions per instruction sequence,
+//   - warps 16..23 (two per SM sub-partition) parse group i-1: a register-only speculative pass per 16-byte lane
+//     segment, a two-level stitch with shuffles, a short real pass from the true entry of every entered segment up to
+//     the point where it meets the speculative one, then the tokens leave in order,
+//   - every warp (the role warps join when done) steals strips of 128 positions of group i and finds the best match of
+//     every position in three phases that keep the lanes busy:
+//       walk     a lane follows the hash chains of 4 consecutive positions; a candidate only has to pass a one-byte test
+//                (the fourth byte: the hash covers four); candidates that pass become tasks (position, distance) in the
+//                warp's queue, their slots handed out with ballots;
+//       compare  the warp's lanes take the tasks 32 at a time, whoever produced them: 16 bytes against 16 bytes, the
+//                result goes into the match word of the position with a shared-memory atomicMax over (length, nearness),
+//                so the order in which tasks are processed does not matter;
+//       finish   3-byte matches at small fixed distances where nothing was found (adaptive), exact extension of matches
+//                that filled the 16 bytes (cooperative, per distinct distance), the too-far filters.
+// Round 1 compared inside the chain loop (three 16-byte compares per position at 16 of 32 lanes active: 17.5 warp
+// instructions per input byte); the task queue runs the same compares at full width.
+// A search only follows links of candidates within 32768 - 2*4096 bytes, which the builder (one group ahead) can not
+// have overwritten, and the best match of a position is a pure function of the data: results do not depend on warp
+// timing.  tools/lzmodel2.cpp is a CPU model of exactly this algorithm; tests compare the two token for token.
 //
 // HBM traffic per input byte: 1 B read (+ 32 KiB halo per unit) and 4 B x tokens/byte written.
 // The symbol histograms are built from the token stream by hist_kernel (zk_huffman.cu).
@@ -40,42 +44,50 @@ namespace zk {
 
 namespace {
 
+constexpr int kThreadsLz = 1024;
+constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
-constexpr int kSeg = 16;                       // bytes per lane segment
-constexpr int kSegs = kGroup / kSeg;           // segments (= search lanes) per group
-constexpr int kSearchWarps = kSegs / 32;
-constexpr int kPrepWarps = 3;
-constexpr int kBuilderWarp = kSearchWarps;     // warp index of the builder
-constexpr int kFirstPrepWarp = kSearchWarps + 1;
-constexpr int kWarpsLz = kSearchWarps + 1 + kPrepWarps;
-constexpr int kThreadsLz = 32 * kWarpsLz;
-constexpr int kMaxM = (kSeg + 2) / 3;          // matches that can start inside one segment
+constexpr int kRun = 4;                      // consecutive positions per lane
+constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
+constexpr int kStripsPerGroup = kGroup / kStrip;
+constexpr int kTaskCap = 128;                // compare tasks a warp queues before it runs them
+constexpr int kParserWarps = 8;
+constexpr int kFirstParserWarp = 16;         // warps 16..23: two per SM sub-partition
+constexpr int kBuilderWarp = 31;
+constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
+constexpr int kSegs = kGroup / kSeg;
 constexpr int kHistGroups = kWindow / kGroup;
 constexpr int kMaxDist = kWindow - 2 * kGroup;
-constexpr int kStages = 4;                     // ring staging barriers
+constexpr int kStages = 4;                   // ring staging barriers
 constexpr int kCap = 16;  // candidates are compared over 16 bytes; the nearest one that fills them is extended
-// The short-distance probes (3-byte matches of binary records and runs) find nothing in text: a warp probes in its
-// first kProbeRounds rounds of a group, and in all of them once it has had kProbeThresh hits in this group or had them
-// in the group before.  The decision is a function of the data of the warp's own segments only.
-constexpr int kProbeRounds = 2;
-constexpr int kProbeThresh = 2;
+// The short-distance probes (3-byte matches of binary records and runs) cost a fifth of the search and find nothing in
+// text: every group probes in its first kProbeSample strips only, and in all of them when the sample of the group
+// before it had at least kProbeThreshold hits.  Strips are fixed ranges of positions, so the decision does not depend
+// on which warp happens to search them.
+constexpr int kProbeSample = 4;
+constexpr int kProbeThreshold = 8;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
-static_assert(kSeg <= 32 && kSegs % 32 == 0, "one visited-position mask per segment, whole warps per group");
+static_assert(kSeg == 16, "the parser's register-only pass is written for 16-position segments");
 
 struct LzSmem {
     uint32_t ring[65536 / 4 + 8];  // + 32 mirrored bytes so a 20-byte read never wraps
     uint16_t prev[32768];
     uint16_t head[1 << kHashBits];  // most recent position (q & 0xFFFF) per hash
-    uint16_t ph[2][kGroup];         // hash of every position of a group to be built
-    uint8_t pi[2][kGroup];          // 0x80 last of its hash in its batch, 0x40 | lane of the nearest lower lane with the same hash
-    uint32_t mt[kMaxM][kSegs];      // match tokens of the speculative parse of segment L, in order
-    uint32_t mt2[kMaxM][kSegs];     // match tokens of the real prefix of segment L
+    // best match per position of a group, skewed: position i sits at mvi(i) = i + 4 * (i / 32), so that the parser lanes
+    // (one 16-position segment each) read their rows with conflict-free 16-byte loads; + slack: one word past the group.
+    // While a strip is being searched: len << 16 | (0xFFFF - dist) (atomicMax); afterwards: len << 16 | (dist - 1).
+    uint32_t match[2][kGroup + kGroup / 8 + 8];
+    uint8_t prep[2][kGroup];  // per position of a group to be built: 0x80 last of its hash in its batch, 0x40 | lane of
+                              // the nearest lower lane with the same hash
+    uint32_t tq[kWarpsLz][kTaskCap];  // compare tasks of the strip a warp is searching: (position - group start) << 16 | dist
     uint32_t jmark[kSegs];          // stitch: segments of L's warp the parse visits from L on
     int16_t jnext[kSegs];           // stitch: first segment after L's warp the parse from L leads to
     uint16_t pstart[kSegs];         // entry position (relative to the group) of an entered segment
     unsigned long long bar[kStages];
-    int wcount[kSearchWarps];
+    int work[2];
+    int probe_hits[4];  // short-distance probe hits in the sampled strips of group t, at [t & 3]
+    int wcount[kParserWarps];
     int32_t pfinal;
     int32_t carry_entry[2];         // first unparsed q, by group parity
     uint32_t carry_tok_off[2];      // tokens emitted so far in this unit
@@ -97,6 +109,8 @@ struct LzArgs {
     uint32_t *block_tok_count;  // [num_blocks]
     unsigned long long *prof;   // optional [num_units][32] cycle counters (nullptr = off)
 };
+
+__device__ __forceinline__ int mvi(int i) { return i + ((i >> 5) << 2); }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -165,7 +179,7 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
     uint8_t *ring8 = reinterpret_cast<uint8_t *>(s.ring);
     const bool tma = lo == q0 && ((hi - lo) & 15) == 0 && ((reinterpret_cast<uintptr_t>(src + lo)) & 15) == 0;
     if (tma) {
-        if (threadIdx.x == kFirstPrepWarp * 32) {
+        if (threadIdx.x == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&s.bar[t & (kStages - 1)], (uint32_t)(hi - lo));
             tma_load(ring8 + (q0 & 0xFFFF), src + lo, (uint32_t)(hi - lo), &s.bar[t & (kStages - 1)]);
@@ -176,24 +190,22 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
     return tma;
 }
 
-// ---- preparation of group t, shared by the prep warps -----------------------------------------------------
-// For every position its hash, which lower lane of its 32-position batch has the same hash, and whether it is the last
-// of its hash in the batch (an exact match.any).  A pure function of the batch, so it runs in parallel and the serial
-// builder is left with table updates only.
-__device__ __forceinline__ void prep_group(LzSmem &s, int t, int pw, int lane) {
-    uint16_t *hh = s.ph[t & 1];
-    uint8_t *pp = s.pi[t & 1];
-    const uint32_t q0 = (uint32_t)t * kGroup + lane;
-    constexpr int kBatches = kGroup / 32;
+// ---- preparation of a strip of group t, done by whichever warp searches the matching strip ------------------
+// For every position: which lower lane of its 32-position batch has the same hash, and whether it is the last of its
+// hash in the batch (an exact match.any; cheap here because many warps share its latency, unlike in the serial builder).
+// It is a pure function of the batch, so it runs in parallel on the searcher warps and the serial builder is left with
+// table updates only.
+__device__ __forceinline__ void prep_strip(LzSmem &s, int t, int pos0, int lane) {
+    uint8_t *pp = s.prep[t & 1] + pos0;
+    const uint32_t q0 = (uint32_t)t * kGroup + pos0 + lane;
 #pragma unroll 2
-    for (int b = pw; b < kBatches; b += kPrepWarps) {
-        const uint32_t hv = hash4(ring_load32(s.ring, q0 + b * 32));
+    for (int u = 0; u < kStrip / 32; ++u) {
+        const uint32_t hv = hash4(ring_load32(s.ring, q0 + u * 32));
         const uint32_t eq = __match_any_sync(kFull, hv);
         const uint32_t below = eq & ((1u << lane) - 1u);
         uint32_t info = below ? (0x40u | (uint32_t)(31 - __clz(below))) : 0u;
         if (((eq >> lane) >> 1) == 0u) info |= 0x80u;
-        hh[b * 32 + lane] = (uint16_t)hv;
-        pp[b * 32 + lane] = (uint8_t)info;
+        pp[u * 32 + lane] = (uint8_t)info;
     }
 }
 
@@ -205,14 +217,13 @@ __device__ __forceinline__ void prep_group(LzSmem &s, int t, int pw, int lane) {
 __device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
     const uint32_t q0 = (uint32_t)t * kGroup + lane;
     volatile uint16_t *vhead = s.head;
-    const uint16_t *hh = s.ph[t & 1] + lane;
-    const uint8_t *pp = s.pi[t & 1] + lane;
+    const uint8_t *pp = s.prep[t & 1] + lane;
 #pragma unroll 1
     for (int b = 0; b < kGroup / 32; b += 8) {
         uint32_t h[8], old[8], info[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            h[u] = hh[(b + u) * 32];
+            h[u] = hash4(ring_load32(s.ring, q0 + (b + u) * 32));
             info[u] = pp[(b + u) * 32];
         }
 #pragma unroll
@@ -230,7 +241,6 @@ __device__ __forceinline__ void build_group(LzSmem &s, int t, int lane) {
     __syncwarp();
 }
 
-// ---- search: the best match at one position ----------------------------------------------------------------
 // 16 bytes at q as four words
 struct Bytes16 {
     uint32_t w[4];
@@ -262,196 +272,256 @@ struct SearchCtx {
     LevelParams lp;
     int32_t h0q;
     int32_t ulen;
+    int32_t data_end_q;
     uint32_t block_shift;
 };
 
-struct Found {
-    int len, dist;
-    bool hit3;
-};
+// ---- searcher: the best match of every position of a strip ------------------------------------------------------
+// The queued compare tasks of a warp: 16 bytes at the position against 16 bytes at the candidate, clipped to the end of
+// the deflate block; the longest, on a tie the nearest, stays in the match word (atomicMax over len << 16 | ~dist).
+__device__ __forceinline__ void run_tasks(LzSmem &s, uint32_t *mv, const uint32_t *tq, int T, int32_t g0, int32_t blk_end_q, int lane) {
+    __syncwarp();
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int ti = t0 + lane;
+        if (ti < T) {
+            const uint32_t task = tq[ti];
+            const uint32_t rel = task >> 16, d = task & 0xFFFFu;
+            const uint32_t p = (uint32_t)g0 + rel;
+            const int maxlen = min(kMaxMatch, blk_end_q - (int32_t)p);
+            const int len = min(common_prefix16(ring_load128(s.ring, p), ring_load128(s.ring, p - d)), maxlen);
+            if (len >= 4) atomicMax(&mv[mvi((int)rel)], ((uint32_t)len << 16) | (0xFFFFu - d));
+        }
+    }
+    __syncwarp();
+}
 
-// The best match at q that is longer than best0 (0: any match).  Called by all lanes of a warp; `act` = this lane wants
-// an answer.  Every loop is uniform across the warp (lanes drop out by predicate).
-__device__ __forceinline__ Found search(const LzSmem &s, const SearchCtx &cx, bool act, int32_t q, int best0, bool probing) {
+__device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int t, int strip, int lane, int warp, bool probe_all) {
     const LevelParams &lp = cx.lp;
-    // matches never cross the end of their deflate block
-    const int32_t off = q - kWindow;
-    const int32_t blk_end = min(cx.ulen, ((off >> cx.block_shift) + 1) << cx.block_shift);
-    const int maxlen = act ? min(kMaxMatch, blk_end - off) : 0;
-    const uint32_t reach = (uint32_t)min(kMaxDist, q - cx.h0q);
-    const Bytes16 cur = ring_load128(s.ring, (uint32_t)q);
-    int best = best0, bestd = 0;
-    bool capped = false;  // the best match filled the 16-byte compare and may be longer
-    // ---- hash-chain candidates.  The walk only applies a one-byte test (the byte a longer match must have); the
-    // candidates that pass are compared over 16 bytes afterwards, nearest first.
+    const bool probing = probe_all || strip < kProbeSample;
+    uint32_t *mv = s.match[t & 1];
+    uint32_t *tq = s.tq[warp];
+    const int32_t g0 = t * kGroup;
+    const int32_t rel0 = strip * kStrip + lane * kRun;  // the first of this lane's positions, relative to the group
+    const int32_t p0 = g0 + rel0;
+    // matches never cross the end of their deflate block (a group lies inside one block)
+    const int32_t blk_end_q = kWindow + min(cx.ulen, (((g0 - kWindow) >> cx.block_shift) + 1) << cx.block_shift);
+    const uint32_t lt = (1u << lane) - 1u;
+    int maxlen[kRun];
+    uint32_t reach[kRun], c16[kRun], lastd[kRun], need[kRun];
+    bool walk[kRun];
     {
-        bool walk = lp.chain > 0 && maxlen >= 4 && best < maxlen && maxlen >= lp.min_len;
-        const uint32_t tidx = (uint32_t)max(best0, 3);
-        const uint32_t need = ring_load8(s.ring, (uint32_t)q + tidx);
-        uint32_t c16 = s.prev[q & 32767];
-        uint32_t lastd = 0;
-        for (int base = 0; base < lp.chain; base += 4) {
-            if (!__any_sync(kFull, walk)) break;
-            unsigned long long passed = 0;  // up to four 16-bit distances, nearest in the low bits
-            int npass = 0;
+        // the links of the four positions (one 8-byte load) and the byte a candidate has to match (index 3)
+        const uint2 lk = *reinterpret_cast<const uint2 *>(&s.prev[p0 & 32767]);
+        c16[0] = lk.x & 0xFFFFu;
+        c16[1] = lk.x >> 16;
+        c16[2] = lk.y & 0xFFFFu;
+        c16[3] = lk.y >> 16;
+        const uint32_t wi = ((uint32_t)p0 >> 2) & 0x3FFFu;
+        const uint32_t w0 = s.ring[wi], w1 = s.ring[wi + 1];
+        need[0] = w0 >> 24;
+        need[1] = w1 & 0xFFu;
+        need[2] = (w1 >> 8) & 0xFFu;
+        need[3] = (w1 >> 16) & 0xFFu;
+    }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t d = ((uint32_t)q - c16) & 0xFFFFu;
-                walk = walk && base + k < lp.chain && d - 1u < reach && d > lastd;
-                if (walk) {
-                    lastd = d;
-                    const uint32_t c = (uint32_t)q - d;
-                    c16 = s.prev[c & 32767u];
-                    if (ring_load8(s.ring, c + tidx) == need) {
-                        passed |= (unsigned long long)d << (16 * npass);
-                        ++npass;
+    for (int r = 0; r < kRun; ++r) {
+        const int32_t p = p0 + r;
+        maxlen[r] = max(0, min(kMaxMatch, blk_end_q - p));
+        reach[r] = (uint32_t)min(kMaxDist, max(p - cx.h0q, 0));
+        lastd[r] = 0;
+        walk[r] = lp.chain > 0 && maxlen[r] >= 4;
+    }
+    *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(0u, 0u, 0u, 0u);
+    // ---- walk: one chain link of each of the four positions per trip; candidates that pass the byte test are queued
+    int T = 0;
+    for (int k = 0; k < lp.chain; ++k) {
+        if (!__any_sync(kFull, walk[0] || walk[1] || walk[2] || walk[3])) break;
+#pragma unroll
+        for (int r = 0; r < kRun; ++r) {
+            const uint32_t p = (uint32_t)(p0 + r);
+            const uint32_t d = (p - c16[r]) & 0xFFFFu;
+            walk[r] = walk[r] && d - 1u < reach[r] && d > lastd[r];
+            bool pass = false;
+            if (walk[r]) {
+                lastd[r] = d;
+                const uint32_t c = p - d;
+                c16[r] = s.prev[c & 32767u];
+                pass = ring_load8(s.ring, c + 3u) == need[r];
+            }
+            const uint32_t b = __ballot_sync(kFull, pass);
+            if (pass) tq[T + __popc(b & lt)] = ((uint32_t)(rel0 + r) << 16) | d;
+            T += __popc(b);
+            if (T > kTaskCap - 32) {  // the next trip may add 32 more
+                run_tasks(s, mv, tq, T, g0, blk_end_q, lane);
+                T = 0;
+            }
+        }
+        if ((k & 1) && k + 1 < lp.chain) {
+            // deep chains: a position whose best candidate already fills the 16-byte compare is done (a farther one can
+            // only tie, and the nearest wins a tie)
+            run_tasks(s, mv, tq, T, g0, blk_end_q, lane);
+            T = 0;
+            const uint4 mw = *reinterpret_cast<const uint4 *>(&mv[mvi(rel0)]);
+            if ((mw.x >> 16) >= (uint32_t)kCap) walk[0] = false;
+            if ((mw.y >> 16) >= (uint32_t)kCap) walk[1] = false;
+            if ((mw.z >> 16) >= (uint32_t)kCap) walk[2] = false;
+            if ((mw.w >> 16) >= (uint32_t)kCap) walk[3] = false;
+        }
+    }
+    run_tasks(s, mv, tq, T, g0, blk_end_q, lane);
+    // ---- finish: probes, extension, filters ----
+    int best[kRun], bestd[kRun];
+    {
+        const uint4 mw = *reinterpret_cast<const uint4 *>(&mv[mvi(rel0)]);
+        const uint32_t w[kRun] = {mw.x, mw.y, mw.z, mw.w};
+#pragma unroll
+        for (int r = 0; r < kRun; ++r) {
+            best[r] = (int)(w[r] >> 16);
+            bestd[r] = best[r] ? (int)(0xFFFFu - (w[r] & 0xFFFFu)) : 0;
+        }
+    }
+    // short matches at small fixed distances (3-byte repeats of binary records, byte runs): the 3 bytes at p against the
+    // 3 bytes at p-1, -2, -3, -4, -6, -8, -12, -16, all of which come from the 16 bytes before p
+    {
+        bool want[kRun];
+        bool any_want = false;
+#pragma unroll
+        for (int r = 0; r < kRun; ++r) {
+            want[r] = probing && best[r] < 4 && maxlen[r] >= 3 && lp.min_len <= 3;
+            any_want = any_want || want[r];
+        }
+        if (__any_sync(kFull, any_want)) {
+            // the 16 bytes before p0 and the 8 bytes from p0 on: six aligned words
+            const uint32_t wi = ((uint32_t)(p0 - 16) >> 2) & 0x3FFFu;
+            uint32_t wd[7];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) wd[j] = s.ring[(wi + j) & 0x3FFFu];
+            wd[6] = 0u;
+            int hits = 0;
+#pragma unroll
+            for (int r = 0; r < kRun; ++r) {
+                const int sh = 8 * r;
+                uint32_t bk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bk[j] = r ? __funnelshift_r(wd[j], wd[j + 1], sh) : wd[j];
+                const uint32_t cw = r ? __funnelshift_r(wd[4], wd[5], sh) : wd[4];
+                const uint32_t c0 = cw & 0xFFFFFFu;
+                int hit = 0;
+                if ((bk[0] & 0xFFFFFFu) == c0) hit = 16;
+                if ((bk[1] & 0xFFFFFFu) == c0) hit = 12;
+                if ((bk[2] & 0xFFFFFFu) == c0) hit = 8;
+                if ((__funnelshift_r(bk[2], bk[3], 16) & 0xFFFFFFu) == c0) hit = 6;
+                if ((bk[3] & 0xFFFFFFu) == c0) hit = 4;
+                if ((__funnelshift_r(bk[3], cw, 8) & 0xFFFFFFu) == c0) hit = 3;
+                if ((__funnelshift_r(bk[3], cw, 16) & 0xFFFFFFu) == c0) hit = 2;
+                if ((__funnelshift_r(bk[3], cw, 24) & 0xFFFFFFu) == c0) hit = 1;
+                if (want[r] && hit && (uint32_t)hit <= reach[r]) {
+                    const uint32_t p = (uint32_t)(p0 + r);
+                    const int len = min(common_prefix16(ring_load128(s.ring, p), ring_load128(s.ring, p - (uint32_t)hit)), maxlen[r]);
+                    if (len >= 3 && len > best[r]) {
+                        best[r] = len;
+                        bestd[r] = hit;
+                        ++hits;
                     }
                 }
             }
-            while (__any_sync(kFull, passed != 0ull)) {
-                if (passed != 0ull) {
-                    const uint32_t d = (uint32_t)passed & 0xFFFFu;
-                    passed >>= 16;
-                    const int len = min(common_prefix16(cur, ring_load128(s.ring, (uint32_t)q - d)), maxlen);
-                    if (len > best && len >= 4) {
-                        best = len;
-                        bestd = (int)d;
-                        if (len >= kCap) {
-                            capped = true;
-                            walk = false;
-                            passed = 0ull;
-                        } else if (len >= lp.nice || len >= maxlen) {
-                            walk = false;
-                            passed = 0ull;
+            if (strip < kProbeSample) {
+                const int h0 = __popc(__ballot_sync(kFull, hits >= 1)), h1 = __popc(__ballot_sync(kFull, hits >= 2)),
+                          h2 = __popc(__ballot_sync(kFull, hits >= 3)), h3 = __popc(__ballot_sync(kFull, hits >= 4));
+                if (lane == 0 && h0) atomicAdd(&s.probe_hits[t & 3], h0 + h1 + h2 + h3);
+            }
+        }
+    }
+    // extension of matches that filled the 16-byte compare: cooperative, one round per distinct distance.  For a
+    // distance d the end of every match of the strip is the first x with byte[x] != byte[x-d]; the lanes of the warp
+    // compare 3 x 32 words (384 bytes from the strip's first position + 16) and ballot the mismatching words, then each
+    // lane with that distance finds the first mismatch at or after its own position + 16.
+#pragma unroll
+    for (int r = 0; r < kRun; ++r) {
+        const int32_t p = p0 + r;
+        bool ext = best[r] >= kCap && best[r] < maxlen[r];
+        uint32_t pending = __ballot_sync(kFull, ext);
+        const uint32_t scan0 = ((uint32_t)(g0 + strip * kStrip + r) + kCap) & ~3u;  // word aligned
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const uint32_t d = (uint32_t)__shfl_sync(kFull, bestd[r], leader);
+            const bool mine = ext && (uint32_t)bestd[r] == d;
+            uint32_t diff[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t x = scan0 + (uint32_t)(k * 32 + lane) * 4u;
+                diff[k] = __ballot_sync(kFull, ring_load32(s.ring, x) != ring_load32(s.ring, x - d));
+            }
+            if (mine) {
+                // first mismatching word at or after my position + 16
+                const uint32_t from = (uint32_t)p + kCap;  // first byte not yet compared
+                const uint32_t w0 = (from - scan0) >> 2;   // its word index in the bitmap
+                int len = maxlen[r];
+                uint32_t wfound = 96;
+#pragma unroll
+                for (int k = 2; k >= 0; --k) {
+                    uint32_t bits = diff[k];
+                    const int lo = (int)w0 - k * 32;
+                    if (lo > 0) bits = lo >= 32 ? 0u : bits & ~((1u << lo) - 1u);
+                    if (bits) wfound = (uint32_t)(k * 32 + __ffs(bits) - 1);
+                }
+                if (wfound < 96) {
+                    // the exact byte: compare from max(from, word start)
+                    const uint32_t wx = scan0 + wfound * 4u;
+                    const uint32_t start = wx > from ? wx : from;
+                    const uint32_t xr = ring_load32(s.ring, start) ^ ring_load32(s.ring, start - d);
+                    if (xr) {
+                        len = (int)(start - (uint32_t)p) + ((__ffs((int)xr) - 1) >> 3);
+                    } else {
+                        // rare: the mismatch of that word was before `from`; continue byte-exact with a short loop
+                        int l2 = (int)(start - (uint32_t)p) + 4;
+                        while (l2 < maxlen[r]) {
+                            const uint32_t y = ring_load32(s.ring, (uint32_t)p + l2) ^ ring_load32(s.ring, (uint32_t)p + l2 - d);
+                            if (y) {
+                                l2 += (__ffs((int)y) - 1) >> 3;
+                                break;
+                            }
+                            l2 += 4;
                         }
+                        len = l2;
                     }
                 }
+                best[r] = min(len, maxlen[r]);
+                ext = false;
             }
+            pending &= ~__ballot_sync(kFull, mine);
         }
     }
-    // ---- short matches at small fixed distances (3-byte repeats of binary records, byte runs) -------------
-    bool hit3 = false;
-    {
-        const bool want = probing && best < 4 && maxlen >= 3 && lp.min_len <= 3;
-        if (__any_sync(kFull, want)) {
-            // the 3 bytes at q against the 3 bytes at q-1, -2, -3, -4, -6, -8, -12, -16: all come from the 16 bytes before q
-            const Bytes16 bk = ring_load128(s.ring, (uint32_t)(q - 16));
-            const uint32_t c0 = cur.w[0] & 0xFFFFFFu;
-            int hit = 0;
-            if ((bk.w[0] & 0xFFFFFFu) == c0) hit = 16;
-            if ((bk.w[1] & 0xFFFFFFu) == c0) hit = 12;
-            if ((bk.w[2] & 0xFFFFFFu) == c0) hit = 8;
-            if ((__funnelshift_r(bk.w[2], bk.w[3], 16) & 0xFFFFFFu) == c0) hit = 6;
-            if ((bk.w[3] & 0xFFFFFFu) == c0) hit = 4;
-            if ((__funnelshift_r(bk.w[3], cur.w[0], 8) & 0xFFFFFFu) == c0) hit = 3;
-            if ((__funnelshift_r(bk.w[3], cur.w[0], 16) & 0xFFFFFFu) == c0) hit = 2;
-            if ((__funnelshift_r(bk.w[3], cur.w[0], 24) & 0xFFFFFFu) == c0) hit = 1;
-            if (want && hit && (uint32_t)hit <= reach) {
-                const int len = min(common_prefix16(cur, ring_load128(s.ring, (uint32_t)(q - hit))), maxlen);
-                if (len >= 3 && len > best) {
-                    best = len;
-                    bestd = hit;
-                    capped = len >= kCap;
-                    hit3 = true;
-                }
-            }
-        }
+    uint32_t word[kRun];
+#pragma unroll
+    for (int r = 0; r < kRun; ++r) {
+        int b = best[r];
+        if (b == 3 && bestd[r] > lp.far3) b = 0;
+        if (b == 4 && bestd[r] > lp.far4) b = 0;
+        if (b < lp.min_len || (lp.filtered && b <= 5)) b = 0;
+        word[r] = b ? ((uint32_t)b << 16) | (uint32_t)(bestd[r] - 1) : 0u;
     }
-    // ---- a match that filled the 16-byte compare is extended, 16 bytes per trip -------------------------------
-    {
-        bool ext = capped && best < maxlen;
-        int len = kCap;
-        while (__any_sync(kFull, ext)) {
-            if (ext) {
-                const int n = common_prefix16(ring_load128(s.ring, (uint32_t)(q + len)), ring_load128(s.ring, (uint32_t)(q + len - bestd)));
-                len += n;
-                if (n < 16 || len >= maxlen) {
-                    ext = false;
-                    best = min(len, maxlen);
-                }
-            }
-        }
-    }
-    if (bestd == 0) best = 0;  // nothing longer than best0
-    if (best == 3 && bestd > lp.far3) best = 0;
-    if (best == 4 && bestd > lp.far4) best = 0;
-    if (best < lp.min_len || (lp.filtered && best <= 5)) best = 0;
-    Found f;
-    f.len = best;
-    f.dist = bestd;
-    f.hit3 = hit3;
-    return f;
+    *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(word[0], word[1], word[2], word[3]);
 }
 
-// ---- the parse of one lane ----------------------------------------------------------------------------------
-struct ParseState {
-    int32_t p;       // current position
-    int phase;       // 1: a match at p is pending (curlen, curdist) and the search looks at p + 1
-    int curlen, curdist;
-    uint32_t visited, ismatch;  // positions of the segment where a token starts / where that token is a match
-    int nm;          // matches emitted
-    int32_t lastd;   // distance of the last emitted match
-};
+// ---- parser: eight warps turn the per-position matches of group t into tokens -------------------------------
+__device__ __forceinline__ int tok_len(uint32_t w) { return (int)((w >> 16) & 0x1FFu); }
 
-// One round: one search, then the decision (literal, match, or wait for the look-ahead).  kReal: the parse of an entered
-// segment from its true entry; it may not pass `stop`, the speculative exit of the segment.
-template <bool kReal>
-__device__ __forceinline__ bool lane_round(LzSmem &s, const SearchCtx &cx, bool act, ParseState &st, uint32_t (*mt)[kSegs], int L,
-                                           int32_t seg0, int32_t limit, int32_t gend, int32_t stop, bool probing) {
-    const LevelParams &lp = cx.lp;
-    const Found R = search(s, cx, act, st.p + st.phase, st.phase ? st.curlen : 0, probing);
-    if (!act) return false;
-    bool emit = false;  // emit the match (curlen, curdist) at st.p
-    if (st.phase == 0) {
-        if (R.len == 0) {
-            st.visited |= 1u << (st.p - seg0);
-            st.p += 1;
-        } else {
-            st.curlen = R.len;
-            st.curdist = R.dist;
-            if (lp.lazy && R.len < lp.max_lazy && st.p + 1 < gend) st.phase = 1;
-            else emit = true;
-        }
-    } else {
-        if (R.len > st.curlen) {
-            // the byte at p becomes a literal, the longer match at p + 1 is the pending one
-            st.visited |= 1u << (st.p - seg0);
-            st.p += 1;
-            st.curlen = R.len;
-            st.curdist = R.dist;
-            if (st.p >= limit) st.phase = 0;  // the pending match belongs to the next segment
-            else if (!(R.len < lp.max_lazy && st.p + 1 < gend)) emit = true;
-        } else {
-            emit = true;
-        }
-    }
-    if (emit) {
-        int len = st.curlen;
-        st.phase = 0;
-        if (kReal && st.p + len > stop) {
-            len = stop - st.p;
-            if (len < 3) {  // cut below a match: a literal, the parse goes on behind it
-                st.visited |= 1u << (st.p - seg0);
-                st.p += 1;
-                return R.hit3;
-            }
-        }
-        st.visited |= 1u << (st.p - seg0);
-        st.ismatch |= 1u << (st.p - seg0);
-        mt[st.nm][L] = ((uint32_t)len << 16) | (uint32_t)(st.curdist - 1);
-        st.nm += 1;
-        st.lastd = st.curdist;
-        st.p += len;
-    }
-    return R.hit3;
+// The step of the parse at p: 1 for a literal, the match length otherwise (greedy with one-step lazy evaluation).
+__device__ __forceinline__ int decide(const uint32_t *mv, const LevelParams &lp, int32_t g0, int32_t gend, int32_t p) {
+    // both words are loaded unconditionally (one slot of slack behind the group keeps p + 1 in bounds)
+    const int len = tok_len(mv[mvi(p - g0)]);
+    const int next = tok_len(mv[mvi(p + 1 - g0)]);
+    const bool defer = lp.lazy && len < lp.max_lazy && p + 1 < gend && next > len;
+    return (len == 0 || defer) ? 1 : len;
 }
 
-__device__ __forceinline__ void team_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kSearchWarps * 32) : "memory"); }
+__device__ __forceinline__ void parser_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kParserWarps * 32) : "memory"); }
 
-// The search team turns group t into tokens.  L = team lane = segment index.  prev_hits: probe hits of this warp in the
-// group before (warp-uniform, carried in a register).
-__device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, const SearchCtx &cx, int t, int L,
-                                            uint32_t unit_index, uint32_t &prev_hits, long long (&pt)[8]) {
+// L = parser lane = segment index.  The carry (first unparsed position, tokens emitted, block start) lives in shared
+// memory by group parity: group t reads [t & 1] and writes the other.
+__device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, int L, uint32_t unit_index,
+                                            long long (&pt)[6]) {
     long long tc = clock64();
 #define ZK_PT(i)                         \
     {                                    \
@@ -459,47 +529,66 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         pt[i] += now - tc;               \
         tc = now;                        \
     }
-    const int lane = L & 31, sw = L >> 5;
+    const LevelParams &lp = a.lp;
+    const uint32_t *mv = s.match[t & 1];
+    const int lane = L & 31, pw = L >> 5;
     const int32_t g0 = t * kGroup;
     const int32_t gend = min(g0 + kGroup, g.data_end_q);
     const int32_t seg0 = min(g0 + L * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
-    const bool adaptive = cx.lp.probe_adaptive != 0;
-
-    // ---- speculative parse of the segment from its first byte ----
-    ParseState sp;
-    sp.p = seg0;
-    sp.phase = 0;
-    sp.curlen = sp.curdist = 0;
-    sp.visited = sp.ismatch = 0u;
-    sp.nm = 0;
-    sp.lastd = -1;
-    uint32_t hits = 0;
+    // ---- pass A: speculative parse of this lane's segment from its first position, in registers: the 17 match words of
+    // the segment arrive with independent 16-byte loads, the step of every position (the lazy rule) is packed 8 bits per
+    // position, and "which positions does the parse visit" is 15 unrolled register operations.
+    uint32_t visited = 0u, ismatch = 0u;
+    int32_t my_exit = seg0, lastd = -1;
     {
-        int round = 0;
-        for (;;) {
-            const bool act = sp.p < seg1;
-            if (!__any_sync(kFull, act)) break;
-            const bool probing = !adaptive || round < kProbeRounds || hits >= kProbeThresh || prev_hits >= kProbeThresh;
-            const bool hit3 = lane_round<false>(s, cx, act, sp, s.mt, L, seg0, seg1, gend, 0, probing);
-            hits += __popc(__ballot_sync(kFull, hit3));
-            ++round;
+        const int seg_len = seg1 - seg0;
+        if (seg_len > 0) {
+            const uint32_t *mp = mv + mvi(seg0 - g0);  // the segment's 16 words are contiguous
+            uint32_t st[4];
+            uint32_t mm = 0u;
+            uint4 cur = *reinterpret_cast<const uint4 *>(mp);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 nxt;
+                if (c < 3) nxt = *reinterpret_cast<const uint4 *>(mp + 4 * c + 4);
+                else nxt = make_uint4(mv[mvi(seg0 - g0 + kSeg)], 0u, 0u, 0u);
+                const uint32_t w[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+                uint32_t packed = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int len = tok_len(w[j]), nextlen = tok_len(w[j + 1]);
+                    const bool defer = lp.lazy && len < lp.max_lazy && seg0 + 4 * c + j + 1 < gend && nextlen > len;
+                    const bool lit = len == 0 || defer;
+                    const uint32_t step = lit ? 1u : (uint32_t)min(len, 64);
+                    packed |= step << (8 * j);
+                    if (!lit) mm |= 1u << (4 * c + j);
+                }
+                st[c] = packed;
+                cur = nxt;
+            }
+            visited = 1u;
+#pragma unroll
+            for (int i = 0; i < kSeg - 1; ++i) {
+                const uint32_t tgt = (uint32_t)i + ((st[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                if (((visited >> i) & 1u) && tgt < (uint32_t)kSeg) visited |= 1u << tgt;
+            }
+            if (seg_len < kSeg) visited &= (1u << seg_len) - 1u;
+            ismatch = visited & mm;
+            const int lastpos = 31 - __clz(visited);
+            const int step = decide(mv, lp, g0, gend, seg0 + lastpos);
+            lastd = step > 1 ? (int32_t)(mp[lastpos] & 0xFFFFu) : -1;  // distance - 1
+            my_exit = seg0 + lastpos + step;
         }
-        pt[6] += round;
     }
-    prev_hits = hits;
-    const bool probing_b = !adaptive || hits >= kProbeThresh;
-    const int32_t my_exit = sp.p;  // >= seg1; an empty segment (seg0 == gend) exits at gend
-    ZK_PT(0)
-
     // ---- stitch.  The real parse enters the segment that holds the carry, and from an entered segment l the one its
     // speculative exit lies in (the real parse of a segment is made to end at the speculative exit, below): which
-    // segments are entered is reachability along those links.  Level 1, inside each warp with shuffles (pointer
-    // doubling, 5 rounds): for every segment of the warp the set of the warp's segments visited from it (a 32-bit
-    // mask) and the first segment after the warp it leads to.  Level 2, after one barrier: every lane walks the hops
-    // from warp to warp.
+    // segments are entered is reachability along those links.  Level 1, inside each parser warp with shuffles (pointer
+    // doubling, 5 rounds): for every segment of the warp the set of the warp's segments visited from it (a 32-bit mask)
+    // and the first segment after the warp it leads to.  Level 2, after one barrier: every lane walks the hops from
+    // warp to warp.
     const int n0 = my_exit >= gend ? kSegs : (my_exit - g0) / kSeg;
     {
-        const int wbase = sw * 32;
+        const int wbase = pw * 32;
         int jl = n0;
         uint32_t vm = 1u << lane;
 #pragma unroll
@@ -515,17 +604,19 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         s.jnext[L] = (int16_t)jl;
         s.jmark[L] = vm;
     }
+    ZK_PT(0)
     const int par = t & 1;
     const int32_t x0 = s.carry_entry[par];
     const int first = x0 >= gend ? kSegs : (x0 - g0) / kSeg;
     if (L == 0) s.pfinal = x0;  // stays when nothing is entered
-    team_barrier();
+    parser_barrier();
+    ZK_PT(1)
     bool entered = false;
     {
         int cur = first;
 #pragma unroll 1
         while (cur < kSegs) {
-            if ((cur >> 5) == sw) entered = (s.jmark[cur] >> lane) & 1u;
+            if ((cur >> 5) == pw) entered = (s.jmark[cur] >> lane) & 1u;
             cur = s.jnext[cur];
         }
         if (L == first) s.pstart[L] = (uint16_t)(x0 - g0);
@@ -534,91 +625,92 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
             else s.pfinal = my_exit;
         }
     }
-    team_barrier();
-    ZK_PT(1)
-
-    // ---- real prefix: from the entry until the parse lands on a position the speculative parse visited ----
-    ParseState rp;
-    rp.p = entered ? g0 + (int32_t)s.pstart[L] : seg0;
-    rp.phase = 0;
-    rp.curlen = rp.curdist = 0;
-    rp.visited = rp.ismatch = 0u;
-    rp.nm = 0;
-    rp.lastd = -1;
-    bool met = true;  // an entry at the first byte of the segment meets at once
-    {
-        bool act = entered && rp.p > seg0;
-        if (act) met = false;
-        int round = 0;
-        for (;;) {
-            if (act) {
-                if (rp.p >= seg1) {
-                    act = false;
-                } else if ((sp.visited >> (rp.p - seg0)) & 1u) {
+    parser_barrier();
+    ZK_PT(2)
+    // ---- pass B: the real parse of an entered segment from its entry, until it lands on a position the speculative
+    // parse visited (usually at once: every literal is such a position).  It may not pass the speculative exit: a
+    // match that would is cut (or becomes a literal), and when the two parses never meet the rest up to the exit -- the
+    // tail of the speculative parse's last match -- is one match at that distance (or up to two literals).
+    uint32_t visited2 = 0u, ismatch2 = 0u;
+    int cut_len = 0, gap = 0, m = 0;  // m: first speculative position used, relative to the segment
+    if (entered) {
+        int32_t p = g0 + (int32_t)s.pstart[L];
+        if (p > seg0) {
+            bool met = false;
+#pragma unroll 1
+            while (p < seg1) {
+                if ((visited >> (p - seg0)) & 1u) {
                     met = true;
-                    act = false;
+                    break;
                 }
+                int step = decide(mv, lp, g0, gend, p);
+                const uint32_t bit = 1u << (p - seg0);
+                if (step > 1 && p + step > my_exit) {
+                    step = my_exit - p;
+                    if (step < 3) step = 1;
+                    else cut_len = step;
+                }
+                visited2 |= bit;
+                if (step > 1) ismatch2 |= bit;
+                p += step;
             }
-            if (!__any_sync(kFull, act)) break;
-            lane_round<true>(s, cx, act, rp, s.mt2, L, seg0, seg1, gend, my_exit, probing_b);
-            ++round;
+            m = met ? p - seg0 : kSeg;
+            gap = met ? 0 : my_exit - p;
         }
-        pt[7] += round;
     }
-    // tokens of this lane: the real prefix [entry, meet), the speculative tokens from meet on, and when the two never
-    // met the rest up to the speculative exit: that gap is the tail of the speculative parse's last match
-    const int m = met ? rp.p - seg0 : kSeg;           // first speculative position used
-    const int gap = met ? 0 : my_exit - rp.p;         // bytes between the real parse's end and the speculative exit
-    const uint32_t spec_mask = m >= 32 ? 0u : sp.visited & ~((1u << m) - 1u);
+    const uint32_t spec_mask = m >= 32 ? 0u : visited & ~((1u << m) - 1u);
     int cnt = 0;
-    if (entered) cnt = __popc(rp.visited) + __popc(spec_mask) + (gap >= 3 ? 1 : gap);
-    // dense offsets across the team
+    if (entered) cnt = __popc(visited2) + __popc(spec_mask) + (gap >= 3 ? 1 : gap);
+    // dense offsets across the parser lanes
     int incl = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const int v = __shfl_up_sync(kFull, incl, off);
         if (lane >= off) incl += v;
     }
-    if (lane == 31) s.wcount[sw] = incl;
-    ZK_PT(2)
-    team_barrier();
+    if (lane == 31) s.wcount[pw] = incl;
     ZK_PT(3)
+    parser_barrier();
+    ZK_PT(4)
     int before = 0, total = 0;
 #pragma unroll
-    for (int k = 0; k < kSearchWarps; ++k) {
+    for (int k = 0; k < kParserWarps; ++k) {
         const int c = s.wcount[k];
-        if (k < sw) before += c;
+        if (k < pw) before += c;
         total += c;
     }
     const uint32_t tok_off = s.carry_tok_off[par];
     if (entered) {
         uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + tok_off + (uint32_t)(before + incl - cnt);
         {
-            uint32_t v = rp.visited;
-            int k = 0;
+            uint32_t v = visited2;
+            const int last2 = ismatch2 ? 31 - __clz(ismatch2) : -1;
             while (v) {
                 const int i = __ffs((int)v) - 1;
                 v &= v - 1u;
                 uint32_t tok;
-                if ((rp.ismatch >> i) & 1u) tok = s.mt2[k++][L];
-                else tok = ring_load8(s.ring, (uint32_t)(seg0 + i));
+                if ((ismatch2 >> i) & 1u) {
+                    const uint32_t w = mv[mvi(seg0 + i - g0)];
+                    tok = (i == last2 && cut_len) ? (((uint32_t)cut_len << 16) | (w & 0xFFFFu)) : w;
+                } else {
+                    tok = ring_load8(s.ring, (uint32_t)(seg0 + i));
+                }
                 *dst++ = tok;
             }
         }
         {
             uint32_t v = spec_mask;
-            int k = m >= 32 ? 0 : __popc(sp.ismatch & ((1u << m) - 1u));
             while (v) {
                 const int i = __ffs((int)v) - 1;
                 v &= v - 1u;
                 uint32_t tok;
-                if ((sp.ismatch >> i) & 1u) tok = s.mt[k++][L];
+                if ((ismatch >> i) & 1u) tok = mv[mvi(seg0 + i - g0)];
                 else tok = ring_load8(s.ring, (uint32_t)(seg0 + i));
                 *dst++ = tok;
             }
         }
         if (gap >= 3) {
-            *dst++ = ((uint32_t)gap << 16) | (uint32_t)(sp.lastd - 1);
+            *dst++ = ((uint32_t)gap << 16) | (uint32_t)lastd;
         } else {
             for (int i = 0; i < gap; ++i) *dst++ = ring_load8(s.ring, (uint32_t)(my_exit - gap + i));
         }
@@ -640,7 +732,7 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
         s.carry_tok_off[par ^ 1] = new_off;
         s.carry_blk_begin[par ^ 1] = blk_begin;
     }
-    ZK_PT(4)
+    ZK_PT(5)
 #undef ZK_PT
 }
 
@@ -648,9 +740,9 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LzSmem &s = *reinterpret_cast<LzSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool is_search = warp < kSearchWarps;
     const bool is_builder = warp == kBuilderWarp;
-    const bool is_prep = warp >= kFirstPrepWarp;
+    const bool is_parser = warp >= kFirstParserWarp && warp < kFirstParserWarp + kParserWarps;
+    const int parser_index = warp - kFirstParserWarp;
 
     for (uint32_t unit = blockIdx.x; unit < a.num_units; unit += gridDim.x) {
         UnitGeom g;
@@ -664,6 +756,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         cx.lp = a.lp;
         cx.h0q = g.h0q;
         cx.ulen = (int32_t)g.ulen;
+        cx.data_end_q = g.data_end_q;
         cx.block_shift = a.block_shift;
 
         // reset tables (deterministic start) and barriers
@@ -671,8 +764,12 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             uint4 *z = reinterpret_cast<uint4 *>(s.prev);
             const int nvec = (int)((sizeof(s.prev) + sizeof(s.head)) / 16);
             for (int i = threadIdx.x; i < nvec; i += kThreadsLz) z[i] = make_uint4(0, 0, 0, 0);
+            // the slack words behind the match arrays are read by the parser's look-ahead at the last position
+            if (threadIdx.x < 16) s.match[threadIdx.x >> 3][kGroup + kGroup / 8 + (threadIdx.x & 7)] = 0u;
             if (threadIdx.x == 0) {
                 for (int b = 0; b < kStages; ++b) mbar_init(&s.bar[b], 1);
+                s.work[0] = s.work[1] = 0;
+                s.probe_hits[0] = s.probe_hits[1] = s.probe_hits[2] = s.probe_hits[3] = 0;
                 s.carry_entry[0] = s.carry_entry[1] = kWindow;
                 s.carry_tok_off[0] = s.carry_tok_off[1] = 0;
                 s.carry_blk_begin[0] = s.carry_blk_begin[1] = 0;
@@ -699,18 +796,39 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         if (threadIdx.x < 8) s.ring[65536 / 4 + threadIdx.x] = s.ring[threadIdx.x];
         __syncthreads();
 
-        // step i: stage(i+4) | prepare(i+2) | build(i+1) | search + parse(i)
-        uint32_t prev_hits = 1u << 30;  // the first group of a unit has no group before it: probe everywhere
-        long long t_role = 0;
-        long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // step i: stage(i+4) | prepare(i+2) | build(i+1) | search(i) | parse(i-1)
+        long long t_role = 0, t_search = 0;
+        long long pt[6] = {0, 0, 0, 0, 0, 0};
         const long long t_unit0 = clock64();
-        for (int i = g.first_group - 2; i <= g.last_group; ++i) {
+        for (int i = g.first_group - 2; i <= g.last_group + 1; ++i) {
             const bool tma_next = (i + 4 <= g.last_group + 1) ? stage_group(s, a, g, i + 4) : false;
+            if (threadIdx.x == 0) {
+                s.work[(i + 1) & 1] = 0;
+                s.probe_hits[(i + 1) & 3] = 0;
+            }
+            // (the first group of a unit has no sample before it: it probes everywhere)
+            const bool probe_all = !a.lp.probe_adaptive || i <= kHistGroups || s.probe_hits[(i - 1) & 3] >= kProbeThreshold;
+
             const long long t0 = clock64();
-            if (is_prep && i + 2 >= g.first_group && i + 2 <= g.last_group) prep_group(s, i + 2, warp - kFirstPrepWarp, lane);
             if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
-            if (is_search && i >= kHistGroups && i <= g.last_group) parse_group(s, a, g, cx, i, warp * 32 + lane, unit, prev_hits, pt);
-            t_role += clock64() - t0;
+            if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
+                parse_group(s, a, g, i - 1, parser_index * 32 + lane, unit, pt);
+            const long long t1 = clock64();
+            const bool searching = i >= kHistGroups && i <= g.last_group;
+            const bool preparing = i + 2 >= g.first_group && i + 2 <= g.last_group;
+            if (searching || preparing) {
+                for (;;) {
+                    int strip = 0;
+                    if (lane == 0) strip = atomicAdd(&s.work[i & 1], 1);
+                    strip = __shfl_sync(kFull, strip, 0);
+                    if (strip >= kStripsPerGroup) break;
+                    if (preparing) prep_strip(s, i + 2, strip * kStrip, lane);
+                    if (searching) search_strip(s, cx, i, strip, lane, warp, probe_all);
+                }
+            }
+            const long long t2 = clock64();
+            t_role += t1 - t0;
+            t_search += t2 - t1;
             if (tma_next) {
                 const int slot = (i + 4) & (kStages - 1);
                 uint32_t spins = 0;
@@ -725,21 +843,16 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             }
             __syncthreads();
         }
-        if (a.prof && lane == 0 && (warp == 0 || warp == kBuilderWarp || warp == kFirstPrepWarp)) {
-            // per unit: [0] total; [1] builder busy; [2] prep busy; [3] search team busy; [4..8] its phases (speculative
-            // parse, stitch, real prefix + count, wait, copy-out); [9] speculative rounds, [10] real rounds (warp 0)
+        if (a.prof && lane == 0 && (warp == kBuilderWarp || warp == kFirstParserWarp || warp == 2)) {
+            // per unit: [0] total; {role, search} cycles of [1,2] the builder, [3,4] the first parser warp, [5,6] a
+            // searcher; [8..13] the parser's phases (pass A + stitch 1, wait, stitch 2, pass B + count, wait, copy-out)
             unsigned long long *o = a.prof + (size_t)unit * 32;
-            if (warp == kBuilderWarp) {
-                o[0] = (unsigned long long)(clock64() - t_unit0);
-                o[1] = (unsigned long long)t_role;
-            } else if (warp == kFirstPrepWarp) {
-                o[2] = (unsigned long long)t_role;
-            } else {
-                o[3] = (unsigned long long)t_role;
-                for (int k = 0; k < 5; ++k) o[4 + k] = (unsigned long long)pt[k];
-                o[9] = (unsigned long long)pt[6];
-                o[10] = (unsigned long long)pt[7];
-            }
+            const int k = warp == kBuilderWarp ? 0 : warp == kFirstParserWarp ? 1 : 2;
+            if (warp == kBuilderWarp) o[0] = (unsigned long long)(clock64() - t_unit0);
+            if (warp == kFirstParserWarp)
+                for (int q = 0; q < 6; ++q) o[8 + q] = (unsigned long long)pt[q];
+            o[1 + 2 * k] = (unsigned long long)t_role;
+            o[2 + 2 * k] = (unsigned long long)t_search;
         }
     }
 }
@@ -763,14 +876,14 @@ LevelParams level_params(int level, int strategy) {
     p.max_lazy = 16;
     switch (level) {
         case 1: p.chain = 1; p.lazy = 0; p.nice = 32; break;
-        case 2: p.chain = 2; p.lazy = 0; p.nice = 32; break;
-        case 3: p.chain = 2; p.nice = 64; p.max_lazy = 8; break;
-        case 4: p.chain = 2; break;
-        case 5: p.chain = 3; p.nice = 64; break;
-        case 6: p.chain = 3; break;
-        case 7: p.chain = 6; p.max_lazy = 32; break;
-        case 8: p.chain = 16; p.nice = 258; p.max_lazy = 128; break;
-        default: p.chain = 32; p.nice = 258; p.max_lazy = 258; break;
+        case 2: p.chain = 1; p.nice = 32; p.max_lazy = 8; break;
+        case 3: p.chain = 1; p.nice = 64; break;
+        case 4: p.chain = 2; p.nice = 64; p.max_lazy = 8; break;
+        case 5: p.chain = 2; p.nice = 64; break;
+        case 6: p.chain = 2; break;
+        case 7: p.chain = 4; p.max_lazy = 32; break;
+        case 8: p.chain = 8; p.nice = 258; p.max_lazy = 128; break;
+        default: p.chain = 16; p.nice = 258; p.max_lazy = 258; break;
     }
     if (level < 1) p.chain = 1;
     if (strategy == ZK_HUFFMAN_ONLY) {
