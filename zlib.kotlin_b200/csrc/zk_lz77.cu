@@ -277,19 +277,56 @@ struct SearchCtx {
 };
 
 // ---- searcher: the best match of every position of a strip ------------------------------------------------------
+// Shared-memory accesses of the hot loops by 32-bit shared address: the address arithmetic stays in plain integer
+// registers (no generic-to-shared conversion per access) and the loads of independent positions are issued together.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// 16 bytes at ring offset q (any alignment), ring_a = shared address of the ring
+__device__ __forceinline__ Bytes16 ring_load128a(uint32_t ring_a, uint32_t q) {
+    const uint32_t wa = ring_a + (q & 0xFFFCu), sh = (q & 3u) << 3;  // words i..i+4; the mirror behind the ring covers the wrap
+    const uint32_t a0 = lds_u32(wa), a1 = lds_u32(wa + 4), a2 = lds_u32(wa + 8), a3 = lds_u32(wa + 12), a4 = lds_u32(wa + 16);
+    Bytes16 r;
+    r.w[0] = __funnelshift_r(a0, a1, sh);
+    r.w[1] = __funnelshift_r(a1, a2, sh);
+    r.w[2] = __funnelshift_r(a2, a3, sh);
+    r.w[3] = __funnelshift_r(a3, a4, sh);
+    return r;
+}
+
+struct StripAddrs {
+    uint32_t ring_a, prev_a, mv_a, tq_a;  // shared addresses: ring, prev, the group's match array, this warp's task queue
+};
+
 // The queued compare tasks of a warp: 16 bytes at the position against 16 bytes at the candidate, clipped to the end of
-// the deflate block; the longest, on a tie the nearest, stays in the match word (atomicMax over len << 16 | ~dist).
-__device__ __forceinline__ void run_tasks(LzSmem &s, uint32_t *mv, const uint32_t *tq, int T, int32_t g0, int32_t blk_end_q, int lane) {
+// the deflate block; the longest, on a tie the nearest, stays in the match word (a shared-memory max over
+// len << 16 | ~dist: the order in which the tasks are processed does not matter).
+__device__ __forceinline__ void run_tasks(const StripAddrs &ad, const uint32_t *tq, int T, int32_t g0, int32_t blk_end_q, int lane) {
     __syncwarp();
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int ti = t0 + lane;
         if (ti < T) {
-            const uint32_t task = tq[ti];
+            const uint32_t task = tq[ti];  // an ordinary load: it must stay behind the __syncwarp above
             const uint32_t rel = task >> 16, d = task & 0xFFFFu;
             const uint32_t p = (uint32_t)g0 + rel;
             const int maxlen = min(kMaxMatch, blk_end_q - (int32_t)p);
-            const int len = min(common_prefix16(ring_load128(s.ring, p), ring_load128(s.ring, p - d)), maxlen);
-            if (len >= 4) atomicMax(&mv[mvi((int)rel)], ((uint32_t)len << 16) | (0xFFFFu - d));
+            const int len = min(common_prefix16(ring_load128a(ad.ring_a, p), ring_load128a(ad.ring_a, p - d)), maxlen);
+            if (len >= 4) {
+                const uint32_t val = ((uint32_t)len << 16) | (0xFFFFu - d);
+                asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ad.mv_a + 4u * (rel + ((rel >> 5) << 2))), "r"(val) : "memory");
+            }
         }
     }
     __syncwarp();
@@ -299,7 +336,11 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
     const LevelParams &lp = cx.lp;
     const bool probing = probe_all || strip < kProbeSample;
     uint32_t *mv = s.match[t & 1];
-    uint32_t *tq = s.tq[warp];
+    StripAddrs ad;
+    ad.ring_a = smem_addr(s.ring);
+    ad.prev_a = smem_addr(s.prev);
+    ad.mv_a = smem_addr(mv);
+    ad.tq_a = smem_addr(s.tq[warp]);
     const int32_t g0 = t * kGroup;
     const int32_t rel0 = strip * kStrip + lane * kRun;  // the first of this lane's positions, relative to the group
     const int32_t p0 = g0 + rel0;
@@ -316,8 +357,8 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
         c16[1] = lk.x >> 16;
         c16[2] = lk.y & 0xFFFFu;
         c16[3] = lk.y >> 16;
-        const uint32_t wi = ((uint32_t)p0 >> 2) & 0x3FFFu;
-        const uint32_t w0 = s.ring[wi], w1 = s.ring[wi + 1];
+        const uint32_t wa = ad.ring_a + ((uint32_t)p0 & 0xFFFCu);
+        const uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4);
         need[0] = w0 >> 24;
         need[1] = w1 & 0xFFu;
         need[2] = (w1 >> 8) & 0xFFu;
@@ -332,35 +373,34 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
         walk[r] = lp.chain > 0 && maxlen[r] >= 4;
     }
     *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(0u, 0u, 0u, 0u);
-    // ---- walk: one chain link of each of the four positions per trip; candidates that pass the byte test are queued
-    int T = 0;
+    // ---- walk: one chain link of each of the four positions per trip, branch-free: the eight loads (next link and test
+    // byte of four candidates) are in flight together; candidates that pass the byte test are queued, then compared
     for (int k = 0; k < lp.chain; ++k) {
         if (!__any_sync(kFull, walk[0] || walk[1] || walk[2] || walk[3])) break;
+        uint32_t d[kRun], nl[kRun], cb[kRun];
 #pragma unroll
         for (int r = 0; r < kRun; ++r) {
-            const uint32_t p = (uint32_t)(p0 + r);
-            const uint32_t d = (p - c16[r]) & 0xFFFFu;
-            walk[r] = walk[r] && d - 1u < reach[r] && d > lastd[r];
-            bool pass = false;
-            if (walk[r]) {
-                lastd[r] = d;
-                const uint32_t c = p - d;
-                c16[r] = s.prev[c & 32767u];
-                pass = ring_load8(s.ring, c + 3u) == need[r];
-            }
-            const uint32_t b = __ballot_sync(kFull, pass);
-            if (pass) tq[T + __popc(b & lt)] = ((uint32_t)(rel0 + r) << 16) | d;
-            T += __popc(b);
-            if (T > kTaskCap - 32) {  // the next trip may add 32 more
-                run_tasks(s, mv, tq, T, g0, blk_end_q, lane);
-                T = 0;
-            }
+            d[r] = ((uint32_t)(p0 + r) - c16[r]) & 0xFFFFu;
+            walk[r] = walk[r] && d[r] - 1u < reach[r] && d[r] > lastd[r];
+            const uint32_t c = (uint32_t)(p0 + r) - d[r];
+            // loaded whether or not the candidate is valid (the addresses are always inside the tables)
+            nl[r] = lds_u16(ad.prev_a + ((c & 32767u) << 1));
+            cb[r] = lds_u8(ad.ring_a + ((c + 3u) & 0xFFFFu));
         }
+        int T = 0;
+#pragma unroll
+        for (int r = 0; r < kRun; ++r) {
+            const bool pass = walk[r] && cb[r] == need[r];
+            const uint32_t b = __ballot_sync(kFull, pass);
+            if (pass) s.tq[warp][T + __popc(b & lt)] = ((uint32_t)(rel0 + r) << 16) | d[r];
+            T += __popc(b);
+            if (walk[r]) lastd[r] = d[r];
+            c16[r] = nl[r];
+        }
+        run_tasks(ad, s.tq[warp], T, g0, blk_end_q, lane);
         if ((k & 1) && k + 1 < lp.chain) {
             // deep chains: a position whose best candidate already fills the 16-byte compare is done (a farther one can
             // only tie, and the nearest wins a tie)
-            run_tasks(s, mv, tq, T, g0, blk_end_q, lane);
-            T = 0;
             const uint4 mw = *reinterpret_cast<const uint4 *>(&mv[mvi(rel0)]);
             if ((mw.x >> 16) >= (uint32_t)kCap) walk[0] = false;
             if ((mw.y >> 16) >= (uint32_t)kCap) walk[1] = false;
@@ -368,7 +408,6 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
             if ((mw.w >> 16) >= (uint32_t)kCap) walk[3] = false;
         }
     }
-    run_tasks(s, mv, tq, T, g0, blk_end_q, lane);
     // ---- finish: probes, extension, filters ----
     int best[kRun], bestd[kRun];
     {
