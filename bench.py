@@ -37,6 +37,8 @@ def parse_args():
     ap.add_argument("--workload", default="mixed", choices=["mixed", "text"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=32)
+    ap.add_argument("--config1-mib", type=int, default=64, help="size of the configs[0] CPU round trip inside cpu_baseline (0 = skip)")
+    ap.add_argument("--no-verify", action="store_true", help="skip handing the timed region's stream to libz")
     return ap.parse_args()
 
 
@@ -104,29 +106,101 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(kind, level, sample_mib, cores_note=""):
-    """The oracle (C restatement of the reference algorithm, kind "port") timed on one host core over a
-    bounded sample of the same workload.  The reference is single-threaded; it could not be built here."""
+def _oracle():
     from tests.oracle_binding import Oracle
 
     so = os.path.join(ROOT, "oracle", "libzk_oracle.so")
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    oracle = Oracle(so)
+    return Oracle(so)
+
+
+def libz_pigz_style(data, level, threads, chunk=128 << 10):
+    """B3 of SURVEY.md 8(d): what pigz does, with libz -- independent chunks, each primed with the previous 32 KiB as its
+    dictionary and ended with a sync flush, compressed on `threads` host threads (libz releases the GIL).  Returns
+    (compressed bytes without the zlib wrapper, seconds)."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    mv = memoryview(data)
+
+    def one(off):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, bytes(mv[max(0, off - 32768): off])) if off \
+            else zlib.compressobj(level, zlib.DEFLATED, -15)
+        return c.compress(mv[off: off + chunk]) + c.flush(zlib.Z_SYNC_FLUSH)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(one, range(0, len(data), chunk)))
+    return sum(len(p) for p in parts), time.perf_counter() - t0
+
+
+def cpu_baseline(kind, level, sample_mib, config1_mib=64):
+    """CPU numbers beside the GPU ones, on bounded samples of the same workload:
+      B1  the oracle (C restatement of the reference algorithm, kind "port"), one host core -- the reference is
+          single-threaded and could not be built here; with what the reference's own inflate makes of that stream;
+      B2  libz 1.3 at the same level, one thread;  B3  libz pigz-style on every host core;
+      C1  BASELINE.json configs[0]: the reference path on a 64 MiB text-like buffer at level 6, round trip."""
+    import zlib
+
+    oracle = _oracle()
+    cores = os.cpu_count() or 1
     data = make_corpus(kind, sample_mib << 20).tobytes()
     t0 = time.perf_counter()
     rc, stream, used = oracle.deflate(data, level)
     dt = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    oracle.inflate(stream, cap=len(data) + 64)
-    dti = time.perf_counter() - t1
-    return {
+    rc_i, out_i, second_i, _ = oracle.inflate(stream, cap=len(data) + 64)
+    try:
+        libz_ok = zlib.decompress(stream) == data
+        libz_says = "ok" if libz_ok else "wrong bytes"
+    except zlib.error as e:
+        libz_says = str(e)
+    t0 = time.perf_counter()
+    z = zlib.compress(data, level)
+    dz = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    zlib.decompress(z)
+    dzi = time.perf_counter() - t0
+    pz_len, dpz = libz_pigz_style(data, level, cores)
+    out = {
         "value": len(data) / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
         "sample": "first %d MiB of the %s corpus, level %d, one pass" % (sample_mib, kind, level),
-        "compressed_ratio": len(stream) / len(data), "inflate_gbs_of_its_own_stream": len(data) / dti / 1e9,
-        "note": "C restatement of the reference algorithm (single thread, -O2): an upper bound on the Kotlin/Native binary, "
-                "which could not be built in this image" + cores_note,
+        "deflate_rc": rc, "bytes_in": used,
+        "reference_stream_ratio": len(stream) / len(data),
+        "reference_round_trip": {"rc": rc_i, "bytes_out": len(out_i), "bit_exact": rc_i == 1 and out_i == data, "libz_on_that_stream": libz_says,
+                                 "note": "the reference's own inflate (oracle) on the reference's own stream; rc -3 with 0 bytes means the "
+                                         "stream is invalid from its first block (stale-window compare, DS:672-691), so its size is "
+                                         "the size of an invalid stream"},
+        "libz_1thread": {"value": len(data) / dz / 1e9, "unit": UNIT, "cores": 1, "ratio": len(z) / len(data),
+                         "inflate_gbs": len(data) / dzi / 1e9, "kind": "libz 1.3 level %d" % level},
+        "libz_pigz_style": {"value": len(data) / dpz / 1e9, "unit": UNIT, "cores": cores, "ratio": pz_len / len(data),
+                            "kind": "libz 1.3 level %d, 128 KiB chunks, 32 KiB dictionary + sync flush per chunk, one thread per host core" % level},
+        "note": "value = B1, the C restatement of the reference algorithm (single thread, -O2): an upper bound on the Kotlin/Native "
+                "binary, which could not be built in this image; libz_1thread / libz_pigz_style are the industry CPU baselines",
     }
+    if config1_mib:
+        text = make_corpus("text", config1_mib << 20).tobytes()
+        t0 = time.perf_counter()
+        rc1, s1, used1 = oracle.deflate(text, 6)
+        d1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rc1i, out1, _, _ = oracle.inflate(s1, cap=len(text) + 64)
+        d1i = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        z1 = zlib.compress(text, 6)
+        dz1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        back = zlib.decompress(z1)
+        dz1i = time.perf_counter() - t0
+        out["config1"] = {
+            "workload": "%d MiB text-like buffer (seed 0x5EED0001), level 6, compress + decompress on the CPU (BASELINE.json configs[0])" % config1_mib,
+            "reference": {"deflate_rc": rc1, "bytes_in": used1, "deflate_gbs": len(text) / d1 / 1e9, "stream_ratio": len(s1) / len(text),
+                          "inflate_rc": rc1i, "inflate_bytes_out": len(out1), "inflate_seconds": d1i,
+                          "round_trip_ok": rc1i == 1 and out1 == text, "kind": "port", "cores": 1},
+            "libz": {"deflate_gbs": len(text) / dz1 / 1e9, "inflate_gbs": len(text) / dz1i / 1e9, "ratio": len(z1) / len(text),
+                     "round_trip_ok": back == text, "cores": 1},
+        }
+    return out
 
 
 def workload_config(args, world):
@@ -141,12 +215,7 @@ def run_reference(args, rank, world):
     not be compiled here), one host thread -- the reference is single-threaded -- on a bounded sample per step."""
     if rank != 0:
         return
-    from tests.oracle_binding import Oracle
-
-    so = os.path.join(ROOT, "oracle", "libzk_oracle.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    oracle = Oracle(so)
+    oracle = _oracle()
     sample_mib = min(args.cpu_sample_mib, 16)
     data = make_corpus(args.workload, sample_mib << 20).tobytes()
     for _ in range(min(args.warmup, 1)):
@@ -162,10 +231,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": dict(workload_config(args, args.gpus), sample="each step deflates the first %d MiB of that corpus on one host core "
-                       "(the reference is single-threaded)" % sample_mib),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "first %d MiB of the %s corpus per step" % (sample_mib, args.workload)},
+                         "sample": "each step deflates the first %d MiB of the %s corpus on one host core (the reference is "
+                                   "single-threaded: one core is every thread it can use)" % (sample_mib, args.workload)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -279,6 +348,19 @@ def main():
         out_len, status = shard.last_body_len, shard.last_status
     if status != 0:
         raise SystemExit("deflate status %d" % status)
+    # the stream the timed region produced goes to libz once (the whole stream, on the host): nothing but the engine's own
+    # inflate would otherwise have seen it
+    verify = None
+    if shard is None and not args.no_verify:
+        import zlib
+
+        t0 = time.perf_counter()
+        back = zlib.decompress(d_out[:out_len].cpu().numpy().tobytes())
+        verify = {"libz_inflate_of_the_timed_stream": "bit-exact" if back == host.tobytes() else "MISMATCH",
+                  "bytes": len(back), "seconds": time.perf_counter() - t0}
+        del back
+        if verify["libz_inflate_of_the_timed_stream"] != "bit-exact":
+            raise SystemExit("libz does not reproduce the input from the timed region's stream")
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -432,10 +514,10 @@ def main():
         "config": workload_config(args, world),
         "compressed_ratio": total_out / (n * world),
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
-        "inflate": inflate, "e2e": e2e,
+        "inflate": inflate, "e2e": e2e, "verify": verify,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, args.level, args.cpu_sample_mib)
+        line["cpu_baseline"] = cpu_baseline(args.workload, args.level, args.cpu_sample_mib, args.config1_mib)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

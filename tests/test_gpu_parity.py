@@ -192,16 +192,47 @@ def test_reference_error_vectors(engine, oracle):
     assert _same_as_reference(engine, oracle, bytes(z), 64) == Z_DATA_ERROR  # trailer mismatch, bytes still out
 
 
+def _truncation_cuts(full):
+    n = len(full)
+    return sorted({2, 3, 4, 5, 10, 11, 12, 20, 40, 64, 65, n // 4, n // 2, n // 2 + 1, n - 9, n - 6, n - 5, n - 4, n - 3, n - 2, n - 1} & set(range(2, n)))
+
+
 def test_truncations_report_like_the_reference(engine, oracle):
+    """Truncated input: the same return code AND the same bytes as the reference.  The reference asks for maxLen bits
+    before every symbol (CH:128 peek(maxLen), BR:48-57 fill) and returns what it had written so far (IS:425-428)."""
+    rng = random.Random(9)
     data = b"truncate me " * 3000
-    full = zlib.compress(data, 6)
-    for cut in (3, 10, len(full) // 2, len(full) - 5, len(full) - 1):
-        piece = full[:cut]
-        want_rc, want_out, _, _ = oracle.inflate(piece, cap=len(data) + 8)
-        rc, out, _ = engine.inflate(piece, len(data) + 8)
-        assert rc == want_rc == Z_BUF_ERROR
-        # the reference needs maxLen bits before each symbol; both stop within a few symbols of each other
-        assert abs(len(out) - len(want_out)) <= 258 * 2
+    mixed = bytes(rng.randrange(256) for _ in range(3000)) + b"abcdefgh" * 500 + bytes(2000) + b"the quick brown fox " * 300
+    streams = [zlib.compress(data, 6), zlib.compress(mixed, 9), zlib.compress(mixed, 1), zlib.compress(mixed, 0),
+               zlib.compress(bytes(rng.randrange(256) for _ in range(70000)), 0)]  # dynamic, fixed, stored (one and two blocks)
+    own = engine.deflate(mixed * 8, 6)
+    assert own[0] == Z_OK
+    streams.append(bytes(own[1]))  # the engine's own framing: sync markers, the lane decoder's fallback
+    for full in streams:
+        cap = len(zlib.decompress(full)) + 8
+        for cut in _truncation_cuts(full):
+            piece = full[:cut]
+            want_rc, want_out, want_second, _ = oracle.inflate(piece, cap=cap)
+            rc, out, _ = engine.inflate(piece, cap)
+            assert rc == want_rc, (cut, len(full), rc, want_rc)
+            assert want_rc in (Z_BUF_ERROR, Z_DATA_ERROR)
+            assert len(out) == len(want_out) == want_second, (cut, len(full), len(out), len(want_out), want_second)
+            assert bytes(out) == want_out, (cut, len(full))
+
+
+def test_truncation_inside_a_dynamic_header_and_stored_length(engine, oracle):
+    data = bytes(range(256)) * 40 + b"header header header " * 200
+    dyn = zlib.compress(data, 9)
+    assert (dyn[2] >> 1) & 3 == 2  # first block is dynamic
+    for cut in range(2, 60):  # the code-length code and the two length sequences end somewhere in here
+        want_rc, want_out, _, _ = oracle.inflate(dyn[:cut], cap=len(data) + 8)
+        rc, out, _ = engine.inflate(dyn[:cut], len(data) + 8)
+        assert (rc, bytes(out)) == (want_rc, want_out), cut
+    stored = zlib.compress(data[:300], 0)
+    for cut in range(2, 12):  # BFINAL/BTYPE, LEN, NLEN, first payload bytes
+        want_rc, want_out, _, _ = oracle.inflate(stored[:cut], cap=400)
+        rc, out, _ = engine.inflate(stored[:cut], 400)
+        assert (rc, bytes(out)) == (want_rc, want_out), cut
 
 
 @pytest.mark.parametrize("level", [0, 1, 6, 9])

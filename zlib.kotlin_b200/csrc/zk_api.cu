@@ -404,7 +404,8 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         return ZK_OK;
     }
     if (!strcmp(name, "host_slab_bytes") || !strcmp(name, "host_first_slab_bytes")) {  // 0 = built-in
-        if (value < 0 || (value && (value < (1 << 20) || value % 65536))) return ZK_STREAM_ERROR;
+        // at most one device slab (run_deflate clamps to that: a larger host slab would index past its per-slab events)
+        if (value < 0 || value > (int64_t)kSlabBytes || (value && (value < (1 << 20) || value % 65536))) return ZK_STREAM_ERROR;
         (name[5] == 's' ? c->opt_host_slab : c->opt_host_first_slab) = value;
         return ZK_OK;
     }
@@ -454,7 +455,9 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
 
 uint32_t zk_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return adler32_combine(a1, a2, len2); }
 
-uint64_t zk_compress_bound(uint64_t n) { return n + (n >> 11) + 64; }  // 10 bytes per stored 32 KiB block + framing
+// 10 bytes per stored block (header + sync marker) of the smallest block span the "block_bytes" option allows (4 KiB),
+// + framing: holds for every block_bytes, on incompressible data too
+uint64_t zk_compress_bound(uint64_t n) { return n + 10 * (n / 4096 + 1) + 64; }
 
 void zk_zlib_header(int level, uint8_t out2[2]) {
     const int flevel = level >= 9 ? 3 : level >= 6 ? 2 : level >= 2 ? 1 : 0;  // DS:27-33

@@ -47,10 +47,10 @@ namespace {
 constexpr int kThreadsLz = 1024;
 constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
-constexpr int kRun = 4;                      // consecutive positions per lane
+constexpr int kRun = 2;                      // consecutive positions per lane
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
 constexpr int kStripsPerGroup = kGroup / kStrip;
-constexpr int kTaskCap = 128;                // compare tasks a warp queues before it runs them
+constexpr int kTaskCap = kStrip;              // compare tasks a warp queues before it runs them
 constexpr int kParserWarps = 8;
 constexpr int kFirstParserWarp = 16;         // warps 16..23: two per SM sub-partition
 constexpr int kBuilderWarp = 31;
@@ -64,7 +64,7 @@ constexpr int kCap = 16;  // candidates are compared over 16 bytes; the nearest 
 // text: every group probes in its first kProbeSample strips only, and in all of them when the sample of the group
 // before it had at least kProbeThreshold hits.  Strips are fixed ranges of positions, so the decision does not depend
 // on which warp happens to search them.
-constexpr int kProbeSample = 4;
+constexpr int kProbeSample = 512 / kStrip;  // 512 positions
 constexpr int kProbeThreshold = 8;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -352,17 +352,25 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
     bool walk[kRun];
     {
         // the links of the four positions (one 8-byte load) and the byte a candidate has to match (index 3)
-        const uint2 lk = *reinterpret_cast<const uint2 *>(&s.prev[p0 & 32767]);
-        c16[0] = lk.x & 0xFFFFu;
-        c16[1] = lk.x >> 16;
-        c16[2] = lk.y & 0xFFFFu;
-        c16[3] = lk.y >> 16;
-        const uint32_t wa = ad.ring_a + ((uint32_t)p0 & 0xFFFCu);
-        const uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4);
-        need[0] = w0 >> 24;
-        need[1] = w1 & 0xFFu;
-        need[2] = (w1 >> 8) & 0xFFu;
-        need[3] = (w1 >> 16) & 0xFFu;
+        if constexpr (kRun == 4) {
+            const uint2 lk = *reinterpret_cast<const uint2 *>(&s.prev[p0 & 32767]);
+            c16[0] = lk.x & 0xFFFFu;
+            c16[1] = lk.x >> 16;
+            c16[2] = lk.y & 0xFFFFu;
+            c16[3] = lk.y >> 16;
+            const uint32_t wa = ad.ring_a + ((uint32_t)p0 & 0xFFFCu);
+            const uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4);
+            need[0] = w0 >> 24;
+            need[1] = w1 & 0xFFu;
+            need[2] = (w1 >> 8) & 0xFFu;
+            need[3] = (w1 >> 16) & 0xFFu;
+        } else {
+            const uint32_t lk = *reinterpret_cast<const uint32_t *>(&s.prev[p0 & 32767]);
+            c16[0] = lk & 0xFFFFu;
+            c16[1] = lk >> 16;
+            need[0] = lds_u8(ad.ring_a + ((uint32_t)(p0 + 3) & 0xFFFFu));
+            need[1] = lds_u8(ad.ring_a + ((uint32_t)(p0 + 4) & 0xFFFFu));
+        }
     }
 #pragma unroll
     for (int r = 0; r < kRun; ++r) {
@@ -372,11 +380,15 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
         lastd[r] = 0;
         walk[r] = lp.chain > 0 && maxlen[r] >= 4;
     }
-    *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (kRun == 4) *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(0u, 0u, 0u, 0u);
+    else *reinterpret_cast<uint2 *>(&mv[mvi(rel0)]) = make_uint2(0u, 0u);
     // ---- walk: one chain link of each of the four positions per trip, branch-free: the eight loads (next link and test
     // byte of four candidates) are in flight together; candidates that pass the byte test are queued, then compared
     for (int k = 0; k < lp.chain; ++k) {
-        if (!__any_sync(kFull, walk[0] || walk[1] || walk[2] || walk[3])) break;
+        bool any_walk = false;
+#pragma unroll
+        for (int r = 0; r < kRun; ++r) any_walk = any_walk || walk[r];
+        if (!__any_sync(kFull, any_walk)) break;
         uint32_t d[kRun], nl[kRun], cb[kRun];
 #pragma unroll
         for (int r = 0; r < kRun; ++r) {
@@ -401,18 +413,22 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
         if ((k & 1) && k + 1 < lp.chain) {
             // deep chains: a position whose best candidate already fills the 16-byte compare is done (a farther one can
             // only tie, and the nearest wins a tie)
-            const uint4 mw = *reinterpret_cast<const uint4 *>(&mv[mvi(rel0)]);
-            if ((mw.x >> 16) >= (uint32_t)kCap) walk[0] = false;
-            if ((mw.y >> 16) >= (uint32_t)kCap) walk[1] = false;
-            if ((mw.z >> 16) >= (uint32_t)kCap) walk[2] = false;
-            if ((mw.w >> 16) >= (uint32_t)kCap) walk[3] = false;
+#pragma unroll
+            for (int r = 0; r < kRun; ++r)
+                if ((mv[mvi(rel0) + r] >> 16) >= (uint32_t)kCap) walk[r] = false;
         }
     }
     // ---- finish: probes, extension, filters ----
     int best[kRun], bestd[kRun];
     {
-        const uint4 mw = *reinterpret_cast<const uint4 *>(&mv[mvi(rel0)]);
-        const uint32_t w[kRun] = {mw.x, mw.y, mw.z, mw.w};
+        uint32_t w[kRun];
+        if constexpr (kRun == 4) {
+            const uint4 mw = *reinterpret_cast<const uint4 *>(&mv[mvi(rel0)]);
+            w[0] = mw.x, w[1] = mw.y, w[2] = mw.z, w[3] = mw.w;
+        } else {
+            const uint2 mw = *reinterpret_cast<const uint2 *>(&mv[mvi(rel0)]);
+            w[0] = mw.x, w[1] = mw.y;
+        }
 #pragma unroll
         for (int r = 0; r < kRun; ++r) {
             best[r] = (int)(w[r] >> 16);
@@ -439,11 +455,11 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
             int hits = 0;
 #pragma unroll
             for (int r = 0; r < kRun; ++r) {
-                const int sh = 8 * r;
+                const int sh = 8 * (int)(((uint32_t)p0 & 3u) + r);  // < 32: p0 is a multiple of kRun
                 uint32_t bk[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bk[j] = r ? __funnelshift_r(wd[j], wd[j + 1], sh) : wd[j];
-                const uint32_t cw = r ? __funnelshift_r(wd[4], wd[5], sh) : wd[4];
+                for (int j = 0; j < 4; ++j) bk[j] = __funnelshift_r(wd[j], wd[j + 1], sh);
+                const uint32_t cw = __funnelshift_r(wd[4], wd[5], sh);
                 const uint32_t c0 = cw & 0xFFFFFFu;
                 int hit = 0;
                 if ((bk[0] & 0xFFFFFFu) == c0) hit = 16;
@@ -465,9 +481,10 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
                 }
             }
             if (strip < kProbeSample) {
-                const int h0 = __popc(__ballot_sync(kFull, hits >= 1)), h1 = __popc(__ballot_sync(kFull, hits >= 2)),
-                          h2 = __popc(__ballot_sync(kFull, hits >= 3)), h3 = __popc(__ballot_sync(kFull, hits >= 4));
-                if (lane == 0 && h0) atomicAdd(&s.probe_hits[t & 3], h0 + h1 + h2 + h3);
+                int total = 0;
+#pragma unroll
+                for (int j = 0; j < kRun; ++j) total += __popc(__ballot_sync(kFull, hits > j));
+                if (lane == 0 && total) atomicAdd(&s.probe_hits[t & 3], total);
             }
         }
     }
@@ -540,7 +557,8 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
         if (b < lp.min_len || (lp.filtered && b <= 5)) b = 0;
         word[r] = b ? ((uint32_t)b << 16) | (uint32_t)(bestd[r] - 1) : 0u;
     }
-    *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(word[0], word[1], word[2], word[3]);
+    if constexpr (kRun == 4) *reinterpret_cast<uint4 *>(&mv[mvi(rel0)]) = make_uint4(word[0], word[1], word[2], word[3]);
+    else *reinterpret_cast<uint2 *>(&mv[mvi(rel0)]) = make_uint2(word[0], word[1]);
 }
 
 // ---- parser: eight warps turn the per-position matches of group t into tokens -------------------------------
@@ -721,33 +739,26 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     const uint32_t tok_off = s.carry_tok_off[par];
     if (entered) {
         uint32_t *dst = a.tokens + (uint64_t)unit_index * a.unit_bytes + tok_off + (uint32_t)(before + incl - cnt);
-        {
-            uint32_t v = visited2;
-            const int last2 = ismatch2 ? 31 - __clz(ismatch2) : -1;
-            while (v) {
-                const int i = __ffs((int)v) - 1;
-                v &= v - 1u;
-                uint32_t tok;
-                if ((ismatch2 >> i) & 1u) {
-                    const uint32_t w = mv[mvi(seg0 + i - g0)];
-                    tok = (i == last2 && cut_len) ? (((uint32_t)cut_len << 16) | (w & 0xFFFFu)) : w;
-                } else {
-                    tok = ring_load8(s.ring, (uint32_t)(seg0 + i));
-                }
-                *dst++ = tok;
+        // the real prefix covers positions before `m`, the speculative tokens the positions from `m` on: one mask.  The 16
+        // match words and the 16 bytes of the segment arrive with five independent vector loads; the stores are
+        // predicated straight-line code (a loop over the set bits waits for shared memory once per token)
+        const uint32_t vm = visited2 | spec_mask, im = ismatch2 | (ismatch & spec_mask);
+        const int last2 = (cut_len && ismatch2) ? 31 - __clz(ismatch2) : -1;
+        const uint32_t *mp = mv + mvi(seg0 - g0);
+        const uint4 m0 = *reinterpret_cast<const uint4 *>(mp), m1 = *reinterpret_cast<const uint4 *>(mp + 4),
+                    m2 = *reinterpret_cast<const uint4 *>(mp + 8), m3 = *reinterpret_cast<const uint4 *>(mp + 12);
+        const uint4 rb = *reinterpret_cast<const uint4 *>(s.ring + (((uint32_t)seg0 >> 2) & 0x3FFFu));
+        const uint32_t mw[16] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w, m3.x, m3.y, m3.z, m3.w};
+        const uint32_t bw[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int i = 0; i < kSeg; ++i) {
+            if ((vm >> i) & 1u) {
+                uint32_t tok = ((im >> i) & 1u) ? mw[i] : ((bw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                if (i == last2) tok = ((uint32_t)cut_len << 16) | (tok & 0xFFFFu);
+                dst[__popc(vm & ((1u << i) - 1u))] = tok;
             }
         }
-        {
-            uint32_t v = spec_mask;
-            while (v) {
-                const int i = __ffs((int)v) - 1;
-                v &= v - 1u;
-                uint32_t tok;
-                if ((ismatch >> i) & 1u) tok = mv[mvi(seg0 + i - g0)];
-                else tok = ring_load8(s.ring, (uint32_t)(seg0 + i));
-                *dst++ = tok;
-            }
-        }
+        dst += __popc(vm);
         if (gap >= 3) {
             *dst++ = ((uint32_t)gap << 16) | (uint32_t)lastd;
         } else {
