@@ -44,7 +44,10 @@ namespace zk {
 
 namespace {
 
-constexpr int kThreadsLz = 1024;
+#ifndef ZK_LZ_THREADS
+#define ZK_LZ_THREADS 768
+#endif
+constexpr int kThreadsLz = ZK_LZ_THREADS;
 constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
 constexpr int kRun = 2;                      // consecutive positions per lane
@@ -52,8 +55,8 @@ constexpr int kStrip = 32 * kRun;            // positions per work-stealing stri
 constexpr int kStripsPerGroup = kGroup / kStrip;
 constexpr int kTaskCap = kStrip;              // compare tasks a warp queues before it runs them
 constexpr int kParserWarps = 8;
-constexpr int kFirstParserWarp = 16;         // warps 16..23: two per SM sub-partition
-constexpr int kBuilderWarp = 31;
+constexpr int kFirstParserWarp = kWarpsLz - kParserWarps;  // the last eight warps: two per SM sub-partition
+constexpr int kBuilderWarp = 0;
 constexpr int kSeg = kGroup / (32 * kParserWarps);  // parser: positions per lane segment
 constexpr int kSegs = kGroup / kSeg;
 constexpr int kHistGroups = kWindow / kGroup;
@@ -313,12 +316,13 @@ struct StripAddrs {
 // The queued compare tasks of a warp: 16 bytes at the position against 16 bytes at the candidate, clipped to the end of
 // the deflate block; the longest, on a tie the nearest, stays in the match word (a shared-memory max over
 // len << 16 | ~dist: the order in which the tasks are processed does not matter).
-__device__ __forceinline__ void run_tasks(const StripAddrs &ad, const uint32_t *tq, int T, int32_t g0, int32_t blk_end_q, int lane) {
+__device__ __forceinline__ void run_tasks(const StripAddrs &ad, int T, int32_t g0, int32_t blk_end_q, int lane) {
     __syncwarp();
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int ti = t0 + lane;
         if (ti < T) {
-            const uint32_t task = tq[ti];  // an ordinary load: it must stay behind the __syncwarp above
+            uint32_t task;  // a volatile load: it stays behind the __syncwarp above
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(task) : "r"(ad.tq_a + 4u * (uint32_t)ti) : "memory");
             const uint32_t rel = task >> 16, d = task & 0xFFFFu;
             const uint32_t p = (uint32_t)g0 + rel;
             const int maxlen = min(kMaxMatch, blk_end_q - (int32_t)p);
@@ -404,15 +408,18 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
         for (int r = 0; r < kRun; ++r) {
             const bool pass = walk[r] && cb[r] == need[r];
             const uint32_t b = __ballot_sync(kFull, pass);
-            if (pass) s.tq[warp][T + __popc(b & lt)] = ((uint32_t)(rel0 + r) << 16) | d[r];
+            if (pass) {
+                const uint32_t task = ((uint32_t)(rel0 + r) << 16) | d[r];
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ad.tq_a + 4u * (uint32_t)(T + __popc(b & lt))), "r"(task) : "memory");
+            }
             T += __popc(b);
             if (walk[r]) lastd[r] = d[r];
             c16[r] = nl[r];
         }
-        run_tasks(ad, s.tq[warp], T, g0, blk_end_q, lane);
-        if ((k & 1) && k + 1 < lp.chain) {
-            // deep chains: a position whose best candidate already fills the 16-byte compare is done (a farther one can
-            // only tie, and the nearest wins a tie)
+        run_tasks(ad, T, g0, blk_end_q, lane);
+        if (k + 1 < lp.chain) {
+            // a position whose best candidate already fills the 16-byte compare is done (a farther one can only tie, and
+            // the nearest wins a tie): long repeats would otherwise queue a task per position and link
 #pragma unroll
             for (int r = 0; r < kRun; ++r)
                 if ((mv[mvi(rel0) + r] >> 16) >= (uint32_t)kCap) walk[r] = false;
@@ -789,7 +796,11 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
 __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LzSmem &s = *reinterpret_cast<LzSmem *>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // read once through volatile asm: the compiler otherwise re-derives lane and warp from %tid wherever it is short of
+    // registers (an S2R plus arithmetic in every inner loop)
+    uint32_t tid_once;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_once));
+    const int lane = (int)(tid_once & 31u), warp = (int)(tid_once >> 5);
     const bool is_builder = warp == kBuilderWarp;
     const bool is_parser = warp >= kFirstParserWarp && warp < kFirstParserWarp + kParserWarps;
     const int parser_index = warp - kFirstParserWarp;
