@@ -118,7 +118,7 @@ def test_ratio_against_reference_and_libz(engine, oracle, level, kind):
     ref_size = len(oracle.deflate(data, level)[1])
     assert len(stream) <= 1.02 * ref_size, (len(stream), ref_size)  # north_star tolerance
     if level >= 6:  # and close to libz at the same level
-        assert len(stream) <= 1.03 * len(zlib.compress(data, level))
+        assert len(stream) <= 1.02 * len(zlib.compress(data, level))  # size <= 1.02 x libz at the same level
 
 
 def test_strategies(engine, oracle):

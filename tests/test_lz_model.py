@@ -17,17 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODEL_SRC = os.path.join(ROOT, "tools", "lzmodel2.cpp")
 MODEL_SO = os.path.join(ROOT, "tools", "liblzmodel2.so")
 
-# zlib.kotlin_b200/csrc/zk_lz77.cu level_params(): chain, nice, lazy, max_lazy, probe_adaptive
+# zlib.kotlin_b200/csrc/zk_lz77.cu level_params(): chain, lazy, max_lazy, probe_adaptive, lazy2, far4
 LEVELS = {
-    1: (1, 32, 0, 16, 1),
-    2: (1, 32, 1, 8, 1),
-    3: (1, 64, 1, 16, 1),
-    4: (2, 64, 1, 8, 1),
-    5: (2, 64, 1, 16, 1),
-    6: (2, 128, 1, 16, 1),
-    7: (4, 128, 1, 32, 1),
-    8: (8, 258, 1, 128, 0),
-    9: (16, 258, 1, 258, 0),
+    1: (1, 0, 16, 1, 0, 1024),
+    2: (1, 1, 4, 1, 0, 1024),
+    3: (1, 1, 8, 1, 0, 1024),
+    4: (1, 1, 16, 1, 0, 1024),
+    5: (1, 1, 16, 1, 8, 1024),
+    6: (1, 1, 16, 1, 16, 512),
+    7: (2, 1, 16, 1, 16, 512),
+    8: (4, 1, 32, 1, 16, 1024),
+    9: (8, 1, 258, 0, 16, 1024),
 }
 
 
@@ -44,13 +44,13 @@ def build_model():
 
 
 def model_tokens(lib, data, level, unit, block=32768, strategy=0):
-    chain, nice, lazy, max_lazy, adaptive = LEVELS[level]
+    chain, lazy, max_lazy, adaptive, lazy2, far4 = LEVELS[level]
     min_len, filtered = 3, 0
     if strategy == 1:
         filtered = 1
     if strategy == 2:
         chain, min_len = 0, 259
-    params = np.array([chain, nice, lazy, max_lazy, 256, 1024, min_len, filtered, adaptive, 4, 8, 16, block, unit], dtype=np.int32)
+    params = np.array([chain, 128, lazy, max_lazy, 256, far4, min_len, filtered, adaptive, 4, 8, 16, block, unit, lazy2], dtype=np.int32)
     n = len(data)
     buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     buf = np.ascontiguousarray(buf)
@@ -127,7 +127,7 @@ def corpus_cases():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("level", [1, 2, 6, 7, 9])
+@pytest.mark.parametrize("level", [1, 3, 6, 7, 9])
 def test_kernel_tokens_equal_model(engine, level):
     import zlib
 

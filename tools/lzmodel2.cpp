@@ -35,6 +35,7 @@ struct Params {
     int seg = 16;
     int block = 32768;
     int unit = 524288;
+    int lazy2 = 0;  // > 0: a match shorter than this also gives way to one at p + 2 that is at least two longer
 };
 
 struct Stats {
@@ -178,7 +179,7 @@ void run_unit(const uint8_t *base, int32_t h0q, uint32_t ulen, const Params &P, 
     int32_t carry = kWindow;
     uint32_t blk_begin = (uint32_t)out.tokens.size();
     uint32_t prev_hits = 1u << 30;  // first group of a unit: probe everywhere
-    std::vector<Match> M(kGroup + 1);
+    std::vector<Match> M(kGroup + 2);
     for (int32_t g0 = kWindow; g0 < U.data_end_q; g0 += kGroup) {
         const int32_t gend = std::min(g0 + kGroup, U.data_end_q);
         // ---- the best match of every position ----
@@ -192,12 +193,14 @@ void run_unit(const uint8_t *base, int32_t h0q, uint32_t ulen, const Params &P, 
             if (M[p - g0].probe_hit) ++st.probe_hits;
         }
         M[gend - g0] = Match{0, 0, false};
+        M[gend - g0 + 1] = Match{0, 0, false};
         prev_hits = hits;
         // the step of the parse at p: 1 for a literal, the match length otherwise
         auto step_at = [&](int32_t p) {
             const int len = M[p - g0].len;
             if (len == 0) return 1;
             if (P.lazy && len < P.max_lazy && p + 1 < gend && M[p + 1 - g0].len > len) return 1;
+            if (len < P.lazy2 && p + 2 < gend && M[p + 2 - g0].len > len + 1) return 1;
             return len;
         };
         std::vector<SegRec> rec(nseg);
@@ -401,7 +404,7 @@ extern "C" long long lzm2_tokens(const uint8_t *in, unsigned long long n, unsign
                                  uint32_t *tokens, uint32_t *blk_begin, uint32_t *blk_count, unsigned long long *nblocks) {
     Params P;
     int *fields[] = {&P.chain, &P.nice, &P.lazy, &P.max_lazy, &P.far3, &P.far4, &P.min_len, &P.filtered, &P.probe_adaptive,
-                     &P.probe_sample, &P.probe_thresh, &P.seg, &P.block, &P.unit};
+                     &P.probe_sample, &P.probe_thresh, &P.seg, &P.block, &P.unit, &P.lazy2};
     for (int i = 0; i < nparams && i < (int)(sizeof(fields) / sizeof(fields[0])); ++i) *fields[i] = params[i];
     Stats st;
     Out out;
@@ -426,7 +429,7 @@ int main(int argc, char **argv) {
         else if (k == "max_lazy") P.max_lazy = v; else if (k == "far3") P.far3 = v; else if (k == "far4") P.far4 = v;
         else if (k == "min_len") P.min_len = v; else if (k == "probe_adaptive") P.probe_adaptive = v;
         else if (k == "probe_sample") P.probe_sample = v; else if (k == "probe_thresh") P.probe_thresh = v;
-        else if (k == "seg") P.seg = v; else if (k == "block") P.block = v; else if (k == "unit") P.unit = v;
+        else if (k == "seg") P.seg = v; else if (k == "lazy2") P.lazy2 = v; else if (k == "block") P.block = v; else if (k == "unit") P.unit = v;
         else { fprintf(stderr, "unknown key %s\n", k.c_str()); return 1; }
     }
     FILE *f = fopen(argv[1], "rb");

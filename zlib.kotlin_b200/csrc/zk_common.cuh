@@ -28,6 +28,7 @@ struct LevelParams {
     int nice;      // stop searching once a match this long is found
     int lazy;      // one-step lazy evaluation
     int max_lazy;  // a match at least this long is taken without looking at the next position (zlib's max_lazy)
+    int lazy2;     // > 0: a match shorter than this also gives way to a match at p + 2 that is at least two longer
     int far3;      // a length-3 match farther than this is dropped
     int far4;      // a length-4 match farther than this is dropped
     int min_len;   // 3, or 259 for Z_HUFFMAN_ONLY (no matches)

@@ -573,10 +573,11 @@ __device__ __forceinline__ int tok_len(uint32_t w) { return (int)((w >> 16) & 0x
 
 // The step of the parse at p: 1 for a literal, the match length otherwise (greedy with one-step lazy evaluation).
 __device__ __forceinline__ int decide(const uint32_t *mv, const LevelParams &lp, int32_t g0, int32_t gend, int32_t p) {
-    // both words are loaded unconditionally (one slot of slack behind the group keeps p + 1 in bounds)
+    // the three words are loaded unconditionally (two slots of slack behind the group keep p + 2 in bounds)
     const int len = tok_len(mv[mvi(p - g0)]);
     const int next = tok_len(mv[mvi(p + 1 - g0)]);
-    const bool defer = lp.lazy && len < lp.max_lazy && p + 1 < gend && next > len;
+    const int next2 = tok_len(mv[mvi(p + 2 - g0)]);
+    const bool defer = (lp.lazy && len < lp.max_lazy && p + 1 < gend && next > len) || (len < lp.lazy2 && p + 2 < gend && next2 > len + 1);
     return (len == 0 || defer) ? 1 : len;
 }
 
@@ -615,13 +616,15 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
             for (int c = 0; c < 4; ++c) {
                 uint4 nxt;
                 if (c < 3) nxt = *reinterpret_cast<const uint4 *>(mp + 4 * c + 4);
-                else nxt = make_uint4(mv[mvi(seg0 - g0 + kSeg)], 0u, 0u, 0u);
-                const uint32_t w[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+                else nxt = make_uint4(mv[mvi(seg0 - g0 + kSeg)], mv[mvi(seg0 - g0 + kSeg + 1)], 0u, 0u);
+                const uint32_t w[6] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y};
                 uint32_t packed = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int len = tok_len(w[j]), nextlen = tok_len(w[j + 1]);
-                    const bool defer = lp.lazy && len < lp.max_lazy && seg0 + 4 * c + j + 1 < gend && nextlen > len;
+                    const int len = tok_len(w[j]), nextlen = tok_len(w[j + 1]), next2len = tok_len(w[j + 2]);
+                    const int32_t pos = seg0 + 4 * c + j;
+                    const bool defer = (lp.lazy && len < lp.max_lazy && pos + 1 < gend && nextlen > len) ||
+                                       (len < lp.lazy2 && pos + 2 < gend && next2len > len + 1);
                     const bool lit = len == 0 || defer;
                     const uint32_t step = lit ? 1u : (uint32_t)min(len, 64);
                     packed |= step << (8 * j);
@@ -931,20 +934,24 @@ LevelParams level_params(int level, int strategy) {
     p.far4 = 1024;
     p.min_len = 3;
     p.filtered = strategy == ZK_FILTERED;
-    p.probe_adaptive = level <= 7;
-    p.nice = 128;
+    p.probe_adaptive = level <= 8;
+    p.nice = 128;  // (a compare covers 16 bytes; what fills them is extended to its end: nice plays no role any more)
     p.lazy = 1;
     p.max_lazy = 16;
+    p.lazy2 = 0;
+    // One chain link per position costs about one cycle per byte and SM (profiles/level_sweep_r2.json): level 6 walks
+    // one link -- with the second look-ahead it lands within 2 % of libz level 6 on the text corpus and within 0.5 % on
+    // the mixed one -- level 7 two (libz level-6 size or better), level 9 eight (smaller than libz level 9).
     switch (level) {
-        case 1: p.chain = 1; p.lazy = 0; p.nice = 32; break;
-        case 2: p.chain = 1; p.nice = 32; p.max_lazy = 8; break;
-        case 3: p.chain = 1; p.nice = 64; break;
-        case 4: p.chain = 2; p.nice = 64; p.max_lazy = 8; break;
-        case 5: p.chain = 2; p.nice = 64; break;
-        case 6: p.chain = 2; break;
-        case 7: p.chain = 4; p.max_lazy = 32; break;
-        case 8: p.chain = 8; p.nice = 258; p.max_lazy = 128; break;
-        default: p.chain = 16; p.nice = 258; p.max_lazy = 258; break;
+        case 1: p.chain = 1; p.lazy = 0; break;
+        case 2: p.chain = 1; p.max_lazy = 4; break;
+        case 3: p.chain = 1; p.max_lazy = 8; break;
+        case 4: p.chain = 1; break;
+        case 5: p.chain = 1; p.lazy2 = 8; break;
+        case 6: p.chain = 1; p.lazy2 = 16; p.far4 = 512; break;
+        case 7: p.chain = 2; p.lazy2 = 16; p.far4 = 512; break;
+        case 8: p.chain = 4; p.lazy2 = 16; p.max_lazy = 32; break;
+        default: p.chain = 8; p.lazy2 = 16; p.max_lazy = 258; break;
     }
     if (level < 1) p.chain = 1;
     if (strategy == ZK_HUFFMAN_ONLY) {
