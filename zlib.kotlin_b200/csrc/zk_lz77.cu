@@ -198,13 +198,23 @@ __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const Un
 // hash in the batch (an exact match.any; cheap here because many warps share its latency, unlike in the serial builder).
 // It is a pure function of the batch, so it runs in parallel on the searcher warps and the serial builder is left with
 // table updates only.
-__device__ __forceinline__ void prep_strip(LzSmem &s, int t, int pos0, int lane) {
-    uint8_t *pp = s.prep[t & 1] + pos0;
+// match.any answers late (a fifth of all stall samples sat behind it when its result was used at once): a strip's two
+// votes are issued before the strip is searched and their results are used after it.
+struct PrepVotes {
+    uint32_t eq[kStrip / 32];
+};
+__device__ __forceinline__ PrepVotes prep_issue(const LzSmem &s, int t, int pos0, int lane) {
+    PrepVotes v;
     const uint32_t q0 = (uint32_t)t * kGroup + pos0 + lane;
-#pragma unroll 2
+#pragma unroll
+    for (int u = 0; u < kStrip / 32; ++u) v.eq[u] = __match_any_sync(kFull, hash4(ring_load32(s.ring, q0 + u * 32)));
+    return v;
+}
+__device__ __forceinline__ void prep_finish(LzSmem &s, int t, int pos0, int lane, const PrepVotes &v) {
+    uint8_t *pp = s.prep[t & 1] + pos0;
+#pragma unroll
     for (int u = 0; u < kStrip / 32; ++u) {
-        const uint32_t hv = hash4(ring_load32(s.ring, q0 + u * 32));
-        const uint32_t eq = __match_any_sync(kFull, hv);
+        const uint32_t eq = v.eq[u];
         const uint32_t below = eq & ((1u << lane) - 1u);
         uint32_t info = below ? (0x40u | (uint32_t)(31 - __clz(below))) : 0u;
         if (((eq >> lane) >> 1) == 0u) info |= 0x80u;
@@ -569,16 +579,16 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
 }
 
 // ---- parser: eight warps turn the per-position matches of group t into tokens -------------------------------
-__device__ __forceinline__ int tok_len(uint32_t w) { return (int)((w >> 16) & 0x1FFu); }
 
 // The step of the parse at p: 1 for a literal, the match length otherwise (greedy with one-step lazy evaluation).
-__device__ __forceinline__ int decide(const uint32_t *mv, const LevelParams &lp, int32_t g0, int32_t gend, int32_t p) {
-    // the three words are loaded unconditionally (two slots of slack behind the group keep p + 2 in bounds)
-    const int len = tok_len(mv[mvi(p - g0)]);
-    const int next = tok_len(mv[mvi(p + 1 - g0)]);
-    const int next2 = tok_len(mv[mvi(p + 2 - g0)]);
-    const bool defer = (lp.lazy && len < lp.max_lazy && p + 1 < gend && next > len) || (len < lp.lazy2 && p + 2 < gend && next2 > len + 1);
-    return (len == 0 || defer) ? 1 : len;
+// (No bounds checks on p + 1 and p + 2: the match words behind the data and the two slack words behind the group are
+// zero, and a zero never makes a match give way.)
+__device__ __forceinline__ int decide(const uint32_t *mv, int max_lazy, int lazy2, int32_t g0, int32_t p) {
+    const int len = (int)(mv[mvi(p - g0)] >> 16);
+    const int next = (int)(mv[mvi(p + 1 - g0)] >> 16);
+    const int next2 = (int)(mv[mvi(p + 2 - g0)] >> 16);
+    const bool defer = ((len < max_lazy) & (next > len)) | ((len < lazy2) & (next2 > len + 1));
+    return ((len == 0) | defer) ? 1 : len;
 }
 
 __device__ __forceinline__ void parser_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kParserWarps * 32) : "memory"); }
@@ -600,49 +610,38 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
     const int32_t g0 = t * kGroup;
     const int32_t gend = min(g0 + kGroup, g.data_end_q);
     const int32_t seg0 = min(g0 + L * kSeg, gend), seg1 = min(seg0 + kSeg, gend);
-    // ---- pass A: speculative parse of this lane's segment from its first position, in registers: the 17 match words of
-    // the segment arrive with independent 16-byte loads, the step of every position (the lazy rule) is packed 8 bits per
-    // position, and "which positions does the parse visit" is 15 unrolled register operations.
+    // ---- pass A: speculative parse of this lane's segment from its first position, in registers: the 18 match words
+    // arrive with independent 16-byte loads; per position the step of the parse (the lazy rule) and, branch-free, "the
+    // parse visits position i + step if it visits i".
+    const int max_lazy = lp.lazy ? lp.max_lazy : 0, lazy2 = lp.lazy2;
     uint32_t visited = 0u, ismatch = 0u;
     int32_t my_exit = seg0, lastd = -1;
     {
         const int seg_len = seg1 - seg0;
         if (seg_len > 0) {
             const uint32_t *mp = mv + mvi(seg0 - g0);  // the segment's 16 words are contiguous
-            uint32_t st[4];
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(mp), q1 = *reinterpret_cast<const uint4 *>(mp + 4),
+                        q2 = *reinterpret_cast<const uint4 *>(mp + 8), q3 = *reinterpret_cast<const uint4 *>(mp + 12);
+            const uint32_t wa = mv[mvi(seg0 - g0 + kSeg)], wb = mv[mvi(seg0 - g0 + kSeg + 1)];
+            const uint32_t w[kSeg + 2] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, wa, wb};
+            int len[kSeg + 2];
+#pragma unroll
+            for (int i = 0; i < kSeg + 2; ++i) len[i] = (int)(w[i] >> 16);
             uint32_t mm = 0u;
-            uint4 cur = *reinterpret_cast<const uint4 *>(mp);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 nxt;
-                if (c < 3) nxt = *reinterpret_cast<const uint4 *>(mp + 4 * c + 4);
-                else nxt = make_uint4(mv[mvi(seg0 - g0 + kSeg)], mv[mvi(seg0 - g0 + kSeg + 1)], 0u, 0u);
-                const uint32_t w[6] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y};
-                uint32_t packed = 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int len = tok_len(w[j]), nextlen = tok_len(w[j + 1]), next2len = tok_len(w[j + 2]);
-                    const int32_t pos = seg0 + 4 * c + j;
-                    const bool defer = (lp.lazy && len < lp.max_lazy && pos + 1 < gend && nextlen > len) ||
-                                       (len < lp.lazy2 && pos + 2 < gend && next2len > len + 1);
-                    const bool lit = len == 0 || defer;
-                    const uint32_t step = lit ? 1u : (uint32_t)min(len, 64);
-                    packed |= step << (8 * j);
-                    if (!lit) mm |= 1u << (4 * c + j);
-                }
-                st[c] = packed;
-                cur = nxt;
-            }
             visited = 1u;
 #pragma unroll
-            for (int i = 0; i < kSeg - 1; ++i) {
-                const uint32_t tgt = (uint32_t)i + ((st[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-                if (((visited >> i) & 1u) && tgt < (uint32_t)kSeg) visited |= 1u << tgt;
+            for (int i = 0; i < kSeg; ++i) {
+                // bitwise, not short-circuit: the && / || form compiles to a branch per term
+                const bool defer = ((len[i] < max_lazy) & (len[i + 1] > len[i])) | ((len[i] < lazy2) & (len[i + 2] > len[i] + 1));
+                const bool lit = (len[i] == 0) | defer;
+                const int step = lit ? 1 : min(len[i], 16);  // anything from 16 on leaves the segment
+                mm |= (lit ? 0u : 1u) << i;
+                visited |= ((visited >> i) & 1u) << (i + step);
             }
-            if (seg_len < kSeg) visited &= (1u << seg_len) - 1u;
+            visited &= seg_len < kSeg ? (1u << seg_len) - 1u : 0xFFFFu;
             ismatch = visited & mm;
             const int lastpos = 31 - __clz(visited);
-            const int step = decide(mv, lp, g0, gend, seg0 + lastpos);
+            const int step = decide(mv, max_lazy, lazy2, g0, seg0 + lastpos);
             lastd = step > 1 ? (int32_t)(mp[lastpos] & 0xFFFFu) : -1;  // distance - 1
             my_exit = seg0 + lastpos + step;
         }
@@ -710,7 +709,7 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
                     met = true;
                     break;
                 }
-                int step = decide(mv, lp, g0, gend, p);
+                int step = decide(mv, max_lazy, lazy2, g0, p);
                 const uint32_t bit = 1u << (p - seg0);
                 if (step > 1 && p + step > my_exit) {
                     step = my_exit - p;
@@ -886,8 +885,10 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                     if (lane == 0) strip = atomicAdd(&s.work[i & 1], 1);
                     strip = __shfl_sync(kFull, strip, 0);
                     if (strip >= kStripsPerGroup) break;
-                    if (preparing) prep_strip(s, i + 2, strip * kStrip, lane);
+                    PrepVotes votes;
+                    if (preparing) votes = prep_issue(s, i + 2, strip * kStrip, lane);
                     if (searching) search_strip(s, cx, i, strip, lane, warp, probe_all);
+                    if (preparing) prep_finish(s, i + 2, strip * kStrip, lane, votes);
                 }
             }
             const long long t2 = clock64();
