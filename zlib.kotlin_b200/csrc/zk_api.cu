@@ -3,7 +3,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "zk_common.cuh"
@@ -343,6 +348,10 @@ static void staging_release(zk_ctx *c);
 
 void zk_ctx_destroy(zk_ctx *c) {
     if (!c) return;
+    for (zk_ctx *&h : c->helpers) {
+        if (h) zk_ctx_destroy(h);
+        h = nullptr;
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     staging_release(c);
@@ -409,6 +418,15 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         (name[5] == 's' ? c->opt_host_slab : c->opt_host_first_slab) = value;
         return ZK_OK;
     }
+    if (!strcmp(name, "inflate_pipe")) {  // 1: large marked streams go through the slab pipeline (default 0: one pass)
+        c->opt_inflate_pipe = value != 0;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "inflate_slab_bytes")) {  // compressed bytes per slab of the pipelined host-buffer inflate, 0 = built-in
+        if (value < 0 || (value && value < (1 << 20))) return ZK_STREAM_ERROR;
+        c->opt_inflate_slab = value;
+        return ZK_OK;
+    }
     if (!strcmp(name, "timing")) {
         c->opt_timing = value != 0;
         return ZK_OK;
@@ -427,6 +445,8 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
     if (!strcmp(name, "kernel_launches")) return c->launches;
     if (!strcmp(name, "h2d_bytes")) return c->h2d_bytes;
     if (!strcmp(name, "d2h_bytes")) return c->d2h_bytes;
+    if (!strcmp(name, "inflate_pipe_slabs")) return c->pipe_slabs;
+    if (!strcmp(name, "inflate_pipe_fallbacks")) return c->pipe_fallbacks;
     // device time per kernel class in microseconds / launches timed; call after zk_ctx_synchronize
     static const char *cls[] = {"lz77", "huffman", "pack", "adler", "inflate_decode", "inflate_other"};
     for (int i = 0; i < zk_ctx::kTimedClasses; ++i) {
@@ -793,6 +813,239 @@ int zk_deflate_shard(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const ui
     return host_deflate(c, hist, hist_len, in, n, level, strategy, out_body, cap, false, body_len, adler);
 }
 
+// ---- pipelined host-buffer inflate ---------------------------------------------------------------------------------
+// InflateStream.inflateZlib as a caller with host buffers sees it (IS:376-438).  In one pass the call is the sum of its
+// three legs: compressed bytes up, decode, output down (8 + 14 + 19.5 ms for 1 GiB in round 1).  A stream of this engine
+// has a sync marker after every block, so it can be cut into slabs at markers and every slab decoded as a shard body
+// (zk_inflate_shard_prepare_device: references into the output before the slab stay symbolic) on its own context, stream
+// and scratch, while the slabs behind it are still arriving; a slab is finished (zk_inflate_shard_finish_device) as soon
+// as the slab before it has been: its entry window is then simply the 32 KiB in front of it in the output buffer, and
+// its bytes go down to the host while the next slabs decode.  The cut points are found on the host with a short search
+// for 00 00 FF FF behind evenly spaced offsets; a false marker makes that slab's decode fail its validation, and then --
+// as for anything else that is not plainly a stream of this shape -- the call falls back to the one-pass path, which
+// owns the reference's return codes.  Returns kNotPiped when it did not handle the call.
+//
+// MEASURED (profiles/inflate_pipeline_r2.md, 1 GiB mixed corpus, one B200): the pipeline is correct and bit-exact but SLOWER
+// than one pass -- 50.7 ms with four slabs, 89 ms with eleven, against 41.2 ms -- because a slab's prepare costs ~12 ms
+// whatever its size (the lane decoder and the expander both run at the latency of ONE 32 KiB block decoded serially) and
+// the prepares of concurrent slabs overlap badly.  It is therefore opt-in ("inflate_pipe" = 1) until the decoder has
+// sub-block parallelism; the one-pass path stays the default.
+namespace {
+constexpr int kNotPiped = -1000;
+constexpr uint64_t kInflatePipeMin = 48ull << 20;   // compressed bytes from which the pipeline pays
+constexpr uint64_t kInflateSlab = 40ull << 20;      // compressed bytes per slab
+constexpr int kPipeWorkers = 4;
+
+struct PipeSlab {
+    uint64_t in_off = 0, in_len = 0, cap = 0;   // compressed range, output room reserved in the worker's scratch
+    uint64_t out_off = 0, out_len = 0;
+    uint32_t adler = 1;
+    cudaEvent_t in_ready = nullptr, done = nullptr;
+    bool prepared = false, finished = false;
+    double t_start = 0, t_prepared = 0, t_finish_begin = 0, t_finished = 0;  // ms since the call began (ZK_PIPE_DEBUG)
+};
+struct PipeState {
+    zk_ctx *c;
+    const uint8_t *d_in;
+    uint8_t *d_out, *out;
+    uint64_t cap;
+    std::vector<PipeSlab> slabs;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<bool> failed{false};
+    std::atomic<uint32_t> next{0};
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// one worker: takes slabs in order, prepares them, and finishes each once its predecessor has been finished
+void pipe_worker(PipeState *ps, zk_ctx *w, uint8_t *d_scratch) {
+    if (cudaSetDevice(ps->c->device) != cudaSuccess) {
+        ps->failed = true;
+        ps->cv.notify_all();
+        return;
+    }
+    uint64_t *d_result = reinterpret_cast<uint64_t *>(d_scratch);
+    uint16_t *d_tail = reinterpret_cast<uint16_t *>(d_scratch + 256);
+    const uint8_t *d_zero_window = d_scratch + 256 + 65536;  // 32 KiB of zeros: the window in front of the first slab
+    for (;;) {
+        const uint32_t k = ps->next.fetch_add(1);
+        if (k >= ps->slabs.size() || ps->failed) break;
+        PipeSlab &sl = ps->slabs[k];
+        sl.t_start = ps->ms();
+        bool ok = cudaStreamWaitEvent(w->stream, sl.in_ready, 0) == cudaSuccess;
+        if (ok) ok = zk_inflate_shard_prepare_device(w, ps->d_in + sl.in_off, sl.in_len, k ? 32768u : 0u, sl.cap, d_tail, d_result) == ZK_OK;
+        uint64_t res[4] = {0, 0, 0, 0};
+        if (ok) ok = cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, w->stream) == cudaSuccess &&
+                     cudaStreamSynchronize(w->stream) == cudaSuccess;
+        // a shard body is good when every block was decoded and it ended exactly at its end without a final block
+        if (ok) ok = (int)(int64_t)res[2] == ZK_OK && res[1] == sl.in_len && res[0] <= sl.cap && w->shard.valid;
+        uint64_t out_off = 0;
+        {
+            std::unique_lock<std::mutex> lk(ps->mu);
+            if (!ok) ps->failed = true;
+            sl.out_len = res[0];
+            sl.prepared = true;
+            sl.t_prepared = ps->ms();
+            ps->cv.notify_all();
+            // the slab before this one must have been finished: its output is this slab's entry window
+            ps->cv.wait(lk, [&] { return ps->failed || k == 0 || ps->slabs[k - 1].finished; });
+            if (ps->failed) break;
+            out_off = k ? ps->slabs[k - 1].out_off + ps->slabs[k - 1].out_len : 0;
+            sl.out_off = out_off;
+            if (out_off + sl.out_len > ps->cap) {
+                ps->failed = true;
+                ps->cv.notify_all();
+                break;
+            }
+        }
+        sl.t_finish_begin = ps->ms();
+        ok = k == 0 || cudaStreamWaitEvent(w->stream, ps->slabs[k - 1].done, 0) == cudaSuccess;
+        // (the first slab of a zlib stream has nothing in front of it; a later one the 32 KiB before its output)
+        const uint8_t *entry = k ? ps->d_out + out_off - 32768 : d_zero_window;
+        if (k && out_off < 32768) ok = false;  // cannot be: every slab before it holds whole 32 KiB blocks
+        if (ok) ok = zk_inflate_shard_finish_device(w, entry, ps->d_out + out_off, d_result) == ZK_OK;
+        if (ok) ok = cudaEventRecord(sl.done, w->stream) == cudaSuccess;
+        if (ok) ok = cudaStreamWaitEvent(ps->c->copy_out, sl.done, 0) == cudaSuccess;
+        if (ok && sl.out_len)
+            ok = cudaMemcpyAsync(ps->out + out_off, ps->d_out + out_off, sl.out_len, cudaMemcpyDeviceToHost, ps->c->copy_out) == cudaSuccess;
+        if (ok) ok = cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, w->stream) == cudaSuccess &&
+                     cudaStreamSynchronize(w->stream) == cudaSuccess;
+        if (ok) ok = (int)(int64_t)res[2] == ZK_OK || (int)(int64_t)res[2] == ZK_STREAM_END;
+        {
+            std::lock_guard<std::mutex> lk(ps->mu);
+            if (!ok) ps->failed = true;
+            sl.adler = (uint32_t)res[3];
+            sl.finished = true;
+            sl.t_finished = ps->ms();
+        }
+        ps->cv.notify_all();
+        if (!ok) break;
+    }
+}
+
+int host_inflate_piped(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, uint64_t cap, uint64_t *out_len, uint64_t *consumed) {
+    if (!c->opt_inflate_pipe || m < kInflatePipeMin || cap < (1u << 20)) return kNotPiped;
+    // a zlib stream without a dictionary whose last block is the empty fixed block this engine (and pigz) ends with
+    if (((in[0] << 8) | in[1]) % 31 != 0 || (in[0] & 15) != 8 || (in[1] & 0x20)) return kNotPiped;
+    if (in[m - 6] != 0x03 || in[m - 5] != 0x00 || memcmp(in + m - 10, "\0\0\xFF\xFF", 4) != 0) return kNotPiped;
+    const uint64_t body_begin = 2, body_end = m - 6;
+    const uint64_t slab_bytes = c->opt_inflate_slab ? (uint64_t)c->opt_inflate_slab : kInflateSlab;
+    // cut points: behind the first marker after every multiple of slab_bytes
+    std::vector<uint64_t> cuts{body_begin};
+    for (uint64_t target = body_begin + slab_bytes; target + (1u << 20) < body_end; target += slab_bytes) {
+        const uint8_t *from = in + target, *end = in + tmin<uint64_t>(target + (1u << 20), body_end);
+        const uint8_t *hit = nullptr;
+        for (const uint8_t *p = from; p + 4 <= end;) {
+            p = static_cast<const uint8_t *>(memchr(p, 0xFF, (size_t)(end - p)));
+            if (!p) break;
+            if (p - in >= 2 && p + 1 < end && p[1] == 0xFF && p[-1] == 0 && p[-2] == 0) {
+                hit = p + 2;
+                break;
+            }
+            ++p;
+        }
+        if (!hit) return kNotPiped;
+        cuts.push_back((uint64_t)(hit - in));
+    }
+    const uint32_t nslabs = (uint32_t)cuts.size();
+    if (nslabs < 2) return kNotPiped;
+    if (cudaSetDevice(c->device) != cudaSuccess) return kNotPiped;
+    int workers = (int)tmin<uint32_t>(nslabs, kPipeWorkers);
+    if (const char *e = getenv("ZK_PIPE_WORKERS")) workers = tmax(1, tmin(workers, atoi(e)));  // tuning aid
+    for (int w = 0; w < workers; ++w)
+        if (!c->helpers[w]) {
+            if (!(c->helpers[w] = zk_ctx_create(c->device))) return kNotPiped;
+            c->helpers[w]->opt_lane_pack = 1;
+        }
+    const size_t in_room = ((size_t)m + 255) / 256 * 256;
+    const size_t per_worker = 256 + 65536 + 32768 + 256;
+    Staging *st = staging_for(c, 256 + in_room + (size_t)cap + 256 + (size_t)workers * per_worker);
+    if (!st) return kNotPiped;
+    uint8_t *d_in = st->base + 256, *d_out = d_in + in_room, *d_work = d_out + ((size_t)cap + 255) / 256 * 256;
+    if (!c->copy_in && cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess) return kNotPiped;
+    if (!c->copy_out && cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) return kNotPiped;
+    PipeState ps;
+    ps.c = c;
+    ps.d_in = d_in;
+    ps.d_out = d_out;
+    ps.out = out;
+    ps.cap = cap;
+    ps.slabs.resize(nslabs);
+    bool ok = true;
+    // output room per slab in its worker's scratch: its share of the caller's buffer by compressed size, times four (a
+    // slab that expands more than that sends the call to the one-pass path)
+    for (uint32_t k = 0; k < nslabs; ++k) {
+        PipeSlab &sl = ps.slabs[k];
+        sl.in_off = cuts[k];
+        sl.in_len = (k + 1 < nslabs ? cuts[k + 1] : body_end) - cuts[k];
+        const double share = (double)sl.in_len / (double)(body_end - body_begin);
+        sl.cap = tmin<uint64_t>(cap, (uint64_t)(share * 4.0 * (double)cap) + (1u << 20));
+        ok = ok && cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) == cudaSuccess;
+    }
+    auto cleanup = [&] {
+        for (PipeSlab &sl : ps.slabs) {
+            if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+            if (sl.done) cudaEventDestroy(sl.done);
+        }
+    };
+    if (!ok) {
+        cleanup();
+        return kNotPiped;
+    }
+    // the staging buffer may still be in use by earlier work on the compute stream
+    cudaEventRecord(ps.slabs[0].done, c->stream);
+    cudaStreamWaitEvent(c->copy_in, ps.slabs[0].done, 0);
+    cudaStreamWaitEvent(c->copy_out, ps.slabs[0].done, 0);
+    ok = cudaMemsetAsync(d_work, 0, (size_t)workers * per_worker, c->copy_in) == cudaSuccess;
+    for (uint32_t k = 0; k < nslabs && ok; ++k) {
+        PipeSlab &sl = ps.slabs[k];
+        // (slab 0 also carries the two header bytes in front of it, so that offsets in d_in equal offsets in `in`)
+        const uint64_t from = k ? sl.in_off : 0, len = sl.in_off + sl.in_len - from + (k + 1 == nslabs ? 6 : 0);
+        ok = cudaMemcpyAsync(d_in + from, in + from, len, cudaMemcpyHostToDevice, c->copy_in) == cudaSuccess &&
+             cudaEventRecord(sl.in_ready, c->copy_in) == cudaSuccess;
+    }
+    c->h2d_bytes += (int64_t)m;
+    if (ok) {
+        std::vector<std::thread> threads;
+        for (int w = 0; w < workers; ++w) threads.emplace_back(pipe_worker, &ps, c->helpers[w], d_work + (size_t)w * per_worker);
+        for (std::thread &t : threads) t.join();
+    }
+    cudaStreamSynchronize(c->copy_in);
+    cudaStreamSynchronize(c->copy_out);
+    for (int w = 0; w < workers; ++w) {
+        cudaStreamSynchronize(c->helpers[w]->stream);
+        c->launches += c->helpers[w]->launches;
+        c->helpers[w]->launches = 0;
+    }
+    cleanup();
+    if (getenv("ZK_PIPE_DEBUG")) {
+        fprintf(stderr, "[pipe] %u slabs, %d workers, total %.2f ms\n", nslabs, workers, ps.ms());
+        for (uint32_t k = 0; k < nslabs; ++k)
+            fprintf(stderr, "[pipe] slab %2u in %6.1f MiB out %6.1f MiB  start %6.2f prepared %6.2f finish %6.2f .. %6.2f\n", k,
+                    ps.slabs[k].in_len / 1048576.0, ps.slabs[k].out_len / 1048576.0, ps.slabs[k].t_start, ps.slabs[k].t_prepared,
+                    ps.slabs[k].t_finish_begin, ps.slabs[k].t_finished);
+    }
+    if (!ok || ps.failed) {
+        c->pipe_fallbacks++;
+        return kNotPiped;
+    }
+    uint64_t total = 0;
+    uint32_t adler = 1;
+    for (const PipeSlab &sl : ps.slabs) {
+        total += sl.out_len;
+        adler = adler32_combine(adler, sl.adler, sl.out_len);
+    }
+    c->d2h_bytes += (int64_t)total;
+    c->pipe_slabs += nslabs;
+    const uint32_t want = ((uint32_t)in[m - 4] << 24) | ((uint32_t)in[m - 3] << 16) | ((uint32_t)in[m - 2] << 8) | in[m - 1];
+    *out_len = total;
+    if (consumed) *consumed = m;
+    return adler == want ? ZK_STREAM_END : ZK_DATA_ERROR;  // IS:419-424
+}
+}  // namespace
+
 static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
                         uint64_t cap, uint64_t *out_len, uint64_t *consumed, int container = 0, uint32_t body_begin = 0,
                         uint32_t *check = nullptr) {
@@ -800,6 +1053,15 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
     if (consumed) *consumed = 0;
     if (!c || !out_len || (!in && m) || (!out && cap) || (!dict && dict_len)) return ZK_STREAM_ERROR;
     ZK_CUDA(cudaSetDevice(c->device));
+    if (container == 0 && !dict && m >= 16) {
+        const int prc = host_inflate_piped(c, in, m, out, cap, out_len, consumed);
+        if (prc != kNotPiped) {
+            if (check) *check = ((uint32_t)in[m - 4] << 24) | ((uint32_t)in[m - 3] << 16) | ((uint32_t)in[m - 2] << 8) | in[m - 1];
+            return prc;
+        }
+        *out_len = 0;
+        if (consumed) *consumed = 0;
+    }
     uint32_t dict_id = 0;
     if (dict) dict_id = dict_len ? zk_adler32(c, 1u, dict, dict_len) : 1u;  // DICTID = Adler-32 of the dictionary
     const size_t in_room = ((size_t)m + 255) / 256 * 256, dict_room = ((size_t)dict_len + 255) / 256 * 256 + 256;

@@ -92,6 +92,12 @@ struct zk_ctx {
     uint8_t *pinned = nullptr; // pinned host staging for small results
     size_t pinned_cap = 0;
     int64_t opt_chunk_bytes = 0; // 0 = auto
+    int64_t opt_inflate_pipe = 0;     // 1: host-buffer inflate of a large stream with sync markers runs as a pipeline of slabs
+                                      // (opt-in: measured slower than one pass, profiles/inflate_pipeline_r2.md)
+    int64_t opt_lane_pack = 0;        // 1: the lane decoder fills whole CTAs (few SMs per call) so that several calls run side by side
+    int64_t opt_inflate_slab = 0;     // compressed bytes per slab of that pipeline, 0 = built-in
+    zk_ctx *helpers[4] = {nullptr, nullptr, nullptr, nullptr};  // contexts of the pipeline's workers (own stream + arena)
+    int64_t pipe_slabs = 0, pipe_fallbacks = 0;  // counters: slabs decoded by the pipeline, calls that fell back to one pass
     int64_t opt_block_bytes = zk::kBlockBytesDefault;
     int64_t opt_lz_chain = -1, opt_lz_max_lazy = -1, opt_lz_nice = -1;  // tuning overrides of the level table (-1 = off)
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;

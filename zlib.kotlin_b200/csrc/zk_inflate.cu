@@ -1845,7 +1845,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         ScopedTimer t(c, 4);
                         const int lane_smem = kLaneWarps * kLaneWarpSmem;
                         const uint32_t tasks = (uint32_t)((n + 31) / 32);
-                        const uint32_t grid = tmin<uint32_t>(tasks, (uint32_t)c->sm_count);  // a warp per SM before a second one
+                        // a warp per SM before a second one -- unless several calls are to run side by side (the slabs of the
+                        // pipelined host-buffer inflate): then whole CTAs, so that a call occupies few SMs
+                        const uint32_t grid = c->opt_lane_pack ? tmin<uint32_t>((tasks + kLaneWarps - 1) / kLaneWarps, (uint32_t)c->sm_count)
+                                                               : tmin<uint32_t>(tasks, (uint32_t)c->sm_count);
                         ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                         ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
                         decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
