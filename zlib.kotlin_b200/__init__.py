@@ -11,5 +11,5 @@ from .binding import (  # noqa: F401
     Z_STREAM_ERROR, Z_SYNC_FLUSH, Engine, EngineError, library, library_path,
 )
 from .api import (  # noqa: F401
-    Adler32, Adler32Utils, DeflateStream, InflateStream, ZInputStream, ZLib, ZStream, ZStreamException, version,
+    Adler32, Adler32Utils, DeflateStream, InflateStream, ZInputStream, ZLib, ZStream, ZStreamException, default_engine, version,
 )

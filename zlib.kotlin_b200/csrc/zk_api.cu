@@ -1063,7 +1063,7 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
         if (consumed) *consumed = 0;
     }
     uint32_t dict_id = 0;
-    if (dict) dict_id = dict_len ? zk_adler32(c, 1u, dict, dict_len) : 1u;  // DICTID = Adler-32 of the dictionary
+    if (dict && container == 0) dict_id = dict_len ? zk_adler32(c, 1u, dict, dict_len) : 1u;  // DICTID = Adler-32 of the dictionary
     const size_t in_room = ((size_t)m + 255) / 256 * 256, dict_room = ((size_t)dict_len + 255) / 256 * 256 + 256;
     Staging *s = staging_for(c, 256 + dict_room + in_room + (size_t)cap + 256);
     if (!s) return ZK_MEM_ERROR;
@@ -1282,6 +1282,16 @@ struct zk_stream {
     bool have_dict = false;            // deflate: emit FDICT + DICTID; inflate: a dictionary has been supplied
     uint32_t dict_id = 0;
     std::vector<uint8_t> dict;         // inflate: the supplied dictionary
+    // inflate state machine: what is carried from call to call (SURVEY.md section 5 "checkpoint / resume")
+    std::vector<uint8_t> window;       // the last <= 32 KiB of output: entry window of the next segment
+    size_t scan_pos = 0;               // pending_in[0, scan_pos) has been searched for sync markers
+    size_t marker_end = 0;             // end of the last marker found in pending_in (0: none)
+    size_t tail_attempt = 0;           // size of pending_in when the end of the stream was last tried and found incomplete
+    bool seen_marker = false;          // a sync marker has been decoded up to: the stream is cut into short blocks
+    bool plain_mode = false;           // a marker turned out not to be a block boundary: gather, try at geometric sizes
+    bool body_done = false;            // the final block has been decoded; the trailer may still be missing
+    uint64_t decoded = 0;              // bytes decoded so far (total_out counts what the caller has taken)
+    int sticky = ZK_OK;                // an error, once met, is the answer of every later call
 };
 
 static const size_t kStreamSlab = 8u << 20;
@@ -1477,60 +1487,236 @@ zk_stream *zk_inflate_init(zk_ctx *ctx) {
     return s;
 }
 
+// ---- streaming inflate: a state machine over complete blocks ---------------------------------------------------------
+// docs/API.md:239-308 (inflate(flush), ZInputStream.read).  Every call appends its input to the unconsumed tail and decodes
+// what can be decoded NOW, once: all complete blocks up to the last sync marker that has arrived (a headerless body whose
+// entry window is the last 32 KiB produced so far -- the shard mechanism), and the end of the stream (final block +
+// trailer) when it looks complete.  Carried between calls: the 32 KiB window, the unconsumed tail, the running checksum
+// and the totals.  A stream without markers (libz, the reference) has nothing to decode before its end: its input is
+// gathered and the end is tried when the tail has doubled since the last try (or at Z_FINISH), so the GPU work stays
+// linear in the stream either way.  total_in counts everything taken from the caller (as zlib does); total_out and adler
+// describe what has been DECODED AND HANDED OUT, which lags behind zlib's by at most the block in flight.
+namespace {
+
+void stream_note_output(zk_stream *s, const uint8_t *p, size_t n) {
+    if (n >= 32768) {
+        s->window.assign(p + n - 32768, p + n);
+    } else if (n) {
+        const size_t keep = tmin<size_t>(s->window.size(), 32768 - n);
+        std::vector<uint8_t> w(s->window.end() - (long)keep, s->window.end());
+        w.insert(w.end(), p, p + n);
+        s->window.swap(w);
+    }
+    s->decoded += n;
+}
+
+// pending_in[0, len) as a headerless body of whole blocks ending on a sync marker.  0: decoded and appended to
+// pending_out; 1: it is not such a body (a false marker, damaged data, a final block inside); < 0: an error to report.
+int stream_decode_marked(zk_stream *s, size_t len) {
+    zk_ctx *c = s->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) return ZK_ERRNO;
+    const uint32_t wl = (uint32_t)s->window.size();
+    uint64_t cap = tmax<uint64_t>((uint64_t)len * 6, 1u << 20);
+    for (int attempt = 0; attempt < 5; ++attempt, cap *= 8) {
+        const size_t in_room = (len + 255) / 256 * 256;
+        Staging *st = staging_for(c, 256 + 65536 + 32768 + in_room + (size_t)cap + 256);
+        if (!st) return ZK_MEM_ERROR;
+        uint64_t *d_result = reinterpret_cast<uint64_t *>(st->base);
+        uint16_t *d_tail = reinterpret_cast<uint16_t *>(st->base + 256);
+        uint8_t *d_window = st->base + 256 + 65536, *d_in = d_window + 32768, *d_out = d_in + in_room;
+        ZK_CUDA(cudaMemsetAsync(d_window, 0, 32768, c->stream));
+        if (wl) ZK_CUDA(cudaMemcpyAsync(d_window + 32768 - wl, s->window.data(), wl, cudaMemcpyHostToDevice, c->stream));
+        ZK_CUDA(cudaMemcpyAsync(d_in, s->pending_in.data(), len, cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += (int64_t)len + wl;
+        int rc = zk_inflate_shard_prepare_device(c, d_in, len, wl, cap, d_tail, d_result);
+        if (rc != ZK_OK) return rc;
+        uint64_t res[4];
+        ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(cudaStreamSynchronize(c->stream));
+        const int status = (int)(int64_t)res[2];
+        if (status == ZK_BUF_ERROR && cap < (uint64_t)len * 1100 + 65536) continue;  // more output than reserved: once more
+        if (status != ZK_OK || res[1] != len || res[0] > cap || !c->shard.valid) return 1;
+        rc = zk_inflate_shard_finish_device(c, d_window, d_out, d_result);
+        if (rc != ZK_OK) return rc;
+        ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(cudaStreamSynchronize(c->stream));
+        if ((int)(int64_t)res[2] != ZK_STREAM_END) return 1;
+        const size_t at = s->pending_out.size();
+        s->pending_out.resize(at + res[0]);
+        if (res[0]) {
+            ZK_CUDA(cudaMemcpyAsync(s->pending_out.data() + at, d_out, res[0], cudaMemcpyDeviceToHost, c->stream));
+            ZK_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        c->d2h_bytes += (int64_t)res[0] + 64;
+        if (s->container == 2) s->crc = res[0] ? zk_crc32(c, s->crc, s->pending_out.data() + at, res[0]) : s->crc;
+        else s->adler = adler32_combine(s->adler, (uint32_t)res[3], res[0]);
+        stream_note_output(s, s->pending_out.data() + at, res[0]);
+        return 0;
+    }
+    return 1;
+}
+
+// The end of the stream: pending_in as raw deflate data that closes with a final block, the window as its dictionary.
+// ZK_STREAM_END: decoded (*used = bytes of deflate data); ZK_BUF_ERROR: incomplete so far; anything else: an error.
+int stream_decode_tail(zk_stream *s, uint64_t *used) {
+    const size_t m = s->pending_in.size();
+    uint64_t cap = (uint64_t)m * 4 + 65536;
+    for (;;) {
+        std::vector<uint8_t> buf(cap);
+        uint64_t got = 0;
+        uint32_t check = 1;
+        const int rc = host_inflate(s->ctx, s->pending_in.data(), m, s->window.empty() ? nullptr : s->window.data(), (uint32_t)s->window.size(),
+                                    buf.data(), cap, &got, used, 1, 0, &check);
+        if (rc == ZK_BUF_ERROR && got == 0 && cap < (uint64_t)m * 1100 + 65536) {  // the output may not have fitted
+            cap *= 16;
+            continue;
+        }
+        if (rc != ZK_STREAM_END) return rc;
+        if (s->container == 2) s->crc = got ? zk_crc32(s->ctx, s->crc, buf.data(), got) : s->crc;
+        else s->adler = adler32_combine(s->adler, check, got);
+        s->pending_out.insert(s->pending_out.end(), buf.begin(), buf.begin() + (long)got);
+        stream_note_output(s, buf.data(), got);
+        return ZK_STREAM_END;
+    }
+}
+
+int stream_inflate_step(zk_stream *s, int flush, uint64_t *unread) {
+    // ---- header ----
+    if (!s->header_done) {
+        const uint8_t *p = s->pending_in.data();
+        const size_t m = s->pending_in.size();
+        size_t body = 0;
+        if (s->container == 0) {
+            if (m < 2) return flush == ZK_FINISH ? ZK_BUF_ERROR : ZK_OK;
+            const int cmf = p[0], flg = p[1];
+            if ((cmf & 0x0F) != 8 || ((cmf >> 4) & 0x0F) > 7 || (((cmf << 8) | flg) % 31) != 0) return ZK_DATA_ERROR;  // IS:28-35
+            body = 2;
+            if (flg & 0x20) {  // FDICT, IS:36-43
+                if (m < 6) return flush == ZK_FINISH ? ZK_BUF_ERROR : ZK_OK;
+                if (!s->have_dict) return ZK_NEED_DICT;  // the input stays pending: zk_inflate_set_dictionary, then call again
+                const uint32_t id = ((uint32_t)p[2] << 24) | ((uint32_t)p[3] << 16) | ((uint32_t)p[4] << 8) | p[5];
+                const uint32_t mine = s->dict.empty() ? 1u : zk_adler32(s->ctx, 1u, s->dict.data(), s->dict.size());
+                if (id != mine) return ZK_DATA_ERROR;
+                const size_t keep = tmin<size_t>(s->dict.size(), 32768);
+                s->window.assign(s->dict.end() - (long)keep, s->dict.end());
+                body = 6;
+            }
+        } else if (s->container == 2) {
+            const uint32_t h = gzip_header_len(p, m);
+            if (h == 0) return ZK_DATA_ERROR;
+            if (h == ~0u) return flush == ZK_FINISH ? ZK_BUF_ERROR : ZK_OK;
+            body = h;
+        } else if (s->have_dict) {  // raw deflate: zlib.h lets inflateSetDictionary prime the window
+            const size_t keep = tmin<size_t>(s->dict.size(), 32768);
+            s->window.assign(s->dict.end() - (long)keep, s->dict.end());
+        }
+        s->pending_in.erase(s->pending_in.begin(), s->pending_in.begin() + (long)body);
+        s->header_done = true;
+        s->adler = s->container == 2 ? 0u : 1u;
+        s->crc = 0;
+    }
+    // ---- whole blocks up to the last sync marker that has arrived ----
+    if (!s->body_done && !s->plain_mode) {
+        const uint8_t *p = s->pending_in.data();
+        const size_t m = s->pending_in.size();
+        for (size_t i = s->scan_pos > 3 ? s->scan_pos - 3 : 0; i + 4 <= m;) {
+            const void *f = memchr(p + i + 2, 0xFF, m - i - 2 - 1);
+            if (!f) break;
+            const size_t k = (size_t)(static_cast<const uint8_t *>(f) - p);  // p[k] == 0xFF, candidate marker p[k-2 .. k+1]
+            if (p[k + 1] == 0xFF && p[k - 1] == 0 && p[k - 2] == 0) s->marker_end = k + 2;
+            i = k - 1;
+        }
+        s->scan_pos = m;
+        if (s->marker_end) {
+            const int rc = stream_decode_marked(s, s->marker_end);
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                s->pending_in.erase(s->pending_in.begin(), s->pending_in.begin() + (long)s->marker_end);
+                s->tail_attempt = 0;
+                s->seen_marker = true;
+            } else {
+                s->plain_mode = true;  // not a block boundary (or damaged data): the end-of-stream decode below decides
+            }
+            s->scan_pos = s->pending_in.size();
+            s->marker_end = 0;
+        }
+    }
+    // ---- the end of the stream ----
+    if (!s->body_done && !s->pending_in.empty()) {
+        const size_t m = s->pending_in.size();
+        // In a stream of short marked blocks the rest behind the last marker is an incomplete block -- unless that block is
+        // the final one (BFINAL is its first bit) or has outgrown any block of such a stream.  Without markers the end is
+        // tried whenever the gathered input has doubled.
+        const bool marked = s->seen_marker && !s->plain_mode;
+        const bool looks_final = marked && (s->pending_in[0] & 1);
+        if (flush == ZK_FINISH || looks_final || m >= tmax<size_t>(2 * s->tail_attempt, marked ? 65536 : 1)) {
+            uint64_t used = 0;
+            const int rc = stream_decode_tail(s, &used);
+            if (rc == ZK_STREAM_END) {
+                s->pending_in.erase(s->pending_in.begin(), s->pending_in.begin() + (long)used);
+                s->body_done = true;
+            } else if (rc == ZK_BUF_ERROR) {
+                s->tail_attempt = m;
+                if (flush == ZK_FINISH && s->pending_out.size() == s->out_pos) return ZK_BUF_ERROR;
+            } else {
+                return rc;
+            }
+        }
+    } else if (!s->body_done && flush == ZK_FINISH && s->header_done && s->pending_out.size() == s->out_pos) {
+        return ZK_BUF_ERROR;  // nothing left to decode and no final block seen
+    }
+    // ---- trailer (IS:414-424; RFC 1952: CRC-32 and ISIZE, little-endian) ----
+    if (s->body_done && !s->finished) {
+        const size_t need = s->container == 0 ? 4 : s->container == 2 ? 8 : 0;
+        if (s->pending_in.size() < need) return flush == ZK_FINISH && s->pending_out.size() == s->out_pos ? ZK_BUF_ERROR : ZK_OK;
+        const uint8_t *t = s->pending_in.data();
+        bool good = true;
+        if (s->container == 0) {
+            good = ((((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3]) == s->adler);
+        } else if (s->container == 2) {
+            uint32_t crc = 0, isize = 0;
+            for (int i = 0; i < 4; ++i) crc |= (uint32_t)t[i] << (8 * i), isize |= (uint32_t)t[4 + i] << (8 * i);
+            good = crc == s->crc && isize == (uint32_t)s->decoded;
+            s->adler = s->crc;
+        }
+        *unread = s->pending_in.size() - need;  // bytes behind the stream are not consumed
+        s->pending_in.clear();
+        s->finished = true;
+        if (!good) return ZK_DATA_ERROR;
+    }
+    return ZK_OK;
+}
+}  // namespace
+
 int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush) {
     if (!s || s->mode != 1 || !in_len || !out_len) return ZK_STREAM_ERROR;
     const uint64_t avail_in = *in_len, avail_out = *out_len;
     *in_len = 0;
     *out_len = 0;
-    if (!s->finished && avail_in) {
-        if (!in) return ZK_STREAM_ERROR;
-        s->pending_in.insert(s->pending_in.end(), in, in + avail_in);
-        *in_len = avail_in;
-        s->total_in += avail_in;
-    }
-    if (!s->finished && !s->pending_in.empty()) {
-        // try to decode what has arrived; a truncated stream reports ZK_BUF_ERROR and we wait for more
-        uint64_t cap = (uint64_t)s->pending_in.size() * 4 + 65536;
-        for (;;) {
-            std::vector<uint8_t> buf(cap);
-            uint64_t got = 0, used = 0;
-            int rc;
-            if (s->container == 2) rc = zk_inflate_gzip(s->ctx, s->pending_in.data(), s->pending_in.size(), buf.data(), cap, &got, &used);
-            else if (s->container == 1) rc = zk_inflate_raw(s->ctx, s->pending_in.data(), s->pending_in.size(), buf.data(), cap, &got, &used);
-            else rc = host_inflate(s->ctx, s->pending_in.data(), s->pending_in.size(), s->have_dict ? s->dict.data() : nullptr,
-                                   s->have_dict ? (uint32_t)s->dict.size() : 0u, buf.data(), cap, &got, &used);
-            if (rc == ZK_NEED_DICT) return ZK_NEED_DICT;  // the input stays pending: zk_inflate_set_dictionary, then call again
-            if (rc == ZK_STREAM_END) {
-                buf.resize(got);
-                s->pending_out.swap(buf);
-                s->out_pos = 0;
-                s->finished = true;
-                s->adler = 0;
-                // Adler-32 of the output is the stream's trailer
-                if (used >= 4 && s->container == 0) {
-                    const uint8_t *t = s->pending_in.data() + used - 4;
-                    s->adler = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
-                }
-                s->total_in -= s->pending_in.size() - used;  // trailing bytes are not consumed
-                *in_len -= tmin<uint64_t>(*in_len, s->pending_in.size() - used);
-                s->pending_in.clear();
-                break;
-            }
-            if (rc == ZK_BUF_ERROR && got == 0 && cap < (1ull << 36)) {
-                // either the output did not fit or the input is still incomplete: grow once, then decide
-                if (cap >= (uint64_t)s->pending_in.size() * 1100 + 65536) {
-                    if (flush == ZK_FINISH) return ZK_BUF_ERROR;
-                    break;  // need more input
-                }
-                cap *= 16;
-                continue;
-            }
-            if (rc == ZK_BUF_ERROR) {
-                if (flush == ZK_FINISH) return ZK_BUF_ERROR;
-                break;  // need more input
-            }
-            return rc;  // ZK_NEED_DICT, ZK_DATA_ERROR, ...
+    if (s->sticky != ZK_OK) return s->sticky;
+    try {
+        if (!s->finished && avail_in) {
+            if (!in) return ZK_STREAM_ERROR;
+            s->pending_in.insert(s->pending_in.end(), in, in + avail_in);
+            *in_len = avail_in;
+            s->total_in += avail_in;
         }
+        if (!s->finished) {
+            uint64_t unread = 0;
+            const int rc = stream_inflate_step(s, flush, &unread);
+            if (unread) {
+                s->total_in -= tmin<uint64_t>(s->total_in, unread);
+                *in_len -= tmin<uint64_t>(*in_len, unread);
+            }
+            if (rc == ZK_NEED_DICT) return rc;
+            if (rc != ZK_OK) {
+                if (rc != ZK_BUF_ERROR) s->sticky = rc;
+                // what was decoded before the error is still handed out below only for a failed checksum (IS:419-424)
+                if (!(rc == ZK_DATA_ERROR && s->finished)) return rc;
+            }
+        }
+    } catch (const std::bad_alloc &) {
+        return ZK_MEM_ERROR;
     }
     const size_t have = s->pending_out.size() - s->out_pos;
     const size_t give = have < avail_out ? have : (size_t)avail_out;
@@ -1541,8 +1727,18 @@ int zk_inflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, 
         s->total_out += give;
         *out_len = give;
     }
-    if (s->finished && s->out_pos == s->pending_out.size()) return ZK_STREAM_END;
-    if (!*in_len && !give) return ZK_BUF_ERROR;
+    if (s->out_pos == s->pending_out.size()) {
+        s->pending_out.clear();
+        s->out_pos = 0;
+    } else if (s->out_pos >= (8u << 20)) {  // drop what has been handed out now and then
+        s->pending_out.erase(s->pending_out.begin(), s->pending_out.begin() + (long)s->out_pos);
+        s->out_pos = 0;
+    }
+    if (s->sticky != ZK_OK) return s->sticky;
+    if (s->finished && s->pending_out.empty()) return ZK_STREAM_END;
+    // zlib.h: Z_FINISH on a stream that does not end in this input is Z_BUF_ERROR (once everything decodable is out)
+    if (flush == ZK_FINISH && !s->finished && s->pending_out.empty()) return ZK_BUF_ERROR;
+    if (!*in_len && !give) return ZK_BUF_ERROR;  // zlib.h: no progress possible
     return ZK_OK;
 }
 
@@ -1551,9 +1747,17 @@ int zk_inflate_reset(zk_stream *s) {
     s->header_done = s->finished = false;
     s->total_in = s->total_out = 0;
     s->adler = 1;
+    s->crc = 0;
     s->pending_in.clear();
     s->pending_out.clear();
     s->out_pos = 0;
+    s->window.clear();
+    s->scan_pos = s->marker_end = s->tail_attempt = 0;
+    s->plain_mode = s->body_done = s->seen_marker = false;
+    s->decoded = 0;
+    s->sticky = ZK_OK;
+    s->have_dict = false;  // zlib.h inflateReset: the stream starts over; a dictionary has to be supplied again
+    s->dict.clear();
     return ZK_OK;
 }
 

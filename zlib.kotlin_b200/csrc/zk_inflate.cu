@@ -1800,8 +1800,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const uint32_t body_begin = (uint32_t)hdr[1];
     // a shard body may reach hist_len bytes back into the output of the shards before it: the same mechanism as a preset
     // dictionary, except that the window's CONTENT arrives later (run_inflate_shard_finish)
+    // (a raw deflate stream may be given a dictionary too: the streaming inflate decodes the end of a stream that way,
+    // with the last 32 KiB of what it has produced so far as the dictionary)
     const uint32_t dict_len = job.container == 3 ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow)
-                              : (job.d_dict && body_begin == 6) ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow) : 0u;
+                              : (job.d_dict && (body_begin == 6 || job.container == 1)) ? tmin<uint32_t>(job.dict_len, (uint32_t)kWindow) : 0u;
     ZK_CUDA(cudaMemsetAsync(d_windows - kWindow, 0, kWindow, st));
     if (dict_len && job.container != 3)
         ZK_CUDA(cudaMemcpyAsync(d_windows - dict_len, job.d_dict + (job.dict_len - dict_len), dict_len, cudaMemcpyDeviceToDevice, st));
