@@ -35,6 +35,9 @@ def parse_args():
     ap.add_argument("--size-mib", type=int, default=1024, help="uncompressed MiB per GPU")
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--workload", default="mixed", choices=["mixed", "text"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --size-mib per GPU (the driver's default); strong: --total-gib cut across the GPUs (BASELINE.json configs[3])")
+    ap.add_argument("--total-gib", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=32)
     ap.add_argument("--config1-mib", type=int, default=64, help="size of the configs[0] CPU round trip inside cpu_baseline (0 = skip)")
@@ -42,9 +45,17 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_corpus(kind, nbytes, rank=0):
+PIECE = 1 << 30  # strong scaling: the job is a sequence of 1 GiB pieces, piece j made with the seed of weak-scaling rank j
+
+
+def make_corpus(kind, nbytes, rank=0, first_piece=None):
     from zlibk_b200 import corpus
 
+    if first_piece is not None:  # strong scaling: pieces first_piece .. of the global buffer
+        import numpy as np
+
+        parts = [make_corpus(kind, min(PIECE, nbytes - off), first_piece + off // PIECE) for off in range(0, nbytes, PIECE)]
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
     seed_shift = 0x10000 * rank
     if kind == "text":
         return corpus.text_like(nbytes, corpus.SEED_TEXT + seed_shift)
@@ -205,8 +216,14 @@ def cpu_baseline(kind, level, sample_mib, config1_mib=64):
 
 def workload_config(args, world):
     """The `config` object both arms print: the workload the metric is quoted on."""
+    kind = "mixed-entropy" if args.workload == "mixed" else "text-like"
+    seed = 2 if args.workload == "mixed" else 1
+    if args.scaling == "strong":
+        return {"workload": "%d GiB %s corpus in all (seed 0x5EED000%d, 1 GiB pieces), level %d, ONE zlib stream cut into chunk ranges, 32 KiB blocks; "
+                            "input larger than L2 (no flush needed)" % (args.total_gib, kind, seed, args.level),
+                "parallelism": "chunk ranges per GPU x%d (strong scaling: %d MiB per GPU)" % (world, args.total_gib * 1024 // world)}
     return {"workload": "%d MiB %s corpus per GPU (seed 0x5EED000%d), level %d, zlib stream, 32 KiB blocks; input larger than L2 (no flush needed)" % (
-                args.size_mib, "mixed-entropy" if args.workload == "mixed" else "text-like", 2 if args.workload == "mixed" else 1, args.level),
+                args.size_mib, kind, seed, args.level),
             "parallelism": "chunk ranges per GPU x%d" % world}
 
 
@@ -264,8 +281,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n = args.size_mib << 20
-    host = make_corpus(args.workload, n, rank)
+    strong = args.scaling == "strong"
+    if strong:
+        if (args.total_gib * 1024) % world:
+            raise SystemExit("--total-gib must divide by the number of GPUs")
+        n = (args.total_gib << 30) // world
+        if n % PIECE and PIECE % n:
+            raise SystemExit("strong scaling: the per-GPU share must be a multiple or a divisor of 1 GiB")
+        if n >= PIECE:
+            host = make_corpus(args.workload, n, 0, first_piece=rank * (n // PIECE))
+        else:  # several ranks share a piece: every rank builds the piece and keeps its slice
+            per = PIECE // n
+            host = make_corpus(args.workload, PIECE, rank // per)[(rank % per) * n: (rank % per + 1) * n].copy()
+    else:
+        n = args.size_mib << 20
+        host = make_corpus(args.workload, n, rank)
     h_in = torch.from_numpy(host).pin_memory()
     d_in = h_in.to(dev, non_blocking=True)
     eng = zlibk_b200.Engine(local_rank)
@@ -286,7 +316,15 @@ def main():
         hist = None
         if rank > 0:
             from zlibk_b200 import corpus
-            hist = torch.from_numpy(corpus.tail(args.workload, n, rank - 1, 32768)).to(dev)
+            if not strong:
+                hist = torch.from_numpy(corpus.tail(args.workload, n, rank - 1, 32768)).to(dev)
+            elif n >= PIECE:
+                hist = torch.from_numpy(corpus.tail(args.workload, PIECE, rank * (n // PIECE) - 1, 32768)).to(dev)
+            else:
+                per = PIECE // n
+                piece = make_corpus(args.workload, PIECE, (rank - 1) // per)
+                hist = torch.from_numpy(piece[((rank - 1) % per + 1) * n - 32768: ((rank - 1) % per + 1) * n].copy()).to(dev)
+                del piece
         shard = sharding.ShardedDeflate(eng, rank, world, dev, hist)
 
     def deflate_step():
@@ -469,6 +507,34 @@ def main():
         dt = float(t.item())
     e2e = {"value": n * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": e2e_out + 32,
            "ms_per_step": dt * 1e3, "note": "per GPU bytes; wall clock around the host-buffer call (max over ranks)"}
+    # what the box allows for these bytes: the same H2D and D2H volumes as bare copies from pinned memory, every rank at
+    # once, nothing else running (the denominator for the end-to-end figure)
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d_tmp = torch.empty(min(n, 64 << 20), dtype=torch.uint8, device=dev)
+
+    def bare_copies():
+        with torch.cuda.stream(s_up):
+            for off in range(0, n, d_tmp.numel()):
+                k = min(d_tmp.numel(), n - off)
+                d_tmp[:k].copy_(h_in[off:off + k], non_blocking=True)
+        with torch.cuda.stream(s_down):
+            for off in range(0, e2e_out, 64 << 20):
+                k = min(64 << 20, e2e_out - off)
+                h_out[off:off + k].copy_(d_out[off:off + k], non_blocking=True)
+
+    bare_copies()
+    barrier()
+    t0 = time.perf_counter()
+    bare_copies()
+    torch.cuda.synchronize(dev)
+    cdt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([cdt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cdt = float(t.item())
+    e2e["copy_ceiling"] = {"value": n * world / cdt / 1e9, "unit": UNIT, "ms": cdt * 1e3,
+                           "what": "bare cudaMemcpyAsync of the same bytes (H2D input, D2H stream) from pinned memory, both directions at once, all ranks at once"}
+    e2e["frac_of_copy_ceiling"] = (n * world / dt) / (n * world / cdt)
 
     if rank != 0:
         if world > 1:
@@ -509,7 +575,7 @@ def main():
                                   "pack": pack_us / 1e3 / args.steps / serial_ms_per_step, "adler": adler_us / 1e3 / args.steps / serial_ms_per_step}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": workload_config(args, world),
         "compressed_ratio": total_out / (n * world),

@@ -75,12 +75,27 @@ int zk_ctx_synchronize(zk_ctx *ctx);
  * "host_slab_bytes" / "host_first_slab_bytes" (slabs of the pipelined host-buffer deflate, default 64 MiB / 32 MiB;
  * multiples of 64 KiB, at least 1 MiB), "slab_overlap" (default 1: slabs alternate between two streams; 0: in series),
  * "lz_chain" / "lz_max_lazy" / "lz_nice" (override the level table, -1 = off),
- * "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
+ * "auto_register" (1: a host-buffer call page-locks caller buffers of 1 MiB or more that CUDA does not know yet, once, and
+ * keeps them locked until the context is destroyed -- for callers that keep and reuse their buffers, up to 16 of them; the
+ * caller must not free such a buffer while the context lives), "inflate_pipe" / "inflate_slab_bytes" (opt-in slab pipeline
+ * of the host-buffer inflate), "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
  * overlap about a tenth of its throughput). */
 int zk_ctx_set_option(zk_ctx *ctx, const char *name, int64_t value);
 /* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes"}; with "timing" on also
  * {"lz77","huffman","pack","adler","inflate_decode","inflate_other"} + "_us" / "_spans"; "reset_timing" clears those. */
 int64_t zk_ctx_get_counter(zk_ctx *ctx, const char *name);
+
+/* ---- caller buffers the copy engines can stream from ------------------------------------
+ * The host-buffer calls below overlap their copies with the kernels only when the caller's memory is page-locked for
+ * CUDA.  A Kotlin ByteArray.usePinned / JVM critical array is pinned for the garbage collector only: to CUDA it is
+ * pageable, every copy is staged through the driver and the overlap is lost (measured: profiles/pageable_r2.md).
+ * zk_host_alloc hands out page-locked memory to keep and reuse (nativeHeap-style, free with zk_host_free);
+ * zk_host_register page-locks a buffer the caller already owns for as long as it lives (costly: do it once per
+ * buffer, not once per call), zk_host_unregister undoes it.  All return ZK_OK / ZK_MEM_ERROR / ZK_STREAM_ERROR. */
+void *zk_host_alloc(uint64_t bytes);
+void zk_host_free(void *p);
+int zk_host_register(void *p, uint64_t bytes);
+int zk_host_unregister(void *p);
 
 /* ---- Adler-32 ------------------------------------------------------------------ */
 /* replaces Adler32Utils.adler32(adler, buf, index, len), bitwise/checksum/Adler32Utils.kt:31-57

@@ -23,6 +23,10 @@ SIGNATURES = {
     "zk_ctx_synchronize": (c_int, [c_void_p]),
     "zk_ctx_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "zk_ctx_get_counter": (c_int64, [c_void_p, c_char_p]),
+    "zk_host_alloc": (c_void_p, [c_uint64]),
+    "zk_host_free": (None, [c_void_p]),
+    "zk_host_register": (c_int, [c_void_p, c_uint64]),
+    "zk_host_unregister": (c_int, [c_void_p]),
     "zk_adler32": (c_uint32, [c_void_p, c_uint32, c_void_p, c_uint64]),
     "zk_adler32_device": (c_int, [c_void_p, c_uint32, c_void_p, c_uint64, c_void_p]),
     "zk_adler32_combine": (c_uint32, [c_uint32, c_uint32, c_uint64]),

@@ -352,6 +352,9 @@ void zk_ctx_destroy(zk_ctx *c) {
         if (h) zk_ctx_destroy(h);
         h = nullptr;
     }
+    for (int i = 0; i < c->num_registered; ++i)
+        if (cudaHostUnregister(c->registered[i]) != cudaSuccess) cudaGetLastError();
+    c->num_registered = 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     staging_release(c);
@@ -416,6 +419,10 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         // at most one device slab (run_deflate clamps to that: a larger host slab would index past its per-slab events)
         if (value < 0 || value > (int64_t)kSlabBytes || (value && (value < (1 << 20) || value % 65536))) return ZK_STREAM_ERROR;
         (name[5] == 's' ? c->opt_host_slab : c->opt_host_first_slab) = value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "auto_register")) {  // 1: page-lock unknown caller buffers on first use and keep them (see the header)
+        c->opt_auto_register = value != 0;
         return ZK_OK;
     }
     if (!strcmp(name, "inflate_pipe")) {  // 1: large marked streams go through the slab pipeline (default 0: one pass)
@@ -609,6 +616,57 @@ static void staging_release(zk_ctx *c) {
         }
 }
 
+// "auto_register": page-lock a caller buffer CUDA does not know yet, once, and remember it (the caller keeps it alive and
+// reuses it -- the contract of the option; include/zlibk_gpu.h)
+static void auto_register(zk_ctx *c, const void *p, uint64_t bytes) {
+    if (!c->opt_auto_register || !p || bytes < (1u << 20)) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (at.type != cudaMemoryTypeUnregistered || c->num_registered >= 16) return;
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    c->registered[c->num_registered++] = const_cast<void *>(p);
+}
+
+void *zk_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void zk_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+int zk_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return ZK_STREAM_ERROR;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return ZK_OK;
+    }
+    if (e != cudaSuccess) {
+        set_last_error("cudaHostRegister", e);
+        cudaGetLastError();
+        return ZK_MEM_ERROR;
+    }
+    return ZK_OK;
+}
+int zk_host_unregister(void *p) {
+    if (!p) return ZK_STREAM_ERROR;
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return ZK_STREAM_ERROR;
+    }
+    return ZK_OK;
+}
+
 uint32_t zk_adler32(zk_ctx *c, uint32_t adler, const uint8_t *buf, uint64_t len) {
     if (buf == nullptr) return 1u;  // AU:37
     if (!c || len == 0) return len == 0 ? adler : 0u;
@@ -683,6 +741,8 @@ static int host_deflate(zk_ctx *c, const uint8_t *hist, uint32_t hist_len, const
                         int strategy, uint8_t *out, uint64_t cap, bool framed, uint64_t *out_len, uint32_t *adler,
                         uint32_t *crc = nullptr) {
     ZK_CUDA(cudaSetDevice(c->device));
+    auto_register(c, in, n);
+    auto_register(c, out, cap);
     const uint64_t bound = zk_compress_bound(n);
     const uint64_t dcap = cap < bound ? cap : bound;
     const size_t in_room = ((size_t)n + 255) / 256 * 256;
@@ -1053,6 +1113,8 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
     if (consumed) *consumed = 0;
     if (!c || !out_len || (!in && m) || (!out && cap) || (!dict && dict_len)) return ZK_STREAM_ERROR;
     ZK_CUDA(cudaSetDevice(c->device));
+    auto_register(c, in, m);
+    auto_register(c, out, cap);
     if (container == 0 && !dict && m >= 16) {
         const int prc = host_inflate_piped(c, in, m, out, cap, out_len, consumed);
         if (prc != kNotPiped) {

@@ -94,6 +94,9 @@ struct zk_ctx {
     int64_t opt_chunk_bytes = 0; // 0 = auto
     int64_t opt_inflate_pipe = 0;     // 1: host-buffer inflate of a large stream with sync markers runs as a pipeline of slabs
                                       // (opt-in: measured slower than one pass, profiles/inflate_pipeline_r2.md)
+    int64_t opt_auto_register = 0;    // 1: host-buffer calls page-lock caller buffers CUDA does not know yet and keep them locked
+    void *registered[16] = {};        // ... those buffers (unlocked by zk_host_unregister or when the context goes)
+    int num_registered = 0;
     int64_t opt_lane_pack = 0;        // 1: the lane decoder fills whole CTAs (few SMs per call) so that several calls run side by side
     int64_t opt_inflate_slab = 0;     // compressed bytes per slab of that pipeline, 0 = built-in
     zk_ctx *helpers[4] = {nullptr, nullptr, nullptr, nullptr};  // contexts of the pipeline's workers (own stream + arena)

@@ -51,6 +51,19 @@ def exchange(meta_tensor, world):
     return out.view(world, 4)
 
 
+def _same_stream(engine, device):
+    """The engine's kernels and torch's copies / collectives must be ordered: run the engine on torch's current stream of
+    the device.  torch's DEFAULT stream has handle 0, which the C ABI reads as "the context's private stream" -- then the
+    caller has to make a stream current first (bench.py does), and this raises rather than race."""
+    import torch
+
+    handle = torch.cuda.current_stream(device).cuda_stream
+    if handle == 0:
+        raise RuntimeError("make a non-default torch.cuda.Stream current before building a Sharded* driver: the engine has to "
+                           "share a stream with torch's copies and collectives")
+    engine.set_stream(handle)
+
+
 class ShardedDeflate:
     """Per-rank driver used by bench.py and the multi-GPU tests."""
 
@@ -58,6 +71,7 @@ class ShardedDeflate:
         import torch
 
         self.eng, self.rank, self.world, self.dev = engine, rank, world, device
+        _same_stream(engine, device)
         self.d_meta = torch.zeros(4, dtype=torch.int64, device=device)
         self.d_hist = hist  # uint8 tensor with the 32 KiB before this shard, or None for rank 0
         self.gathered = None
@@ -109,6 +123,7 @@ class ShardedInflate:
         import torch
 
         self.eng, self.rank, self.world, self.dev = engine, rank, world, device
+        _same_stream(engine, device)
         self.d_record = torch.zeros(self.RECORD, dtype=torch.uint8, device=device)   # tail map | meta of this rank
         self.d_all = torch.zeros(world * self.RECORD, dtype=torch.uint8, device=device)
         self.d_entry = torch.zeros(32768, dtype=torch.uint8, device=device)
