@@ -121,6 +121,21 @@ def test_ratio_against_reference_and_libz(engine, oracle, level, kind):
         assert len(stream) <= 1.02 * len(zlib.compress(data, level))  # size <= 1.02 x libz at the same level
 
 
+def test_level_sizes_are_monotonic(engine):
+    """configs[2] (level 1 vs level 9): a higher level never makes a larger stream on the bench corpora -- the 4 GiB sweep
+    with the reference's sizes beside it is tools/level_sweep.py -> profiles/level_sweep_r2.json."""
+    from zlibk_b200 import corpus
+
+    for data in (corpus.text_like(24 << 20), corpus.mixed_entropy(24 << 20)):
+        sizes = {}
+        for level in (1, 3, 6, 7, 9):
+            rc, stream, _ = engine.deflate(data, level)
+            assert rc == Z_OK
+            sizes[level] = len(stream)
+        assert sizes[9] <= sizes[7] <= sizes[6] <= sizes[3] <= sizes[1], sizes
+        assert zlib.decompress(bytes(stream)) == data.tobytes()
+
+
 def test_strategies(engine, oracle):
     from zlibk_b200 import Z_FILTERED, Z_HUFFMAN_ONLY, corpus
 
