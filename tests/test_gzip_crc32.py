@@ -165,3 +165,19 @@ def test_zstream_deflate_copy(engine):
     prefix = bytes(z.next_out[: z.next_out_index])
     z.deflateEnd()
     assert zlib.decompress(prefix + stream_b) == head + tail_b
+
+
+@pytest.mark.gpu
+def test_level_zero_in_raw_and_gzip_containers_is_stored(engine):
+    """level 0 means stored blocks in every container (DS:307-308), not a silent level 1."""
+    data = _text(12, 300_000) + bytes(range(256)) * 300
+    for level in (0, -1):
+        rc, raw, _ = engine.deflate_container(data, level, container="raw")
+        assert rc == 0 and zlib.decompress(bytes(raw), -15) == data
+        assert len(raw) >= len(data)  # stored: no compression at all
+        assert bytes(raw)[0] & 6 == 0  # BTYPE = 00
+        rc, gz, crc = engine.deflate_container(data, level, container="gzip")
+        assert rc == 0 and gzip.decompress(bytes(gz)) == data and crc == zlib.crc32(data)
+        assert len(gz) >= len(data)
+        rc, back, used = engine.inflate_container(gz, len(data), container="gzip")
+        assert rc == 1 and bytes(back) == data and used == len(gz)

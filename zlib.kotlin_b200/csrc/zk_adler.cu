@@ -166,7 +166,8 @@ int adler_grid(const zk_ctx *c, uint64_t n) {
 
 }  // namespace
 
-size_t adler_partials_bytes(uint64_t n) { return sizeof(AdlerPartial) * (size_t)(148 * 16 + 2); }
+// (sized for the largest grid adler_grid hands out on any device this can run on: 8 CTAs per SM, up to 256 SMs)
+size_t adler_partials_bytes(uint64_t n) { return sizeof(AdlerPartial) * (size_t)(256 * 8 + 2); }
 
 int launch_adler32(zk_ctx *c, uint32_t seed, const uint8_t *d_buf, uint64_t n, void *d_partials, uint32_t *d_out) {
     const int grid = adler_grid(c, n);

@@ -1232,13 +1232,14 @@ uint32_t zk_crc32(zk_ctx *c, uint32_t crc, const uint8_t *buf, uint64_t len) {
 
 int zk_deflate_raw(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int strategy, uint8_t *out, uint64_t cap,
                    uint64_t *out_len) {
-    // a complete raw deflate stream (RFC 1951): the shard body and the final empty fixed block
+    // a complete raw deflate stream (RFC 1951): the shard body and the final empty fixed block (level <= 0: the body is
+    // stored blocks, as in the zlib container, DS:307-308)
     if (out_len) *out_len = 0;
     if (!c || !out_len || (!in && n) || !out) return ZK_STREAM_ERROR;
     if (level > 9 || strategy < 0 || strategy > ZK_HUFFMAN_ONLY) return ZK_STREAM_ERROR;
     if (cap < 2) return ZK_BUF_ERROR;
     uint64_t body = 0;
-    int rc = host_deflate(c, nullptr, 0, in, n, level < 1 ? 1 : level, strategy, out, cap - 2, false, &body, nullptr);
+    int rc = host_deflate(c, nullptr, 0, in, n, level, strategy, out, cap - 2, false, &body, nullptr);
     if (rc != ZK_OK) return rc;
     out[body] = 0x03, out[body + 1] = 0x00;
     *out_len = body + 2;
@@ -1255,7 +1256,7 @@ int zk_deflate_gzip(zk_ctx *c, const uint8_t *in, uint64_t n, int level, int str
     const uint8_t head[10] = {0x1F, 0x8B, 8, 0, 0, 0, 0, 0, (uint8_t)(level >= 9 ? 2 : level <= 1 ? 4 : 0), 3 /* Unix */};
     uint64_t body = 0;
     uint32_t cr = 0;
-    int rc = host_deflate(c, nullptr, 0, in, n, level < 1 ? 1 : level, strategy, out + 10, cap - 20, false, &body, nullptr, &cr);
+    int rc = host_deflate(c, nullptr, 0, in, n, level, strategy, out + 10, cap - 20, false, &body, nullptr, &cr);
     if (rc != ZK_OK) return rc;
     memcpy(out, head, 10);
     uint8_t *t = out + 10 + body;
@@ -1417,7 +1418,16 @@ static int stream_flush_slab(zk_stream *s) {
     return ZK_OK;
 }
 
+static int zk_deflate_impl(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush);
+// The header promises "never throws": the streaming calls grow std::vectors, so an allocation failure becomes ZK_MEM_ERROR.
 int zk_deflate(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush) {
+    try {
+        return zk_deflate_impl(s, in, in_len, out, out_len, flush);
+    } catch (const std::bad_alloc &) {
+        return ZK_MEM_ERROR;
+    }
+}
+static int zk_deflate_impl(zk_stream *s, const uint8_t *in, uint64_t *in_len, uint8_t *out, uint64_t *out_len, int flush) {
     if (!s || s->mode != 0 || !in_len || !out_len || flush < 0 || flush > ZK_FINISH) return ZK_STREAM_ERROR;
     const uint64_t avail_in = *in_len, avail_out = *out_len;
     *in_len = 0;
@@ -1510,7 +1520,11 @@ zk_stream *zk_inflate_init2(zk_ctx *ctx, int container) {
 zk_stream *zk_deflate_copy(const zk_stream *src) {
     // zlib.h deflateCopy: an independent stream with the same state (pending input and output, history, checksums)
     if (!src || src->mode != 0) return nullptr;
-    return new (std::nothrow) zk_stream(*src);
+    try {
+        return new zk_stream(*src);
+    } catch (const std::bad_alloc &) {
+        return nullptr;
+    }
 }
 
 int zk_deflate_params(zk_stream *s, int level, int strategy) {
@@ -1529,7 +1543,11 @@ int zk_deflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len) {
     // last 32 KiB of the dictionary prime the match finder (the same mechanism as a shard's history)
     if (!s || s->mode != 0 || !dict || s->total_in || s->header_done) return ZK_STREAM_ERROR;
     const uint32_t keep = len > 32768 ? 32768 : len;
-    s->history.assign(dict + (len - keep), dict + len);
+    try {
+        s->history.assign(dict + (len - keep), dict + len);
+    } catch (const std::bad_alloc &) {
+        return ZK_MEM_ERROR;
+    }
     s->have_dict = true;
     s->dict_id = len ? zk_adler32(s->ctx, 1u, dict, len) : 1u;
     return ZK_OK;
@@ -1828,8 +1846,11 @@ int zk_inflate_set_dictionary(zk_stream *s, const uint8_t *dict, uint32_t len) {
     // no dictionary API and stops at Z_NEED_DICT (IS:36-43); this is the SURVEY.md 8(f) row built on the same priming
     // mechanism as the chunk halos.  A dictionary whose Adler-32 is not the stream's DICTID gives ZK_DATA_ERROR at decode.
     if (!s || s->mode != 1 || (!dict && len)) return ZK_STREAM_ERROR;
-    s->dict.assign(dict, dict + len);
-    if (s->dict.empty()) s->dict.push_back(0), s->dict.clear();
+    try {
+        s->dict.assign(dict, dict + len);
+    } catch (const std::bad_alloc &) {
+        return ZK_MEM_ERROR;
+    }
     s->have_dict = true;
     return ZK_OK;
 }

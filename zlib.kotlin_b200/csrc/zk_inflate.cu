@@ -1874,6 +1874,12 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
         }
     }
     uint64_t total = verdict[3];
+    if (!lane_path_done && m >= (1ull << 32)) {
+        // the chunk path below keeps candidate positions in 32 bits: a stream of 4 GiB or more that is not cut
+        // by sync markers would have to be decoded by one warp anyway -- refuse it instead of wrapping positions
+        set_last_error("inflate: compressed input of 4 GiB or more without sync markers is not supported", cudaErrorInvalidValue);
+        return ZK_STREAM_ERROR;
+    }
     if (!lane_path_done) {
         // ---- candidates -> chunks -------------------------------------------------------------------------
         fill_u32_kernel<<<32, 256, 0, st>>>(d_cand, num_spans, kNoCand);
