@@ -27,8 +27,45 @@ class GpuEngine(device: Int = 0) {
 
 private val engine by lazy { GpuEngine(0) }
 
-/** Drains an Okio source into one ByteArray slab (the ABI is 64-bit; a ByteArray caps a slab at 2 GiB - 1). */
-private fun BufferedSource.drain(): ByteArray = Buffer().also { it.writeAll(this) }.readByteArray()
+/**
+ * Page-locked slabs for the host-buffer calls.  A Kotlin ByteArray.usePinned is pinned for the garbage collector only: to
+ * CUDA it is pageable memory, every copy is staged through the driver and the engine's copy / compute overlap is lost
+ * (8 GB/s instead of 41 GB/s, profiles/pageable_r2.md).  The adapters therefore move the data of an Okio stream through
+ * slabs from zk_host_alloc, at most SLAB bytes at a time: no 2 GiB ByteArray ceiling, and the sizes of BASELINE.json
+ * configs[2] and [3] (4 GiB, 8 GiB) pass through in 256 MiB steps.
+ */
+private const val SLAB = 256L shl 20
+private const val WINDOW = 32768
+
+private class PinnedSlab(val bytes: Long) {
+    val ptr: CPointer<UByteVar> = zk_host_alloc(bytes.toULong())?.reinterpret()
+        ?: throw ZStreamException("zk_host_alloc($bytes) failed")
+    fun free() = zk_host_free(ptr)
+}
+
+/** Reads up to `max` bytes of the source into pinned memory at `dst`; returns the count (0 at the end of the source). */
+private fun BufferedSource.readInto(dst: CPointer<UByteVar>, max: Long): Long {
+    val chunk = ByteArray(1 shl 20)
+    var got = 0L
+    while (got < max) {
+        val n = read(chunk, 0, minOf(chunk.size.toLong(), max - got).toInt())
+        if (n <= 0) break
+        chunk.usePinned { platform.posix.memcpy(dst + got, it.addressOf(0), n.toULong()) }
+        got += n
+    }
+    return got
+}
+
+private fun BufferedSink.writeFrom(src: CPointer<UByteVar>, count: Long) {
+    val chunk = ByteArray(1 shl 20)
+    var at = 0L
+    while (at < count) {
+        val n = minOf(chunk.size.toLong(), count - at).toInt()
+        chunk.usePinned { platform.posix.memcpy(it.addressOf(0), src + at, n.toULong()) }
+        write(chunk, 0, n)
+        at += n
+    }
+}
 
 object DeflateStream {
     /** DeflateStream.compressZlib (DS:302-311): returns the bytes consumed. */
@@ -38,63 +75,99 @@ object DeflateStream {
         return n
     }
 
-    /** DeflateStream.compressZlibResult (DS:318-328): (Z_STREAM_ERROR, 0) and an untouched sink for level > 9. */
+    /**
+     * DeflateStream.compressZlibResult (DS:318-328): (Z_STREAM_ERROR, 0) and an untouched sink for level > 9.
+     * One zlib stream made of slab bodies: every slab is compressed as a headerless, byte-aligned body primed with the
+     * 32 KiB before it (zk_deflate_shard, the multi-GPU sharding primitive), the checksums fold with zk_adler32_combine,
+     * the header goes in front and the final block + Adler-32 behind (zk_zlib_header / zk_zlib_tail).
+     */
     fun compressZlibResult(source: BufferedSource, sink: BufferedSink, level: Int = 6): Pair<Int, Long> {
         if (level > 9) return ZK_STREAM_ERROR to 0L
-        val input = source.drain()
-        val bound = zk_compress_bound(input.size.toULong()).toInt()
-        val out = ByteArray(bound)
-        memScoped {
-            val outLen = alloc<ULongVar>()
-            val rc = input.usePinned { inp ->
-                out.usePinned { o ->
-                    zk_deflate_zlib(
-                        engine.ctx,
-                        if (input.isEmpty()) null else inp.addressOf(0).reinterpret(), input.size.toULong(),
-                        level, ZK_DEFAULT_STRATEGY,
-                        o.addressOf(0).reinterpret(), bound.toULong(), outLen.ptr, null,
+        val input = PinnedSlab(WINDOW + SLAB)          // [32 KiB of history | slab]
+        val output = PinnedSlab(zk_compress_bound(SLAB.toULong()).toLong())
+        try {
+            memScoped {
+                val head = allocArray<UByteVar>(2)
+                zk_zlib_header(level, head)
+                sink.writeFrom(head, 2)
+                val bodyLen = alloc<ULongVar>()
+                val slabAdler = alloc<UIntVar>()
+                var adler = 1u
+                var total = 0L
+                var hist = 0
+                while (true) {
+                    val n = source.readInto((input.ptr + WINDOW)!!, SLAB)
+                    if (n == 0L) break
+                    val rc = zk_deflate_shard(
+                        engine.ctx, if (hist > 0) (input.ptr + (WINDOW - hist)) else null, hist.toUInt(),
+                        input.ptr + WINDOW, n.toULong(), level, ZK_DEFAULT_STRATEGY,
+                        output.ptr, output.bytes.toULong(), bodyLen.ptr, slabAdler.ptr,
                     )
+                    if (rc != ZK_OK) return rc to total
+                    sink.writeFrom(output.ptr, bodyLen.value.toLong())
+                    adler = zk_adler32_combine(adler, slabAdler.value, n.toULong())
+                    total += n
+                    // the last 32 KiB of this slab prime the next one
+                    hist = minOf(WINDOW.toLong(), if (n >= WINDOW) WINDOW.toLong() else hist + n).toInt()
+                    platform.posix.memmove(input.ptr + (WINDOW - hist), input.ptr + (WINDOW + n - hist), hist.toULong())
+                    if (n < SLAB) break
                 }
+                val tail = allocArray<UByteVar>(6)
+                zk_zlib_tail(adler, tail)
+                sink.writeFrom(tail, 6)
+                sink.flush()
+                return ZK_OK to total
             }
-            if (rc != ZK_OK) return rc to 0L
-            sink.write(out, 0, outLen.value.toInt())
-            sink.flush()
+        } finally {
+            input.free()
+            output.free()
         }
-        return ZK_OK to input.size.toLong()
     }
 }
 
 object InflateStream {
-    /** InflateStream.inflateZlib (IS:376-438): (Z_STREAM_END, bytesOut) on success. */
+    /**
+     * InflateStream.inflateZlib (IS:376-438): (Z_STREAM_END, bytesOut) on success, the bytes written so far beside any
+     * other code.  The stream goes through the inflate handle slab by slab (zk_inflate carries the 32 KiB window, the
+     * unconsumed tail, the checksum and the totals from call to call and decodes every block once).
+     */
     fun inflateZlib(source: BufferedSource, sink: BufferedSink): Pair<Int, Long> {
-        val input = source.drain()
-        var cap = maxOf(65536L, input.size.toLong() * 8)
-        memScoped {
-            val outLen = alloc<ULongVar>()
-            val used = alloc<ULongVar>()
-            while (true) {
-                val out = ByteArray(cap.toInt())
-                val rc = input.usePinned { inp ->
-                    out.usePinned { o ->
-                        zk_inflate_zlib(
-                            engine.ctx,
-                            if (input.isEmpty()) null else inp.addressOf(0).reinterpret(), input.size.toULong(),
-                            o.addressOf(0).reinterpret(), cap.toULong(), outLen.ptr, used.ptr,
-                        )
-                    }
+        val h = zk_inflate_init(engine.ctx) ?: return ZK_MEM_ERROR to 0L
+        val input = PinnedSlab(SLAB / 4)
+        val output = PinnedSlab(SLAB)
+        var written = 0L
+        try {
+            memScoped {
+                val inLen = alloc<ULongVar>()
+                val outLen = alloc<ULongVar>()
+                var ended = false
+                while (true) {
+                    val n = if (ended) 0L else source.readInto(input.ptr, input.bytes)
+                    if (n < input.bytes) ended = true
+                    var fed = 0L
+                    do {  // hand the slab over, then drain what the engine has decoded
+                        inLen.value = (n - fed).toULong()
+                        outLen.value = output.bytes.toULong()
+                        val rc = zk_inflate(h, if (n > fed) input.ptr + fed else null, inLen.ptr, output.ptr, outLen.ptr,
+                                            if (ended) ZK_FINISH else ZK_NO_FLUSH)
+                        fed += inLen.value.toLong()
+                        if (outLen.value > 0uL) {
+                            sink.writeFrom(output.ptr, outLen.value.toLong())
+                            written += outLen.value.toLong()
+                        }
+                        if (rc == ZK_STREAM_END) { sink.flush(); return ZK_STREAM_END to written }
+                        if (rc != ZK_OK && !(rc == ZK_BUF_ERROR && !ended)) { sink.flush(); return rc to written }  // IS:425-437
+                    } while (fed < n || outLen.value == output.bytes.toULong())
+                    if (ended && n == 0L) { sink.flush(); return ZK_BUF_ERROR to written }
                 }
-                // ZK_BUF_ERROR with nothing written: the output did not fit (or the input is truncated); DEFLATE
-                // expands at most 1032:1
-                if (rc == ZK_BUF_ERROR && outLen.value == 0uL && cap < input.size.toLong() * 1100 + 65536) {
-                    cap *= 8
-                    continue
-                }
-                if (outLen.value > 0uL) sink.write(out, 0, outLen.value.toInt())
-                return rc to outLen.value.toLong()
             }
+        } finally {
+            zk_stream_end(h)
+            input.free()
+            output.free()
         }
         @Suppress("UNREACHABLE_CODE")
-        return ZK_STREAM_ERROR to 0L
+        return ZK_STREAM_ERROR to written
     }
 }
 
