@@ -50,7 +50,10 @@ namespace {
 constexpr int kThreadsLz = ZK_LZ_THREADS;
 constexpr int kWarpsLz = kThreadsLz / 32;
 constexpr int kHashBits = 14;  // 16384 buckets of 16-bit positions (q & 0xFFFF: the ring holds 64 KiB, links are 16-bit too)
-constexpr int kRun = 2;                      // consecutive positions per lane
+#ifndef ZK_LZ_RUN
+#define ZK_LZ_RUN 2
+#endif
+constexpr int kRun = ZK_LZ_RUN;                     // consecutive positions per lane
 constexpr int kStrip = 32 * kRun;            // positions per work-stealing strip
 constexpr int kStripsPerGroup = kGroup / kStrip;
 constexpr int kTaskCap = kStrip;              // compare tasks a warp queues before it runs them
@@ -882,7 +885,8 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             if (searching || preparing) {
                 for (;;) {
                     int strip = 0;
-                    if (lane == 0) strip = atomicAdd(&s.work[i & 1], 1);
+                    // (one lane, one instruction: atomicAdd() here compiles to a warp-aggregated sequence of twenty)
+                    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(strip) : "r"(smem_addr(&s.work[i & 1])) : "memory");
                     strip = __shfl_sync(kFull, strip, 0);
                     if (strip >= kStripsPerGroup) break;
                     PrepVotes votes;
