@@ -885,8 +885,9 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             if (searching || preparing) {
                 for (;;) {
                     int strip = 0;
-                    // (one lane, one instruction: atomicAdd() here compiles to a warp-aggregated sequence of twenty)
-                    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(strip) : "r"(smem_addr(&s.work[i & 1])) : "memory");
+                    // (one lane, one instruction: an add of the constant 1 -- atomicAdd() or atom.add in PTX -- is turned into a
+                    // warp-aggregated sequence of twenty instructions by ptxas; inc is not)
+                    if (lane == 0) asm volatile("atom.shared.inc.u32 %0, [%1], 0x7FFFFFFF;" : "=r"(strip) : "r"(smem_addr(&s.work[i & 1])) : "memory");
                     strip = __shfl_sync(kFull, strip, 0);
                     if (strip >= kStripsPerGroup) break;
                     PrepVotes votes;
