@@ -508,64 +508,79 @@ __device__ __forceinline__ void search_strip(LzSmem &s, const SearchCtx &cx, int
             }
         }
     }
-    // extension of matches that filled the 16-byte compare: cooperative, one round per distinct distance.  For a
-    // distance d the end of every match of the strip is the first x with byte[x] != byte[x-d]; the lanes of the warp
-    // compare 3 x 32 words (384 bytes from the strip's first position + 16) and ballot the mismatching words, then each
-    // lane with that distance finds the first mismatch at or after its own position + 16.
+    // extension of matches that filled the 16-byte compare: cooperative, one round per distinct distance of the strip
+    // (both positions of a lane usually share it).  For a distance d the end of every match of the strip is the first x
+    // with byte[x] != byte[x-d]; the lanes of the warp compare 3 x 32 words (384 bytes from the strip's first position +
+    // 16) and ballot the mismatching words, then each position with that distance finds the first mismatch at or after
+    // itself + 16.
+    {
+        static_assert(kStrip + kCap + kMaxMatch + 4 <= 3 * 32 * 4, "the three ballots cover every match end of the strip");
+        bool ext[kRun];
+        uint32_t pend[kRun], any_pending = 0u;
 #pragma unroll
-    for (int r = 0; r < kRun; ++r) {
-        const int32_t p = p0 + r;
-        bool ext = best[r] >= kCap && best[r] < maxlen[r];
-        uint32_t pending = __ballot_sync(kFull, ext);
-        const uint32_t scan0 = ((uint32_t)(g0 + strip * kStrip + r) + kCap) & ~3u;  // word aligned
-        while (pending) {
-            const int leader = __ffs(pending) - 1;
-            const uint32_t d = (uint32_t)__shfl_sync(kFull, bestd[r], leader);
-            const bool mine = ext && (uint32_t)bestd[r] == d;
+        for (int r = 0; r < kRun; ++r) {
+            ext[r] = best[r] >= kCap && best[r] < maxlen[r];
+            pend[r] = __ballot_sync(kFull, ext[r]);
+            any_pending |= pend[r];
+        }
+        const uint32_t scan0 = ((uint32_t)(g0 + strip * kStrip) + kCap) & ~3u;  // word aligned
+        while (any_pending) {
+            // the distance of the first pending position of the strip
+            uint32_t d = 0u;
+#pragma unroll
+            for (int r = kRun - 1; r >= 0; --r)
+                if (pend[r]) d = (uint32_t)__shfl_sync(kFull, bestd[r], __ffs(pend[r]) - 1);
             uint32_t diff[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const uint32_t x = scan0 + (uint32_t)(k * 32 + lane) * 4u;
                 diff[k] = __ballot_sync(kFull, ring_load32(s.ring, x) != ring_load32(s.ring, x - d));
             }
-            if (mine) {
-                // first mismatching word at or after my position + 16
-                const uint32_t from = (uint32_t)p + kCap;  // first byte not yet compared
-                const uint32_t w0 = (from - scan0) >> 2;   // its word index in the bitmap
-                int len = maxlen[r];
-                uint32_t wfound = 96;
+            any_pending = 0u;
 #pragma unroll
-                for (int k = 2; k >= 0; --k) {
-                    uint32_t bits = diff[k];
-                    const int lo = (int)w0 - k * 32;
-                    if (lo > 0) bits = lo >= 32 ? 0u : bits & ~((1u << lo) - 1u);
-                    if (bits) wfound = (uint32_t)(k * 32 + __ffs(bits) - 1);
-                }
-                if (wfound < 96) {
-                    // the exact byte: compare from max(from, word start)
-                    const uint32_t wx = scan0 + wfound * 4u;
-                    const uint32_t start = wx > from ? wx : from;
-                    const uint32_t xr = ring_load32(s.ring, start) ^ ring_load32(s.ring, start - d);
-                    if (xr) {
-                        len = (int)(start - (uint32_t)p) + ((__ffs((int)xr) - 1) >> 3);
-                    } else {
-                        // rare: the mismatch of that word was before `from`; continue byte-exact with a short loop
-                        int l2 = (int)(start - (uint32_t)p) + 4;
-                        while (l2 < maxlen[r]) {
-                            const uint32_t y = ring_load32(s.ring, (uint32_t)p + l2) ^ ring_load32(s.ring, (uint32_t)p + l2 - d);
-                            if (y) {
-                                l2 += (__ffs((int)y) - 1) >> 3;
-                                break;
-                            }
-                            l2 += 4;
-                        }
-                        len = l2;
+            for (int r = 0; r < kRun; ++r) {
+                const int32_t p = p0 + r;
+                const bool mine = ext[r] && (uint32_t)bestd[r] == d;
+                if (mine) {
+                    // first mismatching word at or after my position + 16
+                    const uint32_t from = (uint32_t)p + kCap;  // first byte not yet compared
+                    const uint32_t w0 = (from - scan0) >> 2;   // its word index in the bitmap
+                    int len = maxlen[r];
+                    uint32_t wfound = 96;
+#pragma unroll
+                    for (int k = 2; k >= 0; --k) {
+                        uint32_t bits = diff[k];
+                        const int lo = (int)w0 - k * 32;
+                        if (lo > 0) bits = lo >= 32 ? 0u : bits & ~((1u << lo) - 1u);
+                        if (bits) wfound = (uint32_t)(k * 32 + __ffs(bits) - 1);
                     }
+                    if (wfound < 96) {
+                        // the exact byte: compare from max(from, word start)
+                        const uint32_t wx = scan0 + wfound * 4u;
+                        const uint32_t start = wx > from ? wx : from;
+                        const uint32_t xr = ring_load32(s.ring, start) ^ ring_load32(s.ring, start - d);
+                        if (xr) {
+                            len = (int)(start - (uint32_t)p) + ((__ffs((int)xr) - 1) >> 3);
+                        } else {
+                            // rare: the mismatch of that word was before `from`; continue byte-exact with a short loop
+                            int l2 = (int)(start - (uint32_t)p) + 4;
+                            while (l2 < maxlen[r]) {
+                                const uint32_t y = ring_load32(s.ring, (uint32_t)p + l2) ^ ring_load32(s.ring, (uint32_t)p + l2 - d);
+                                if (y) {
+                                    l2 += (__ffs((int)y) - 1) >> 3;
+                                    break;
+                                }
+                                l2 += 4;
+                            }
+                            len = l2;
+                        }
+                    }
+                    best[r] = min(len, maxlen[r]);
+                    ext[r] = false;
                 }
-                best[r] = min(len, maxlen[r]);
-                ext = false;
+                pend[r] &= ~__ballot_sync(kFull, mine);
+                any_pending |= pend[r];
             }
-            pending &= ~__ballot_sync(kFull, mine);
         }
     }
     uint32_t word[kRun];
