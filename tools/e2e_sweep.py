@@ -44,7 +44,7 @@ run("default")
 run("overlap off", slab_overlap=0)
 run("per-kernel timing events on", timing=1)
 run("default again")
-for slab, first in ((128, 64), (64, 32), (48, 24), (32, 16), (16, 16)):
+for slab, first in ((148, 74), (148, 37), (128, 64), (111, 37), (96, 32), (74, 37), (74, 74), (64, 32), (48, 24), (37, 37), (32, 16)):
     run("slab %d first %d" % (slab, first), host_slab_bytes=slab * M, host_first_slab_bytes=first * M)
 for unit in (256, 512):
     run("unit %d KiB (every slab)" % unit, chunk_bytes=unit << 10)
