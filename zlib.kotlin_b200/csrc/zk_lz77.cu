@@ -164,12 +164,24 @@ struct UnitGeom {
     int32_t data_end_q;   // kWindow + ulen
     int first_group;      // group holding h0q
     int last_group;       // last data group
+    bool in_aligned;      // the shard's bytes of this unit start on a 16-byte boundary in global memory
 };
 
 // Stage group t of the unit into the ring.  Source bytes may come from the shard itself or, for the
 // history of unit 0, from the separate history buffer.  Returns true when the TMA path was used.
 __device__ __forceinline__ bool stage_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t) {
     const int32_t q0 = t * kGroup;
+    // the common case -- a whole group of the shard itself, 16-byte aligned in global memory -- is decided with three
+    // compares; only the issuing thread does the address arithmetic
+    if (q0 >= kWindow && q0 + kGroup <= g.data_end_q && g.in_aligned) {
+        if (threadIdx.x == 0) {
+            const uint8_t *src = a.in + g.unit_start - kWindow + q0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s.bar[t & (kStages - 1)], (uint32_t)kGroup);
+            tma_load(reinterpret_cast<uint8_t *>(s.ring) + (q0 & 0xFFFF), src, (uint32_t)kGroup, &s.bar[t & (kStages - 1)]);
+        }
+        return true;
+    }
     // valid source range of this group in q coordinates
     int32_t lo = max(q0, g.h0q);
     // bytes past the unit end are only ever hashed, never matched: stage what the input still has
@@ -613,14 +625,15 @@ __device__ __forceinline__ void parser_barrier() { asm volatile("bar.sync 1, %0;
 
 // L = parser lane = segment index.  The carry (first unparsed position, tokens emitted, block start) lives in shared
 // memory by group parity: group t reads [t & 1] and writes the other.
+template <bool kProf>
 __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const UnitGeom &g, int t, int L, uint32_t unit_index,
                                             long long (&pt)[6]) {
-    long long tc = clock64();
-#define ZK_PT(i)                         \
-    {                                    \
-        const long long now = clock64(); \
-        pt[i] += now - tc;               \
-        tc = now;                        \
+    long long tc = kProf ? clock64() : 0;
+#define ZK_PT(i)                             \
+    if (kProf) {                             \
+        const long long now = clock64();     \
+        pt[i] += now - tc;                   \
+        tc = now;                            \
     }
     const LevelParams &lp = a.lp;
     const uint32_t *mv = s.match[t & 1];
@@ -813,6 +826,8 @@ __device__ __forceinline__ void parse_group(LzSmem &s, const LzArgs &a, const Un
 #undef ZK_PT
 }
 
+// kProf: per-role cycle counters for tools/lz_profile.py (a second instantiation: the clock reads are not free)
+template <bool kProf>
 __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LzSmem &s = *reinterpret_cast<LzSmem *>(smem_raw);
@@ -833,6 +848,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         g.data_end_q = kWindow + (int32_t)g.ulen;
         g.first_group = g.h0q / kGroup;
         g.last_group = (g.data_end_q - 1) / kGroup;
+        g.in_aligned = ((reinterpret_cast<uintptr_t>(a.in) + g.unit_start) & 15u) == 0;
         SearchCtx cx;
         cx.lp = a.lp;
         cx.h0q = g.h0q;
@@ -880,7 +896,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
         // step i: stage(i+4) | prepare(i+2) | build(i+1) | search(i) | parse(i-1)
         long long t_role = 0, t_search = 0;
         long long pt[6] = {0, 0, 0, 0, 0, 0};
-        const long long t_unit0 = clock64();
+        const long long t_unit0 = kProf ? clock64() : 0;
         for (int i = g.first_group - 2; i <= g.last_group + 1; ++i) {
             const bool tma_next = (i + 4 <= g.last_group + 1) ? stage_group(s, a, g, i + 4) : false;
             if (threadIdx.x == 0) {
@@ -890,11 +906,11 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             // (the first group of a unit has no sample before it: it probes everywhere)
             const bool probe_all = !a.lp.probe_adaptive || i <= kHistGroups || s.probe_hits[(i - 1) & 3] >= kProbeThreshold;
 
-            const long long t0 = clock64();
+            const long long t0 = kProf ? clock64() : 0;
             if (is_builder && i + 1 <= g.last_group && i + 1 >= g.first_group) build_group(s, i + 1, lane);
             if (is_parser && i - 1 >= kHistGroups && i - 1 <= g.last_group)
-                parse_group(s, a, g, i - 1, parser_index * 32 + lane, unit, pt);
-            const long long t1 = clock64();
+                parse_group<kProf>(s, a, g, i - 1, parser_index * 32 + lane, unit, pt);
+            const long long t1 = kProf ? clock64() : 0;
             const bool searching = i >= kHistGroups && i <= g.last_group;
             const bool preparing = i + 2 >= g.first_group && i + 2 <= g.last_group;
             if (searching || preparing) {
@@ -911,7 +927,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
                     if (preparing) prep_finish(s, i + 2, strip * kStrip, lane, votes);
                 }
             }
-            const long long t2 = clock64();
+            const long long t2 = kProf ? clock64() : 0;
             t_role += t1 - t0;
             t_search += t2 - t1;
             if (tma_next) {
@@ -928,7 +944,7 @@ __global__ void __launch_bounds__(kThreadsLz, 1) lz77_kernel(const LzArgs a) {
             }
             __syncthreads();
         }
-        if (a.prof && lane == 0 && (warp == kBuilderWarp || warp == kFirstParserWarp || warp == 2)) {
+        if (kProf && a.prof && lane == 0 && (warp == kBuilderWarp || warp == kFirstParserWarp || warp == 2)) {
             // per unit: [0] total; {role, search} cycles of [1,2] the builder, [3,4] the first parser warp, [5,6] a
             // searcher; [8..13] the parser's phases (pass A + stitch 1, wait, stitch 2, pass B + count, wait, copy-out)
             unsigned long long *o = a.prof + (size_t)unit * 32;
@@ -1003,9 +1019,14 @@ int launch_lz77(zk_ctx *c, const uint8_t *d_in, uint64_t n, const uint8_t *d_his
     a.block_tok_begin = block_tok_begin;
     a.block_tok_count = block_tok_count;
     // per-device attribute: set on every launch (cheap) so multi-device processes stay correct
-    ZK_CUDA(cudaFuncSetAttribute(lz77_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzSmem)));
     const uint32_t grid = a.num_units;
-    lz77_kernel<<<grid, kThreadsLz, sizeof(LzSmem), c->stream>>>(a);
+    if (prof) {
+        ZK_CUDA(cudaFuncSetAttribute(lz77_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzSmem)));
+        lz77_kernel<true><<<grid, kThreadsLz, sizeof(LzSmem), c->stream>>>(a);
+    } else {
+        ZK_CUDA(cudaFuncSetAttribute(lz77_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzSmem)));
+        lz77_kernel<false><<<grid, kThreadsLz, sizeof(LzSmem), c->stream>>>(a);
+    }
     c->launches += 1;
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
