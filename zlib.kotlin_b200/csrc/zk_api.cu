@@ -425,6 +425,10 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         c->opt_auto_register = value != 0;
         return ZK_OK;
     }
+    if (!strcmp(name, "inflate_foreign")) {  // 0: streams without sync markers are decoded by one warp (default 1: entry points
+        c->opt_foreign_path = value != 0;    // are searched at dynamic block headers, zk_inflate.cu block_find_kernel)
+        return ZK_OK;
+    }
     if (!strcmp(name, "inflate_pipe")) {  // 1: large marked streams go through the slab pipeline (default 0: one pass)
         c->opt_inflate_pipe = value != 0;
         return ZK_OK;
@@ -452,6 +456,8 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
     if (!strcmp(name, "kernel_launches")) return c->launches;
     if (!strcmp(name, "h2d_bytes")) return c->h2d_bytes;
     if (!strcmp(name, "d2h_bytes")) return c->d2h_bytes;
+    if (!strcmp(name, "inflate_foreign_chunks")) return c->foreign_chunks;
+    if (!strcmp(name, "inflate_foreign_merges")) return c->foreign_merges;
     if (!strcmp(name, "inflate_pipe_slabs")) return c->pipe_slabs;
     if (!strcmp(name, "inflate_pipe_fallbacks")) return c->pipe_fallbacks;
     // device time per kernel class in microseconds / launches timed; call after zk_ctx_synchronize

@@ -97,6 +97,8 @@ struct zk_ctx {
     int64_t opt_auto_register = 0;    // 1: host-buffer calls page-lock caller buffers CUDA does not know yet and keep them locked
     void *registered[16] = {};        // ... those buffers (unlocked by zk_host_unregister or when the context goes)
     int num_registered = 0;
+    int64_t opt_foreign_path = 1;     // 0: streams without sync markers are decoded by one warp (the round-1 behaviour)
+    int64_t foreign_chunks = 0, foreign_merges = 0;  // counters: chunks decoded through found entry points, false entry points merged
     int64_t opt_lane_pack = 0;        // 1: the lane decoder fills whole CTAs (few SMs per call) so that several calls run side by side
     int64_t opt_inflate_slab = 0;     // compressed bytes per slab of that pipeline, 0 = built-in
     zk_ctx *helpers[4] = {nullptr, nullptr, nullptr, nullptr};  // contexts of the pipeline's workers (own stream + arena)

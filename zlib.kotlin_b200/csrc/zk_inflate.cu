@@ -32,6 +32,10 @@
 // decodes them; the two exceptions that escape inflateZlib (IS:243 -> CH:127,133) become Z_DATA_ERROR.
 #include "zk_common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 namespace zk {
 
 namespace {
@@ -115,8 +119,8 @@ struct BitReader {
 // the lane through a ring of kRing 32-bit words in shared memory filled by cp.async: the word requested at one refill
 // is consumed kRing - 1 refills (~30 tokens) later, and no register waits on a load in between (in-order issue would
 // stall the warp at the first instruction that touches such a register).  An L2 prefetch runs half a KiB further on.
-// Words that are not entirely inside [base, base + len) read as zero in the hot path (that can only be the tail of the
-// Adler trailer); seek_bits() reads edge words byte by byte.
+// A word that is not entirely inside [base, base + len) is read byte by byte (the last word of a raw deflate stream may
+// hold its last codes); words behind the stream read as zero.
 constexpr int kRing = 8;
 struct FastReader {
     uint64_t hold;
@@ -161,6 +165,9 @@ struct FastReader {
     __device__ __forceinline__ void refill(bool pred) {
         const uint32_t take = (pred && held <= 32) ? 1u : 0u;
         const uint32_t nroff = (roff + 128u) & (uint32_t)((kRing - 1) * 128);
+        const uint32_t slot = ring + roff;
+        const bool tail_word = take && words_left == 0 && (uintptr_t)at < hi;  // the last, partial word of the stream
+        const uintptr_t tail_at = (uintptr_t)at;
         asm volatile(
             "{\n\t.reg .pred t, p, q, f;\n\t.reg .b64 tmp;\n\t.reg .b32 lowat;\n\t"
             "setp.ne.u32 t, %6, 0;\n\t"
@@ -184,8 +191,14 @@ struct FastReader {
             "@t add.u64 %4, %4, 4;\n\t"
             "@t add.s32 %5, %5, -1;\n\t}"
             : "+l"(hold), "+r"(held), "+r"(w0), "+r"(roff), "+l"(at), "+r"(words_left)
-            : "r"(take), "r"(ring + roff), "r"(ring + nroff), "r"(nroff)
+            : "r"(take), "r"(slot), "r"(ring + nroff), "r"(nroff)
             : "memory");
+        // a raw deflate stream may end inside a word (zlib and gzip streams end with a trailer of four or eight bytes, so their
+        // partial word never holds a code): that word is read byte by byte, once per lane at most
+        if (tail_word) {
+            const uint32_t w = fetch_edge(tail_at);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot), "r"(w) : "memory");
+        }
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)hold & ((1u << n) - 1u); }  // n <= 16
     __device__ __forceinline__ void drop(int n) {
@@ -1196,7 +1209,7 @@ __global__ void __launch_bounds__(1024) marker_scan_kernel(const uint32_t *__res
 }
 
 struct LaneChunk {
-    uint64_t in_begin, in_end;
+    uint64_t in_begin, in_end;  // bytes (the bytes that hold begin_bits / target_bits)
     uint64_t out_begin;
     uint32_t out_len;
     int32_t status;
@@ -1206,7 +1219,13 @@ struct LaneChunk {
     uint64_t stored_src;  // a chunk that is one stored block: byte offset of its payload in the stream ...
     uint32_t stored_len;  // ... and its length (then units == 0)
     uint32_t pad;
+    uint64_t begin_bits;   // bit position of the chunk's first block (a multiple of 8 behind a sync marker)
+    uint64_t target_bits;  // where it must end: the next chunk's begin_bits, or the end of the stream
+    uint64_t end_bits;     // where its last block did end
+    uint64_t slot_off;     // first unit of its token stream in the slot array
 };
+// a chunk of a foreign stream whose decode passed target_bits inside a block: the entry point behind it was not one
+constexpr int32_t kLaneOverrun = 1000;
 
 __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32_t num_markers, uint64_t m,
                                   LaneChunk *__restrict__ lc, uint32_t body_begin) {
@@ -1214,6 +1233,10 @@ __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32
     if (k > num_markers) return;
     lc[k].in_begin = k == 0 ? body_begin : positions[k - 1];
     lc[k].in_end = k < num_markers ? positions[k] : m;
+    lc[k].begin_bits = lc[k].in_begin * 8;
+    lc[k].target_bits = lc[k].in_end * 8;
+    lc[k].end_bits = 0;
+    lc[k].slot_off = (uint64_t)k * kSlotSyms;
     lc[k].out_begin = 0;
     lc[k].out_len = 0;
     lc[k].status = ZK_OK;
@@ -1290,6 +1313,274 @@ struct LongCodes {
     }
 };
 
+// ===== entry points into streams somebody else made ==========================================================
+// A stream written by libz (or by the reference) has no sync markers, but most of its blocks are dynamic-Huffman blocks,
+// and the header of such a block is very unlike random bits: BFINAL/BTYPE, HLIT and HDIST in range, a COMPLETE code-length
+// code (Kraft sum exactly 1), code lengths that decode without overflow, a literal/length code that is complete and has an
+// end-of-block code, a distance code that is complete or a single code.  Those are the checks parse_huffman_header applies
+// (IS:299-348, 102-152) -- an accepted position is a header the decoder will take -- plus the complete code-length code.
+// Measured on libz output (tools/blockfind_model.cpp, the CPU model of this kernel): 12.5 % of all bit positions pass the
+// type test, 0.045 % have a complete code-length code as well, and of 16 M positions per file every accepted one was a true
+// block start.  block_find_kernel: one CTA per span of 8 KiB; the FIRST accepted bit position of the span is a candidate
+// chunk start.  Per tile of 1 KiB every thread tests its 32 bit positions for the type / HLIT / HDIST pattern and queues the
+// hits (at most every third position can be one); the queue is worked off with the Kraft sum (seven lookups in a 512-entry
+// table of three 3-bit lengths); what passes is queued again, and once a warp's worth has gathered warp 0 decodes those
+// headers completely, one per lane.  A false candidate costs a second decode of the chunk before it (run_inflate merges
+// the two), a missed block start only its entry point.
+constexpr uint32_t kFindSpan = 8192;
+constexpr uint64_t kForeignMinBytes = 256 << 10;  // below that the warp-per-chunk decoder is as quick
+constexpr uint64_t kForeignMinChunks = 8;
+constexpr int kForeignRounds = 8;                 // merges of consecutive false entry points before the slow path takes over
+constexpr uint32_t kFindSlack = 1024;   // bytes staged behind the span: a header is at most ~560 bytes
+constexpr uint32_t kFindTile = 1024;    // bytes per tile: 32 bit positions per thread
+constexpr int kFindThreads = 256;
+constexpr uint32_t kFindQ1 = kFindTile * 8 / 3 + 8, kFindQ2 = kFindTile * 8 / 3 + 64;
+constexpr uint64_t kNoBits = ~0ull;
+
+struct FindSmem {
+    uint32_t data[(kFindSpan + kFindSlack) / 4 + 8];
+    uint32_t q2[kFindQ2];   // bit positions in the span whose code-length code is complete
+    uint16_t q1[kFindQ1];   // bit positions in the tile that look like BFINAL 0, BTYPE 2, HLIT <= 29, HDIST <= 29
+    uint8_t kraft3[512];
+    uint8_t pre[32][128];   // warp 0: every lane's table of the code-length code (length << 5 | symbol)
+    uint32_t n1, n2;
+    uint32_t best;
+};
+
+// 32 bits of the stream at bit position `bit` of the span: from the staged bytes, or from global memory behind them; bits
+// past the end of the stream read as zero
+__device__ __forceinline__ uint32_t find_bits32(const FindSmem &sm, const uint8_t *__restrict__ in, uint64_t m, uint64_t span_byte,
+                                                uint32_t bit) {
+    const uint32_t w = bit >> 5, sh = bit & 31;
+    if ((w + 2) * 4 <= kFindSpan + kFindSlack) return __funnelshift_r(sm.data[w], sm.data[w + 1], sh);
+    uint64_t v = 0;
+    const uint64_t b0 = span_byte + (uint64_t)w * 4;
+    for (int i = 0; i < 8; ++i)
+        if (b0 + i < m) v |= (uint64_t)in[b0 + i] << (8 * i);
+    return (uint32_t)(v >> sh);
+}
+
+// the rest of the checks for one position whose code-length code is complete.  `tab` = this lane's 128-entry table.
+__device__ bool find_check_lengths(const FindSmem &sm, const uint8_t *__restrict__ in, uint64_t m, uint64_t span_byte, uint32_t at,
+                                   uint8_t *tab) {
+    const uint64_t nbits = m * 8, abs0 = span_byte * 8;
+    const uint32_t h = find_bits32(sm, in, m, span_byte, at);
+    const int hlit = (int)((h >> 3) & 31u) + 257, hdist = (int)((h >> 8) & 31u) + 1, hclen = (int)((h >> 13) & 15u) + 4;
+    uint32_t pos = at + 17;
+    {
+        int clen[19];
+#pragma unroll
+        for (int i = 0; i < 19; ++i) clen[i] = 0;
+        const uint32_t f0 = find_bits32(sm, in, m, span_byte, pos), f1 = find_bits32(sm, in, m, span_byte, pos + 30);
+#pragma unroll
+        for (int i = 0; i < 19; ++i) {
+            const int l = i < hclen ? (int)((i < 10 ? f0 >> (3 * i) : f1 >> (3 * (i - 10))) & 7u) : 0;
+            clen[i_cl_order[i]] = l;
+        }
+        pos += 3 * hclen;
+        int per[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nextc[8];
+#pragma unroll
+        for (int i = 0; i < 19; ++i) per[clen[i]]++;
+        per[0] = 0;
+        int code = 0;
+        nextc[0] = 0;
+#pragma unroll
+        for (int b = 1; b <= 7; ++b) {
+            code = (code + per[b - 1]) << 1;
+            nextc[b] = code;
+        }
+        for (int sym = 0; sym < 19; ++sym) {
+            const int l = clen[sym];
+            if (!l) continue;
+            const uint32_t c = (uint32_t)nextc[l]++;
+            for (uint32_t idx = rev_bits(c, l); idx < 128u; idx += 1u << l) tab[idx] = (uint8_t)(l << 5 | sym);
+        }
+    }
+    int per[2][16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) per[0][b] = per[1][b] = 0;
+    int used0 = 0, used1 = 0, eob = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int count = pass == 0 ? hlit : hdist;
+        int i = 0, prev = 0;
+        while (i < count) {
+            if (abs0 + pos + 1 > nbits) return false;
+            const uint32_t look = find_bits32(sm, in, m, span_byte, pos);
+            const uint32_t e = tab[look & 127u];
+            const int sym = (int)(e & 31u);
+            pos += e >> 5;
+            if (sym <= 15) {
+                if (sym) {
+                    per[pass][sym]++;
+                    if (pass == 0) {
+                        ++used0;
+                        if (i == 256) eob = 1;
+                    } else {
+                        ++used1;
+                    }
+                }
+                prev = sym;
+                ++i;
+                continue;
+            }
+            if (sym == 16 && i == 0) return false;  // IS:246
+            const int nb = sym == 16 ? 2 : sym == 17 ? 3 : 7;
+            const int rep = (sym == 18 ? 11 : 3) + (int)((look >> (e >> 5)) & ((1u << nb) - 1u));
+            pos += nb;
+            if (i + rep > count) return false;
+            const int v = sym == 16 ? prev : 0;
+            if (v) {
+                per[pass][v] += rep;
+                if (pass == 0) {
+                    used0 += rep;
+                    if (i <= 256 && 256 < i + rep) eob = 1;
+                } else {
+                    used1 += rep;
+                }
+            }
+            prev = v;
+            i += rep;
+        }
+    }
+    if (abs0 + pos > nbits) return false;
+    if (!eob || !used1) return false;  // IS:102-152: an end-of-block code and a distance code
+    for (int pass = 0; pass < 2; ++pass) {
+        int left = 1;
+        for (int b = 1; b <= 15; ++b) {
+            left = (left << 1) - per[pass][b];
+            if (left < 0) return false;
+        }
+        if (left != 0 && (pass == 0 ? used0 : used1) > 1) return false;
+    }
+    return true;
+}
+
+// cand[span] = the first accepted bit position of the span behind min_bits (kNoBits if there is none), flags[span] = 1 / 0
+__global__ void __launch_bounds__(kFindThreads) block_find_kernel(const uint8_t *__restrict__ in, uint64_t m, uint64_t min_bits,
+                                                                uint64_t *__restrict__ cand, uint32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint8_t find_smem_raw[];
+    FindSmem &sm = *reinterpret_cast<FindSmem *>(find_smem_raw);
+    const uint64_t span_byte = (uint64_t)blockIdx.x * kFindSpan;
+    const uint64_t nbits = m * 8, span_bits0 = span_byte * 8;
+    const int tid = threadIdx.x;
+    {
+        // stage the span and its slack; bytes past the stream are zero
+        const uint32_t words = (kFindSpan + kFindSlack) / 4 + 8;
+        const bool aligned = (reinterpret_cast<uintptr_t>(in) & 3u) == 0;
+        for (uint32_t w = tid; w < words; w += kFindThreads) {
+            const uint64_t b = span_byte + (uint64_t)w * 4;
+            uint32_t v = 0;
+            if (aligned && b + 4 <= m) {
+                v = __ldg(reinterpret_cast<const uint32_t *>(in + b));
+            } else {
+                for (int i = 0; i < 4; ++i)
+                    if (b + i < m) v |= (uint32_t)in[b + i] << (8 * i);
+            }
+            sm.data[w] = v;
+        }
+        for (int i = tid; i < 512; i += kFindThreads) {  // Kraft weight of three 3-bit lengths: 128 >> l for l != 0
+            int k = 0;
+            for (int f = 0; f < 3; ++f) {
+                const int l = (i >> (3 * f)) & 7;
+                if (l) k += 128 >> l;
+            }
+            sm.kraft3[i] = (uint8_t)k;
+        }
+        if (tid == 0) {
+            sm.n1 = 0;
+            sm.n2 = 0;
+            sm.best = 0xFFFFFFFFu;
+        }
+    }
+    __syncthreads();
+    const uint32_t span_bytes = (uint32_t)tmin<uint64_t>(kFindSpan, m > span_byte ? m - span_byte : 0);
+    for (uint32_t tile = 0; tile < span_bytes; tile += kFindTile) {
+        {
+            // type / HLIT / HDIST at 32 positions per thread: its own word and the next
+            const uint32_t w = tile / 4 + tid;
+            const uint32_t w0 = sm.data[w], w1 = sm.data[w + 1];
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t x = __funnelshift_r(w0, w1, j);
+                const bool hit = ((x & 7u) == 4u) & (((x >> 3) & 31u) <= 29u) & (((x >> 8) & 31u) <= 29u);
+                if (hit) sm.q1[atomicAdd(&sm.n1, 1u)] = (uint16_t)(tid * 32 + j);
+            }
+        }
+        __syncthreads();
+        const uint32_t n1 = sm.n1;
+        for (uint32_t i = tid; i < n1; i += kFindThreads) {
+            // complete code-length code: HCLEN + 4 lengths of 3 bits from bit 17 on, 57 bits at most
+            const uint32_t at = tile * 8 + sm.q1[i];
+            const uint32_t w = at >> 5, sh = at & 31;
+            const uint32_t a = sm.data[w], b = sm.data[w + 1], c2 = sm.data[w + 2], d = sm.data[w + 3];
+            const uint32_t x0 = __funnelshift_r(a, b, sh), x1 = __funnelshift_r(b, c2, sh), x2 = __funnelshift_r(c2, d, sh);
+            const int hclen = (int)((x0 >> 13) & 15u) + 4;
+            uint64_t f = ((uint64_t)__funnelshift_r(x1, x2, 17) << 32) | __funnelshift_r(x0, x1, 17);
+            f &= (1ull << (3 * hclen)) - 1ull;
+            int k = 0;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) k += sm.kraft3[(uint32_t)(f >> (9 * t)) & 511u];
+            if (k == 128 && span_bits0 + at + 33 <= nbits && span_bits0 + at > min_bits) sm.q2[atomicAdd(&sm.n2, 1u)] = at;
+        }
+        __syncthreads();
+        const uint32_t n2 = sm.n2;
+        const bool last_tile = tile + kFindTile >= span_bytes;
+        if (n2 >= 32u || (last_tile && n2)) {
+            if (tid < 32) {
+                for (uint32_t i = tid; i < n2; i += 32) {
+                    const uint32_t at = sm.q2[i];
+                    if (find_check_lengths(sm, in, m, span_byte, at, sm.pre[tid])) atomicMin(&sm.best, at);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sm.n2 = 0;
+        }
+        if (tid == 0) sm.n1 = 0;
+        __syncthreads();
+        if (sm.best != 0xFFFFFFFFu) break;
+    }
+    if (tid == 0) {
+        const uint32_t best = sm.best;
+        cand[blockIdx.x] = best != 0xFFFFFFFFu ? span_bits0 + best : kNoBits;
+        flags[blockIdx.x] = best != 0xFFFFFFFFu ? 1u : 0u;
+    }
+}
+
+// candidates -> chunk table: chunk 0 starts at the first block of the stream, chunk k at the k-th candidate
+__global__ void foreign_table_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ flags,
+                                     const uint64_t *__restrict__ off, uint32_t spans, uint64_t total, uint64_t m,
+                                     uint32_t body_begin, LaneChunk *__restrict__ lc) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > spans) return;
+    uint64_t k, begin;
+    if (s == spans) {  // chunk 0
+        k = 0;
+        begin = (uint64_t)body_begin * 8;
+    } else {
+        if (!flags[s]) return;
+        k = off[s] + 1;
+        begin = cand[s];
+        lc[k - 1].target_bits = begin;
+        lc[k - 1].in_end = begin >> 3;
+    }
+    lc[k].in_begin = begin >> 3;
+    lc[k].begin_bits = begin;
+    if (k == total) {
+        lc[k].target_bits = m * 8;
+        lc[k].in_end = m;
+    }
+    lc[k].out_begin = 0;
+    lc[k].out_len = 0;
+    lc[k].status = ZK_OK;
+    lc[k].end_byte = 0;
+    lc[k].end_bits = 0;
+    lc[k].final_seen = 0;
+    lc[k].units = 0;
+    lc[k].stored_src = 0;
+    lc[k].stored_len = 0;
+    lc[k].slot_off = (begin + 3) & ~3ull;  // a unit per bit position, four-unit groups aligned
+}
+
 // Longest blocks first: the decode of a block is serial, so the kernel can not end before its longest block does, and a
 // warp waits for the slowest of its 32 lanes.  Blocks are bucketed by compressed size (a proxy for their token count)
 // in descending order; a warp then takes 32 blocks of similar size, the big ones start at once.
@@ -1322,6 +1613,15 @@ constexpr int kLaneDistBits = 6;  // ... distance codes up to 6 bits decode from
 constexpr int kLaneWarps = 6;     // 6 x 37 KiB of tables and rings: one persistent CTA per SM, 192 blocks in flight on it
 constexpr int kLaneLitEntries = 1 << kLaneLitBits, kLaneDistEntries = 1 << kLaneDistBits;
 constexpr int kLaneWarpSmem = (kLaneLitEntries + kLaneDistEntries) * 32 * 2 + kRing * 32 * 4;
+// kForeign = false: the blocks of this engine's own streams (one block per lane, at most kSlotSyms symbols, a stored block
+// only alone).  kForeign = true: chunks of a stream somebody else made, cut at the dynamic block headers block_find_kernel
+// found: any number of blocks of any type and size per lane, positions in bits.  Such a chunk's tokens go to the slot array
+// at the chunk's own bit position: a literal costs at least one bit and one unit, a match at least two bits and two units,
+// a stored block at least 35 bits and five units, and a chunk starts with a dynamic header of 40 bits or more -- so a
+// chunk's units stay below the bit position its decode has reached, and chunks never meet.  A token is only written when
+// the position behind it is not past the chunk's target: a lane that runs into the next chunk (the entry point was false)
+// stops with kLaneOverrun before it touches that chunk's units, and is decoded again with the chunks merged.
+template <bool kForeign>
 __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const uint8_t *__restrict__ in, uint64_t m,
                                                                           LaneChunk *lc, uint32_t num_chunks,
                                                                           WarpState *tables, uint16_t *slots,
@@ -1344,14 +1644,15 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         enum { kHeader = 0, kSymbols = 1, kDone = 2 };
         int state = live ? kHeader : kDone;
         int status = ZK_OK, final_seen = 0, last = 0;
-        uint64_t end_byte = 0;
+        uint64_t end_byte = 0, end_bits = 0;
         uint32_t produced = 0, stored_len = 0;
         uint64_t stored_src = 0;
         const uint32_t kk = live ? k : 0;
         WarpState &ws = tables[kk];
-        uint16_t *out = slots + (uint64_t)kk * kSlotSyms;
+        uint16_t *out = slots + lc[kk].slot_off;
         TokenSink sink{0ull, 0u, out};
-        const uint64_t in_end = lc[kk].in_end;
+        const uint64_t target = lc[kk].target_bits;
+        constexpr uint32_t kOutCap = kForeign ? 0x7FFF0000u : kSlotSyms;  // symbols a chunk may decode to
         // bytes that exist before the block: the preset dictionary for block 0 (IS:287-291), a full window otherwise
         const uint32_t reach_before = (live && k == 0) ? dict_len : (uint32_t)kWindow;
         LongCodes long_lit, long_dist;
@@ -1359,7 +1660,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         fr.ring = (uint32_t)__cvta_generic_to_shared(s_dist + kLaneDistEntries * 32) + lane * 4;
         fr.lo = (uintptr_t)in;
         fr.hi = fr.lo + m;
-        fr.seek_bits(lc[kk].in_begin * 8);
+        fr.seek_bits(lc[kk].begin_bits);
         while (__any_sync(0xFFFFFFFFu, state != kDone)) {
             if (state == kHeader) {
                 // once or twice per block: the plain byte-wise reader parses the header, the fast one is re-seated after
@@ -1393,31 +1694,46 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                             if (((~len) & 0xFFFFu) != nlen) {
                                 status = ZK_DATA_ERROR;
                                 state = kDone;
-                            } else if (src0 + len > m || produced + len > kSlotSyms || (len && (produced || stored_len))) {
-                                // truncated, more than this path's slot holds, or a chunk that mixes a stored payload
-                                // with other data (not made by this engine): the warp-per-chunk path takes the stream
+                            } else if (src0 + len > m || produced + len > kOutCap ||
+                                       (!kForeign && len && (produced || stored_len))) {
+                                // truncated, more than this path's slot holds, or (this engine's streams) a chunk that
+                                // mixes a stored payload with other data: the warp-per-chunk path takes the stream
                                 status = ZK_BUF_ERROR;
+                                state = kDone;
+                            } else if (kForeign && !last && (src0 + len) * 8 > target) {
+                                status = kLaneOverrun;
                                 state = kDone;
                             } else {
                                 if (len) {  // the payload is copied by the expansion kernel, in parallel
-                                    stored_src = src0;
-                                    stored_len = len;
+                                    if (kForeign) {
+                                        // five units: 0x8000 (a match head of length 0), then 45 + 3 bits in units that are
+                                        // skipped like the distance of a match -- the source offset and the length
+                                        const uint32_t s32 = (uint32_t)src0;
+                                        sink.put(0x8000u | ((0x8000u | (s32 & 0x7FFFu)) << 16), 2u);
+                                        sink.put((0x8000u | ((s32 >> 15) & 0x7FFFu)) | ((0x8000u | (s32 >> 30) | ((len & 0x1FFFu) << 2)) << 16), 2u);
+                                        sink.put(len >> 13, 1u);
+                                    } else {
+                                        stored_src = src0;
+                                        stored_len = len;
+                                    }
                                 }
                                 produced += len;
-                                const uint64_t at = src0 + len;
+                                const uint64_t at = (src0 + len) * 8;
                                 // block boundary (a stored block ends on a byte)
                                 if (last) {
                                     final_seen = 1;
-                                    end_byte = at;
+                                    end_byte = at >> 3;
+                                    end_bits = at;
                                     state = kDone;
-                                } else if (at == in_end) {
-                                    end_byte = at;
+                                } else if (at == target) {
+                                    end_byte = at >> 3;
+                                    end_bits = at;
                                     state = kDone;
-                                } else if (at > in_end) {
+                                } else if (at > target) {
                                     status = ZK_DATA_ERROR;
                                     state = kDone;
                                 } else {
-                                    fr.seek_bits(at * 8);
+                                    fr.seek_bits(at);
                                 }
                             }
                         }
@@ -1469,8 +1785,11 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     if (sym < 0) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
-                    } else if (produced >= kSlotSyms) {
+                    } else if (produced >= kOutCap) {
                         status = ZK_BUF_ERROR;
+                        state = kDone;
+                    } else if (kForeign && fr.bit_pos() > target) {
+                        status = kLaneOverrun;
                         state = kDone;
                     } else {
                         sink.put((uint32_t)sym, 1u);
@@ -1481,12 +1800,14 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     if (last) {
                         final_seen = 1;
                         end_byte = (bits + 7) >> 3;
+                        end_bits = bits;
                         state = kDone;
-                    } else if ((bits & 7) == 0 && (bits >> 3) == in_end) {
+                    } else if (bits == target) {
                         end_byte = bits >> 3;
+                        end_bits = bits;
                         state = kDone;
-                    } else if ((bits >> 3) >= in_end) {
-                        status = ZK_DATA_ERROR;
+                    } else if (bits > target) {
+                        status = kForeign ? kLaneOverrun : ZK_DATA_ERROR;
                         state = kDone;
                     } else {
                         state = kHeader;
@@ -1523,8 +1844,11 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     if (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow || dist > produced + reach_before) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
-                    } else if (produced + length > kSlotSyms) {
+                    } else if (produced + length > kOutCap) {
                         status = ZK_BUF_ERROR;
+                        state = kDone;
+                    } else if (kForeign && fr.bit_pos() > target) {
+                        status = kLaneOverrun;
                         state = kDone;
                     } else {
                         sink.put((0x8000u | length) | ((dist - 1u) << 16), 2u);
@@ -1539,7 +1863,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                 for (int b = 0; b < 2; ++b) {
                     const uint32_t e = s_lit[fr.peek(kLaneLitBits) * 32 + lane];
                     const bool lit = state == kSymbols && e != 0u && (e & 0x0F00u) == 0u && fr.held >= kLaneLitBits &&
-                                     produced < kSlotSyms;
+                                     produced < kOutCap && (!kForeign || fr.bit_pos() + (e >> 12) <= target);
                     if (lit) {
                         fr.drop((int)(e >> 12));
                         sink.put(e & 0xFFu, 1u);
@@ -1558,6 +1882,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
             lc[k].status = status;
             lc[k].out_len = produced;
             lc[k].end_byte = end_byte;
+            lc[k].end_bits = end_bits;
             lc[k].final_seen = final_seen;
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -1566,7 +1891,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
 }
 
 // Verify the blocks, prefix-sum their sizes, build the coarse chunk table for the window chain.
-// verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen
+// verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen,
+// [6] 1 = a chunk failed or did not end where the next one starts
 __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_t n, ChunkInfo *coarse,
                                                           uint32_t *num_coarse, uint64_t *verdict, uint64_t cap, uint64_t m,
                                                           uint32_t trailer, bool shard_body) {
@@ -1585,8 +1911,8 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
             v = lc[i].out_len;
             const bool last = i + 1 == n;
             // every block but the last must end exactly on the next one; the last must close the stream
-            const bool last_ok = shard_body ? (!lc[i].final_seen && lc[i].end_byte == lc[i].in_end) : (lc[i].final_seen != 0);
-            if (lc[i].status != ZK_OK || (last ? !last_ok : (lc[i].final_seen || lc[i].end_byte != lc[i].in_end))) bad = 1;
+            const bool last_ok = shard_body ? (!lc[i].final_seen && lc[i].end_bits == lc[i].target_bits) : (lc[i].final_seen != 0);
+            if (lc[i].status != ZK_OK || (last ? !last_ok : (lc[i].final_seen || lc[i].end_bits != lc[i].target_bits))) bad = 1;
             // a stream cut inside its trailer: the warp-per-chunk decoder reports what the reference reports (BR:48-57)
             if (last && lc[i].end_byte + trailer > m) bad = 1;
         }
@@ -1628,6 +1954,7 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
         verdict[3] = total;
         verdict[4] = lc[n - 1].end_byte;
         verdict[5] = (uint64_t)lc[n - 1].final_seen;
+        verdict[6] = (uint64_t)bad;
     }
 }
 
@@ -1654,7 +1981,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
         return;
     }
     const uint32_t units = lc[j].units;
-    const uint16_t *tok = slots + (uint64_t)j * kSlotSyms;
+    const uint16_t *tok = slots + lc[j].slot_off;
     uint32_t base_out = 0;
     uint32_t carry_prev = 0;  // last unit of the previous pass
     for (uint32_t u0 = 0; u0 < units; u0 += 32) {
@@ -1667,7 +1994,16 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
         const bool is_dist = (prevu & 0x8000u) != 0 && u < units;
         const bool is_match = !is_dist && (me & 0x8000u) != 0 && u < units;
         const bool is_lit = !is_dist && !is_match && u < units;
-        const uint32_t len = is_match ? (me & 0x7FFFu) : (is_lit ? 1u : 0u);
+        uint32_t len = is_match ? (me & 0x7FFFu) : (is_lit ? 1u : 0u);
+        // a match head of length 0 is a stored block of a foreign stream (decode_lanes_kernel<true>): the four units
+        // behind it hold the byte offset of its payload and its length
+        uint32_t stored_at = 0;
+        const bool is_stored = is_match && len == 0u;
+        if (is_stored) {
+            const uint32_t a = tok[u + 1] & 0x7FFFu, b = tok[u + 2] & 0x7FFFu, cc = tok[u + 3] & 0x7FFFu, d = tok[u + 4];
+            stored_at = a | (b << 15) | ((cc & 3u) << 30);
+            len = (cc >> 2) | (d << 13);
+        }
         uint32_t incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1684,18 +2020,42 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
             const uint32_t moff = __shfl_sync(0xFFFFFFFFu, off, src_lane);
             const uint32_t mlen = __shfl_sync(0xFFFFFFFFu, len, src_lane);
             const uint32_t mdist = __shfl_sync(0xFFFFFFFFu, nxt, src_lane) + 1u;
-            if (mdist >= mlen && mlen <= 32u) {  // the common case: one pass, no overlap
+            const uint32_t msrc = __shfl_sync(0xFFFFFFFFu, stored_at, src_lane);
+            if (__shfl_sync(0xFFFFFFFFu, (uint32_t)is_stored, src_lane)) {
+                // up to 64 KiB of payload: eight loads per lane in flight
+                for (uint32_t i0 = 0; i0 < mlen; i0 += 256) {
+                    uint8_t v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t i = i0 + 32 * q + lane;
+                        v[q] = i < mlen ? __ldg(in + msrc + i) : (uint8_t)0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t i = i0 + 32 * q + lane;
+                        if (i < mlen) out[moff + i] = v[q];
+                    }
+                }
+            } else if (mdist >= mlen && mlen <= 32u) {  // the common case: one pass, no overlap
                 if ((uint32_t)lane < mlen) {
                     const int32_t rel = (int32_t)moff - (int32_t)mdist + lane;  // position inside this block
                     out[moff + lane] = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
                 }
             } else {
-#pragma unroll 1
-                for (uint32_t i = lane; i < mlen; i += 32) {
+                // a long or overlapping match: every source lies before the match (i % dist < dist), so the loads of all
+                // nine passes (258 symbols at most) are issued before the first store
+                uint16_t v[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const uint32_t i = 32 * q + lane;
                     const uint32_t kk = mdist >= mlen ? i : i % mdist;
                     const int32_t rel = (int32_t)moff - (int32_t)mdist + (int32_t)kk;
-                    const uint16_t v = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
-                    out[moff + i] = v;
+                    v[q] = i >= mlen ? (uint16_t)0 : rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
+                }
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const uint32_t i = 32 * q + lane;
+                    if (i < mlen) out[moff + i] = v[q];
                 }
             }
             __syncwarp();
@@ -1767,13 +2127,18 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     uint64_t lane_blocks_reserved = tmin<uint64_t>(job.cap / 16384 + 1024, m / 16 + 1);
     if (lane_blocks_reserved < 512) lane_blocks_reserved = 0;
     const uint32_t pieces_reserved = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
-    const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2);
+    // foreign streams: one candidate chunk per 8 KiB span (block_find_kernel), a unit of token space per bit of stream
+    const bool foreign_ok = c->opt_foreign_path && job.container != 3 && m >= kForeignMinBytes && m < (1ull << 32);
+    const uint64_t find_spans = foreign_ok ? (m + kFindSpan - 1) / kFindSpan : 0;
+    const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2),
+                                                         find_spans / kCoarse + 2);
     c->arena.reset();
     if (job.container != 3) c->shard.valid = false;
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
                         (size_t)(max_chunks + 1) * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + crc_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
-                        (size_t)lane_blocks_reserved * (12 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024);
+                        (size_t)lane_blocks_reserved * (12 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024) +
+                        (size_t)find_spans * (24 + sizeof(LaneChunk) + sizeof(WarpState) + 8) + (foreign_ok ? (size_t)(m * 8 + 256) * 2 + 16384 : 0);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
     int32_t *d_header = static_cast<int32_t *>(c->arena.take(256));
     uint32_t *d_cand = static_cast<uint32_t *>(c->arena.take((size_t)num_spans * 4));
@@ -1817,7 +2182,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     ZK_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
     // ---- lane-per-block path: every marker is a block start -------------------------------------------------
     bool lane_path_done = false;
-    uint64_t verdict[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t verdict[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     {
         const uint32_t pieces = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
         uint32_t *d_counts = static_cast<uint32_t *>(c->arena.take((size_t)pieces * 4 + 16));
@@ -1851,9 +2216,9 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         // pipelined host-buffer inflate): then whole CTAs, so that a call occupies few SMs
                         const uint32_t grid = c->opt_lane_pack ? tmin<uint32_t>((tasks + kLaneWarps - 1) / kLaneWarps, (uint32_t)c->sm_count)
                                                                : tmin<uint32_t>(tasks, (uint32_t)c->sm_count);
-                        ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
+                        ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                         ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
-                        decode_lanes_kernel<<<grid, kLaneWarps * 32, lane_smem, st>>>(
+                        decode_lanes_kernel<false><<<grid, kLaneWarps * 32, lane_smem, st>>>(
                             job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm, dict_len);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
@@ -1869,6 +2234,117 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         c->launches += 2;
                         lane_path_done = true;
                     }
+                }
+            }
+        }
+    }
+
+    // ---- a stream somebody else made: entry points at the dynamic block headers block_find_kernel accepts ------------------
+    if (!lane_path_done && foreign_ok) {
+        const uint32_t spans = (uint32_t)find_spans;
+        uint64_t *d_cand64 = static_cast<uint64_t *>(c->arena.take((size_t)spans * 8));
+        uint32_t *d_flags = static_cast<uint32_t *>(c->arena.take((size_t)spans * 4 + 16));
+        uint64_t *d_off = static_cast<uint64_t *>(c->arena.take((size_t)spans * 8 + 16));
+        uint64_t *d_count = static_cast<uint64_t *>(c->arena.take(256));
+        LaneChunk *d_lc = static_cast<LaneChunk *>(c->arena.take((size_t)(spans + 1) * sizeof(LaneChunk)));
+        WarpState *d_tables = static_cast<WarpState *>(c->arena.take((size_t)(spans + 1) * sizeof(WarpState)));
+        uint32_t *d_perm = static_cast<uint32_t *>(c->arena.take((size_t)(spans + 1) * 4));
+        uint32_t *d_redo = static_cast<uint32_t *>(c->arena.take((size_t)(spans + 1) * 4));
+        uint16_t *d_slots = static_cast<uint16_t *>(c->arena.take((size_t)(m * 8 + 256) * 2));
+        if (d_cand64 && d_flags && d_off && d_count && d_lc && d_tables && d_perm && d_redo && d_slots) {
+            uint64_t found = 0;
+            {
+                ScopedTimer t(c, 5);
+                ZK_CUDA(cudaFuncSetAttribute(block_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FindSmem)));
+                block_find_kernel<<<spans, kFindThreads, sizeof(FindSmem), st>>>(job.d_in, m, (uint64_t)body_begin * 8, d_cand64, d_flags);
+                marker_scan_kernel<<<1, 1024, 0, st>>>(d_flags, spans, d_off, d_count);
+                c->launches += 2;
+            }
+            ZK_CUDA(cudaMemcpyAsync(&found, d_count, 8, cudaMemcpyDeviceToHost, st));
+            ZK_CUDA(cudaStreamSynchronize(st));
+            const bool dbg = getenv("ZK_FOREIGN_DEBUG") != nullptr;
+            if (dbg) fprintf(stderr, "[zk foreign] m %llu spans %u entry points %llu\n", (unsigned long long)m, spans, (unsigned long long)found);
+            if (found >= kForeignMinChunks) {
+                uint64_t n = found + 1;
+                foreign_table_kernel<<<(spans + 256) / 256, 256, 0, st>>>(d_cand64, d_flags, d_off, spans, found, m, body_begin, d_lc);
+                lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
+                c->launches += 2;
+                const int lane_smem = kLaneWarps * kLaneWarpSmem;
+                ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
+                const uint32_t *d_todo = d_perm;
+                uint64_t todo = n;
+                std::vector<LaneChunk> host_lc;
+                std::vector<uint32_t> redo;
+                for (int round = 0; round < kForeignRounds && !lane_path_done; ++round) {
+                    {
+                        ScopedTimer t(c, 4);
+                        const uint32_t tasks = (uint32_t)((todo + 31) / 32);
+                        ZK_CUDA(cudaMemsetAsync(d_count, 0, 4, st));  // the task counter
+                        decode_lanes_kernel<true><<<tmin<uint32_t>(tasks, (uint32_t)c->sm_count), kLaneWarps * 32, lane_smem, st>>>(
+                            job.d_in, m, d_lc, (uint32_t)todo, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_count), d_todo, dict_len);
+                    }
+                    plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
+                                                          job.container == 0 ? 4u : job.container == 2 ? 8u : 0u, false);
+                    c->launches += 2;
+                    ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
+                    ZK_CUDA(cudaStreamSynchronize(st));
+                    if (dbg)
+                        fprintf(stderr, "[zk foreign] round %d: chunks %llu decoded %llu bad %llu valid %llu total %llu coarse %llu (max %u)\n", round,
+                                (unsigned long long)n, (unsigned long long)todo, (unsigned long long)verdict[6], (unsigned long long)verdict[1],
+                                (unsigned long long)verdict[3], (unsigned long long)verdict[0], max_chunks);
+                    if (!verdict[6]) {
+                        if (verdict[1] == 1 && verdict[0] <= max_chunks) {
+                            lane_path_done = true;
+                        } else if (verdict[3] > job.cap) {  // the output does not fit: nothing is written
+                            set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, 0, ZK_BUF_ERROR, 1);
+                            c->launches++;
+                            ZK_CUDA(cudaGetLastError());
+                            return ZK_OK;
+                        }
+                        break;
+                    }
+                    // a chunk that ran past its target had a false entry point behind it: merge the two and decode the merged
+                    // chunk again; chunks behind the stream's last block go; anything else is the slow path's to report
+                    host_lc.resize(n);
+                    ZK_CUDA(cudaMemcpyAsync(host_lc.data(), d_lc, n * sizeof(LaneChunk), cudaMemcpyDeviceToHost, st));
+                    ZK_CUDA(cudaStreamSynchronize(st));
+                    redo.clear();
+                    uint64_t w = 0;
+                    bool give_up = false;
+                    for (uint64_t i = 0; i < n && !give_up; ++i) {
+                        LaneChunk cur = host_lc[i];
+                        if (cur.status == kLaneOverrun && i + 1 < n) {
+                            cur.target_bits = host_lc[i + 1].target_bits;
+                            cur.in_end = host_lc[i + 1].in_end;
+                            cur.status = ZK_OK;
+                            redo.push_back((uint32_t)w);
+                            ++i;
+                        } else if (cur.status != ZK_OK) {
+                            if (dbg)
+                                fprintf(stderr, "[zk foreign] chunk %llu at bit %llu (target %llu): status %d after %u bytes\n", (unsigned long long)i,
+                                        (unsigned long long)cur.begin_bits, (unsigned long long)cur.target_bits, cur.status, cur.out_len);
+                            give_up = true;
+                        }
+                        host_lc[w++] = cur;
+                        if (cur.status == ZK_OK && cur.final_seen && redo.empty()) break;  // the stream ends here
+                    }
+                    if (give_up || redo.empty()) break;
+                    n = w;
+                    todo = redo.size();
+                    ZK_CUDA(cudaMemcpyAsync(d_lc, host_lc.data(), n * sizeof(LaneChunk), cudaMemcpyHostToDevice, st));
+                    ZK_CUDA(cudaMemcpyAsync(d_redo, redo.data(), todo * 4, cudaMemcpyHostToDevice, st));
+                    ZK_CUDA(cudaStreamSynchronize(st));  // the vectors are reused
+                    d_todo = d_redo;
+                    c->foreign_merges += (int64_t)todo;
+                }
+                if (lane_path_done) {
+                    ScopedTimer t(c, 5);
+                    lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
+                    expand_blocks_kernel<<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
+                        job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm);
+                    resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
+                    c->launches += 3;
+                    c->foreign_chunks += (int64_t)n;
                 }
             }
         }
