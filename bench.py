@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=32)
     ap.add_argument("--config1-mib", type=int, default=64, help="size of the configs[0] CPU round trip inside cpu_baseline (0 = skip)")
     ap.add_argument("--no-verify", action="store_true", help="skip handing the timed region's stream to libz")
+    ap.add_argument("--foreign-mib", type=int, default=256,
+                    help="inflate leg on a stream libz made of the first MiB of the corpus (no sync markers); 0 = skip")
     return ap.parse_args()
 
 
@@ -212,6 +214,78 @@ def cpu_baseline(kind, level, sample_mib, config1_mib=64):
                      "round_trip_ok": back == text, "cores": 1},
         }
     return out
+
+
+def libz_stream(data, level, piece=32 << 20):
+    """ONE zlib stream of `data` whose blocks libz made: pieces of 32 MiB are deflated on all host threads as raw bodies primed
+    with the 32 KiB before them and joined (a sync flush per join: 8 markers in 256 MiB, nothing an inflater could use)."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    view = memoryview(data)
+
+    def one(i):
+        lo = i * piece
+        hi = min(len(data), lo + piece)
+        if lo:
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, bytes(view[lo - 32768: lo]))
+        else:
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return co.compress(view[lo:hi]) + co.flush(zlib.Z_FINISH if hi == len(data) else zlib.Z_SYNC_FLUSH)
+
+    with ThreadPoolExecutor(os.cpu_count() or 8) as ex:
+        bodies = list(ex.map(one, range((len(data) + piece - 1) // piece)))
+    return b"\x78\x9c" + b"".join(bodies) + zlib.adler32(data).to_bytes(4, "big")
+
+
+def foreign_leg(eng, dev, host, nbytes, level):
+    """Inflate of a stream this engine did not make: the first `nbytes` of the corpus deflated by libz.  Such a stream has no
+    entry points; the engine finds the dynamic block headers itself (zk_inflate.cu block_find_kernel)."""
+    import numpy as np
+    import torch
+
+    data = host[:nbytes].tobytes()
+    stream = libz_stream(data, level)
+    m = len(stream)
+    d_s = torch.from_numpy(np.frombuffer(stream, dtype=np.uint8).copy()).to(dev)
+    d_b = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+    d_r = torch.zeros(4, dtype=torch.int64, device=dev)
+    eng.set_option("timing", 1)
+    c0, m0 = eng.counter("inflate_foreign_chunks"), eng.counter("inflate_foreign_merges")
+    best = None
+    for i in range(4):
+        torch.cuda.synchronize(dev)
+        eng.counter("reset_timing")
+        t0 = time.perf_counter()
+        eng.inflate_device(d_s.data_ptr(), m, d_b.data_ptr(), nbytes, d_r.data_ptr())
+        eng.synchronize()
+        dt = time.perf_counter() - t0
+        if i and (best is None or dt < best[0]):
+            best = (dt, eng.counter("inflate_decode_us") / 1e3, eng.counter("inflate_other_us") / 1e3)
+    eng.set_option("timing", 0)
+    r = d_r.cpu().tolist()
+    ok = r[2] == 1 and r[0] == nbytes and bytes(d_b[:nbytes].cpu().numpy()) == data
+    runs = 4
+    h_s = torch.from_numpy(np.frombuffer(stream, dtype=np.uint8).copy()).pin_memory()
+    h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    eng.inflate(h_s, nbytes, out=h_b)
+    t0 = time.perf_counter()
+    rc, _, _ = eng.inflate(h_s, nbytes, out=h_b)
+    e2e = time.perf_counter() - t0
+    eng.set_option("inflate_foreign", 0)
+    small = min(nbytes, 16 << 20)  # the one-warp decoder the engine had before, on a stream it can finish in a second
+    s_small = libz_stream(data[:small], level, piece=small)
+    t0 = time.perf_counter()
+    rc0, _, _ = eng.inflate(s_small, small)
+    t_one_warp = time.perf_counter() - t0
+    eng.set_option("inflate_foreign", 1)
+    return {"stream": "libz 1.3 level %d of the first %d MiB of the corpus: no sync markers" % (level, nbytes >> 20), "compressed_bytes": m,
+            "value": nbytes / best[0] / 1e9, "unit": UNIT, "ms": best[0] * 1e3, "decode_kernel_ms": best[1], "other_kernels_ms": best[2],
+            "entry_points": (eng.counter("inflate_foreign_chunks") - c0) // (runs + 2) - 1,
+            "false_entry_points_merged": (eng.counter("inflate_foreign_merges") - m0) // (runs + 2), "bit_exact": bool(ok), "status": r[2],
+            "e2e": {"value": nbytes / e2e / 1e9, "unit": UNIT, "status": rc},
+            "without_entry_points": {"value": small / t_one_warp / 1e9, "unit": UNIT, "bytes": small, "status": rc0,
+                                     "note": "option inflate_foreign = 0: the whole stream is one chunk for one warp"}}
 
 
 def workload_config(args, world):
@@ -476,6 +550,8 @@ def main():
         idt = float(t.item())
     inflate["e2e"] = {"value": n * world / idt / 1e9, "unit": UNIT, "h2d_bytes_per_step": m, "d2h_bytes_per_step": n, "status": rc_i}
     del h_stream, h_back
+    if world == 1 and args.foreign_mib > 0:
+        inflate["libz_made_stream"] = foreign_leg(eng, dev, host, min(n, args.foreign_mib << 20), args.level)
 
     # ---- e2e through the host-buffer C-ABI call (pinned memory; H2D + D2H inside) ----------------------------
     e2e = None

@@ -131,6 +131,7 @@ struct FastReader {
     const uint8_t *at;   // address of the next word to request (kRing words after w0)
     int32_t words_left;  // whole words of the stream at and after `at`
     uintptr_t lo, hi;    // [base, base + len)
+    uint32_t tailw;      // the word that holds the last 1..3 bytes of the stream when it does not end on a word, else 0
 
     __device__ __forceinline__ uint32_t fetch_edge(uintptr_t a) const {
         if (a >= lo && a + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t *>(a));
@@ -165,11 +166,8 @@ struct FastReader {
     __device__ __forceinline__ void refill(bool pred) {
         const uint32_t take = (pred && held <= 32) ? 1u : 0u;
         const uint32_t nroff = (roff + 128u) & (uint32_t)((kRing - 1) * 128);
-        const uint32_t slot = ring + roff;
-        const bool tail_word = take && words_left == 0 && (uintptr_t)at < hi;  // the last, partial word of the stream
-        const uintptr_t tail_at = (uintptr_t)at;
         asm volatile(
-            "{\n\t.reg .pred t, p, q, f;\n\t.reg .b64 tmp;\n\t.reg .b32 lowat;\n\t"
+            "{\n\t.reg .pred t, p, q, f, z;\n\t.reg .b64 tmp;\n\t.reg .b32 lowat, tw;\n\t"
             "setp.ne.u32 t, %6, 0;\n\t"
             "cvt.u64.u32 tmp, %2;\n\t"
             "shl.b64 tmp, tmp, %1;\n\t"
@@ -178,7 +176,9 @@ struct FastReader {
             "setp.gt.and.s32 p, %5, 0, t;\n\t"
             "setp.le.and.s32 q, %5, 0, t;\n\t"
             "@p cp.async.ca.shared.global [%7], [%4], 4;\n\t"
-            "@q st.shared.u32 [%7], 0;\n\t"
+            "setp.eq.s32 z, %5, 0;\n\t"
+            "selp.b32 tw, %10, 0, z;\n\t"
+            "@q st.shared.u32 [%7], tw;\n\t"
             "cp.async.commit_group;\n\t"
             "cp.async.wait_group 7;\n\t"
             "@t ld.shared.u32 %2, [%8];\n\t"
@@ -191,14 +191,15 @@ struct FastReader {
             "@t add.u64 %4, %4, 4;\n\t"
             "@t add.s32 %5, %5, -1;\n\t}"
             : "+l"(hold), "+r"(held), "+r"(w0), "+r"(roff), "+l"(at), "+r"(words_left)
-            : "r"(take), "r"(slot), "r"(ring + nroff), "r"(nroff)
+            : "r"(take), "r"(ring + roff), "r"(ring + nroff), "r"(nroff), "r"(tailw)
             : "memory");
-        // a raw deflate stream may end inside a word (zlib and gzip streams end with a trailer of four or eight bytes, so their
-        // partial word never holds a code): that word is read byte by byte, once per lane at most
-        if (tail_word) {
-            const uint32_t w = fetch_edge(tail_at);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot), "r"(w) : "memory");
-        }
+    }
+    // a raw deflate stream may end inside a word (zlib and gzip streams end with a trailer of four or eight bytes, so their
+    // partial word never holds a code): that word is read byte by byte once, and refill() stores it when its turn comes
+    __device__ __forceinline__ void set_bounds(const uint8_t *base, uint64_t len) {
+        lo = (uintptr_t)base;
+        hi = lo + len;
+        tailw = (hi & 3u) ? fetch_edge(hi & ~(uintptr_t)3) : 0u;
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)hold & ((1u << n) - 1u); }  // n <= 16
     __device__ __forceinline__ void drop(int n) {
@@ -1658,8 +1659,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         LongCodes long_lit, long_dist;
         FastReader fr;
         fr.ring = (uint32_t)__cvta_generic_to_shared(s_dist + kLaneDistEntries * 32) + lane * 4;
-        fr.lo = (uintptr_t)in;
-        fr.hi = fr.lo + m;
+        fr.set_bounds(in, m);
         fr.seek_bits(lc[kk].begin_bits);
         while (__any_sync(0xFFFFFFFFu, state != kDone)) {
             if (state == kHeader) {
@@ -1963,7 +1963,11 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
 // matches are done in stream order with all 32 lanes copying.  A source before the block becomes 0x8000 | (index into the
 // 32 KiB before the block); resolve_coarse_kernel re-bases those afterwards.  Many warps per SM hide the L2 round trip
 // of each copy.
+// kForeign: the chunks of a foreign stream (decode_lanes_kernel<true>) -- stored blocks inside the token stream, matches of
+// any length with all their loads in flight (long runs and repeats decode to megabytes per chunk there); the plain version
+// keeps the 30 registers that let 64 warps share an SM.
 constexpr int kExpandWarps = 8;
+template <bool kForeign>
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const uint8_t *__restrict__ in,
                                                                         const LaneChunk *__restrict__ lc, uint32_t n,
                                                                         const uint16_t *__restrict__ slots, uint16_t *dense,
@@ -1998,7 +2002,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
         // a match head of length 0 is a stored block of a foreign stream (decode_lanes_kernel<true>): the four units
         // behind it hold the byte offset of its payload and its length
         uint32_t stored_at = 0;
-        const bool is_stored = is_match && len == 0u;
+        const bool is_stored = kForeign && is_match && len == 0u;
         if (is_stored) {
             const uint32_t a = tok[u + 1] & 0x7FFFu, b = tok[u + 2] & 0x7FFFu, cc = tok[u + 3] & 0x7FFFu, d = tok[u + 4];
             stored_at = a | (b << 15) | ((cc & 3u) << 30);
@@ -2019,10 +2023,10 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
             todo &= todo - 1;
             const uint32_t moff = __shfl_sync(0xFFFFFFFFu, off, src_lane);
             const uint32_t mlen = __shfl_sync(0xFFFFFFFFu, len, src_lane);
-            const uint32_t mdist = __shfl_sync(0xFFFFFFFFu, nxt, src_lane) + 1u;
-            const uint32_t msrc = __shfl_sync(0xFFFFFFFFu, stored_at, src_lane);
-            if (__shfl_sync(0xFFFFFFFFu, (uint32_t)is_stored, src_lane)) {
+            const uint32_t mdist = __shfl_sync(0xFFFFFFFFu, is_stored ? 0xFFFFFFFFu : nxt, src_lane) + 1u;  // 0: a stored block
+            if (kForeign && mdist == 0u) {
                 // up to 64 KiB of payload: eight loads per lane in flight
+                const uint32_t msrc = __shfl_sync(0xFFFFFFFFu, stored_at, src_lane);
                 for (uint32_t i0 = 0; i0 < mlen; i0 += 256) {
                     uint8_t v[8];
 #pragma unroll
@@ -2041,14 +2045,24 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
                     const int32_t rel = (int32_t)moff - (int32_t)mdist + lane;  // position inside this block
                     out[moff + lane] = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
                 }
+            } else if (!kForeign) {
+#pragma unroll 1
+                for (uint32_t i = lane; i < mlen; i += 32) {
+                    const uint32_t kk = mdist >= mlen ? i : i % mdist;
+                    const int32_t rel = (int32_t)moff - (int32_t)mdist + (int32_t)kk;
+                    const uint16_t v = rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
+                    out[moff + i] = v;
+                }
             } else {
-                // a long or overlapping match: every source lies before the match (i % dist < dist), so the loads of all
-                // nine passes (258 symbols at most) are issued before the first store
-                uint16_t v[9];
+                // a long or overlapping match: every source lies before the match (i % dist < dist), so all its loads
+                // are issued before the first store
+                const bool overlap = mdist < mlen;
+                uint16_t v[9];  // 258 symbols at most
 #pragma unroll
                 for (int q = 0; q < 9; ++q) {
                     const uint32_t i = 32 * q + lane;
-                    const uint32_t kk = mdist >= mlen ? i : i % mdist;
+                    if (32u * q >= mlen) break;
+                    const uint32_t kk = overlap ? i % mdist : i;
                     const int32_t rel = (int32_t)moff - (int32_t)mdist + (int32_t)kk;
                     v[q] = i >= mlen ? (uint16_t)0 : rel >= 0 ? __ldcg(out + rel) : (uint16_t)(0x8000u | (uint32_t)(kWindow + rel));
                 }
@@ -2196,8 +2210,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             ZK_CUDA(cudaMemcpyAsync(&num_markers, d_total, 8, cudaMemcpyDeviceToHost, st));
             ZK_CUDA(cudaStreamSynchronize(st));
             const uint64_t n = num_markers + 1;
-            // worth it from a few hundred blocks on, and only if the scratch was reserved for it
-            if (num_markers >= 256 && n <= lane_blocks_reserved) {
+            // worth it from a few hundred blocks on, only if the scratch was reserved for it, and only when the markers are
+            // as close as this engine's blocks are (32 KiB of output each): pigz's 128 KiB pieces would fail on the slot size
+            // after decoding a third of the stream
+            if (num_markers >= 256 && n <= lane_blocks_reserved && m <= n * (uint64_t)(kSlotSyms + 64)) {
                 uint64_t *d_pos = static_cast<uint64_t *>(c->arena.take((size_t)n * 8));
                 LaneChunk *d_lc = static_cast<LaneChunk *>(c->arena.take((size_t)n * sizeof(LaneChunk)));
                 WarpState *d_tables = static_cast<WarpState *>(c->arena.take((size_t)n * sizeof(WarpState)));
@@ -2228,7 +2244,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     ZK_CUDA(cudaStreamSynchronize(st));
                     if (verdict[1] == 1 && verdict[0] <= max_chunks) {
                         ScopedTimer t(c, 5);
-                        expand_blocks_kernel<<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
+                        expand_blocks_kernel<false><<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
                             job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm);
                         resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
                         c->launches += 2;
@@ -2340,7 +2356,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                 if (lane_path_done) {
                     ScopedTimer t(c, 5);
                     lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
-                    expand_blocks_kernel<<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
+                    expand_blocks_kernel<true><<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
                         job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm);
                     resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
                     c->launches += 3;
