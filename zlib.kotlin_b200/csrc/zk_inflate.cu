@@ -1344,6 +1344,7 @@ struct FindSmem {
     uint16_t q1[kFindQ1];   // bit positions in the tile that look like BFINAL 0, BTYPE 2, HLIT <= 29, HDIST <= 29
     uint8_t kraft3[512];
     uint8_t pre[32][128];   // warp 0: every lane's table of the code-length code (length << 5 | symbol)
+    uint32_t warp_tot[kFindThreads / 32];
     uint32_t n1, n2;
     uint32_t best;
 };
@@ -1362,6 +1363,9 @@ __device__ __forceinline__ uint32_t find_bits32(const FindSmem &sm, const uint8_
 }
 
 // the rest of the checks for one position whose code-length code is complete.  `tab` = this lane's 128-entry table.
+// Everything but that table lives in registers: the 19 lengths by static index, the next canonical code of each length
+// as a byte of a 64-bit word, the two trees as their Kraft sums (2^15 = complete; the per-length "over-subscribed" test of
+// IS:102-152 is the same as sum <= 2^15, because the partial sums only grow).
 __device__ bool find_check_lengths(const FindSmem &sm, const uint8_t *__restrict__ in, uint64_t m, uint64_t span_byte, uint32_t at,
                                    uint8_t *tab) {
     const uint64_t nbits = m * 8, abs0 = span_byte * 8;
@@ -1369,41 +1373,39 @@ __device__ bool find_check_lengths(const FindSmem &sm, const uint8_t *__restrict
     const int hlit = (int)((h >> 3) & 31u) + 257, hdist = (int)((h >> 8) & 31u) + 1, hclen = (int)((h >> 13) & 15u) + 4;
     uint32_t pos = at + 17;
     {
-        int clen[19];
-#pragma unroll
-        for (int i = 0; i < 19; ++i) clen[i] = 0;
+        constexpr int ord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
         const uint32_t f0 = find_bits32(sm, in, m, span_byte, pos), f1 = find_bits32(sm, in, m, span_byte, pos + 30);
+        int clen[19];
+        uint64_t count = 0;  // byte l: symbols of length l
 #pragma unroll
         for (int i = 0; i < 19; ++i) {
             const int l = i < hclen ? (int)((i < 10 ? f0 >> (3 * i) : f1 >> (3 * (i - 10))) & 7u) : 0;
-            clen[i_cl_order[i]] = l;
+            clen[ord[i]] = l;
+            count += 1ull << (8 * l);
         }
         pos += 3 * hclen;
-        int per[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nextc[8];
-#pragma unroll
-        for (int i = 0; i < 19; ++i) per[clen[i]]++;
-        per[0] = 0;
-        int code = 0;
-        nextc[0] = 0;
+        uint64_t next = 0;  // byte l: next canonical code of length l
+        uint32_t code = 0;
 #pragma unroll
         for (int b = 1; b <= 7; ++b) {
-            code = (code + per[b - 1]) << 1;
-            nextc[b] = code;
+            code = (code + (b > 1 ? (uint32_t)(count >> (8 * (b - 1))) & 0xFFu : 0u)) << 1;
+            next |= (uint64_t)(code & 0xFFu) << (8 * b);
         }
+#pragma unroll
         for (int sym = 0; sym < 19; ++sym) {
             const int l = clen[sym];
             if (!l) continue;
-            const uint32_t c = (uint32_t)nextc[l]++;
+            const uint32_t c = (uint32_t)(next >> (8 * l)) & 0xFFu;
+            next += 1ull << (8 * l);
             for (uint32_t idx = rev_bits(c, l); idx < 128u; idx += 1u << l) tab[idx] = (uint8_t)(l << 5 | sym);
         }
     }
-    int per[2][16];
-#pragma unroll
-    for (int b = 0; b < 16; ++b) per[0][b] = per[1][b] = 0;
+    uint32_t kraft0 = 0, kraft1 = 0;
     int used0 = 0, used1 = 0, eob = 0;
     for (int pass = 0; pass < 2; ++pass) {
         const int count = pass == 0 ? hlit : hdist;
-        int i = 0, prev = 0;
+        uint32_t kraft = 0;
+        int i = 0, prev = 0, used = 0;
         while (i < count) {
             if (abs0 + pos + 1 > nbits) return false;
             const uint32_t look = find_bits32(sm, in, m, span_byte, pos);
@@ -1412,13 +1414,9 @@ __device__ bool find_check_lengths(const FindSmem &sm, const uint8_t *__restrict
             pos += e >> 5;
             if (sym <= 15) {
                 if (sym) {
-                    per[pass][sym]++;
-                    if (pass == 0) {
-                        ++used0;
-                        if (i == 256) eob = 1;
-                    } else {
-                        ++used1;
-                    }
+                    kraft += 32768u >> sym;
+                    ++used;
+                    if (pass == 0 && i == 256) eob = 1;
                 }
                 prev = sym;
                 ++i;
@@ -1431,33 +1429,30 @@ __device__ bool find_check_lengths(const FindSmem &sm, const uint8_t *__restrict
             if (i + rep > count) return false;
             const int v = sym == 16 ? prev : 0;
             if (v) {
-                per[pass][v] += rep;
-                if (pass == 0) {
-                    used0 += rep;
-                    if (i <= 256 && 256 < i + rep) eob = 1;
-                } else {
-                    used1 += rep;
-                }
+                kraft += (uint32_t)rep * (32768u >> v);
+                used += rep;
+                if (pass == 0 && i <= 256 && 256 < i + rep) eob = 1;
             }
             prev = v;
             i += rep;
         }
+        if (pass == 0) {
+            kraft0 = kraft;
+            used0 = used;
+        } else {
+            kraft1 = kraft;
+            used1 = used;
+        }
     }
     if (abs0 + pos > nbits) return false;
     if (!eob || !used1) return false;  // IS:102-152: an end-of-block code and a distance code
-    for (int pass = 0; pass < 2; ++pass) {
-        int left = 1;
-        for (int b = 1; b <= 15; ++b) {
-            left = (left << 1) - per[pass][b];
-            if (left < 0) return false;
-        }
-        if (left != 0 && (pass == 0 ? used0 : used1) > 1) return false;
-    }
+    if (kraft0 > 32768u || (kraft0 != 32768u && used0 > 1)) return false;
+    if (kraft1 > 32768u || (kraft1 != 32768u && used1 > 1)) return false;
     return true;
 }
 
 // cand[span] = the first accepted bit position of the span behind min_bits (kNoBits if there is none), flags[span] = 1 / 0
-__global__ void __launch_bounds__(kFindThreads) block_find_kernel(const uint8_t *__restrict__ in, uint64_t m, uint64_t min_bits,
+__global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const uint8_t *__restrict__ in, uint64_t m, uint64_t min_bits,
                                                                 uint64_t *__restrict__ cand, uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) uint8_t find_smem_raw[];
     FindSmem &sm = *reinterpret_cast<FindSmem *>(find_smem_raw);
@@ -1497,15 +1492,40 @@ __global__ void __launch_bounds__(kFindThreads) block_find_kernel(const uint8_t 
     const uint32_t span_bytes = (uint32_t)tmin<uint64_t>(kFindSpan, m > span_byte ? m - span_byte : 0);
     for (uint32_t tile = 0; tile < span_bytes; tile += kFindTile) {
         {
-            // type / HLIT / HDIST at 32 positions per thread: its own word and the next
+            // type / HLIT / HDIST at 32 positions per thread (its own word and the next): a mask of hits, a scan of their
+            // counts over the CTA, the positions written in order
             const uint32_t w = tile / 4 + tid;
             const uint32_t w0 = sm.data[w], w1 = sm.data[w + 1];
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t x = __funnelshift_r(w0, w1, j);
-                const bool hit = ((x & 7u) == 4u) & (((x >> 3) & 31u) <= 29u) & (((x >> 8) & 31u) <= 29u);
-                if (hit) sm.q1[atomicAdd(&sm.n1, 1u)] = (uint16_t)(tid * 32 + j);
+            // all 32 positions at once, a bit per position: bit j of (W >> k) is stream bit j + k.  BFINAL 0 and BTYPE 10b are
+            // bits (0, 0, 1); a 5-bit field is 30 or 31 when its upper four bits are set
+            const uint64_t W = ((uint64_t)w1 << 32) | w0;
+            const uint64_t type = ~W & ~(W >> 1) & (W >> 2);
+            const uint64_t hlit_bad = (W >> 4) & (W >> 5) & (W >> 6) & (W >> 7);
+            const uint64_t hdist_bad = (W >> 9) & (W >> 10) & (W >> 11) & (W >> 12);
+            uint32_t hits = (uint32_t)(type & ~hlit_bad & ~hdist_bad);
+            const uint32_t mine = (uint32_t)__popc(hits);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((tid & 31) >= o) incl += v;
             }
+            if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < kFindThreads / 32; ++q) {
+                const uint32_t t = sm.warp_tot[q];
+                if (q < (tid >> 5)) before += t;
+                total += t;
+            }
+            uint32_t at = before + incl - mine;
+            while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                sm.q1[at++] = (uint16_t)(tid * 32 + j);
+            }
+            if (tid == 0) sm.n1 = total;
         }
         __syncthreads();
         const uint32_t n1 = sm.n1;
@@ -1536,7 +1556,6 @@ __global__ void __launch_bounds__(kFindThreads) block_find_kernel(const uint8_t 
             __syncthreads();
             if (tid == 0) sm.n2 = 0;
         }
-        if (tid == 0) sm.n1 = 0;
         __syncthreads();
         if (sm.best != 0xFFFFFFFFu) break;
     }
