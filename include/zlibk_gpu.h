@@ -78,10 +78,13 @@ int zk_ctx_synchronize(zk_ctx *ctx);
  * "auto_register" (1: a host-buffer call page-locks caller buffers of 1 MiB or more that CUDA does not know yet, once, and
  * keeps them locked until the context is destroyed -- for callers that keep and reuse their buffers, up to 16 of them; the
  * caller must not free such a buffer while the context lives), "inflate_pipe" / "inflate_slab_bytes" (opt-in slab pipeline
- * of the host-buffer inflate), "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
+ * of the host-buffer inflate), "inflate_foreign" (default 1: a stream without sync markers -- libz, gzip tools, the reference --
+ * is cut at the dynamic block headers the engine finds in it and decoded in parallel; 0: one warp decodes it),
+ * "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
  * overlap about a tenth of its throughput). */
 int zk_ctx_set_option(zk_ctx *ctx, const char *name, int64_t value);
-/* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes"}; with "timing" on also
+/* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes","inflate_foreign_chunks",
+ * "inflate_foreign_merges","inflate_pipe_slabs","inflate_pipe_fallbacks"}; with "timing" on also
  * {"lz77","huffman","pack","adler","inflate_decode","inflate_other"} + "_us" / "_spans"; "reset_timing" clears those. */
 int64_t zk_ctx_get_counter(zk_ctx *ctx, const char *name);
 

@@ -5,7 +5,7 @@ import os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = os.path.join(ROOT, "zlib.kotlin_b200", "build")
 KERNELS = {"zk_lz77": ["lz77_kernel"], "zk_huffman": ["hist_kernel", "huffman_kernel", "plan_offsets_kernel"], "zk_pack": ["pack_kernel", "stored_kernel"],
-           "zk_adler": ["adler_spans_kernel"], "zk_inflate": ["decode_lanes_kernel", "expand_blocks_kernel", "marker_compact_kernel", "materialize_kernel"]}
+           "zk_adler": ["adler_spans_kernel"], "zk_inflate": ["decode_lanes_kernel", "expand_blocks_kernel", "block_find_kernel", "marker_compact_kernel", "materialize_kernel"]}
 PATTERNS = ["UBLKCP", "SYNCS", "LDGSTS", "MATCH.ANY", "ATOMS", "RED.", "VOTE", "SHFL", "IDP", "LDS.128", "STS.128", "LDG.E.128", "STG.E.128", "BAR.SYNC", "POPC", "FLO"]
 print("# SASS and ptxas facts of the hot kernels (round 2)\n")
 print("`nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -Xptxas -v`; counts are static SASS instructions per kernel")
