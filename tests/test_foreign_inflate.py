@@ -19,7 +19,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tools", "blockfind_model.cpp")
 SO = os.path.join(ROOT, "tools", "libblockfind_model.so")
-SPAN = 8192  # zk_inflate.cu kFindSpan
+SPAN = 2048  # zk_inflate.cu kFindSpan / kFindSub: one entry point per quarter span
 MIN_BYTES = 256 << 10  # kForeignMinBytes
 
 

@@ -1219,11 +1219,16 @@ struct LaneChunk {
     uint32_t units;  // 16-bit units of the block's token stream
     uint64_t stored_src;  // a chunk that is one stored block: byte offset of its payload in the stream ...
     uint32_t stored_len;  // ... and its length (then units == 0)
-    uint32_t pad;
+    uint32_t dead;        // set by plan_lanes_kernel: the chunk started at a false entry point, the chunk before it covers it
     uint64_t begin_bits;   // bit position of the chunk's first block (a multiple of 8 behind a sync marker)
     uint64_t target_bits;  // where it must end: the next chunk's begin_bits, or the end of the stream
     uint64_t end_bits;     // where its last block did end
     uint64_t slot_off;     // first unit of its token stream in the slot array
+    // a chunk of a foreign stream that ran past its target (the entry point behind it was false) goes on into the next
+    // chunk's range; the units of that part are in the spill pool
+    uint64_t slot_off_b;   // first unit of the second part in the spill pool
+    uint32_t units_a;      // units of the first part (== units when the chunk stayed inside its range)
+    uint32_t ext;          // 1: the chunk covers the next chunk's range as well, and that chunk is dead
 };
 // a chunk of a foreign stream whose decode passed target_bits inside a block: the entry point behind it was not one
 constexpr int32_t kLaneOverrun = 1000;
@@ -1238,6 +1243,10 @@ __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32
     lc[k].target_bits = lc[k].in_end * 8;
     lc[k].end_bits = 0;
     lc[k].slot_off = (uint64_t)k * kSlotSyms;
+    lc[k].dead = 0;
+    lc[k].slot_off_b = 0;
+    lc[k].units_a = 0;
+    lc[k].ext = 0;
     lc[k].out_begin = 0;
     lc[k].out_len = 0;
     lc[k].status = ZK_OK;
@@ -1335,6 +1344,8 @@ constexpr int kForeignRounds = 8;                 // merges of consecutive false
 constexpr uint32_t kFindSlack = 1024;   // bytes staged behind the span: a header is at most ~560 bytes
 constexpr uint32_t kFindTile = 1024;    // bytes per tile: 32 bit positions per thread
 constexpr int kFindThreads = 256;
+constexpr uint32_t kFindSub = 4;        // candidates per span: the first accepted position of every quarter (2 KiB)
+constexpr uint32_t kFindSubBits = kFindSpan * 8 / kFindSub;
 constexpr uint32_t kFindQ1 = kFindTile * 8 / 3 + 8, kFindQ2 = kFindTile * 8 / 3 + 64;
 constexpr uint64_t kNoBits = ~0ull;
 
@@ -1346,7 +1357,7 @@ struct FindSmem {
     uint8_t pre[32][128];   // warp 0: every lane's table of the code-length code (length << 5 | symbol)
     uint32_t warp_tot[kFindThreads / 32];
     uint32_t n1, n2;
-    uint32_t best;
+    uint32_t best[kFindSub];
 };
 
 // 32 bits of the stream at bit position `bit` of the span: from the staged bytes, or from global memory behind them; bits
@@ -1451,7 +1462,9 @@ __device__ bool find_check_lengths(const FindSmem &sm, const uint8_t *__restrict
     return true;
 }
 
-// cand[span] = the first accepted bit position of the span behind min_bits (kNoBits if there is none), flags[span] = 1 / 0
+// cand[span * 4 + q] = the first accepted bit position of quarter q of the span behind min_bits (kNoBits if there is none),
+// flags[...] = 1 / 0.  Quarters, so that streams of small blocks (a flush every few KiB, pigz pieces of very compressible
+// data) do not end up with eight blocks, eight header parses, behind one entry point.
 __global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const uint8_t *__restrict__ in, uint64_t m, uint64_t min_bits,
                                                                 uint64_t *__restrict__ cand, uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) uint8_t find_smem_raw[];
@@ -1485,7 +1498,7 @@ __global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const uint8
         if (tid == 0) {
             sm.n1 = 0;
             sm.n2 = 0;
-            sm.best = 0xFFFFFFFFu;
+            for (uint32_t q = 0; q < kFindSub; ++q) sm.best[q] = 0xFFFFFFFFu;
         }
     }
     __syncthreads();
@@ -1550,19 +1563,18 @@ __global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const uint8
             if (tid < 32) {
                 for (uint32_t i = tid; i < n2; i += 32) {
                     const uint32_t at = sm.q2[i];
-                    if (find_check_lengths(sm, in, m, span_byte, at, sm.pre[tid])) atomicMin(&sm.best, at);
+                    if (find_check_lengths(sm, in, m, span_byte, at, sm.pre[tid])) atomicMin(&sm.best[at / kFindSubBits], at);
                 }
             }
             __syncthreads();
             if (tid == 0) sm.n2 = 0;
         }
         __syncthreads();
-        if (sm.best != 0xFFFFFFFFu) break;
     }
-    if (tid == 0) {
-        const uint32_t best = sm.best;
-        cand[blockIdx.x] = best != 0xFFFFFFFFu ? span_bits0 + best : kNoBits;
-        flags[blockIdx.x] = best != 0xFFFFFFFFu ? 1u : 0u;
+    if (tid < (int)kFindSub) {
+        const uint32_t best = sm.best[tid];
+        cand[(uint64_t)blockIdx.x * kFindSub + tid] = best != 0xFFFFFFFFu ? span_bits0 + best : kNoBits;
+        flags[(uint64_t)blockIdx.x * kFindSub + tid] = best != 0xFFFFFFFFu ? 1u : 0u;
     }
 }
 
@@ -1599,6 +1611,10 @@ __global__ void foreign_table_kernel(const uint64_t *__restrict__ cand, const ui
     lc[k].stored_src = 0;
     lc[k].stored_len = 0;
     lc[k].slot_off = (begin + 3) & ~3ull;  // a unit per bit position, four-unit groups aligned
+    lc[k].dead = 0;
+    lc[k].slot_off_b = 0;
+    lc[k].units_a = 0;
+    lc[k].ext = 0;
 }
 
 // Longest blocks first: the decode of a block is serial, so the kernel can not end before its longest block does, and a
@@ -1646,7 +1662,9 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                                                                           LaneChunk *lc, uint32_t num_chunks,
                                                                           WarpState *tables, uint16_t *slots,
                                                                           uint32_t *next_task,
-                                                                          const uint32_t *__restrict__ perm, uint32_t dict_len) {
+                                                                          const uint32_t *__restrict__ perm, uint32_t dict_len,
+                                                                          uint16_t *spill, unsigned long long *spill_next,
+                                                                          uint64_t spill_units) {
     // every lane's short-code tables, interleaved so that the lanes of a warp fall into different banks: entry i of
     // lane l sits at [i * 32 + l].  Longer codes go through the lane's WarpState in global memory.
     extern __shared__ __align__(16) uint16_t s_lut_all[];
@@ -1671,7 +1689,27 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
         WarpState &ws = tables[kk];
         uint16_t *out = slots + lc[kk].slot_off;
         TokenSink sink{0ull, 0u, out};
-        const uint64_t target = lc[kk].target_bits;
+        uint64_t target = lc[kk].target_bits;
+        // foreign streams: the chunk has passed its target inside a block (the entry point there was false).  It goes on
+        // through that chunk's range -- once -- with its further units in the spill pool, so nothing of the other lane's is
+        // touched; -> false when that is not possible (second time, last chunk, pool full): kLaneOverrun, decoded again.
+        bool extended = false;
+        uint32_t units_a = 0;
+        uint64_t slot_b = 0;
+        auto extend = [&]() -> bool {
+            if (!kForeign || extended || target >= m * 8) return false;
+            const uint64_t target2 = lc[kk + 1].target_bits;
+            const unsigned long long need = ((target2 - target) + 64ull + 3ull) & ~3ull;  // a unit per bit, as in the slot array
+            const unsigned long long at = atomicAdd(spill_next, need);
+            if (at + need > spill_units) return false;
+            units_a = sink.finish(out);
+            slot_b = at;
+            out = spill + at;
+            sink = TokenSink{0ull, 0u, out};
+            target = target2;
+            extended = true;
+            return true;
+        };
         constexpr uint32_t kOutCap = kForeign ? 0x7FFF0000u : kSlotSyms;  // symbols a chunk may decode to
         // bytes that exist before the block: the preset dictionary for block 0 (IS:287-291), a full window otherwise
         const uint32_t reach_before = (live && k == 0) ? dict_len : (uint32_t)kWindow;
@@ -1719,7 +1757,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                                 // mixes a stored payload with other data: the warp-per-chunk path takes the stream
                                 status = ZK_BUF_ERROR;
                                 state = kDone;
-                            } else if (kForeign && !last && (src0 + len) * 8 > target) {
+                            } else if (kForeign && (src0 + len) * 8 > target && !(extend() && (src0 + len) * 8 <= target)) {
                                 status = kLaneOverrun;
                                 state = kDone;
                             } else {
@@ -1807,7 +1845,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     } else if (produced >= kOutCap) {
                         status = ZK_BUF_ERROR;
                         state = kDone;
-                    } else if (kForeign && fr.bit_pos() > target) {
+                    } else if (kForeign && fr.bit_pos() > target && !extend()) {
                         status = kLaneOverrun;
                         state = kDone;
                     } else {
@@ -1816,7 +1854,10 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     }
                 } else if (sym == 256) {
                     const uint64_t bits = fr.bit_pos();
-                    if (last) {
+                    if (kForeign && bits > target && !extend()) {  // only the end-of-block code lies in the next chunk's range
+                        status = kLaneOverrun;
+                        state = kDone;
+                    } else if (last) {
                         final_seen = 1;
                         end_byte = (bits + 7) >> 3;
                         end_bits = bits;
@@ -1866,7 +1907,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     } else if (produced + length > kOutCap) {
                         status = ZK_BUF_ERROR;
                         state = kDone;
-                    } else if (kForeign && fr.bit_pos() > target) {
+                    } else if (kForeign && fr.bit_pos() > target && !extend()) {
                         status = kLaneOverrun;
                         state = kDone;
                     } else {
@@ -1891,11 +1932,15 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                 }
             }
         }
-        const uint32_t units = sink.finish(out);
+        const uint32_t units_tail = sink.finish(out);
+        const uint32_t units = extended ? units_a + units_tail : units_tail;
         // a block that used bits past the end of the stream is not a block of this path
         if (live && status == ZK_OK && end_byte > m) status = ZK_BUF_ERROR;
         if (live) {
             lc[k].units = units;
+            lc[k].units_a = extended ? units_a : units;
+            lc[k].slot_off_b = slot_b;
+            lc[k].ext = extended ? 1u : 0u;
             lc[k].stored_src = stored_src;
             lc[k].stored_len = stored_len;
             lc[k].status = status;
@@ -1911,29 +1956,51 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
 
 // Verify the blocks, prefix-sum their sizes, build the coarse chunk table for the window chain.
 // verdict: [0] coarse chunks, [1] 1 = this path is valid, [2] status, [3] total output, [4] end byte, [5] final seen,
-// [6] 1 = a chunk failed or did not end where the next one starts
+// [6] 1 = a chunk failed or did not end where the next one starts, [7] chunks behind false entry points (dead)
 __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_t n, ChunkInfo *coarse,
                                                           uint32_t *num_coarse, uint64_t *verdict, uint64_t cap, uint64_t m,
                                                           uint32_t trailer, bool shard_body) {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
     __shared__ int bad;
+    __shared__ uint32_t dead_count, last_alive;
     if (threadIdx.x == 0) {
         carry = 0;
         bad = 0;
+        dead_count = 0;
+        last_alive = n - 1;
     }
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 1024) {
         const uint32_t i = base + threadIdx.x;
         uint64_t v = 0;
         if (i < n) {
-            v = lc[i].out_len;
-            const bool last = i + 1 == n;
-            // every block but the last must end exactly on the next one; the last must close the stream
-            const bool last_ok = shard_body ? (!lc[i].final_seen && lc[i].end_bits == lc[i].target_bits) : (lc[i].final_seen != 0);
-            if (lc[i].status != ZK_OK || (last ? !last_ok : (lc[i].final_seen || lc[i].end_bits != lc[i].target_bits))) bad = 1;
-            // a stream cut inside its trailer: the warp-per-chunk decoder reports what the reference reports (BR:48-57)
-            if (last && lc[i].end_byte + trailer > m) bad = 1;
+            // A chunk that went on through the next chunk's range (ext: the entry point there was false) makes that chunk
+            // dead; a dead chunk's own ext flag means nothing.  So in a run of ext flags the chunks are alive, dead,
+            // alive, ...: chunk i is alive when an even number of ext flags stand directly in front of it.
+            uint32_t run = 0;
+            while (run < i && lc[i - 1 - run].ext) ++run;
+            const bool alive = (run & 1u) == 0;
+            if (!alive) {
+                lc[i].out_len = 0;
+                lc[i].units = 0;
+                lc[i].units_a = 0;
+                lc[i].stored_len = 0;
+                lc[i].dead = 1;  // (ext stays as the lane left it: other threads count the flags)
+                atomicAdd(&dead_count, 1u);
+            } else {
+                lc[i].dead = 0;
+                v = lc[i].out_len;
+                const bool ext = lc[i].ext != 0 && i + 1 < n;
+                const uint64_t must_end = ext ? lc[i + 1].target_bits : lc[i].target_bits;
+                const bool last = ext ? i + 2 == n : i + 1 == n;
+                if (last) last_alive = i;
+                // every chunk but the last must end exactly on the next living one; the last must close the stream
+                const bool last_ok = shard_body ? (!lc[i].final_seen && lc[i].end_bits == must_end) : (lc[i].final_seen != 0);
+                if (lc[i].status != ZK_OK || (last ? !last_ok : (lc[i].final_seen || lc[i].end_bits != must_end))) bad = 1;
+                // a stream cut inside its trailer: the warp-per-chunk decoder reports what the reference reports (BR:48-57)
+                if (last && lc[i].end_byte + trailer > m) bad = 1;
+            }
         }
         uint64_t incl = v;
 #pragma unroll
@@ -1971,9 +2038,10 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
         verdict[1] = (!bad && total <= cap) ? 1 : 0;
         verdict[2] = (uint64_t)(int64_t)ZK_OK;
         verdict[3] = total;
-        verdict[4] = lc[n - 1].end_byte;
-        verdict[5] = (uint64_t)lc[n - 1].final_seen;
+        verdict[4] = lc[last_alive].end_byte;
+        verdict[5] = (uint64_t)lc[last_alive].final_seen;
         verdict[6] = (uint64_t)bad;
+        verdict[7] = dead_count;
     }
 }
 
@@ -1990,7 +2058,8 @@ template <bool kForeign>
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const uint8_t *__restrict__ in,
                                                                         const LaneChunk *__restrict__ lc, uint32_t n,
                                                                         const uint16_t *__restrict__ slots, uint16_t *dense,
-                                                                        const uint32_t *__restrict__ perm) {
+                                                                        const uint32_t *__restrict__ perm,
+                                                                        const uint16_t *__restrict__ spill) {
     const int lane = threadIdx.x & 31;
     const uint32_t slot = blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
     if (slot >= n) return;
@@ -2005,12 +2074,16 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
     }
     const uint32_t units = lc[j].units;
     const uint16_t *tok = slots + lc[j].slot_off;
+    // foreign chunks: units from units_a on are in the spill pool (the chunk went on through a false entry point's range)
+    const uint32_t units_a = kForeign ? lc[j].units_a : units;
+    const uint16_t *tok_b = kForeign ? spill + lc[j].slot_off_b : tok;
+    auto unit = [&](uint32_t x) -> uint32_t { return (!kForeign || x < units_a) ? tok[x] : tok_b[x - units_a]; };
     uint32_t base_out = 0;
     uint32_t carry_prev = 0;  // last unit of the previous pass
     for (uint32_t u0 = 0; u0 < units; u0 += 32) {
         const uint32_t u = u0 + lane;
-        const uint32_t me = u < units ? tok[u] : 0u;
-        const uint32_t nxt = u + 1 < units ? tok[u + 1] : 0u;
+        const uint32_t me = u < units ? unit(u) : 0u;
+        const uint32_t nxt = u + 1 < units ? unit(u + 1) : 0u;
         uint32_t prevu = __shfl_up_sync(0xFFFFFFFFu, me, 1);
         if (lane == 0) prevu = carry_prev;
         carry_prev = __shfl_sync(0xFFFFFFFFu, me, 31);
@@ -2023,7 +2096,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_blocks_kernel(const 
         uint32_t stored_at = 0;
         const bool is_stored = kForeign && is_match && len == 0u;
         if (is_stored) {
-            const uint32_t a = tok[u + 1] & 0x7FFFu, b = tok[u + 2] & 0x7FFFu, cc = tok[u + 3] & 0x7FFFu, d = tok[u + 4];
+            const uint32_t a = unit(u + 1) & 0x7FFFu, b = unit(u + 2) & 0x7FFFu, cc = unit(u + 3) & 0x7FFFu, d = unit(u + 4);
             stored_at = a | (b << 15) | ((cc & 3u) << 30);
             len = (cc >> 2) | (d << 13);
         }
@@ -2164,14 +2237,14 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     const bool foreign_ok = c->opt_foreign_path && job.container != 3 && m >= kForeignMinBytes && m < (1ull << 32);
     const uint64_t find_spans = foreign_ok ? (m + kFindSpan - 1) / kFindSpan : 0;
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2),
-                                                         find_spans / kCoarse + 2);
+                                                         find_spans * kFindSub / kCoarse + 2);
     c->arena.reset();
     if (job.container != 3) c->shard.valid = false;
     const size_t need = 4096 + (size_t)num_spans * 4 + (size_t)max_chunks * sizeof(ChunkInfo) + 1024 +
                         (size_t)(max_chunks + 1) * kWindow * 3 + (job.cap + 64) * 2 + adler_partials_bytes(job.cap) + crc_partials_bytes(job.cap) + 8192 +
                         (size_t)pieces_reserved * 12 + 1024 +
                         (size_t)lane_blocks_reserved * (12 + sizeof(LaneChunk) + sizeof(WarpState) + (size_t)kSlotSyms * 2 + 1024) +
-                        (size_t)find_spans * (24 + sizeof(LaneChunk) + sizeof(WarpState) + 8) + (foreign_ok ? (size_t)(m * 8 + 256) * 2 + 16384 : 0);
+                        (size_t)find_spans * kFindSub * (24 + sizeof(LaneChunk) + sizeof(WarpState) + 8) + (foreign_ok ? (size_t)(m * 8 + 256) * 2 + (size_t)(m + (4ull << 20)) * 2 + 16384 : 0);
     if (c->arena.reserve(need) != ZK_OK) return ZK_MEM_ERROR;
     int32_t *d_header = static_cast<int32_t *>(c->arena.take(256));
     uint32_t *d_cand = static_cast<uint32_t *>(c->arena.take((size_t)num_spans * 4));
@@ -2254,7 +2327,8 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                         ZK_CUDA(cudaMemsetAsync(d_total, 0, 4, st));  // reused as the task counter
                         decode_lanes_kernel<false><<<grid, kLaneWarps * 32, lane_smem, st>>>(
-                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm, dict_len);
+                            job.d_in, m, d_lc, (uint32_t)n, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_total), d_perm, dict_len,
+                            nullptr, nullptr, 0);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
                                                           job.container == 0 ? 4u : job.container == 2 ? 8u : 0u, job.container == 3);
@@ -2264,7 +2338,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     if (verdict[1] == 1 && verdict[0] <= max_chunks) {
                         ScopedTimer t(c, 5);
                         expand_blocks_kernel<false><<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
-                            job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm);
+                            job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm, nullptr);
                         resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
                         c->launches += 2;
                         lane_path_done = true;
@@ -2276,7 +2350,8 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
 
     // ---- a stream somebody else made: entry points at the dynamic block headers block_find_kernel accepts ------------------
     if (!lane_path_done && foreign_ok) {
-        const uint32_t spans = (uint32_t)find_spans;
+        const uint32_t find_ctas = (uint32_t)find_spans;
+        const uint32_t spans = find_ctas * kFindSub;  // candidate slots
         uint64_t *d_cand64 = static_cast<uint64_t *>(c->arena.take((size_t)spans * 8));
         uint32_t *d_flags = static_cast<uint32_t *>(c->arena.take((size_t)spans * 4 + 16));
         uint64_t *d_off = static_cast<uint64_t *>(c->arena.take((size_t)spans * 8 + 16));
@@ -2286,19 +2361,23 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
         uint32_t *d_perm = static_cast<uint32_t *>(c->arena.take((size_t)(spans + 1) * 4));
         uint32_t *d_redo = static_cast<uint32_t *>(c->arena.take((size_t)(spans + 1) * 4));
         uint16_t *d_slots = static_cast<uint16_t *>(c->arena.take((size_t)(m * 8 + 256) * 2));
-        if (d_cand64 && d_flags && d_off && d_count && d_lc && d_tables && d_perm && d_redo && d_slots) {
+        // units of chunks that go on through a false entry point's range: a unit per bit of that range, rarely needed
+        const uint64_t spill_units = m + (4ull << 20);
+        uint16_t *d_spill = static_cast<uint16_t *>(c->arena.take((size_t)spill_units * 2));
+        unsigned long long *d_spill_next = static_cast<unsigned long long *>(c->arena.take(256));
+        if (d_cand64 && d_flags && d_off && d_count && d_lc && d_tables && d_perm && d_redo && d_slots && d_spill && d_spill_next) {
             uint64_t found = 0;
             {
                 ScopedTimer t(c, 5);
                 ZK_CUDA(cudaFuncSetAttribute(block_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FindSmem)));
-                block_find_kernel<<<spans, kFindThreads, sizeof(FindSmem), st>>>(job.d_in, m, (uint64_t)body_begin * 8, d_cand64, d_flags);
+                block_find_kernel<<<find_ctas, kFindThreads, sizeof(FindSmem), st>>>(job.d_in, m, (uint64_t)body_begin * 8, d_cand64, d_flags);
                 marker_scan_kernel<<<1, 1024, 0, st>>>(d_flags, spans, d_off, d_count);
                 c->launches += 2;
             }
             ZK_CUDA(cudaMemcpyAsync(&found, d_count, 8, cudaMemcpyDeviceToHost, st));
             ZK_CUDA(cudaStreamSynchronize(st));
             const bool dbg = getenv("ZK_FOREIGN_DEBUG") != nullptr;
-            if (dbg) fprintf(stderr, "[zk foreign] m %llu spans %u entry points %llu\n", (unsigned long long)m, spans, (unsigned long long)found);
+            if (dbg) fprintf(stderr, "[zk foreign] m %llu candidate slots %u entry points %llu\n", (unsigned long long)m, spans, (unsigned long long)found);
             if (found >= kForeignMinChunks) {
                 uint64_t n = found + 1;
                 foreign_table_kernel<<<(spans + 256) / 256, 256, 0, st>>>(d_cand64, d_flags, d_off, spans, found, m, body_begin, d_lc);
@@ -2308,6 +2387,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                 ZK_CUDA(cudaFuncSetAttribute(decode_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lane_smem));
                 const uint32_t *d_todo = d_perm;
                 uint64_t todo = n;
+                ZK_CUDA(cudaMemsetAsync(d_spill_next, 0, 8, st));
                 std::vector<LaneChunk> host_lc;
                 std::vector<uint32_t> redo;
                 for (int round = 0; round < kForeignRounds && !lane_path_done; ++round) {
@@ -2316,7 +2396,8 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         const uint32_t tasks = (uint32_t)((todo + 31) / 32);
                         ZK_CUDA(cudaMemsetAsync(d_count, 0, 4, st));  // the task counter
                         decode_lanes_kernel<true><<<tmin<uint32_t>(tasks, (uint32_t)c->sm_count), kLaneWarps * 32, lane_smem, st>>>(
-                            job.d_in, m, d_lc, (uint32_t)todo, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_count), d_todo, dict_len);
+                            job.d_in, m, d_lc, (uint32_t)todo, d_tables, d_slots, reinterpret_cast<uint32_t *>(d_count), d_todo, dict_len,
+                            d_spill, d_spill_next, spill_units);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
                                                           job.container == 0 ? 4u : job.container == 2 ? 8u : 0u, false);
@@ -2348,6 +2429,13 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     bool give_up = false;
                     for (uint64_t i = 0; i < n && !give_up; ++i) {
                         LaneChunk cur = host_lc[i];
+                        if (cur.dead) {  // marked by the plan of this round: the picture may change, decode it again
+                            cur.dead = 0;
+                            cur.status = ZK_OK;
+                            redo.push_back((uint32_t)w);
+                            host_lc[w++] = cur;
+                            continue;
+                        }
                         if (cur.status == kLaneOverrun && i + 1 < n) {
                             cur.target_bits = host_lc[i + 1].target_bits;
                             cur.in_end = host_lc[i + 1].in_end;
@@ -2376,10 +2464,11 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     ScopedTimer t(c, 5);
                     lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
                     expand_blocks_kernel<true><<<(uint32_t)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, st>>>(
-                        job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm);
+                        job.d_in, d_lc, (uint32_t)n, d_slots, d_sym, d_perm, d_spill);
                     resolve_coarse_kernel<<<(uint32_t)verdict[0], 1024, 0, st>>>(d_lc, (uint32_t)n, d_sym);
                     c->launches += 3;
-                    c->foreign_chunks += (int64_t)n;
+                    c->foreign_chunks += (int64_t)(n - verdict[7]);
+                    c->foreign_merges += (int64_t)verdict[7];
                 }
             }
         }
