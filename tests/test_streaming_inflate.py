@@ -122,3 +122,27 @@ def test_streaming_errors_and_trailing_bytes(engine):
     # bad header
     out, trace, rc, _ = _feed(zk, b"\x78\x9d" + own[2:], 4096)
     assert rc == zk.Z_DATA_ERROR and out == b""
+
+
+@pytest.mark.gpu
+def test_large_foreign_stream_in_pieces_fails_fast_while_unfinished(engine):
+    """A libz stream has nothing to decode before its end, so the handle gathers it and tries the end when the input has
+    doubled.  Every try on the unfinished stream used to cost a one-warp decode of everything gathered; now the entry-point
+    search sees that only the last chunk runs out of input and says so at once (counter inflate_quick_incomplete)."""
+    import time
+
+    import zlibk_b200 as zk
+    from zlibk_b200 import corpus
+
+    data = corpus.text_like(24 << 20).tobytes()
+    stream = zlib.compress(data, 6)
+    eng = zk.default_engine()
+    q0, f0 = eng.counter("inflate_quick_incomplete"), eng.counter("inflate_foreign_chunks")
+    t0 = time.perf_counter()
+    out, trace, rc, adler = _feed(zk, stream, 512 << 10, out_room=8 << 20)
+    dt = time.perf_counter() - t0
+    assert rc == zk.Z_STREAM_END and out == data and adler == zlib.adler32(data)
+    assert eng.counter("inflate_quick_incomplete") - q0 >= 3, "the unfinished tries went through the slow decoder"
+    assert eng.counter("inflate_foreign_chunks") - f0 > 100
+    assert trace[-1][0] == len(stream) and trace[-1][1] == len(data)
+    print("24 MiB through the handle in 512 KiB pieces: %.2f s" % dt)

@@ -458,6 +458,7 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
     if (!strcmp(name, "d2h_bytes")) return c->d2h_bytes;
     if (!strcmp(name, "inflate_foreign_chunks")) return c->foreign_chunks;
     if (!strcmp(name, "inflate_foreign_merges")) return c->foreign_merges;
+    if (!strcmp(name, "inflate_quick_incomplete")) return c->quick_incomplete;
     if (!strcmp(name, "inflate_pipe_slabs")) return c->pipe_slabs;
     if (!strcmp(name, "inflate_pipe_fallbacks")) return c->pipe_fallbacks;
     // device time per kernel class in microseconds / launches timed; call after zk_ctx_synchronize
@@ -1114,7 +1115,7 @@ int host_inflate_piped(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, u
 
 static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
                         uint64_t cap, uint64_t *out_len, uint64_t *consumed, int container = 0, uint32_t body_begin = 0,
-                        uint32_t *check = nullptr) {
+                        uint32_t *check = nullptr, bool quick_incomplete = false) {
     if (out_len) *out_len = 0;
     if (consumed) *consumed = 0;
     if (!c || !out_len || (!in && m) || (!out && cap) || (!dict && dict_len)) return ZK_STREAM_ERROR;
@@ -1150,6 +1151,7 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
     }
     job.container = container;
     job.body_begin = body_begin;
+    job.quick_incomplete = quick_incomplete;
     int rc = run_inflate(c, job);
     if (rc != ZK_OK) return rc;
     uint64_t res[4];
@@ -1652,8 +1654,8 @@ int stream_decode_tail(zk_stream *s, uint64_t *used) {
         uint64_t got = 0;
         uint32_t check = 1;
         const int rc = host_inflate(s->ctx, s->pending_in.data(), m, s->window.empty() ? nullptr : s->window.data(), (uint32_t)s->window.size(),
-                                    buf.data(), cap, &got, used, 1, 0, &check);
-        if (rc == ZK_BUF_ERROR && got == 0 && cap < (uint64_t)m * 1100 + 65536) {  // the output may not have fitted
+                                    buf.data(), cap, &got, used, 1, 0, &check, true);
+        if (rc == ZK_BUF_ERROR && got == 0 && *used == 0 && cap < (uint64_t)m * 1100 + 65536) {  // the output may not have fitted
             cap *= 16;
             continue;
         }

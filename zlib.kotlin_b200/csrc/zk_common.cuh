@@ -98,7 +98,7 @@ struct zk_ctx {
     void *registered[16] = {};        // ... those buffers (unlocked by zk_host_unregister or when the context goes)
     int num_registered = 0;
     int64_t opt_foreign_path = 1;     // 0: streams without sync markers are decoded by one warp (the round-1 behaviour)
-    int64_t foreign_chunks = 0, foreign_merges = 0;  // counters: chunks decoded through found entry points, false entry points merged
+    int64_t foreign_chunks = 0, foreign_merges = 0, quick_incomplete = 0;  // counters: chunks decoded through found entry points, false entry points merged
     int64_t opt_lane_pack = 0;        // 1: the lane decoder fills whole CTAs (few SMs per call) so that several calls run side by side
     int64_t opt_inflate_slab = 0;     // compressed bytes per slab of that pipeline, 0 = built-in
     zk_ctx *helpers[4] = {nullptr, nullptr, nullptr, nullptr};  // contexts of the pipeline's workers (own stream + arena)
@@ -185,6 +185,10 @@ struct InflateJob {
     int container = 0;                // 0 zlib, 1 raw deflate, 2 gzip member (header already parsed by the host), 3 shard body
     uint16_t *d_tail_map = nullptr;   // shard body: receives the shard's total tail map (u16[32768])
     uint32_t body_begin = 0;          // raw / gzip: offset of the deflate data in d_in
+    // the streaming inflate tries the end of a stream while input is still arriving: when the chunks found by the entry-point
+    // search are fine and only the last one runs out of input, answer ZK_BUF_ERROR at once instead of letting the one-warp
+    // decoder walk the whole input to say the same
+    bool quick_incomplete = false;
 };
 int run_inflate(zk_ctx *c, const InflateJob &job);
 int run_inflate_shard_finish(zk_ctx *c, const uint8_t *d_entry_window, uint8_t *d_out, uint64_t *d_result);

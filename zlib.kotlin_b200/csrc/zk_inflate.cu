@@ -1839,14 +1839,14 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     }
                 }
                 if (sym < 256) {
-                    if (sym < 0) {
+                    if (kForeign && fr.bit_pos() > target && !extend()) {  // first: what lies behind the target is not this chunk's
+                        status = kLaneOverrun;
+                        state = kDone;
+                    } else if (sym < 0) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
                     } else if (produced >= kOutCap) {
                         status = ZK_BUF_ERROR;
-                        state = kDone;
-                    } else if (kForeign && fr.bit_pos() > target && !extend()) {
-                        status = kLaneOverrun;
                         state = kDone;
                     } else {
                         sink.put((uint32_t)sym, 1u);
@@ -1901,14 +1901,14 @@ __global__ void __launch_bounds__(kLaneWarps * 32, 1) decode_lanes_kernel(const 
                     const uint32_t dbase = dcl < 4 ? 1u + (uint32_t)dcl : 1u + ((2u + (uint32_t)(dcl & 1)) << de);
                     const uint32_t dist = dbase + fr.peek(de);
                     fr.drop(de);
-                    if (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow || dist > produced + reach_before) {
+                    if (kForeign && fr.bit_pos() > target && !extend()) {
+                        status = kLaneOverrun;
+                        state = kDone;
+                    } else if (lcode > 28 || dsym < 0 || dsym > 29 || dist > (uint32_t)kWindow || dist > produced + reach_before) {
                         status = ZK_DATA_ERROR;
                         state = kDone;
                     } else if (produced + length > kOutCap) {
                         status = ZK_BUF_ERROR;
-                        state = kDone;
-                    } else if (kForeign && fr.bit_pos() > target && !extend()) {
-                        status = kLaneOverrun;
                         state = kDone;
                     } else {
                         sink.put((0x8000u | length) | ((dist - 1u) << 16), 2u);
@@ -2426,7 +2426,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                     ZK_CUDA(cudaStreamSynchronize(st));
                     redo.clear();
                     uint64_t w = 0;
-                    bool give_up = false;
+                    bool give_up = false, incomplete = false;
                     for (uint64_t i = 0; i < n && !give_up; ++i) {
                         LaneChunk cur = host_lc[i];
                         if (cur.dead) {  // marked by the plan of this round: the picture may change, decode it again
@@ -2443,6 +2443,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                             redo.push_back((uint32_t)w);
                             ++i;
                         } else if (cur.status != ZK_OK) {
+                            // the last chunk ran out of input and everything before it is in order
+                            if (job.quick_incomplete && redo.empty() && (i + 1 == n || (cur.ext && i + 2 == n)) &&
+                                (cur.status == ZK_BUF_ERROR || cur.status == kLaneOverrun))
+                                incomplete = true;
                             if (dbg)
                                 fprintf(stderr, "[zk foreign] chunk %llu at bit %llu (target %llu): status %d after %u bytes\n", (unsigned long long)i,
                                         (unsigned long long)cur.begin_bits, (unsigned long long)cur.target_bits, cur.status, cur.out_len);
@@ -2450,6 +2454,17 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                         }
                         host_lc[w++] = cur;
                         if (cur.status == ZK_OK && cur.final_seen && redo.empty()) break;  // the stream ends here
+                    }
+                    // (a last chunk that ends on the last byte without a final block is an unfinished stream too)
+                    if (job.quick_incomplete && !give_up && redo.empty() && n && host_lc[w - 1].status == ZK_OK && !host_lc[w - 1].final_seen)
+                        incomplete = true;
+                    if (incomplete) {
+                        c->quick_incomplete++;
+                        // (consumed = m: the input ran out -- an output buffer that is too small reports 0 consumed)
+                        set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, m, ZK_BUF_ERROR, 1);
+                        c->launches++;
+                        ZK_CUDA(cudaGetLastError());
+                        return ZK_OK;
                     }
                     if (give_up || redo.empty()) break;
                     n = w;
