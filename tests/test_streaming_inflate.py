@@ -146,3 +146,34 @@ def test_large_foreign_stream_in_pieces_fails_fast_while_unfinished(engine):
     assert eng.counter("inflate_foreign_chunks") - f0 > 100
     assert trace[-1][0] == len(stream) and trace[-1][1] == len(data)
     print("24 MiB through the handle in 512 KiB pieces: %.2f s" % dt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wbits", [15, 31, -15])
+def test_unfinished_foreign_stream_is_decoded_up_to_its_last_entry_point(engine, wbits):
+    """A libz stream fed in pieces: once enough has gathered (option inflate_prefix_bytes, 1 MiB here), everything up to the
+    last entry point found in it is decoded and handed out, and the rest -- which may begin inside a byte -- is kept.  The
+    bytes, totals and checksum are libz's; output must appear long before the input ends."""
+    import zlibk_b200 as zk
+    from zlibk_b200 import corpus
+
+    data = corpus.mixed_entropy(20 << 20).tobytes()
+    co = zlib.compressobj(6, zlib.DEFLATED, wbits)
+    stream = co.compress(data) + co.flush()
+    eng = zk.default_engine()
+    eng.set_option("inflate_prefix_bytes", 1 << 20)
+    try:
+        p0 = eng.counter("inflate_prefix_decodes")
+        out, trace, rc, adler = _feed(zk, stream, 700 << 10, wbits=wbits, out_room=8 << 20)
+        steps = eng.counter("inflate_prefix_decodes") - p0
+    finally:
+        eng.set_option("inflate_prefix_bytes", 0)
+    assert rc == zk.Z_STREAM_END and out == data
+    assert trace[-1][0] == len(stream) and trace[-1][1] == len(data)
+    if wbits == 15:
+        assert adler == zlib.adler32(data)
+    elif wbits == 31:
+        assert adler == zlib.crc32(data)
+    assert steps >= 3, steps
+    early = [t for t in trace if t[0] <= len(stream) // 2]
+    assert early and early[-1][1] >= len(data) // 5, "no output before half of the input had arrived"

@@ -245,14 +245,20 @@ class ZStream:
             return _b.Z_STREAM_ERROR
         src = bytes(memoryview(self.next_in)[self.next_in_index:self.next_in_index + self.avail_in])
         in_len = ctypes.c_uint64(len(src))
-        out_buf = (ctypes.c_uint8 * max(self.avail_out, 1))()
         out_len = ctypes.c_uint64(self.avail_out)
+        # the engine writes straight into next_out when that is a bytearray with the room it claims (no staging copy)
+        direct = isinstance(self.next_out, bytearray) and self.avail_out > 0 and len(self.next_out) >= self.next_out_index + self.avail_out
+        if direct:
+            out_buf = (ctypes.c_uint8 * self.avail_out).from_buffer(self.next_out, self.next_out_index)
+        else:
+            out_buf = (ctypes.c_uint8 * max(self.avail_out, 1))()
         rc = fn(self._h, src if src else None, ctypes.byref(in_len), out_buf, ctypes.byref(out_len), flush)
         used, made = in_len.value, out_len.value
         self.next_in_index += used
         self.avail_in -= used
-        if made:
-            self.next_out[self.next_out_index:self.next_out_index + made] = bytes(out_buf[:made])
+        if made and not direct:
+            self.next_out[self.next_out_index:self.next_out_index + made] = ctypes.string_at(out_buf, made)
+        del out_buf
         self.next_out_index += made
         self.avail_out -= made
         self.total_in = self._lib.zk_stream_total_in(self._h)

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <memory>
 #include <vector>
 
 #include "zk_common.cuh"
@@ -433,6 +434,11 @@ int zk_ctx_set_option(zk_ctx *c, const char *name, int64_t value) {
         c->opt_inflate_pipe = value != 0;
         return ZK_OK;
     }
+    if (!strcmp(name, "inflate_prefix_bytes")) {  // stream handle: a stream without markers is decoded up to its last entry point
+        if (value < 0 || (value && value < (256 << 10))) return ZK_STREAM_ERROR;  // whenever this much has gathered (0 = 32 MiB; huge = never)
+        c->opt_prefix_bytes = value;
+        return ZK_OK;
+    }
     if (!strcmp(name, "inflate_slab_bytes")) {  // compressed bytes per slab of the pipelined host-buffer inflate, 0 = built-in
         if (value < 0 || (value && value < (1 << 20))) return ZK_STREAM_ERROR;
         c->opt_inflate_slab = value;
@@ -459,6 +465,7 @@ int64_t zk_ctx_get_counter(zk_ctx *c, const char *name) {
     if (!strcmp(name, "inflate_foreign_chunks")) return c->foreign_chunks;
     if (!strcmp(name, "inflate_foreign_merges")) return c->foreign_merges;
     if (!strcmp(name, "inflate_quick_incomplete")) return c->quick_incomplete;
+    if (!strcmp(name, "inflate_prefix_decodes")) return c->prefix_decodes;
     if (!strcmp(name, "inflate_pipe_slabs")) return c->pipe_slabs;
     if (!strcmp(name, "inflate_pipe_fallbacks")) return c->pipe_fallbacks;
     // device time per kernel class in microseconds / launches timed; call after zk_ctx_synchronize
@@ -563,6 +570,7 @@ int zk_inflate_shard_prepare_device(zk_ctx *c, const uint8_t *d_body, uint64_t m
     job.container = 3;
     job.dict_len = hist_len;
     job.d_tail_map = d_tail_map;
+    job.quick_incomplete = c->stream_quick;
     c->shard.valid = false;
     return run_inflate(c, job);
 }
@@ -1115,7 +1123,7 @@ int host_inflate_piped(zk_ctx *c, const uint8_t *in, uint64_t m, uint8_t *out, u
 
 static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t *dict, uint32_t dict_len, uint8_t *out,
                         uint64_t cap, uint64_t *out_len, uint64_t *consumed, int container = 0, uint32_t body_begin = 0,
-                        uint32_t *check = nullptr, bool quick_incomplete = false) {
+                        uint32_t *check = nullptr, bool quick_incomplete = false, uint32_t begin_bit = 0, bool prefix = false) {
     if (out_len) *out_len = 0;
     if (consumed) *consumed = 0;
     if (!c || !out_len || (!in && m) || (!out && cap) || (!dict && dict_len)) return ZK_STREAM_ERROR;
@@ -1152,6 +1160,8 @@ static int host_inflate(zk_ctx *c, const uint8_t *in, uint64_t m, const uint8_t 
     job.container = container;
     job.body_begin = body_begin;
     job.quick_incomplete = quick_incomplete;
+    job.begin_bit = begin_bit;
+    job.prefix = prefix;
     int rc = run_inflate(c, job);
     if (rc != ZK_OK) return rc;
     uint64_t res[4];
@@ -1362,6 +1372,8 @@ struct zk_stream {
     bool plain_mode = false;           // a marker turned out not to be a block boundary: gather, try at geometric sizes
     bool body_done = false;            // the final block has been decoded; the trailer may still be missing
     uint64_t decoded = 0;              // bytes decoded so far (total_out counts what the caller has taken)
+    uint32_t bit_off = 0;              // bits of pending_in[0] that belong to blocks already decoded (after a prefix decode)
+    size_t prefix_attempt = 0;         // size of pending_in when a prefix decode last made no progress
     int sticky = ZK_OK;                // an error, once met, is the answer of every later call
 };
 
@@ -1608,7 +1620,7 @@ int stream_decode_marked(zk_stream *s, size_t len) {
     for (int attempt = 0; attempt < 5; ++attempt, cap *= 8) {
         const size_t in_room = (len + 255) / 256 * 256;
         Staging *st = staging_for(c, 256 + 65536 + 32768 + in_room + (size_t)cap + 256);
-        if (!st) return ZK_MEM_ERROR;
+        if (!st) return attempt ? 1 : ZK_MEM_ERROR;  // (a retry with eight times the room: then this is not such a body)
         uint64_t *d_result = reinterpret_cast<uint64_t *>(st->base);
         uint16_t *d_tail = reinterpret_cast<uint16_t *>(st->base + 256);
         uint8_t *d_window = st->base + 256 + 65536, *d_in = d_window + 32768, *d_out = d_in + in_room;
@@ -1616,13 +1628,17 @@ int stream_decode_marked(zk_stream *s, size_t len) {
         if (wl) ZK_CUDA(cudaMemcpyAsync(d_window + 32768 - wl, s->window.data(), wl, cudaMemcpyHostToDevice, c->stream));
         ZK_CUDA(cudaMemcpyAsync(d_in, s->pending_in.data(), len, cudaMemcpyHostToDevice, c->stream));
         c->h2d_bytes += (int64_t)len + wl;
+        c->stream_quick = true;  // a false marker: the body runs out of input; no need to walk it with one warp to learn that
         int rc = zk_inflate_shard_prepare_device(c, d_in, len, wl, cap, d_tail, d_result);
+        c->stream_quick = false;
         if (rc != ZK_OK) return rc;
         uint64_t res[4];
         ZK_CUDA(cudaMemcpyAsync(res, d_result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
         ZK_CUDA(cudaStreamSynchronize(c->stream));
         const int status = (int)(int64_t)res[2];
-        if (status == ZK_BUF_ERROR && cap < (uint64_t)len * 1100 + 65536) continue;  // more output than reserved: once more
+        // more output than reserved (nothing written, nothing consumed): once more.  A body that runs out of INPUT -- a
+        // false marker, e.g. the 00 | 00 FF FF of a stored block header behind a zero byte -- reports what it consumed.
+        if (status == ZK_BUF_ERROR && res[0] == 0 && res[1] == 0 && cap < (uint64_t)len * 1100 + 65536) continue;
         if (status != ZK_OK || res[1] != len || res[0] > cap || !c->shard.valid) return 1;
         rc = zk_inflate_shard_finish_device(c, d_window, d_out, d_result);
         if (rc != ZK_OK) return rc;
@@ -1654,7 +1670,7 @@ int stream_decode_tail(zk_stream *s, uint64_t *used) {
         uint64_t got = 0;
         uint32_t check = 1;
         const int rc = host_inflate(s->ctx, s->pending_in.data(), m, s->window.empty() ? nullptr : s->window.data(), (uint32_t)s->window.size(),
-                                    buf.data(), cap, &got, used, 1, 0, &check, true);
+                                    buf.data(), cap, &got, used, 1, 0, &check, true, s->bit_off);
         if (rc == ZK_BUF_ERROR && got == 0 && *used == 0 && cap < (uint64_t)m * 1100 + 65536) {  // the output may not have fitted
             cap *= 16;
             continue;
@@ -1666,6 +1682,31 @@ int stream_decode_tail(zk_stream *s, uint64_t *used) {
         stream_note_output(s, buf.data(), got);
         return ZK_STREAM_END;
     }
+}
+
+// A stream without markers whose end has not arrived: decode the chunks between the entry points found in pending_in, all
+// but the last (it may be cut), hand their bytes out and keep the rest -- which may begin inside a byte (bit_off).
+// 0: progress; 1: none (too few entry points, more output than reserved, ...): the input goes on gathering.
+int stream_decode_prefix(zk_stream *s) {
+    const size_t m = s->pending_in.size();
+    const uint64_t cap = (uint64_t)m * 5 + (1u << 20);
+    std::unique_ptr<uint8_t[]> buf(new uint8_t[cap]);
+    uint64_t got = 0, used_bits = 0;
+    uint32_t check = 1;
+    const int rc = host_inflate(s->ctx, s->pending_in.data(), m, s->window.empty() ? nullptr : s->window.data(), (uint32_t)s->window.size(),
+                                buf.get(), cap, &got, &used_bits, 1, 0, &check, false, s->bit_off, true);
+    if (rc != ZK_OK || got == 0 || (used_bits >> 3) > m) return 1;
+    if (s->container == 2) s->crc = zk_crc32(s->ctx, s->crc, buf.get(), got);
+    else s->adler = adler32_combine(s->adler, check, got);
+    s->pending_out.insert(s->pending_out.end(), buf.get(), buf.get() + got);
+    stream_note_output(s, buf.get(), got);
+    s->pending_in.erase(s->pending_in.begin(), s->pending_in.begin() + (long)(used_bits >> 3));
+    s->bit_off = (uint32_t)(used_bits & 7);
+    s->plain_mode = true;  // from here on positions are bits: the marker logic is out
+    s->scan_pos = s->pending_in.size();
+    s->marker_end = 0;
+    s->ctx->prefix_decodes++;
+    return 0;
 }
 
 int stream_inflate_step(zk_stream *s, int flush, uint64_t *unread) {
@@ -1730,6 +1771,19 @@ int stream_inflate_step(zk_stream *s, int flush, uint64_t *unread) {
         }
     }
     // ---- the end of the stream ----
+    if (!s->body_done && !s->pending_in.empty() && flush != ZK_FINISH && !(s->seen_marker && !s->plain_mode)) {
+        // no markers: a prefix up to the last entry point, whenever enough has gathered
+        const size_t m = s->pending_in.size();
+        const size_t least = s->ctx->opt_prefix_bytes ? (size_t)s->ctx->opt_prefix_bytes : (size_t)(32u << 20);
+        if (m >= least && m >= 2 * s->prefix_attempt) {
+            if (stream_decode_prefix(s) == 0) {
+                s->prefix_attempt = 0;
+                s->tail_attempt = s->pending_in.size();  // what is left is an unfinished chunk: try its end when it has grown
+            } else {
+                s->prefix_attempt = m;
+            }
+        }
+    }
     if (!s->body_done && !s->pending_in.empty()) {
         const size_t m = s->pending_in.size();
         // In a stream of short marked blocks the rest behind the last marker is an incomplete block -- unless that block is
@@ -1840,9 +1894,10 @@ int zk_inflate_reset(zk_stream *s) {
     s->pending_out.clear();
     s->out_pos = 0;
     s->window.clear();
-    s->scan_pos = s->marker_end = s->tail_attempt = 0;
+    s->scan_pos = s->marker_end = s->tail_attempt = s->prefix_attempt = 0;
     s->plain_mode = s->body_done = s->seen_marker = false;
     s->decoded = 0;
+    s->bit_off = 0;
     s->sticky = ZK_OK;
     s->have_dict = false;  // zlib.h inflateReset: the stream starts over; a dictionary has to be supplied again
     s->dict.clear();

@@ -97,6 +97,9 @@ struct zk_ctx {
     int64_t opt_auto_register = 0;    // 1: host-buffer calls page-lock caller buffers CUDA does not know yet and keep them locked
     void *registered[16] = {};        // ... those buffers (unlocked by zk_host_unregister or when the context goes)
     int num_registered = 0;
+    bool stream_quick = false;        // set by the stream handle around a marked-body try: a body that runs out of input is answered at once
+    int64_t opt_prefix_bytes = 0;     // stream handle: gathered bytes of a stream without markers from which a prefix is decoded (0 = 32 MiB)
+    int64_t prefix_decodes = 0;       // counter: such prefix decodes that made progress
     int64_t opt_foreign_path = 1;     // 0: streams without sync markers are decoded by one warp (the round-1 behaviour)
     int64_t foreign_chunks = 0, foreign_merges = 0, quick_incomplete = 0;  // counters: chunks decoded through found entry points, false entry points merged
     int64_t opt_lane_pack = 0;        // 1: the lane decoder fills whole CTAs (few SMs per call) so that several calls run side by side
@@ -189,6 +192,11 @@ struct InflateJob {
     // search are fine and only the last one runs out of input, answer ZK_BUF_ERROR at once instead of letting the one-warp
     // decoder walk the whole input to say the same
     bool quick_incomplete = false;
+    // the stream handle, on a stream without markers whose end has not arrived: decode the chunks between found entry points
+    // except the last (it may be cut), report the bit position where that one begins in result[1] and ZK_OK in result[2];
+    // no progress possible -> {0, 0, ZK_BUF_ERROR}.  Raw container only.
+    bool prefix = false;
+    uint32_t begin_bit = 0;           // raw: the deflate data starts at this bit of byte body_begin (0..7)
 };
 int run_inflate(zk_ctx *c, const InflateJob &job);
 int run_inflate_shard_finish(zk_ctx *c, const uint8_t *d_entry_window, uint8_t *d_out, uint64_t *d_result);

@@ -477,10 +477,14 @@ struct ChunkResult {
 template <bool kWrite, bool kCoop, bool kTokens = false>
 __device__ ChunkResult decode_chunk(WarpState &ws, const uint8_t *in, uint64_t m, uint64_t in_begin, uint64_t in_end,
                                     uint64_t reach_before, uint16_t *sym, uint64_t out_begin, uint64_t out_cap, int lane,
-                                    uint32_t *units_out = nullptr) {
+                                    uint32_t *units_out = nullptr, uint32_t first_bit = 0) {
     constexpr int kStep = kCoop ? 32 : 1;
     uint32_t units = 0;
     BitReader br{in, m, in_begin, 0, 0};
+    if (first_bit) {  // the data starts inside the first byte (a stream handle that has decoded a prefix)
+        br.refill();
+        if (br.held >= (int)first_bit) br.drop((int)first_bit);
+    }
     uint64_t produced = 0;
     ChunkResult res{0, 0, ZK_OK, 0};
     // every lane runs the same decode; only the copies are split across lanes
@@ -740,7 +744,8 @@ __global__ void chunk_list_kernel(const uint32_t *cand, uint32_t num_spans, uint
 template <bool kWrite>
 __global__ void __launch_bounds__(kInfWarps * 32) decode_kernel(const uint8_t *__restrict__ in, uint64_t m,
                                                                 ChunkInfo *chunks, const uint32_t *num_chunks,
-                                                                uint16_t *sym, uint64_t out_cap, uint32_t dict_len) {
+                                                                uint16_t *sym, uint64_t out_cap, uint32_t dict_len,
+                                                                uint32_t first_bit) {
     __shared__ WarpState state[kInfWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t c = blockIdx.x * kInfWarps + wid;
@@ -748,7 +753,8 @@ __global__ void __launch_bounds__(kInfWarps * 32) decode_kernel(const uint8_t *_
     ChunkInfo &ci = chunks[c];
     if (!kWrite && ci.out_len != ~0ull) return;  // sized in an earlier round
     const uint64_t room = kWrite ? (ci.out_begin <= out_cap ? out_cap - ci.out_begin : 0) : ~0ull;
-    const ChunkResult r = decode_chunk<kWrite, true>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0 ? (uint64_t)dict_len : (uint64_t)kWindow, sym, ci.out_begin, room, lane);
+    const ChunkResult r = decode_chunk<kWrite, true>(state[wid], in, m, ci.in_begin, ci.in_end, c == 0 ? (uint64_t)dict_len : (uint64_t)kWindow, sym,
+                                                     ci.out_begin, room, lane, nullptr, c == 0 ? first_bit : 0u);
     if (lane == 0) {
         ci.status = r.status;
         if (!kWrite) {
@@ -1066,6 +1072,10 @@ __global__ void finish_inflate_kernel(const uint8_t *in, uint64_t m, const uint6
         if (container == 3) {
             // a shard body: it carries no final block and must end exactly on the end of its range
             status = (!verdict[5] && end_byte == m) ? ZK_STREAM_END : ZK_DATA_ERROR;
+        } else if (container == 4) {
+            // a prefix of a stream without markers: whole chunks up to an entry point; consumed counts BITS
+            status = !verdict[5] ? ZK_OK : ZK_DATA_ERROR;
+            consumed = verdict[8];
         } else if (!verdict[5]) status = ZK_BUF_ERROR;  // ran out of input before a final block
         else if (end_byte + need > m) status = ZK_BUF_ERROR;  // IS:414-418 trailer bytes missing
         else if (container == 0) {
@@ -1234,12 +1244,12 @@ struct LaneChunk {
 constexpr int32_t kLaneOverrun = 1000;
 
 __global__ void lane_table_kernel(const uint64_t *__restrict__ positions, uint32_t num_markers, uint64_t m,
-                                  LaneChunk *__restrict__ lc, uint32_t body_begin) {
+                                  LaneChunk *__restrict__ lc, uint32_t body_begin, uint32_t first_bit) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > num_markers) return;
     lc[k].in_begin = k == 0 ? body_begin : positions[k - 1];
     lc[k].in_end = k < num_markers ? positions[k] : m;
-    lc[k].begin_bits = lc[k].in_begin * 8;
+    lc[k].begin_bits = lc[k].in_begin * 8 + (k == 0 ? first_bit : 0u);
     lc[k].target_bits = lc[k].in_end * 8;
     lc[k].end_bits = 0;
     lc[k].slot_off = (uint64_t)k * kSlotSyms;
@@ -1581,13 +1591,13 @@ __global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const uint8
 // candidates -> chunk table: chunk 0 starts at the first block of the stream, chunk k at the k-th candidate
 __global__ void foreign_table_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ flags,
                                      const uint64_t *__restrict__ off, uint32_t spans, uint64_t total, uint64_t m,
-                                     uint32_t body_begin, LaneChunk *__restrict__ lc) {
+                                     uint64_t first_bits, LaneChunk *__restrict__ lc) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > spans) return;
     uint64_t k, begin;
     if (s == spans) {  // chunk 0
         k = 0;
-        begin = (uint64_t)body_begin * 8;
+        begin = first_bits;
     } else {
         if (!flags[s]) return;
         k = off[s] + 1;
@@ -2042,6 +2052,7 @@ __global__ void __launch_bounds__(1024) plan_lanes_kernel(LaneChunk *lc, uint32_
         verdict[5] = (uint64_t)lc[last_alive].final_seen;
         verdict[6] = (uint64_t)bad;
         verdict[7] = dead_count;
+        verdict[8] = lc[last_alive].end_bits;
     }
 }
 
@@ -2234,7 +2245,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     if (lane_blocks_reserved < 512) lane_blocks_reserved = 0;
     const uint32_t pieces_reserved = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
     // foreign streams: one candidate chunk per 8 KiB span (block_find_kernel), a unit of token space per bit of stream
-    const bool foreign_ok = c->opt_foreign_path && job.container != 3 && m >= kForeignMinBytes && m < (1ull << 32);
+    const bool foreign_ok = c->opt_foreign_path && m >= kForeignMinBytes && m < (1ull << 32);
     const uint64_t find_spans = foreign_ok ? (m + kFindSpan - 1) / kFindSpan : 0;
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2),
                                                          find_spans * kFindSub / kCoarse + 2);
@@ -2305,14 +2316,14 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             // worth it from a few hundred blocks on, only if the scratch was reserved for it, and only when the markers are
             // as close as this engine's blocks are (32 KiB of output each): pigz's 128 KiB pieces would fail on the slot size
             // after decoding a third of the stream
-            if (num_markers >= 256 && n <= lane_blocks_reserved && m <= n * (uint64_t)(kSlotSyms + 64)) {
+            if (num_markers >= 256 && n <= lane_blocks_reserved && m <= n * (uint64_t)(kSlotSyms + 64) && !job.prefix) {
                 uint64_t *d_pos = static_cast<uint64_t *>(c->arena.take((size_t)n * 8));
                 LaneChunk *d_lc = static_cast<LaneChunk *>(c->arena.take((size_t)n * sizeof(LaneChunk)));
                 WarpState *d_tables = static_cast<WarpState *>(c->arena.take((size_t)n * sizeof(WarpState)));
                 uint16_t *d_slots = static_cast<uint16_t *>(c->arena.take((size_t)n * kSlotSyms * 2));
                 if (d_pos && d_lc && d_tables && d_slots) {
                     marker_compact_kernel<true><<<pieces, 256, 0, st>>>(job.d_in, m, nullptr, d_piece_off, d_pos, num_markers);
-                    lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc, body_begin);
+                    lane_table_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_pos, (uint32_t)num_markers, m, d_lc, body_begin, job.begin_bit);
                     uint32_t *d_perm = static_cast<uint32_t *>(c->arena.take((size_t)n * 4));
                     lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
                     c->launches += 1;
@@ -2349,6 +2360,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     }
 
     // ---- a stream somebody else made: entry points at the dynamic block headers block_find_kernel accepts ------------------
+    const uint64_t first_bits = (uint64_t)body_begin * 8 + job.begin_bit;
     if (!lane_path_done && foreign_ok) {
         const uint32_t find_ctas = (uint32_t)find_spans;
         const uint32_t spans = find_ctas * kFindSub;  // candidate slots
@@ -2370,7 +2382,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             {
                 ScopedTimer t(c, 5);
                 ZK_CUDA(cudaFuncSetAttribute(block_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FindSmem)));
-                block_find_kernel<<<find_ctas, kFindThreads, sizeof(FindSmem), st>>>(job.d_in, m, (uint64_t)body_begin * 8, d_cand64, d_flags);
+                block_find_kernel<<<find_ctas, kFindThreads, sizeof(FindSmem), st>>>(job.d_in, m, first_bits, d_cand64, d_flags);
                 marker_scan_kernel<<<1, 1024, 0, st>>>(d_flags, spans, d_off, d_count);
                 c->launches += 2;
             }
@@ -2378,9 +2390,12 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             ZK_CUDA(cudaStreamSynchronize(st));
             const bool dbg = getenv("ZK_FOREIGN_DEBUG") != nullptr;
             if (dbg) fprintf(stderr, "[zk foreign] m %llu candidate slots %u entry points %llu\n", (unsigned long long)m, spans, (unsigned long long)found);
-            if (found >= kForeignMinChunks) {
+            if (found >= kForeignMinChunks + (job.prefix ? 1 : 0)) {
                 uint64_t n = found + 1;
-                foreign_table_kernel<<<(spans + 256) / 256, 256, 0, st>>>(d_cand64, d_flags, d_off, spans, found, m, body_begin, d_lc);
+                foreign_table_kernel<<<(spans + 256) / 256, 256, 0, st>>>(d_cand64, d_flags, d_off, spans, found, m, first_bits, d_lc);
+                // prefix mode: the last chunk may be cut; it stays in the table as the target of the one before it and is
+                // left alone otherwise
+                if (job.prefix) n -= 1;
                 lane_order_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_perm);
                 c->launches += 2;
                 const int lane_smem = kLaneWarps * kLaneWarpSmem;
@@ -2400,7 +2415,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
                             d_spill, d_spill_next, spill_units);
                     }
                     plan_lanes_kernel<<<1, 1024, 0, st>>>(d_lc, (uint32_t)n, d_chunks, d_num, d_verdict, job.cap, m,
-                                                          job.container == 0 ? 4u : job.container == 2 ? 8u : 0u, false);
+                                                          job.container == 0 ? 4u : job.container == 2 ? 8u : 0u, job.prefix || job.container == 3);
                     c->launches += 2;
                     ZK_CUDA(cudaMemcpyAsync(verdict, d_verdict, sizeof(verdict), cudaMemcpyDeviceToHost, st));
                     ZK_CUDA(cudaStreamSynchronize(st));
@@ -2489,6 +2504,12 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
         }
     }
     uint64_t total = verdict[3];
+    if (job.prefix && !lane_path_done) {  // no progress possible: the caller gathers more input
+        set_result_kernel<<<1, 32, 0, st>>>(job.d_result, 0, 0, ZK_BUF_ERROR, 1);
+        c->launches++;
+        ZK_CUDA(cudaGetLastError());
+        return ZK_OK;
+    }
     if (!lane_path_done && m >= (1ull << 32)) {
         // the chunk path below keeps candidate positions in 32 bits: a stream of 4 GiB or more that is not cut
         // by sync markers would have to be decoded by one warp anyway -- refuse it instead of wrapping positions
@@ -2509,7 +2530,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             const uint32_t grid = (max_chunks + kInfWarps - 1) / kInfWarps;
             {
                 ScopedTimer t(c, 4);
-                decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0, dict_len);
+                decode_kernel<false><<<grid, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, nullptr, 0, dict_len, job.begin_bit);
             }
             plan_chunks_kernel<<<1, 32, 0, st>>>(d_chunks, d_num, d_verdict);
             c->launches += 2;
@@ -2529,7 +2550,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
             const uint32_t nchunks = (uint32_t)verdict[0];
             const uint32_t grid = (nchunks + kInfWarps - 1) / kInfWarps;
             ScopedTimer t(c, 4);
-            decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap, dict_len);
+            decode_kernel<true><<<grid ? grid : 1, kInfWarps * 32, 0, st>>>(job.d_in, m, d_chunks, d_num, d_sym, job.cap, dict_len, job.begin_bit);
             c->launches += 1;
         }
     }
@@ -2576,7 +2597,7 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     int rc = job.container == 2 ? launch_crc32(c, 0u, job.d_out, total, d_partials, d_adler)
                                 : launch_adler32(c, 1u, job.d_out, total, d_partials, d_adler);
     if (rc != ZK_OK) return rc;
-    finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result, job.container);
+    finish_inflate_kernel<<<1, 32, 0, st>>>(job.d_in, m, d_verdict, d_adler, d_flag, job.d_result, job.prefix ? 4 : job.container);
     c->launches++;
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
