@@ -80,11 +80,13 @@ int zk_ctx_synchronize(zk_ctx *ctx);
  * caller must not free such a buffer while the context lives), "inflate_pipe" / "inflate_slab_bytes" (opt-in slab pipeline
  * of the host-buffer inflate), "inflate_foreign" (default 1: a stream without sync markers -- libz, gzip tools, the reference --
  * is cut at the dynamic block headers the engine finds in it and decoded in parallel; 0: one warp decodes it),
+ * "inflate_prefix_bytes" (stream handle: gathered bytes of a stream without markers from which everything up to the last
+ * entry point is decoded and handed out; 0 = 32 MiB, at least 256 KiB),
  * "timing" (1: CUDA events around every launch, read with the "*_us" counters; a profiling aid that costs the slab
  * overlap about a tenth of its throughput). */
 int zk_ctx_set_option(zk_ctx *ctx, const char *name, int64_t value);
 /* Counters since creation: name in {"kernel_launches","h2d_bytes","d2h_bytes","inflate_foreign_chunks",
- * "inflate_foreign_merges","inflate_pipe_slabs","inflate_pipe_fallbacks"}; with "timing" on also
+ * "inflate_foreign_merges","inflate_prefix_decodes","inflate_quick_incomplete","inflate_pipe_slabs","inflate_pipe_fallbacks"}; with "timing" on also
  * {"lz77","huffman","pack","adler","inflate_decode","inflate_other"} + "_us" / "_spans"; "reset_timing" clears those. */
 int64_t zk_ctx_get_counter(zk_ctx *ctx, const char *name);
 
