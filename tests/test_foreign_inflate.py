@@ -251,3 +251,41 @@ def test_reference_made_stream(engine, oracle):
     fast, slow, _, _ = _inflate_both(engine, stream, len(data) + 1024)
     orc, oout, _, _ = oracle.inflate(stream, len(data) + 1024)
     assert fast == slow and fast[0] == orc and fast[1] == oout
+
+
+@pytest.mark.gpu
+def test_random_libz_streams(engine):
+    """a few dozen streams over libz's parameter space (level, memLevel, strategy, flushes at random places, content cut from
+    every corpus kind at random boundaries): the entry-point path and the one-warp path agree with libz on all of them"""
+    import zlibk_b200 as zk
+    from zlibk_b200 import corpus
+
+    rng = np.random.default_rng(20261018)
+    kinds = [corpus.text_like(2 << 20).tobytes(), corpus.mixed_entropy(4 << 20).tobytes(), bytes(1 << 20),
+             rng.integers(0, 256, size=1 << 20, dtype=np.uint8).tobytes(), (b"0123456789abcdef" * 65536)]
+    used_fast = 0
+    for case in range(36):
+        parts = []
+        for _ in range(int(rng.integers(2, 7))):
+            src = kinds[int(rng.integers(0, len(kinds)))]
+            lo = int(rng.integers(0, len(src) - 1000))
+            parts.append(src[lo: lo + int(rng.integers(1000, 900000))])
+        data = b"".join(parts)
+        level = int(rng.integers(1, 10))
+        mem = int(rng.integers(1, 10))
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_DEFAULT_STRATEGY, zlib.Z_RLE][int(rng.integers(0, 4))]
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, mem, strategy)
+        out = []
+        pos = 0
+        while pos < len(data):
+            step = int(rng.integers(50000, 700000))
+            out.append(co.compress(data[pos: pos + step]))
+            pos += step
+            if rng.random() < 0.15:
+                out.append(co.flush([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_PARTIAL_FLUSH if hasattr(zlib, "Z_PARTIAL_FLUSH") else zlib.Z_SYNC_FLUSH][int(rng.integers(0, 3))]))
+        out.append(co.flush())
+        stream = b"".join(out)
+        fast, slow, chunks, _ = _inflate_both(engine, stream, len(data))
+        assert fast == slow == (zk.Z_STREAM_END, data, len(stream)), (case, level, mem, strategy, fast[0], slow[0], len(fast[1]), len(data))
+        used_fast += chunks > 0
+    assert used_fast >= 12, used_fast

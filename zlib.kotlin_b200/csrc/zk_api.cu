@@ -1666,20 +1666,20 @@ int stream_decode_tail(zk_stream *s, uint64_t *used) {
     const size_t m = s->pending_in.size();
     uint64_t cap = (uint64_t)m * 4 + 65536;
     for (;;) {
-        std::vector<uint8_t> buf(cap);
+        std::unique_ptr<uint8_t[]> buf(new uint8_t[cap]);  // (not a vector: no need to clear gigabytes for a try that may fail)
         uint64_t got = 0;
         uint32_t check = 1;
         const int rc = host_inflate(s->ctx, s->pending_in.data(), m, s->window.empty() ? nullptr : s->window.data(), (uint32_t)s->window.size(),
-                                    buf.data(), cap, &got, used, 1, 0, &check, true, s->bit_off);
+                                    buf.get(), cap, &got, used, 1, 0, &check, true, s->bit_off);
         if (rc == ZK_BUF_ERROR && got == 0 && *used == 0 && cap < (uint64_t)m * 1100 + 65536) {  // the output may not have fitted
             cap *= 16;
             continue;
         }
         if (rc != ZK_STREAM_END) return rc;
-        if (s->container == 2) s->crc = got ? zk_crc32(s->ctx, s->crc, buf.data(), got) : s->crc;
+        if (s->container == 2) s->crc = got ? zk_crc32(s->ctx, s->crc, buf.get(), got) : s->crc;
         else s->adler = adler32_combine(s->adler, check, got);
-        s->pending_out.insert(s->pending_out.end(), buf.begin(), buf.begin() + (long)got);
-        stream_note_output(s, buf.data(), got);
+        s->pending_out.insert(s->pending_out.end(), buf.get(), buf.get() + got);
+        stream_note_output(s, buf.get(), got);
         return ZK_STREAM_END;
     }
 }
