@@ -29,15 +29,20 @@ __constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+// The kernel is one lane's dependent chain through shared memory for most of its time, so what counts is how many warps
+// an SM holds: arrays that are never alive together share their bytes (5 176 instead of 6 904 per warp: 44 instead of 32
+// warps per SM).
 struct WarpScratch {
-    uint32_t freq[kMaxSyms];      // working copy of the counts (>= 1 for coded symbols)
-    uint16_t order[kMaxSyms];     // symbols sorted by ascending (freq, symbol)
-    uint32_t weight[2 * kMaxSyms];
     union {
-        uint16_t parent[2 * kMaxSyms];
-        uint32_t parent32[16];
+        uint32_t freq[kMaxSyms];          // working copy of the counts (>= 1 for coded symbols): dead once the leaf weights are set
+        uint16_t parent[2 * kMaxSyms];    // ... which is when the tree loop starts to write the parents
+        uint32_t parent32[16];            // (assign_codes: next code per length)
     };
-    uint8_t depth[2 * kMaxSyms];
+    uint16_t order[kMaxSyms];     // symbols sorted by ascending (freq, symbol)
+    union {
+        uint32_t weight[2 * kMaxSyms];    // sort keys, then node weights: dead once the tree stands
+        uint8_t depth[2 * kMaxSyms];      // ... which is when the depths are computed
+    };
     uint8_t lit_len[kMaxSyms];
     uint8_t dist_len[32];
     uint8_t cl_len[20];
