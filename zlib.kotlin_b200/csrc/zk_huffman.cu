@@ -1,4 +1,4 @@
-// zk_huffman.cu -- K2: per-block code construction and block planning, one warp per deflate block.
+// zk_huffman.cu -- K2: per-block code construction and block planning, eight lanes per deflate block (four blocks per warp).
 //
 // Replaces HuffmanBuilder.buildLengths (deflate/HuffmanBuilder.kt:10-83), CanonicalHuffman.buildEncoder
 // (inflate/CanonicalHuffman.kt:85-120), the code-length RLE + header of DeflateStream.kt:818-900 and the
@@ -24,6 +24,19 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kMaxSyms = 288;
+// Most of a block's work is sequential (the two-queue tree, the depths, the run-length coding, the header bits) and runs
+// on one lane; a warp per block issued those one-lane instruction streams one block at a time, and that -- not latency, not
+// occupancy -- bounded the kernel.  So a block gets a GROUP of kG lanes: the parallel parts stride by kG, the sequential ones
+// run on the group's first lane, and the four leaders of a warp execute their streams in lockstep.
+constexpr int kG = 8;
+constexpr int kPerWarp = 32 / kG;
+__device__ __forceinline__ int group_leader() { return (int)(threadIdx.x & 31u) & ~(kG - 1); }
+template <class T>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int off = kG / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+    return v;
+}
 
 __constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
@@ -55,19 +68,19 @@ struct WarpScratch {
 
 __device__ __forceinline__ uint32_t bit_reverse(uint32_t code, int len) { return __brev(code) >> (32 - len); }
 
-// Length-limited Huffman code lengths for freq[0,n).  Warp-cooperative where it is cheap (sort by rank),
-// lane 0 for the sequential tree walk.  Every lane returns after the lengths are in `out`.
+// Length-limited Huffman code lengths for freq[0,n).  Group-cooperative where it is cheap (sort by rank),
+// the group's first lane for the sequential tree walk.  Every lane returns after the lengths are in `out`.
+// lane = lane in the group (0 .. kG-1).
 __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, int maxbits, uint8_t *out, int lane) {
     // 1. working counts; make sure at least two symbols are coded
     int used = 0;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += kG) {
         const uint32_t f = freq_in[i];
         w.freq[i] = f;
         out[i] = 0;
         used += f != 0;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) used += __shfl_xor_sync(0xFFFFFFFFu, used, off);
+    used = group_sum(used);
     __syncwarp();
     if (lane == 0 && used < 2) {
         for (int i = 0; i < n && used < 2; ++i)
@@ -76,34 +89,35 @@ __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, in
                 ++used;
             }
     }
-    used = __shfl_sync(0xFFFFFFFFu, used, 0);
+    used = __shfl_sync(0xFFFFFFFFu, used, group_leader());
     __syncwarp();
     // 2. rank sort of the coded symbols by (freq, symbol): one key per symbol (freq << 9 | symbol; counts are below
-    // 2^22), every lane ranks its up to nine symbols against all keys, which are read as broadcasts
+    // 2^22), every lane ranks its symbols, nine at a time, against all keys, which are read as broadcasts in the group
     {
         uint32_t *key = w.weight;  // free until step 3
-        for (int i = lane; i < n; i += 32) key[i] = w.freq[i] ? ((w.freq[i] << 9) | (uint32_t)i) : 0xFFFFFFFFu;
+        for (int i = lane; i < n; i += kG) key[i] = w.freq[i] ? ((w.freq[i] << 9) | (uint32_t)i) : 0xFFFFFFFFu;
         __syncwarp();
-        uint32_t mykey[9];
-        int rank[9];
+        for (int base = 0; base < n; base += 9 * kG) {  // (the trip count depends on n alone: uniform over the warp's groups
+            uint32_t mykey[9];                           //  only when they build the same alphabet -- they do)
+            int rank[9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            mykey[t] = lane + 32 * t < n ? key[lane + 32 * t] : 0xFFFFFFFFu;
-            rank[t] = 0;
+            for (int t = 0; t < 9; ++t) {
+                mykey[t] = base + lane + kG * t < n ? key[base + lane + kG * t] : 0xFFFFFFFFu;
+                rank[t] = 0;
+            }
+            for (int j = 0; j < n; ++j) {
+                const uint32_t kj = key[j];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) rank[t] += kj < mykey[t];
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (mykey[t] != 0xFFFFFFFFu) w.order[rank[t]] = (uint16_t)(base + lane + kG * t);
         }
-        for (int j = 0; j < n; ++j) {
-            const uint32_t kj = key[j];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) rank[t] += kj < mykey[t];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-            if (mykey[t] != 0xFFFFFFFFu) w.order[rank[t]] = (uint16_t)(lane + 32 * t);
     }
     __syncwarp();
     // 3. tree with two queues (leaves in sorted order, internal nodes in creation order)
-    for (int i = lane; i < used; i += 32) w.weight[i] = w.freq[w.order[i]];
+    for (int i = lane; i < used; i += kG) w.weight[i] = w.freq[w.order[i]];
     __syncwarp();
     if (lane == 0) {
         int leaf = 0, inner = used, next = used;
@@ -156,14 +170,14 @@ __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, in
 
 // Canonical codes for `len`, bit-reversed for LSB-first emission; packed as code | len << 16.
 __device__ void assign_codes(WarpScratch &w, const uint8_t *len, int n, int maxbits, uint32_t *packed, int lane) {
-    // symbols per length with shared atomics, first code of each length by lane 0, then the symbols in chunks of 32 in
+    // symbols per length with shared atomics, first code of each length by lane 0, then the symbols in chunks of kG in
     // symbol order: a symbol's rank among the codes of its length is the running count of that length plus the number
     // of lower lanes of the chunk with the same length (match.any)
     uint32_t *count = w.cl_freq;   // 16 counters; the code-length frequencies are not needed any more when this runs ...
     uint32_t *next = w.parent32;   // ... and neither is the tree
-    if (lane < 16) count[lane] = 0;
+    for (int i = lane; i < 16; i += kG) count[i] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32)
+    for (int i = lane; i < n; i += kG)
         if (len[i]) atomicAdd(&count[len[i]], 1u);
     __syncwarp();
     if (lane == 0) {
@@ -175,14 +189,15 @@ __device__ void assign_codes(WarpScratch &w, const uint8_t *len, int n, int maxb
         }
     }
     __syncwarp();
-    for (int c = 0; c * 32 < n; ++c) {
-        const int i = c * 32 + lane;
+    const uint32_t wl = threadIdx.x & 31u;  // lane in the warp: the groups of a warp match among themselves only
+    for (int c = 0; c * kG < n; ++c) {
+        const int i = c * kG + lane;
         const int l = i < n ? len[i] : 0;
-        const uint32_t same = __match_any_sync(0xFFFFFFFFu, l);
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, (uint32_t)l | ((wl / kG) << 8));
         uint32_t v = 0;
-        if (l) v = bit_reverse(next[l] + (uint32_t)__popc(same & ((1u << lane) - 1u)), l) | ((uint32_t)l << 16);
+        if (l) v = bit_reverse(next[l] + (uint32_t)__popc(same & ((1u << wl) - 1u)), l) | ((uint32_t)l << 16);
         __syncwarp();
-        if (l && (same & ((1u << lane) - 1u)) == 0u) next[l] += (uint32_t)__popc(same);
+        if (l && (same & ((1u << wl) - 1u)) == 0u) next[l] += (uint32_t)__popc(same);
         if (i < n) packed[i] = v;
         __syncwarp();
     }
@@ -317,11 +332,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
                                                                     uint64_t n, uint32_t block_bytes,
                                                                     uint32_t num_blocks, int force_type,
                                                                     BlockPlan *__restrict__ plans) {
-    __shared__ WarpScratch scratch[kWarpsPerCta];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t blk = blockIdx.x * kWarpsPerCta + wid;
-    if (blk >= num_blocks) return;
-    WarpScratch &w = scratch[wid];
+    extern __shared__ __align__(16) uint8_t huff_smem[];
+    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(huff_smem);
+    const int lane = (int)(threadIdx.x & 31u) % kG, wid = threadIdx.x >> 5, sub = (int)(threadIdx.x & 31u) / kG;
+    // a group behind the last block repeats the last block (same values to the same places): every lane of the warp has
+    // to reach the warp-wide votes and barriers below
+    const uint32_t blk = tmin<uint32_t>((blockIdx.x * kWarpsPerCta + wid) * kPerWarp + sub, num_blocks - 1);
+    WarpScratch &w = scratch[wid * kPerWarp + sub];
     const uint32_t *hist = block_hist + (uint64_t)blk * kHistStride;
     BlockPlan &plan = plans[blk];
 
@@ -338,31 +355,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
         for (int i = 0; i < 19; ++i) w.cl_freq[i] = 0;
         for (int i = 0; i < ncl; ++i) w.cl_freq[w.cl_sym[i]]++;
     }
-    hlit = __shfl_sync(0xFFFFFFFFu, hlit, 0);
-    hdist = __shfl_sync(0xFFFFFFFFu, hdist, 0);
-    ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
+    hlit = __shfl_sync(0xFFFFFFFFu, hlit, group_leader());
+    hdist = __shfl_sync(0xFFFFFFFFu, hdist, group_leader());
+    ncl = __shfl_sync(0xFFFFFFFFu, ncl, group_leader());
     __syncwarp();
     build_lengths(w, w.cl_freq, 19, 7, w.cl_len, lane);
     assign_codes(w, w.cl_len, 19, 7, w.cl_code, lane);
 
     // exact sizes of the three encodings
     uint64_t dyn_bits = 0, fix_bits = 0;
-    for (int i = lane; i < kNumLitLen; i += 32) {
+    for (int i = lane; i < kNumLitLen; i += kG) {
         const uint64_t f = hist[i];
         const int extra = i >= 257 ? c_len_extra[i - 257] : 0;
         dyn_bits += f * (uint64_t)(w.lit_len[i] + extra);
         fix_bits += f * (uint64_t)(fixed_litlen_bits(i) + extra);
     }
-    if (lane < kNumDist) {
-        const uint64_t f = hist[kDistHistBase + lane];
-        dyn_bits += f * (uint64_t)(w.dist_len[lane] + c_dist_extra[lane]);
-        fix_bits += f * (uint64_t)(5 + c_dist_extra[lane]);
+    for (int i = lane; i < kNumDist; i += kG) {
+        const uint64_t f = hist[kDistHistBase + i];
+        dyn_bits += f * (uint64_t)(w.dist_len[i] + c_dist_extra[i]);
+        fix_bits += f * (uint64_t)(5 + c_dist_extra[i]);
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        dyn_bits += __shfl_xor_sync(0xFFFFFFFFu, dyn_bits, off);
-        fix_bits += __shfl_xor_sync(0xFFFFFFFFu, fix_bits, off);
-    }
+    dyn_bits = group_sum(dyn_bits);
+    fix_bits = group_sum(fix_bits);
     int hclen = 19;
     uint32_t head_bits = 0;
     if (lane == 0) {
@@ -373,8 +387,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
             head_bits += w.cl_len[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
         }
     }
-    hclen = __shfl_sync(0xFFFFFFFFu, hclen, 0);
-    head_bits = __shfl_sync(0xFFFFFFFFu, head_bits, 0);
+    hclen = __shfl_sync(0xFFFFFFFFu, hclen, group_leader());
+    head_bits = __shfl_sync(0xFFFFFFFFu, head_bits, group_leader());
 
     const uint32_t raw = (uint32_t)tmin<uint64_t>(block_bytes, n - (uint64_t)blk * block_bytes);
     const uint64_t dyn_total = head_bits + dyn_bits, fix_total = 3 + fix_bits;
@@ -391,16 +405,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
     // a forced encoding must still fit the packer's shared image (block span + header slack)
     if (type != 0 && (type == 2 ? dyn_bytes : fix_bytes) > sto_bytes + 256) type = 0;
 
-    if (type == 2) {
-        assign_codes(w, w.lit_len, kNumLitLen, 15, plan.litlen_code, lane);
-        assign_codes(w, w.dist_len, kNumDist, 15, plan.dist_code, lane);
-    } else {
+    // (every group assigns the dynamic codes -- the votes and barriers inside are the whole warp's -- and a group whose block
+    // is not dynamic overwrites them)
+    assign_codes(w, w.lit_len, kNumLitLen, 15, plan.litlen_code, lane);
+    assign_codes(w, w.dist_len, kNumDist, 15, plan.dist_code, lane);
+    if (type != 2) {
         // fixed codes (RFC 1951 3.2.6); also filled for stored blocks so the plan is always defined
-        for (int i = lane; i < kNumLitLen; i += 32) w.lit_len[i] = (uint8_t)fixed_litlen_bits(i);
-        if (lane < kNumDist) w.dist_len[lane] = 5;
-        __syncwarp();
-        for (int i = lane; i < kNumLitLen; i += 32) {
-            const int l = w.lit_len[i];
+        for (int i = lane; i < kNumLitLen; i += kG) {
+            const int l = fixed_litlen_bits(i);
             uint32_t code;
             if (i < 144) code = 0x30 + i;
             else if (i < 256) code = 0x190 + (i - 144);
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
             else code = 0xC0 + (i - 280);
             plan.litlen_code[i] = bit_reverse(code, l) | ((uint32_t)l << 16);
         }
-        if (lane < kNumDist) plan.dist_code[lane] = bit_reverse((uint32_t)lane, 5) | (5u << 16);
+        for (int i = lane; i < kNumDist; i += kG) plan.dist_code[i] = bit_reverse((uint32_t)i, 5) | (5u << 16);
     }
     __syncwarp();
 
@@ -487,8 +499,11 @@ int launch_hist(zk_ctx *c, const uint32_t *tokens, const uint32_t *block_tok_beg
 
 int launch_huffman(zk_ctx *c, const uint32_t *block_hist, uint64_t n, uint32_t block_bytes, uint32_t num_blocks,
                    int force_type, BlockPlan *plans) {
-    const uint32_t grid = (num_blocks + kWarpsPerCta - 1) / kWarpsPerCta;
-    huffman_kernel<<<grid, kWarpsPerCta * 32, 0, c->stream>>>(block_hist, n, block_bytes, num_blocks, force_type, plans);
+    const uint32_t per_cta = kWarpsPerCta * kPerWarp;
+    const uint32_t grid = (num_blocks + per_cta - 1) / per_cta;
+    const int smem = (int)(sizeof(WarpScratch) * per_cta);
+    ZK_CUDA(cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    huffman_kernel<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(block_hist, n, block_bytes, num_blocks, force_type, plans);
     c->launches += 1;
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
