@@ -545,3 +545,41 @@ def test_sharded_inflate_with_emulated_ranks(engine, world, n):
         assert d_out[: b - a].cpu().numpy().tobytes() == host[a:b].tobytes()
         adler = engine.adler32_combine(adler, a32 & 0xFFFFFFFF, b - a)
     assert adler == zlib.adler32(host.tobytes()) == folded
+
+
+@pytest.mark.gpu
+def test_machine_fitted_units_round_trip(engine):
+    """From ~75 MiB on the LZ units are cut to fit the SMs (a few hundred KiB to MiB, not a power of two): the stream of a
+    200 MiB input decodes to the input with libz and with the GPU inflate, and its size stays within 1 % of the 512 KiB units'."""
+    import zlib
+
+    import torch
+    from zlibk_b200 import corpus
+
+    n = 200 << 20
+    host = corpus.mixed_entropy(n)
+    dev = torch.device("cuda", engine.device)
+    d_in = torch.from_numpy(host).to(dev)
+    cap = engine.compress_bound(n)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    sizes = {}
+    for unit in (0, 512 << 10):
+        engine.set_option("chunk_bytes", unit)
+        try:
+            assert engine.deflate_device(d_in.data_ptr(), n, 6, 0, d_out.data_ptr(), cap, d_res.data_ptr()) == 0
+            engine.synchronize()
+        finally:
+            engine.set_option("chunk_bytes", 0)
+        res = d_res.cpu().tolist()
+        assert res[2] == 0
+        sizes[unit] = res[0]
+        if unit == 0:
+            stream = bytes(d_out[: res[0]].cpu().numpy())
+            assert zlib.decompress(stream) == host.tobytes()
+            d_back = torch.empty(n, dtype=torch.uint8, device=dev)
+            d_res2 = torch.zeros(4, dtype=torch.int64, device=dev)
+            engine.inflate_device(d_out.data_ptr(), res[0], d_back.data_ptr(), n, d_res2.data_ptr())
+            engine.synchronize()
+            assert d_res2.cpu().tolist()[2] == 1 and bool(torch.equal(d_back, d_in))
+    assert abs(sizes[0] - sizes[512 << 10]) <= 0.01 * sizes[512 << 10], sizes

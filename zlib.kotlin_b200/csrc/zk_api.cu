@@ -112,12 +112,27 @@ static uint32_t pick_unit_bytes(const zk_ctx *c, uint64_t n, uint32_t block_byte
         uint64_t u = (uint64_t)c->opt_chunk_bytes / block_bytes * block_bytes;
         return (uint32_t)tmax<uint64_t>(u, block_bytes);
     }
+    // Units fitted to the machine: n cut into waves x SMs equal units (a multiple of the block span).  A unit pays for its
+    // 32 KiB of history and for filling its software pipeline once, and a whole number of waves leaves no SM idle at the end
+    // of the kernel -- measured at 1 GiB (tools/unit_sweep.py): 512 KiB units 51.0 GB/s, 1 184 KiB (three waves per 512 MiB slab)
+    // 52.2, 1 792 KiB (two) 52.4, 3 552 KiB (one) 52.8, but 2 048 KiB (1.7 waves) 49.3.
+    const uint64_t sms = (uint64_t)c->sm_count;
+    auto fitted = [&](uint64_t waves) {
+        uint64_t v = (n + sms * waves - 1) / (sms * waves);
+        v = (v + block_bytes - 1) / block_bytes * block_bytes;
+        return tmin<uint64_t>(tmax<uint64_t>(v, block_bytes), 8u << 20);
+    };
     uint64_t u = 512u << 10;
     if (mode == kUnitTailFilled) {
-        // the next slab's LZ kernel fills the tail: large units, as long as two slabs in flight cover every SM
+        // the next slab's LZ kernel takes over an SM as soon as its unit is done: one unit per SM, no tail to keep short
+        if (fitted(1) >= (1u << 20)) return (uint32_t)fitted(1);
+        // (small slabs: large units, as long as two slabs in flight cover every SM)
         while (u > block_bytes && n / u < (uint64_t)c->sm_count / 2) u >>= 1;
         return (uint32_t)tmax<uint64_t>(u, block_bytes);
     }
+    // nothing fills the tail of a single or last slab: two waves, so that units of different cost (long repeats take twice as
+    // long as text) even out -- from the size on where such a unit is worth its fixed cost
+    if (fitted(2) >= (1u << 20)) return (uint32_t)fitted(2);
     if (mode == kUnitLastOfMany) {
         // short last slab of a pipelined job: fewest waves x (unit + what a unit pays for its 32 KiB of history and for
         // filling its software pipeline, ~52 KiB worth of steps)

@@ -29,6 +29,8 @@ constexpr int kMaxSyms = 288;
 // occupancy -- bounded the kernel.  So a block gets a GROUP of kG lanes: the parallel parts stride by kG, the sequential ones
 // run on the group's first lane, and the four leaders of a warp execute their streams in lockstep.
 constexpr int kG = 8;
+constexpr int kLitFastBits = 9;            // == zk_inflate.cu kLaneLitBits
+constexpr uint32_t kLongSymsPerBlock = 512;  // symbols with longer codes a block may hold before it is coded again, limited
 constexpr int kPerWarp = 32 / kG;
 __device__ __forceinline__ int group_leader() { return (int)(threadIdx.x & 31u) & ~(kG - 1); }
 template <class T>
@@ -151,14 +153,22 @@ __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, in
                 count[d]++;
             }
         }
-        // 5. repair: move one leaf down from the deepest non-full level per two overflowing leaves
-        while (overflow > 0) {
+        // 5. repair.  Folding the deeper leaves up to maxbits over-subscribes the code by an exact number of units of
+        // 2^-maxbits (the tree was complete).  One step -- a leaf of the deepest level below maxbits that has one becomes an
+        // inner node over itself and one of the folded leaves -- takes exactly one unit away: 2^-b turns into 2 * 2^-(b+1),
+        // and a leaf leaves level maxbits.  (zlib counts "overflow" over inner nodes as well and gets the same number; counting
+        // the leaves alone does not, which only shows when the limit is tight.)
+        (void)overflow;
+        long long excess = -(1ll << maxbits);
+        for (int b = 1; b <= maxbits; ++b) excess += (long long)count[b] << (maxbits - b);
+        while (excess > 0 && count[maxbits] > 0) {
             int bits = maxbits - 1;
-            while (count[bits] == 0) --bits;
+            while (bits > 0 && count[bits] == 0) --bits;
+            if (bits == 0) break;
             count[bits]--;
             count[bits + 1] += 2;
             count[maxbits]--;
-            overflow -= 2;
+            --excess;
         }
         // 6. longest codes to the rarest symbols (order[] is ascending by weight)
         int idx = 0;
@@ -343,6 +353,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
     BlockPlan &plan = plans[blk];
 
     build_lengths(w, hist, kNumLitLen, 15, w.lit_len, lane);
+    {
+        // The inflate side decodes literal/length codes of up to kLaneLitBits = 9 bits from shared memory (zk_inflate.cu); a
+        // longer one costs the lane decoder a dependent load from global memory, which the 31 other lanes of its warp wait
+        // for.  A text block has a hundred such symbols and nobody notices; a block with a flat literal distribution (binary
+        // counters: 3 000 of 18 000 symbols at 10 bits) became the block the whole inflate waited for (6 -> 10 ms per GiB).
+        // Such a block is coded again with the lengths limited to 9 bits, which costs a flat distribution next to nothing
+        // (limiting EVERY block costs 1.2 % of the output: text pays for its rare symbols).  The votes and barriers inside
+        // build_lengths are the whole warp's, so all four groups go again when one has to, the others with the old limit.
+        uint32_t long_syms = 0;
+        for (int i = lane; i < kNumLitLen; i += kG) long_syms += w.lit_len[i] > kLitFastBits ? hist[i] : 0u;
+        long_syms = group_sum(long_syms);
+        const bool again = long_syms > kLongSymsPerBlock;
+        if (__any_sync(0xFFFFFFFFu, again)) build_lengths(w, hist, kNumLitLen, again ? kLitFastBits : 15, w.lit_len, lane);
+    }
     build_lengths(w, hist + kDistHistBase, kNumDist, 15, w.dist_len, lane);
 
     // header: run-length code the two length sequences separately, then code the RLE alphabet
