@@ -14,15 +14,18 @@
 //      16-bit symbols -- a byte, or 0x8000 | i for "byte i of the 32 KiB that precede this block" (the dictionary of a
 //      block is not known yet, so references into it are carried symbolically, copies included); eight blocks are
 //      re-based into one coarse chunk (resolve_coarse_kernel);
-//      otherwise (pigz chunks, foreign streams): one WARP per candidate chunk, first only to SIZE it (it must end
-//      exactly on the next candidate; a false candidate fails and is merged into its predecessor), then to WRITE its
-//      symbols (decode_kernel);
+//      otherwise (pigz chunks, libz / gzip-tool / reference streams): entry points are FOUND -- block_find_kernel accepts
+//      the bit positions where a dynamic block header passes every check of the decoder -- and one lane decodes each chunk
+//      between two of them (decode_lanes_kernel<true>), a chunk that meets a false entry point going on through its range;
+//      only small, damaged or entry-less streams are left to one WARP per marker-delimited chunk (decode_kernel: first to
+//      SIZE a chunk, which must end exactly on the next candidate, then to WRITE its symbols), which owns the reference's
+//      error codes;
 //   3. resolves the last 32 KiB of every chunk: the tail of a chunk is a map over the window before it, maps compose,
 //      and the chain becomes a two-level scan (window_compose / window_chain / window_apply kernels);
 //   4. turns all symbols into bytes in parallel (materialize_kernel) and checks the trailer (Adler-32 for zlib,
 //      CRC-32 + ISIZE for gzip, nothing for raw deflate).
-// A preset dictionary is "window -1" in front of the first chunk.  A stream with no candidates (reference or libz
-// output) is one chunk decoded by one warp -- "replicas only".
+// A preset dictionary is "window -1" in front of the first chunk.  The deflate data may begin inside a byte (begin_bit:
+// the stream handle decodes an unfinished stream up to its last entry point and carries the rest).
 //
 // Error behaviour follows the reference: Z_STREAM_END on success (IS:424), Z_NEED_DICT for FDICT (IS:36-43),
 // Z_DATA_ERROR for bad headers / block type 3 / LEN-NLEN / invalid codes / distance too far back
