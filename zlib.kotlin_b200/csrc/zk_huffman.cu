@@ -70,10 +70,54 @@ struct WarpScratch {
 
 __device__ __forceinline__ uint32_t bit_reverse(uint32_t code, int len) { return __brev(code) >> (32 - len); }
 
+// Code lengths from the tree that stands in w.parent (leaves 0 .. used-1 in the order of w.order), limited to maxbits.  One
+// lane; no votes or barriers inside, so one group of a warp may call it again with a tighter limit while the others wait.
+__device__ void limit_lengths(WarpScratch &w, int used, int maxbits, uint8_t *out) {
+    // 4. depths from the root down, counts per length with the overflow folded to maxbits
+    const int root = 2 * used - 2;
+    w.depth[root] = 0;
+    int count[40];
+    for (int b = 0; b < 40; ++b) count[b] = 0;
+    int overflow = 0;
+    for (int i = root - 1; i >= 0; --i) {
+        int d = w.depth[w.parent[i]] + 1;
+        if (d > 39) d = 39;  // counts beyond maxbits are folded below; keep the byte from wrapping
+        w.depth[i] = (uint8_t)d;
+        if (i < used) {
+            if (d > maxbits) {
+                d = maxbits;
+                ++overflow;
+            }
+            count[d]++;
+        }
+    }
+    // 5. repair.  Folding the deeper leaves up to maxbits over-subscribes the code by an exact number of units of
+    // 2^-maxbits (the tree was complete).  One step -- a leaf of the deepest level below maxbits that has one becomes an
+    // inner node over itself and one of the folded leaves -- takes exactly one unit away: 2^-b turns into 2 * 2^-(b+1),
+    // and a leaf leaves level maxbits.  (zlib counts "overflow" over inner nodes as well and gets the same number; counting
+    // the leaves alone does not, which only shows when the limit is tight.)
+    (void)overflow;
+    long long excess = -(1ll << maxbits);
+    for (int b = 1; b <= maxbits; ++b) excess += (long long)count[b] << (maxbits - b);
+    while (excess > 0 && count[maxbits] > 0) {
+        int bits = maxbits - 1;
+        while (bits > 0 && count[bits] == 0) --bits;
+        if (bits == 0) break;
+        count[bits]--;
+        count[bits + 1] += 2;
+        count[maxbits]--;
+        --excess;
+    }
+    // 6. longest codes to the rarest symbols (order[] is ascending by weight)
+    int idx = 0;
+    for (int bits = maxbits; bits >= 1; --bits)
+        for (int k = count[bits]; k > 0; --k) out[w.order[idx++]] = (uint8_t)bits;
+}
+
 // Length-limited Huffman code lengths for freq[0,n).  Group-cooperative where it is cheap (sort by rank),
 // the group's first lane for the sequential tree walk.  Every lane returns after the lengths are in `out`.
 // lane = lane in the group (0 .. kG-1).
-__device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, int maxbits, uint8_t *out, int lane) {
+__device__ int build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, int maxbits, uint8_t *out, int lane) {
     // 1. working counts; make sure at least two symbols are coded
     int used = 0;
     for (int i = lane; i < n; i += kG) {
@@ -135,47 +179,10 @@ __device__ void build_lengths(WarpScratch &w, const uint32_t *freq_in, int n, in
             w.parent[pick[1]] = (uint16_t)next;
             ++next;
         }
-        // 4. depths from the root down, counts per length with the overflow folded to maxbits
-        const int root = 2 * used - 2;
-        w.depth[root] = 0;
-        int count[40];
-        for (int b = 0; b < 40; ++b) count[b] = 0;
-        int overflow = 0;
-        for (int i = root - 1; i >= 0; --i) {
-            int d = w.depth[w.parent[i]] + 1;
-            if (d > 39) d = 39;  // counts beyond maxbits are folded below; keep the byte from wrapping
-            w.depth[i] = (uint8_t)d;
-            if (i < used) {
-                if (d > maxbits) {
-                    d = maxbits;
-                    ++overflow;
-                }
-                count[d]++;
-            }
-        }
-        // 5. repair.  Folding the deeper leaves up to maxbits over-subscribes the code by an exact number of units of
-        // 2^-maxbits (the tree was complete).  One step -- a leaf of the deepest level below maxbits that has one becomes an
-        // inner node over itself and one of the folded leaves -- takes exactly one unit away: 2^-b turns into 2 * 2^-(b+1),
-        // and a leaf leaves level maxbits.  (zlib counts "overflow" over inner nodes as well and gets the same number; counting
-        // the leaves alone does not, which only shows when the limit is tight.)
-        (void)overflow;
-        long long excess = -(1ll << maxbits);
-        for (int b = 1; b <= maxbits; ++b) excess += (long long)count[b] << (maxbits - b);
-        while (excess > 0 && count[maxbits] > 0) {
-            int bits = maxbits - 1;
-            while (bits > 0 && count[bits] == 0) --bits;
-            if (bits == 0) break;
-            count[bits]--;
-            count[bits + 1] += 2;
-            count[maxbits]--;
-            --excess;
-        }
-        // 6. longest codes to the rarest symbols (order[] is ascending by weight)
-        int idx = 0;
-        for (int bits = maxbits; bits >= 1; --bits)
-            for (int k = count[bits]; k > 0; --k) out[w.order[idx++]] = (uint8_t)bits;
+        limit_lengths(w, used, maxbits, out);
     }
     __syncwarp();
+    return used;
 }
 
 // Canonical codes for `len`, bit-reversed for LSB-first emission; packed as code | len << 16.
@@ -352,20 +359,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) huffman_kernel(const uint32
     const uint32_t *hist = block_hist + (uint64_t)blk * kHistStride;
     BlockPlan &plan = plans[blk];
 
-    build_lengths(w, hist, kNumLitLen, 15, w.lit_len, lane);
+    const int used_lit = build_lengths(w, hist, kNumLitLen, 15, w.lit_len, lane);
     {
         // The inflate side decodes literal/length codes of up to kLaneLitBits = 9 bits from shared memory (zk_inflate.cu); a
         // longer one costs the lane decoder a dependent load from global memory, which the 31 other lanes of its warp wait
         // for.  A text block has a hundred such symbols and nobody notices; a block with a flat literal distribution (binary
         // counters: 3 000 of 18 000 symbols at 10 bits) became the block the whole inflate waited for (6 -> 10 ms per GiB).
-        // Such a block is coded again with the lengths limited to 9 bits, which costs a flat distribution next to nothing
-        // (limiting EVERY block costs 1.2 % of the output: text pays for its rare symbols).  The votes and barriers inside
-        // build_lengths are the whole warp's, so all four groups go again when one has to, the others with the old limit.
+        // Such a block gets its lengths from the same tree again, limited to 9 bits, which costs a flat distribution next to
+        // nothing (limiting EVERY block costs 1.2 % of the output: text pays for its rare symbols).
         uint32_t long_syms = 0;
         for (int i = lane; i < kNumLitLen; i += kG) long_syms += w.lit_len[i] > kLitFastBits ? hist[i] : 0u;
         long_syms = group_sum(long_syms);
-        const bool again = long_syms > kLongSymsPerBlock;
-        if (__any_sync(0xFFFFFFFFu, again)) build_lengths(w, hist, kNumLitLen, again ? kLitFastBits : 15, w.lit_len, lane);
+        if (long_syms > kLongSymsPerBlock && lane == 0) limit_lengths(w, used_lit, kLitFastBits, w.lit_len);
+        __syncwarp();
     }
     build_lengths(w, hist + kDistHistBase, kNumDist, 15, w.dist_len, lane);
 
