@@ -2248,7 +2248,10 @@ int run_inflate(zk_ctx *c, const InflateJob &job) {
     if (lane_blocks_reserved < 512) lane_blocks_reserved = 0;
     const uint32_t pieces_reserved = (uint32_t)((m + kPieceBytes - 1) / kPieceBytes);
     // foreign streams: one candidate chunk per 8 KiB span (block_find_kernel), a unit of token space per bit of stream
-    const bool foreign_ok = c->opt_foreign_path && m >= kForeignMinBytes && m < (1ull << 32);
+    // (up to 2 GiB of stream in one call: the path's scratch -- 16 B of token space per compressed byte above all -- is reserved
+    //  with everything else before the stream has been looked at; larger streams without markers go through the stream handle,
+    //  which decodes them in pieces)
+    const bool foreign_ok = c->opt_foreign_path && m >= kForeignMinBytes && m < (1ull << 31);
     const uint64_t find_spans = foreign_ok ? (m + kFindSpan - 1) / kFindSpan : 0;
     const uint32_t max_chunks = (uint32_t)tmax<uint64_t>(tmax<uint64_t>(num_spans + 1, lane_blocks_reserved / kCoarse + 2),
                                                          find_spans * kFindSub / kCoarse + 2);
